@@ -1,0 +1,131 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container).
+
+TEST INFRASTRUCTURE -- see `oracle/__init__.py`.
+
+    python -m oracle.make_golden            # needs /root/reference
+
+Every array stored here was produced by reference code executed verbatim
+(`oracle/ref_import.py`): `extract_normalized_eigenvector`, `MagStftExtractor.extract`,
+the per-clip driver bodies, `interpolate_tensor` and `SeldModel.forward`.  The only
+non-reference arithmetic underneath is the `librosa.stft` / `power_to_db` shim
+(`oracle/stft.py`), because librosa is not installable here.
+"""
+import os
+import sys
+
+import numpy as np
+
+from . import ref_import, synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+DATA_CFG = {
+    'foa': dict(format='foa', fs=24000, n_fft=512, win_len=512, hop_len=300, fmin_doa=50, fmax_doa=9000),
+    'mic': dict(format='mic', fs=24000, n_fft=512, win_len=512, hop_len=300, fmin_doa=50, fmax_doa=4000),
+    'lite': dict(format='mic', fs=24000, n_fft=512, win_len=512, hop_len=300, fmin_doa=50, fmax_doa=2000),
+}
+
+
+def structured_spectrum(seed=7, n_bins=24, n_frames=60, n_chans=4):
+    """Random complex spectrum with a dominant rank-1 part in a random subset of TF bins, so
+    that tracker, coherence test and normalisation all see both outcomes."""
+    rng = np.random.default_rng(seed)
+    steer = rng.standard_normal((n_bins, 1, n_chans)) + 1j * rng.standard_normal((n_bins, 1, n_chans))
+    steer[:, :, 0] = 1.0 + 0.2 * rng.standard_normal((n_bins, 1))
+    src = rng.standard_normal((n_bins, n_frames, 1)) + 1j * rng.standard_normal((n_bins, n_frames, 1))
+    envelope = (rng.uniform(size=(n_bins, n_frames // 10 + 1, 1)) > 0.4).repeat(10, axis=1)[:, :n_frames]
+    noise = rng.standard_normal((n_bins, n_frames, n_chans)) + 1j * rng.standard_normal((n_bins, n_frames, n_chans))
+    return 3.0 * envelope * src * steer + 0.15 * noise
+
+
+def eigvec_cases():
+    ref = ref_import.features_module()
+    X = structured_spectrum()
+    out = {'X': X}
+    for fmt in ('foa', 'mic'):
+        for tag, trk, cond in (('t5', True, 5.0), ('t0', True, 0.0), ('n5', False, 5.0), ('t2', True, 2.0)):
+            out['{}_{}'.format(fmt, tag)] = ref.extract_normalized_eigenvector(
+                X.copy(), condition_number=cond, n_hopframes=3, is_tracking=trk, audio_format=fmt,
+                fs=24000, n_fft=512, lower_bin=1)
+    return out
+
+
+def clip_cases(seconds=1.0):
+    out = {}
+    ref = ref_import.features_module()
+    foa = synth.make_clip(3, 'foa', seconds=seconds)
+    mic = synth.make_clip(4, 'mic', seconds=seconds)
+    out['audio_foa'] = foa
+    out['audio_mic'] = mic
+    out['salsa_foa'] = ref_import.run_driver_body('salsa', foa, DATA_CFG['foa'])
+    out['salsa_mic'] = ref_import.run_driver_body('salsa', mic, DATA_CFG['mic'])
+    out['salsa_foa_notracking'] = ref_import.run_driver_body('salsa', foa, DATA_CFG['foa'], is_tracking=False)
+    out['salsa_lite'] = ref_import.run_driver_body('salsa_lite', mic, DATA_CFG['lite'], feature_type='salsa_lite')
+    out['salsa_ipd'] = ref_import.run_driver_body('salsa_lite', mic, DATA_CFG['lite'], feature_type='salsa_ipd')
+    out['logspec_foa'] = ref.MagStftExtractor(n_fft=512, hop_length=300, win_length=512).extract(foa)
+    out['logspec_foa_nocompress'] = ref.MagStftExtractor(
+        n_fft=512, hop_length=300, win_length=512, is_compress_high_freq=False).extract(foa)
+    out['W512'] = ref.MagStftExtractor(n_fft=512, hop_length=300).W
+    out['W256'] = ref.MagStftExtractor(n_fft=256, hop_length=150).W
+    return out
+
+
+def model_cases():
+    import torch
+    models = ref_import.models_module()
+    from models.model_utils import interpolate_tensor
+    out = {}
+    x = torch.arange(24).reshape(2, -1, 3)
+    out['interp_in'] = x.numpy()
+    out['interp_half'] = interpolate_tensor(x, ratio=0.5).numpy()
+    out['interp_double'] = interpolate_tensor(x, ratio=2.0).numpy()
+    out['interp_40_to_80'] = interpolate_tensor(torch.arange(40).reshape(1, 40, 1), ratio=2.0).numpy().ravel()
+
+    torch.manual_seed(0)
+    model = ref_import.build_reference_seld_model()
+    # zero-init bn2 makes every residual branch vanish at init (model_utils.py:343): randomise the
+    # BN affine parameters and running statistics so the golden forward exercises every layer.
+    g = torch.Generator().manual_seed(1)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.empty_like(m.weight).uniform_(0.5, 1.5, generator=g)
+            m.bias.data = torch.empty_like(m.bias).uniform_(-0.2, 0.2, generator=g)
+            m.running_mean.data = torch.empty_like(m.running_mean).uniform_(-0.2, 0.2, generator=g)
+            m.running_var.data = torch.empty_like(m.running_var).uniform_(0.5, 1.5, generator=g)
+    for name, p in model.named_parameters():
+        if name.startswith('decoder.gru.bias') or (name.startswith('decoder.') and name.endswith('fc_1.bias')) \
+                or (name.startswith('decoder.') and name.endswith('fc_2.bias')):
+            p.data = torch.empty_like(p).uniform_(-0.1, 0.1, generator=g)
+    model.eval()
+    xin = torch.randn(2, 7, 128, 200, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        y = model(xin)
+        enc = model.encoder(xin)
+    out['model_in'] = xin.numpy()
+    out['model_encoder_out'] = enc.numpy()
+    out['model_event_frame_logit'] = y['event_frame_logit'].numpy()
+    out['model_doa_frame_output'] = y['doa_frame_output'].numpy()
+    state = {k: v.numpy() for k, v in model.state_dict().items()}
+    return out, state
+
+
+def main(argv=None):
+    if not ref_import.available():
+        print('reference checkout not found; golden vectors can only be generated in the build container')
+        return 1
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'eigvec_cases.npz'), **eigvec_cases())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'clip_cases.npz'), **clip_cases())
+    if argv and 'model' in argv:
+        cases, state = model_cases()
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'model_cases.npz'), **cases)
+        # weights are regenerated from the seed by tests (torch.manual_seed(0) + the BN recipe above)
+        # only when the reference is mounted; the frozen copy travels as float16-free npz
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'model_state.npz'), **state)
+    for fn in sorted(os.listdir(GOLDEN_DIR)):
+        print('{:32s} {:10d} B'.format(fn, os.path.getsize(os.path.join(GOLDEN_DIR, fn))))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main(sys.argv[1:]))

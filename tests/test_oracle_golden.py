@@ -1,0 +1,147 @@
+"""The oracle restatement against the reference: frozen golden vectors (always) and the
+live reference checkout (when mounted).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import salsa, stft, synth
+
+EIG_CASES = [(fmt, tag, trk, cond) for fmt in ('foa', 'mic')
+             for tag, trk, cond in (('t5', True, 5.0), ('t0', True, 0.0), ('n5', False, 5.0), ('t2', True, 2.0))]
+
+
+@pytest.mark.parametrize('fmt,tag,trk,cond', EIG_CASES)
+@pytest.mark.parametrize('batched', [False, True])
+def test_eigenvector_matches_golden(golden, fmt, tag, trk, cond, batched):
+    g = golden('eigvec_cases')
+    fn = salsa.extract_normalized_eigenvector_batched if batched else salsa.extract_normalized_eigenvector
+    out = fn(g['X'].copy(), condition_number=cond, n_hopframes=3, is_tracking=trk, audio_format=fmt,
+             fs=24000, n_fft=512, lower_bin=1)
+    ref = g['{}_{}'.format(fmt, tag)]
+    assert out.shape == ref.shape and out.dtype == np.float64
+    assert np.array_equal(out != 0, ref != 0)            # valid-bin mask: exact
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12)
+
+
+def test_eigenvector_bad_format():
+    X = np.ones((2, 8, 4), dtype=complex)
+    with pytest.raises(ValueError):
+        salsa.extract_normalized_eigenvector(X, audio_format='xyz', fs=24000, n_fft=512, lower_bin=1)
+
+
+def test_band_matrix_matches_golden(golden):
+    g = golden('clip_cases')
+    assert np.array_equal(salsa.band_matrix(512), g['W512'])
+    assert np.array_equal(salsa.band_matrix(256), g['W256'])
+    first, count, weight = salsa.band_table(512)
+    assert first[0] == 1 and first[191] == 192 and first[192] == 193 and first[199] == 249
+    assert count[191] == 1 and count[192] == 8 and count[199] == 7 and weight[199] == np.float32(0.125)
+    with pytest.raises(AssertionError):
+        salsa.band_matrix(1024)
+
+
+def test_doa_bins():
+    assert salsa.doa_bins(24000, 512, 50, 9000) == (1, 192)
+    assert salsa.doa_bins(24000, 512, 50, 4000) == (1, 85)
+    assert salsa.doa_bins(24000, 512, 50, 2000) == (1, 42)
+    assert salsa.doa_bins(24000, 256, 50, 9000) == (1, 96)
+    assert salsa.doa_bins(24000, 512, 50, 20000) == (1, 256)
+
+
+def test_logspec_matches_golden(golden):
+    g = golden('clip_cases')
+    out = salsa.MagStftExtractor(512, 300, 512).extract(g['audio_foa'])
+    assert out.dtype == np.float32
+    np.testing.assert_array_equal(out, g['logspec_foa'])
+    out = salsa.MagStftExtractor(512, 300, 512, is_compress_high_freq=False).extract(g['audio_foa'])
+    np.testing.assert_array_equal(out, g['logspec_foa_nocompress'])
+
+
+@pytest.mark.parametrize('key,fmt,fmax,trk', [('salsa_foa', 'foa', 9000, True), ('salsa_mic', 'mic', 4000, True),
+                                              ('salsa_foa_notracking', 'foa', 9000, False)])
+def test_salsa_clip_matches_golden(golden, key, fmt, fmax, trk):
+    g = golden('clip_cases')
+    out = salsa.salsa_clip(g['audio_' + fmt], fmt, fmax_doa=fmax, is_tracking=trk)
+    assert out.shape == (7, 81, 200) and out.dtype == np.float32
+    assert np.array_equal(out != 0, g[key] != 0)
+    np.testing.assert_allclose(out, g[key], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('ft', ['salsa_lite', 'salsa_ipd'])
+def test_salsa_lite_matches_golden(golden, ft):
+    g = golden('clip_cases')
+    out = salsa.salsa_lite_clip(g['audio_mic'], ft)
+    assert out.shape == (7, 81, 191) and out.dtype == np.float32
+    np.testing.assert_array_equal(out, g[ft])
+    assert np.all(out[4:, :, 42:] == 0) and np.any(out[4:, :, 41] != 0)   # crop quirk, lite :118-120
+
+
+def test_synth_is_deterministic(golden):
+    g = golden('clip_cases')
+    np.testing.assert_allclose(synth.make_clip(3, 'foa', seconds=1.0), g['audio_foa'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(synth.make_clip(4, 'mic', seconds=1.0), g['audio_mic'], rtol=0, atol=1e-6)
+
+
+def test_stft_against_torch_and_scipy():
+    """The librosa restatement has no librosa to be pinned against; cross-check two other
+    independent implementations of the same transform."""
+    import scipy.signal
+    import torch
+    y = synth.make_clip(5, 'foa', seconds=0.5)[0]
+    S = stft.stft(y, n_fft=512, hop_length=300, center=True, window='hann', pad_mode='reflect')
+    assert S.shape == (257, 1 + len(y) // 300) and S.dtype == np.complex64
+    T = torch.stft(torch.from_numpy(y).double(), n_fft=512, hop_length=300,
+                   window=torch.hann_window(512, periodic=True, dtype=torch.float64), center=True,
+                   pad_mode='reflect', return_complex=True).numpy()
+    assert np.abs(S - T).max() <= 2e-7 * np.abs(T).max()
+    ypad = np.pad(y.astype(np.float64), 256, mode='reflect')
+    _, _, Z = scipy.signal.stft(ypad, window=scipy.signal.get_window('hann', 512, fftbins=True), nperseg=512,
+                                noverlap=212, nfft=512, boundary=None, padded=False, scaling='spectrum')
+    Z = Z * scipy.signal.get_window('hann', 512, fftbins=True).sum()
+    assert np.abs(S - Z[:, :S.shape[1]]).max() <= 2e-7 * np.abs(Z).max()
+
+
+def test_power_to_db():
+    x = np.array([0.0, 1e-12, 1.0, 100.0], dtype=np.float32)
+    out = stft.power_to_db(x, ref=1.0, amin=1e-10, top_db=None)
+    assert out.dtype == np.float32
+    np.testing.assert_allclose(out, [-100.0, -100.0, 0.0, 20.0], atol=1e-5)
+
+
+def test_scaler_matches_sklearn():
+    from sklearn import preprocessing
+    rng = np.random.default_rng(0)
+    feats = [rng.standard_normal((7, 11, 6)).astype(np.float32) * 3 + 1 for _ in range(3)]
+    mean, std = salsa.compute_scaler(feats)
+    for ch in range(4):
+        sc = preprocessing.StandardScaler()
+        for f in feats:
+            sc.partial_fit(f[ch])
+        np.testing.assert_allclose(mean[ch, 0], sc.mean_, rtol=1e-6)
+        np.testing.assert_allclose(std[ch, 0], np.sqrt(sc.var_), rtol=1e-6)
+
+
+# ---------------------------------------------------------------- live reference (build container only)
+@pytest.mark.reference
+def test_live_reference_eigenvector():
+    from oracle import ref_import
+    from oracle.make_golden import structured_spectrum
+    ref = ref_import.features_module()
+    X = structured_spectrum(seed=11, n_bins=12, n_frames=40)
+    for fmt in ('foa', 'mic'):
+        a = ref.extract_normalized_eigenvector(X.copy(), condition_number=5.0, is_tracking=True, audio_format=fmt,
+                                               fs=24000, n_fft=512, lower_bin=1)
+        b = salsa.extract_normalized_eigenvector_batched(X.copy(), condition_number=5.0, is_tracking=True,
+                                                         audio_format=fmt, fs=24000, n_fft=512, lower_bin=1)
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
+
+
+@pytest.mark.reference
+def test_live_reference_driver_bodies():
+    from oracle import ref_import
+    from oracle.make_golden import DATA_CFG
+    clip = synth.make_clip(6, 'mic', seconds=0.6)
+    a = ref_import.run_driver_body('salsa', clip, DATA_CFG['mic'])
+    np.testing.assert_allclose(a, salsa.salsa_clip(clip, 'mic', fmax_doa=4000), rtol=0, atol=1e-6)
+    for ft in ('salsa_lite', 'salsa_ipd'):
+        a = ref_import.run_driver_body('salsa_lite', clip, DATA_CFG['lite'], feature_type=ft)
+        np.testing.assert_array_equal(a, salsa.salsa_lite_clip(clip, ft))
