@@ -1,0 +1,12 @@
+"""salsa_b200 -- B200-native (sm_100a) SALSA feature extraction and SELD CRNN forward.
+
+Drop-in for the hot path of thomeou/SALSA: `dataset/salsa_feature_extraction.py`,
+`dataset/salsa_lite_feature_extraction.py` and `models.seld_models.SeldModel.forward`.
+All compute runs in libsalsa_b200.so (hand-written CUDA behind a C ABI, include/salsa_b200.h);
+this package is the thin host side.  There is no CPU fallback.
+"""
+from . import _native  # noqa: F401
+from .features import (MagStftExtractor, SalsaExtractor, SalsaLiteExtractor, doa_bins,  # noqa: F401
+                       extract_normalized_eigenvector, stft)
+
+__version__ = '0.1.0'

@@ -1,0 +1,38 @@
+"""Builds libsalsa_b200.so in-tree with nvcc for sm_100a (no torch headers involved)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, 'csrc')
+OUT = os.path.join(HERE, 'libsalsa_b200.so')
+SOURCES = ['salsa_abi.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force=False, verbose=False):
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, 'include', 'salsa_b200.h')]
+    if not force and os.path.isfile(OUT) and os.path.getmtime(OUT) >= _newest(deps):
+        return OUT
+    objs = []
+    for src in srcs:
+        obj = os.path.join(HERE, '_build', os.path.basename(src) + '.o')
+        os.makedirs(os.path.dirname(obj), exist_ok=True)
+        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    subprocess.run([nvcc, '-shared', '-o', OUT] + objs + ['-lcudart'], check=True)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,165 @@
+// Warp-level 512-point real FFT (one warp = one frame of one channel), sm_100a.
+//
+// Replaces the librosa.stft call sites of the reference
+// (dataset/salsa_feature_extraction.py:186-192, :360-361; salsa_lite_feature_extraction.py:97-98):
+// periodic Hann window (float64 in the reference), centre padding by reflection, rfft.
+//
+// The 512 real samples are packed as 256 complex points z[n] = x[2n] + i x[2n+1] and transformed
+// with a 8 x 8 x 4 decimation: every lane owns 8 complex values, the two exchanges between the
+// three butterfly passes go through a per-warp shared-memory scratch, and a final split turns
+// Z[k] into the 257 bins of the real transform.  `T` is the arithmetic type: double reproduces the
+// reference's float64 transform (results rounded to float32 afterwards, as librosa stores complex64),
+// float is the fast variant.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace salsa {
+
+constexpr int kNfft = 512;
+constexpr int kHalf = 256;        // complex points of the packed transform
+constexpr int kScratchPad = 36;   // row stride (complex elements) of the 8 x 32 buffer between pass 1 and 2
+constexpr int kUStrideK = 39;     // strides of the [k1][m2][j1] buffer between pass 2 and 3
+constexpr int kUStrideM = 10;
+constexpr int kScratchElems = 8 * kUStrideK;   // complex elements of per-warp scratch (312)
+
+template <typename T>
+struct alignas(2 * sizeof(T)) Cx {
+    T re, im;
+};
+
+template <typename T> __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return {a.re + b.re, a.im + b.im}; }
+template <typename T> __device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) { return {a.re - b.re, a.im - b.im}; }
+template <typename T> __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+// multiply by -i (forward-transform quarter turn)
+template <typename T> __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.im, -a.re}; }
+
+// In-place forward 8-point DFT: out[k] = sum_n in[n] exp(-2 pi i n k / 8).
+template <typename T>
+__device__ __forceinline__ void dft8(Cx<T> (&v)[8]) {
+    const T h = (T)0.70710678118654752440084436210485;
+    Cx<T> a0 = cadd(v[0], v[4]), a1 = csub(v[0], v[4]);
+    Cx<T> a2 = cadd(v[2], v[6]), a3 = mul_mi(csub(v[2], v[6]));
+    Cx<T> a4 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+    Cx<T> a6 = cadd(v[3], v[7]), a7 = mul_mi(csub(v[3], v[7]));
+    Cx<T> b0 = cadd(a0, a2), b2 = csub(a0, a2);          // even half, 4-point
+    Cx<T> b1 = cadd(a1, a3), b3 = csub(a1, a3);
+    Cx<T> c0 = cadd(a4, a6), c2 = mul_mi(csub(a4, a6));  // odd half, 4-point then W8 twiddles
+    Cx<T> c1 = cadd(a5, a7), c3 = csub(a5, a7);
+    c1 = {(c1.re + c1.im) * h, (c1.im - c1.re) * h};     // * exp(-i pi/4)
+    c3 = {(c3.im - c3.re) * h, -(c3.re + c3.im) * h};    // * exp(-3 i pi/4)
+    v[0] = cadd(b0, c0); v[4] = csub(b0, c0);
+    v[1] = cadd(b1, c1); v[5] = csub(b1, c1);
+    v[2] = cadd(b2, c2); v[6] = csub(b2, c2);
+    v[3] = cadd(b3, c3); v[7] = csub(b3, c3);
+}
+
+// Forward 4-point DFT.
+template <typename T>
+__device__ __forceinline__ void dft4(Cx<T> (&v)[4]) {
+    Cx<T> a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+    Cx<T> a2 = cadd(v[1], v[3]), a3 = mul_mi(csub(v[1], v[3]));
+    v[0] = cadd(a0, a2); v[2] = csub(a0, a2);
+    v[1] = cadd(a1, a3); v[3] = csub(a1, a3);
+}
+
+// Per-lane twiddle tables, built once by the host in long double and rounded (salsa_abi.cu).
+//   tw_a[k1][lane] = exp(-2 pi i * lane*k1 / 256)          k1 = 0..7   (pass 1 -> pass 2)
+//   tw_b[j1][lane] = exp(-2 pi i * (lane&3)*j1 / 32)       j1 = 0..7   (pass 2 -> pass 3)
+//   tw_r[k]        = exp(-2 pi i * k / 512)                k = 0..255  (real split)
+template <typename T>
+struct FftTables {
+    const Cx<T>* tw_a;
+    const Cx<T>* tw_b;
+    const Cx<T>* tw_r;
+    const T* window;   // n_fft entries
+};
+
+// Reflect-padded sample index (np.pad mode='reflect'): valid for -n < i < 2n-1.
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+
+// One warp: 256-point complex FFT of the windowed frame starting at sample `start`
+// (in un-padded coordinates, may be negative / run past the end -> reflection) of channel
+// signal `x` of length n.  Result Z[0..255] is left in `scratch` in natural order
+// (scratch must hold kScratchElems complex values).  `win` points to the window in shared memory.
+template <typename T>
+__device__ __forceinline__ void warp_fft256_frame(const float* __restrict__ x, int n, int start,
+                                                  const T* __restrict__ win, const FftTables<T>& tb,
+                                                  Cx<T>* scratch, int lane) {
+    Cx<T> v[8];
+    // ---- load + window: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1],  m = lane + 32 n1
+    const bool interior = (start >= 0) && (start + kNfft <= n) &&
+                          ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
+    if (interior) {
+        const float2* xp = reinterpret_cast<const float2*>(x + start);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int m = lane + 32 * n1;
+            const float2 s = __ldg(xp + m);
+            v[n1] = {(T)s.x * win[2 * m], (T)s.y * win[2 * m + 1]};
+        }
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int m = lane + 32 * n1;
+            const float s0 = x[reflect_index(start + 2 * m, n)];
+            const float s1 = x[reflect_index(start + 2 * m + 1, n)];
+            v[n1] = {(T)s0 * win[2 * m], (T)s1 * win[2 * m + 1]};
+        }
+    }
+    // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1)
+    dft8(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) v[k1] = cmul(v[k1], tb.tw_a[k1 * 32 + lane]);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) scratch[k1 * kScratchPad + lane] = v[k1];
+    __syncwarp();
+    // ---- pass 2: lane = (k1, m2); 8-point DFT over m1 of y[k1][4 m1 + m2], twiddle W32^(m2*j1)
+    const int k1 = lane >> 2, m2 = lane & 3;
+#pragma unroll
+    for (int m1 = 0; m1 < 8; ++m1) v[m1] = scratch[k1 * kScratchPad + 4 * m1 + m2];
+    __syncwarp();
+    dft8(v);
+#pragma unroll
+    for (int j1 = 1; j1 < 8; ++j1) v[j1] = cmul(v[j1], tb.tw_b[j1 * 32 + lane]);
+    // u[k1][m2][j1] at k1*kUStrideK + m2*kUStrideM + j1  (strides chosen bank-conflict free)
+#pragma unroll
+    for (int j1 = 0; j1 < 8; ++j1) scratch[k1 * kUStrideK + m2 * kUStrideM + j1] = v[j1];
+    __syncwarp();
+    // ---- pass 3: lane owns (k1 = lane&7, j1 = (lane>>3) + 4p), p = 0,1; 4-point DFT over m2
+    //      -> Z[k1 + 8 j1 + 64 j2] = Z[lane + 32 p + 64 j2]
+    Cx<T> w[2][4];
+    const int pk1 = lane & 7;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int pj1 = (lane >> 3) + 4 * p;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[p][q] = scratch[pk1 * kUStrideK + q * kUStrideM + pj1];
+        dft4(w[p]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) scratch[lane + 32 * p + 64 * j2] = w[p][j2];
+    __syncwarp();
+}
+
+// Bin k (0..256) of the 512-point real transform from the packed spectrum Z (natural order).
+template <typename T>
+__device__ __forceinline__ Cx<T> real_bin(const Cx<T>* Z, const Cx<T>* tw_r, int k) {
+    if (k == kHalf) return {Z[0].re - Z[0].im, (T)0};
+    const Cx<T> a = Z[k];
+    const Cx<T> b = Z[(kHalf - k) & (kHalf - 1)];
+    const Cx<T> e = {(T)0.5 * (a.re + b.re), (T)0.5 * (a.im - b.im)};     // (Z[k] + conj Z[N-k]) / 2
+    const Cx<T> o = {(T)0.5 * (a.im + b.im), (T)0.5 * (b.re - a.re)};     // -i (Z[k] - conj Z[N-k]) / 2
+    const Cx<T> t = cmul(o, tw_r[k]);
+    return {e.re + t.re, e.im + t.im};
+}
+
+}  // namespace salsa

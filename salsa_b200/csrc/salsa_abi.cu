@@ -1,0 +1,624 @@
+// C ABI of libsalsa_b200.so: feature-extraction entry points (see include/salsa_b200.h).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "salsa_kernels.cuh"
+
+namespace salsa {
+
+// ---------------------------------------------------------------------------------------------
+// errors, launch counter
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string t_error;
+static thread_local uint64_t t_launches = 0;
+
+void set_error(const std::string& msg) { t_error = msg; }
+int fail(int code, const std::string& msg) {
+    set_error(msg);
+    return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return SALSA_OK;
+    return fail(SALSA_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+void count_launch(int n) { t_launches += (uint64_t)n; }
+
+static int check_launch(const char* name) {
+    count_launch();
+    return check_cuda(cudaGetLastError(), name);
+}
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+struct ProfRecord {
+    const char* name;
+    cudaEvent_t start, stop;
+};
+static thread_local bool t_profiling = false;
+static thread_local std::vector<ProfRecord> t_prof;
+
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfRecord rec;
+    ProfScope(const char* name, cudaStream_t s) : st(s), on(t_profiling) {
+        if (!on) return;
+        rec.name = name;
+        cudaEventCreate(&rec.start);
+        cudaEventCreate(&rec.stop);
+        cudaEventRecord(rec.start, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(rec.stop, st);
+        t_prof.push_back(rec);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-device tables (twiddles once per device, windows cached by value)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct WindowEntry {
+    std::vector<double> values;
+    double* d;
+    float* f;
+};
+struct DeviceState {
+    bool ready = false;
+    Cx<double>*tw_a_d = nullptr, *tw_b_d = nullptr, *tw_r_d = nullptr;
+    Cx<float>*tw_a_f = nullptr, *tw_b_f = nullptr, *tw_r_f = nullptr;
+    std::vector<WindowEntry> windows;
+};
+std::mutex g_mutex;
+DeviceState g_state[64];
+
+template <typename T>
+int upload(const std::vector<Cx<long double>>& src, Cx<T>** dst) {
+    std::vector<Cx<T>> h(src.size());
+    for (size_t i = 0; i < src.size(); ++i) h[i] = {(T)src[i].re, (T)src[i].im};
+    SALSA_CUDA(cudaMalloc((void**)dst, h.size() * sizeof(Cx<T>)));
+    SALSA_CUDA(cudaMemcpy(*dst, h.data(), h.size() * sizeof(Cx<T>), cudaMemcpyHostToDevice));
+    return SALSA_OK;
+}
+
+Cx<long double> unit_root(long long num, long long den) {   // exp(-2 pi i num / den)
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    num %= den;
+    const long double ang = two_pi * (long double)num / (long double)den;
+    return {cosl(ang), -sinl(ang)};
+}
+}  // namespace
+
+int get_tables(const double* window_host, DeviceTables* out) {
+    int dev = 0;
+    SALSA_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(SALSA_EINVAL, "device index out of range");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState& st = g_state[dev];
+    if (!st.ready) {
+        std::vector<Cx<long double>> ta(8 * 32), tb(8 * 32), tr(kHalf);
+        for (int k1 = 0; k1 < 8; ++k1)
+            for (int lane = 0; lane < 32; ++lane) {
+                ta[k1 * 32 + lane] = unit_root((long long)lane * k1, 256);
+                tb[k1 * 32 + lane] = unit_root((long long)(lane & 3) * k1, 32);
+            }
+        for (int k = 0; k < kHalf; ++k) tr[k] = unit_root(k, 512);
+        int rc;
+        if ((rc = upload(ta, &st.tw_a_d)) || (rc = upload(tb, &st.tw_b_d)) || (rc = upload(tr, &st.tw_r_d)) ||
+            (rc = upload(ta, &st.tw_a_f)) || (rc = upload(tb, &st.tw_b_f)) || (rc = upload(tr, &st.tw_r_f)))
+            return rc;
+        st.ready = true;
+    }
+    const WindowEntry* hit = nullptr;
+    for (const WindowEntry& w : st.windows)
+        if (memcmp(w.values.data(), window_host, kNfft * sizeof(double)) == 0) hit = &w;
+    if (!hit) {
+        WindowEntry w;
+        w.values.assign(window_host, window_host + kNfft);
+        std::vector<float> wf(kNfft);
+        for (int i = 0; i < kNfft; ++i) wf[i] = (float)window_host[i];
+        SALSA_CUDA(cudaMalloc((void**)&w.d, kNfft * sizeof(double)));
+        SALSA_CUDA(cudaMalloc((void**)&w.f, kNfft * sizeof(float)));
+        SALSA_CUDA(cudaMemcpy(w.d, window_host, kNfft * sizeof(double), cudaMemcpyHostToDevice));
+        SALSA_CUDA(cudaMemcpy(w.f, wf.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
+        st.windows.push_back(w);
+        hit = &st.windows.back();
+    }
+    out->d = {st.tw_a_d, st.tw_b_d, st.tw_r_d, hit->d};
+    out->f = {st.tw_a_f, st.tw_b_f, st.tw_r_f, hit->f};
+    return SALSA_OK;
+}
+
+void host_window(const salsa_params_t* p, double* out) {
+    if (p->window) {
+        memcpy(out, p->window, p->n_fft * sizeof(double));
+        return;
+    }
+    // scipy.signal.get_window('hann', win_len, fftbins=True), centred in n_fft (librosa pad_center)
+    const double two_pi = 6.283185307179586476925286766559;
+    const int lpad = (p->n_fft - p->win_len) / 2;
+    for (int i = 0; i < p->n_fft; ++i) out[i] = 0.0;
+    for (int i = 0; i < p->win_len; ++i) out[lpad + i] = 0.5 - 0.5 * cos(two_pi * (double)i / (double)p->win_len);
+}
+
+int validate_params(const salsa_params_t* p, bool with_stft) {
+    if (!p) return fail(SALSA_EINVAL, "params is NULL");
+    if (p->n_chans != 4) return fail(SALSA_EINVAL, "n_chans must be 4");
+    if (p->n_clips < 0) return fail(SALSA_EINVAL, "n_clips is negative");
+    if (p->fs <= 0 || p->n_fft <= 0) return fail(SALSA_EINVAL, "fs and n_fft must be positive");
+    if (with_stft) {
+        if (p->n_fft != 512)
+            return fail(SALSA_EINVAL, "only n_fft = 512 is implemented (reference asserts 512 or 256)");
+        if (p->hop_len <= 0) return fail(SALSA_EINVAL, "hop_len must be positive");
+        if (p->win_len <= 0 || p->win_len > p->n_fft)
+            return fail(SALSA_EINVAL, "Windown length is greater than nfft!");
+        if (p->n_samples <= p->n_fft / 2)
+            return fail(SALSA_EINVAL, "n_samples must exceed n_fft/2 (reflect padding)");
+        if (p->upper_bin > p->n_fft / 2) return fail(SALSA_EINVAL, "upper_bin exceeds n_fft/2");
+    }
+    if (p->lower_bin < 1 || p->upper_bin <= p->lower_bin)
+        return fail(SALSA_EINVAL, "need 1 <= lower_bin < upper_bin");
+    if (p->audio_format != SALSA_FORMAT_FOA && p->audio_format != SALSA_FORMAT_MIC)
+        return fail(SALSA_EINVAL, "audio format is not valid");
+    if (p->n_hopframes != kHop) return fail(SALSA_EINVAL, "n_hopframes must be 3");
+    if (p->stft_precision != 32 && p->stft_precision != 64)
+        return fail(SALSA_EINVAL, "stft_precision must be 32 or 64");
+    return SALSA_OK;
+}
+
+static BandLayout band_layout(const salsa_params_t* p) {
+    const int half = p->n_fft / 2;
+    if (!p->is_compress_high_freq) return {half, half};
+    return {half * 3 / 4, half * 3 / 4 + 8};   // 512: 192 linear + 8 compressed = 200 (:153-162)
+}
+
+static EigArgs eig_args(const salsa_params_t* p) {
+    EigArgs e;
+    e.format = p->audio_format;
+    e.test = p->is_tracking ? 1 : 0;
+    e.cond = (float)p->cond_num;
+    e.cond_d = p->cond_num;
+    // squarings so that cond^-(2^n) < 1e-7; without a usable gap (no test, cond <= 1) iterate longer
+    int n_sq = 10;
+    if (e.test && p->cond_num > 1.0) {
+        const double need = log(1e7) / log(p->cond_num);
+        n_sq = (int)ceil(log2(need));
+        n_sq = std::max(3, std::min(10, n_sq));
+    }
+    e.n_sq = n_sq;
+    const double delta = 2.0 * M_PI * (double)p->fs / ((double)p->n_fft * 343.0);
+    e.inv_delta = 1.0 / delta;
+    e.lower = p->lower_bin;
+    return e;
+}
+
+static TrackerConsts tracker_consts() {
+    const double alpha = 0.02, slow_scale = 0.1;    // salsa_feature_extraction.py:30-31
+    TrackerConsts c;
+    c.floor_up = 1 + alpha;
+    c.floor_up_slow = 1 + slow_scale * alpha;
+    c.floor_down = 1 - alpha;
+    c.snr_ratio = 1.5;
+    c.floor_min = 1e-6;
+    c.n_sig_frames = 3;
+    c.n_init_frames = 5;
+    return c;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                      "cudaFuncSetAttribute");
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float2* X, float* spec,
+                       long long spec_clip_stride, double* power0, int ch_count, cudaStream_t st) {
+    if (p->n_clips == 0) return SALSA_OK;
+    const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
+    StftArgs a;
+    a.audio = audio;
+    a.n_chans = p->n_chans;
+    a.n_samples = p->n_samples;
+    a.hop = p->hop_len;
+    a.n_frames = n_frames;
+    a.lower = p->lower_bin;
+    a.upper = p->upper_bin;
+    a.ch_count = ch_count;
+    a.frames_per_block = 32;
+    a.bands = band_layout(p);
+    a.X = X;
+    a.spec = spec;
+    a.spec_clip_stride = spec_clip_stride;
+    a.spec_chan_stride = (long long)n_frames * a.bands.n_out;
+    a.power0 = power0;
+    dim3 grid((n_frames + a.frames_per_block - 1) / a.frames_per_block, p->n_clips);
+    ProfScope prof("stft_kernel", st);
+    if (p->stft_precision == 64) {
+        const size_t smem = sizeof(FftSmem<double>);
+        int rc = set_smem(stft_kernel<double>, smem);
+        if (rc) return rc;
+        stft_kernel<double><<<grid, kThreads, smem, st>>>(a, tb.d);
+    } else {
+        const size_t smem = sizeof(FftSmem<float>);
+        int rc = set_smem(stft_kernel<float>, smem);
+        if (rc) return rc;
+        stft_kernel<float><<<grid, kThreads, smem, st>>>(a, tb.f);
+    }
+    return check_launch("stft_kernel");
+}
+
+static int launch_tracker(const double* power0, uint32_t* mask, int n_clips, int n_frames, int n_bins,
+                          cudaStream_t st) {
+    if (n_clips == 0) return SALSA_OK;
+    const int n_words = (n_bins + 31) / 32;
+    const int wpb = std::min(n_words, 8);                       // warps per block
+    dim3 grid((n_words + wpb - 1) / wpb, n_clips);
+    ProfScope prof("tracker_kernel", st);
+    tracker_kernel<<<grid, wpb * 32, 0, st>>>(power0, mask, n_frames, n_bins, tracker_consts());
+    return check_launch("tracker_kernel");
+}
+
+constexpr int kFusedFT = 4;   // new frames per step of salsa_fused_kernel
+
+static int choose_seg_len(int n_clips, int n_frames) {
+    // aim for >= 4 CTAs per SM slot (2 resident CTAs x 148 SMs) while keeping the 6-frame halo small
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const long long want = 4LL * 2 * sms;
+    long long segs_per_clip = (want + n_clips - 1) / std::max(1, n_clips);
+    segs_per_clip = std::max(1LL, std::min<long long>(segs_per_clip, (n_frames + 31) / 32));
+    int seg = (int)((n_frames + segs_per_clip - 1) / segs_per_clip);
+    seg = std::min(seg, 240);
+    seg = (seg + kFusedFT - 1) / kFusedFT * kFusedFT;
+    return std::max(seg, kFusedFT);
+}
+
+static int launch_fused(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float* feature,
+                        const uint32_t* mask, cudaStream_t st) {
+    if (p->n_clips == 0) return SALSA_OK;
+    FusedArgs a;
+    a.audio = audio;
+    a.feature = feature;
+    a.mask = mask;
+    a.n_samples = p->n_samples;
+    a.hop = p->hop_len;
+    a.n_frames = salsa_n_frames(p->n_samples, p->hop_len);
+    a.lower = p->lower_bin;
+    a.upper = p->upper_bin;
+    a.nbp = (p->upper_bin - p->lower_bin + 31) / 32 * 32;
+    a.seg_len = choose_seg_len(p->n_clips, a.n_frames);
+    a.bands = band_layout(p);
+    a.eig = eig_args(p);
+    dim3 grid((a.n_frames + a.seg_len - 1) / a.seg_len, p->n_clips);
+    const size_t ring = (size_t)(kFusedFT + 2 * kHop) * 4 * a.nbp * sizeof(float2);
+    ProfScope prof("salsa_fused_kernel", st);
+    if (p->stft_precision == 64) {
+        const size_t smem = sizeof(FftSmem<double>) + ring;
+        int rc = set_smem(salsa_fused_kernel<double, kFusedFT>, smem);
+        if (rc) return rc;
+        salsa_fused_kernel<double, kFusedFT><<<grid, kThreads, smem, st>>>(a, tb.d);
+    } else {
+        const size_t smem = sizeof(FftSmem<float>) + ring;
+        int rc = set_smem(salsa_fused_kernel<float, kFusedFT>, smem);
+        if (rc) return rc;
+        salsa_fused_kernel<float, kFusedFT><<<grid, kThreads, smem, st>>>(a, tb.f);
+    }
+    return check_launch("salsa_fused_kernel");
+}
+
+struct Workspace {
+    double* power0;
+    uint32_t* mask;
+    size_t bytes;
+};
+
+static Workspace carve_workspace(const salsa_params_t* p, void* base) {
+    const size_t n_frames = (size_t)salsa_n_frames(p->n_samples, p->hop_len);
+    const size_t n_bins = (size_t)(p->upper_bin - p->lower_bin);
+    const size_t pw = (size_t)p->n_clips * n_frames * n_bins * sizeof(double);
+    const size_t mk = (size_t)p->n_clips * n_frames * ((n_bins + 31) / 32) * sizeof(uint32_t);
+    Workspace w;
+    w.power0 = reinterpret_cast<double*>(base);
+    w.mask = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(base) + ((pw + 255) / 256) * 256);
+    w.bytes = ((pw + 255) / 256) * 256 + ((mk + 255) / 256) * 256;
+    if (!p->is_tracking) w.bytes = 256;
+    return w;
+}
+
+}  // namespace salsa
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+using namespace salsa;
+
+extern "C" {
+
+const char* salsa_last_error(void) { return t_error.c_str(); }
+const char* salsa_version(void) { return "salsa_b200 0.1 (sm_100a)"; }
+
+int32_t salsa_n_frames(int32_t n_samples, int32_t hop_len) { return hop_len > 0 ? 1 + n_samples / hop_len : 0; }
+
+int32_t salsa_feat_dim(const salsa_params_t* p) { return p ? band_layout(p).n_out : 0; }
+
+uint64_t salsa_launch_count(int reset) {
+    const uint64_t v = t_launches;
+    if (reset) t_launches = 0;
+    return v;
+}
+
+int salsa_profile_enable(int on) {
+    t_profiling = on != 0;
+    return SALSA_OK;
+}
+
+int salsa_profile_read(int32_t max_entries, char* names, double* total_ms, int64_t* launches) {
+    int n = 0;
+    for (const ProfRecord& r : t_prof) {
+        float ms = 0.0f;
+        cudaEventSynchronize(r.stop);
+        cudaEventElapsedTime(&ms, r.start, r.stop);
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+        int slot = -1;
+        for (int i = 0; i < n; ++i)
+            if (strncmp(names + 32 * i, r.name, 31) == 0) slot = i;
+        if (slot < 0) {
+            if (n >= max_entries) continue;
+            slot = n++;
+            strncpy(names + 32 * slot, r.name, 31);
+            names[32 * slot + 31] = 0;
+            total_ms[slot] = 0.0;
+            launches[slot] = 0;
+        }
+        total_ms[slot] += ms;
+        launches[slot] += 1;
+    }
+    t_prof.clear();
+    return n;
+}
+
+int salsa_stft(const salsa_params_t* p, const float* audio, float* X, float* logspec, double* power0, void* stream) {
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (p->n_clips == 0) return SALSA_OK;
+    if (!audio) return fail(SALSA_EINVAL, "audio is NULL");
+    double win[kNfft];
+    host_window(p, win);
+    DeviceTables tb;
+    if ((rc = get_tables(win, &tb))) return rc;
+    const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
+    const long long clip_stride = (long long)p->n_chans * n_frames * band_layout(p).n_out;
+    const int ch_count = (X || logspec) ? p->n_chans : 1;
+    return launch_stft(p, tb, audio, reinterpret_cast<float2*>(X), logspec, clip_stride, power0, ch_count,
+                       (cudaStream_t)stream);
+}
+
+int salsa_tracker(const double* power0, uint32_t* mask, int32_t n_clips, int32_t n_frames, int32_t n_bins,
+                  void* stream) {
+    if (!power0 || !mask) return fail(SALSA_EINVAL, "power0 / mask is NULL");
+    if (n_clips < 0 || n_frames <= 0 || n_bins <= 0) return fail(SALSA_EINVAL, "bad tracker dimensions");
+    return launch_tracker(power0, mask, n_clips, n_frames, n_bins, (cudaStream_t)stream);
+}
+
+int salsa_spectrum_from_reference(const double* X_ref, float* X, double* power0, int32_t n_bins, int32_t n_frames,
+                                  int32_t n_chans, void* stream) {
+    if (!X_ref || !X) return fail(SALSA_EINVAL, "X_ref / X is NULL");
+    if (n_chans != 4) return fail(SALSA_EINVAL, "n_chans must be 4");
+    if (n_bins <= 0 || n_frames <= 0) return fail(SALSA_EINVAL, "bad spectrum dimensions");
+    const long long total = (long long)n_bins * n_frames;
+    from_reference_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(X_ref), reinterpret_cast<float2*>(X), power0, n_bins, n_frames);
+    return check_launch("from_reference_kernel");
+}
+
+int salsa_eigenvector(const salsa_params_t* p, const float* X, const uint32_t* mask, float* eig, int32_t n_frames,
+                      void* stream) {
+    int rc = validate_params(p, false);
+    if (rc) return rc;
+    if (!X || !eig) return fail(SALSA_EINVAL, "X / eig is NULL");
+    if (n_frames <= 0) return fail(SALSA_EINVAL, "n_frames must be positive");
+    if (p->is_tracking && !mask) return fail(SALSA_EINVAL, "is_tracking needs the tracker mask");
+    if (p->n_clips == 0) return SALSA_OK;
+    const int n_bins = p->upper_bin - p->lower_bin;
+    dim3 grid((n_bins + 255) / 256, n_frames, p->n_clips);
+    eig_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(X),
+                                                       p->is_tracking ? mask : nullptr, eig, n_frames, n_bins,
+                                                       eig_args(p));
+    return check_launch("eig_kernel");
+}
+
+size_t salsa_workspace_bytes(const salsa_params_t* p) {
+    if (validate_params(p)) return 0;
+    return carve_workspace(p, nullptr).bytes;
+}
+
+int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (p->n_clips == 0) return SALSA_OK;
+    if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    const Workspace w = carve_workspace(p, workspace);
+    if (p->is_tracking && (!workspace || workspace_bytes < w.bytes))
+        return fail(SALSA_ENOMEM, "workspace smaller than salsa_workspace_bytes()");
+    double win[kNfft];
+    host_window(p, win);
+    DeviceTables tb;
+    if ((rc = get_tables(win, &tb))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t* mask = nullptr;
+    if (p->is_tracking) {
+        // pass A: channel-0 spectrum in float64 -> tracker (a sequential recurrence over the whole clip,
+        // so it has to finish before any bin can be selected).  Always float64: one flipped
+        // comparison would shift the floor of that bin for the rest of the clip.
+        salsa_params_t pa = *p;
+        pa.stft_precision = 64;
+        if ((rc = launch_stft(&pa, tb, audio, nullptr, nullptr, 0, w.power0, 1, st))) return rc;
+        const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
+        if ((rc = launch_tracker(w.power0, w.mask, p->n_clips, n_frames, p->upper_bin - p->lower_bin, st))) return rc;
+        mask = w.mask;
+    }
+    return launch_fused(p, tb, audio, feature, mask, st);
+}
+
+int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode, const float* audio, float* feature,
+                       void* stream) {
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (mode != SALSA_LITE_NIPD && mode != SALSA_LITE_IPD) return fail(SALSA_EINVAL, "Invalid feature type");
+    if (p->upper_bin > cutoff_bin || cutoff_bin > p->n_fft / 2)
+        return fail(SALSA_EINVAL, "Upper bin for spatial feature is higher than cutoff bin for spectrogram!");
+    if (p->n_clips == 0) return SALSA_OK;
+    if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    double win[kNfft];
+    host_window(p, win);
+    DeviceTables tb;
+    if ((rc = get_tables(win, &tb))) return rc;
+    LiteArgs a;
+    a.audio = audio;
+    a.feature = feature;
+    a.n_samples = p->n_samples;
+    a.hop = p->hop_len;
+    a.n_frames = salsa_n_frames(p->n_samples, p->hop_len);
+    a.lower = p->lower_bin;
+    a.cutoff = cutoff_bin;
+    a.upper_cropped = p->upper_bin;     // applied to the CROPPED axis, as salsa_lite_feature_extraction.py:120 does
+    a.mode = mode;
+    a.inv_delta = eig_args(p).inv_delta;
+    a.frames_per_block = 32;
+    dim3 grid((a.n_frames + a.frames_per_block - 1) / a.frames_per_block, p->n_clips);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof("lite_kernel", st);
+    if (p->stft_precision == 64) {
+        const size_t smem = sizeof(FftSmem<double>);
+        if ((rc = set_smem(lite_kernel<double>, smem))) return rc;
+        lite_kernel<double><<<grid, kThreads, smem, st>>>(a, tb.d);
+    } else {
+        const size_t smem = sizeof(FftSmem<float>);
+        if ((rc = set_smem(lite_kernel<float>, smem))) return rc;
+        lite_kernel<float><<<grid, kThreads, smem, st>>>(a, tb.f);
+    }
+    return check_launch("lite_kernel");
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer variants: 3-stage pipeline over chunks of clips (H2D | kernels | D2H)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct HostPipeline {
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, run_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    float* d_audio[2] = {nullptr, nullptr};
+    float* d_feat[2] = {nullptr, nullptr};
+    void* d_work = nullptr;
+    ~HostPipeline() {
+        for (int i = 0; i < 2; ++i) {
+            if (d_audio[i]) cudaFree(d_audio[i]);
+            if (d_feat[i]) cudaFree(d_feat[i]);
+            if (in_done[i]) cudaEventDestroy(in_done[i]);
+            if (run_done[i]) cudaEventDestroy(run_done[i]);
+            if (out_done[i]) cudaEventDestroy(out_done[i]);
+        }
+        if (d_work) cudaFree(d_work);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_run) cudaStreamDestroy(s_run);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+};
+
+template <typename Run>
+int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_t work_bytes, const float* audio_host,
+                      float* feature_host, int clips_per_chunk, Run run) {
+    if (p->n_clips == 0) return SALSA_OK;
+    if (clips_per_chunk <= 0) clips_per_chunk = 16;
+    clips_per_chunk = std::min(clips_per_chunk, p->n_clips);
+    const size_t audio_elems = (size_t)p->n_chans * p->n_samples;
+    HostPipeline hp;
+    SALSA_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    SALSA_CUDA(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
+    SALSA_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SALSA_CUDA(cudaEventCreateWithFlags(&hp.in_done[i], cudaEventDisableTiming));
+        SALSA_CUDA(cudaEventCreateWithFlags(&hp.run_done[i], cudaEventDisableTiming));
+        SALSA_CUDA(cudaEventCreateWithFlags(&hp.out_done[i], cudaEventDisableTiming));
+        SALSA_CUDA(cudaMalloc((void**)&hp.d_audio[i], clips_per_chunk * audio_elems * sizeof(float)));
+        SALSA_CUDA(cudaMalloc((void**)&hp.d_feat[i], clips_per_chunk * feat_elems_per_clip * sizeof(float)));
+    }
+    if (work_bytes) SALSA_CUDA(cudaMalloc(&hp.d_work, work_bytes));
+    const int n_chunks = (p->n_clips + clips_per_chunk - 1) / clips_per_chunk;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        const int first = c * clips_per_chunk;
+        const int n = std::min(clips_per_chunk, p->n_clips - first);
+        // the audio buffer is free once the kernels of chunk c-2 are done, the feature buffer once its
+        // copy-out is done
+        if (c >= 2) {
+            SALSA_CUDA(cudaStreamWaitEvent(hp.s_in, hp.run_done[buf], 0));
+            SALSA_CUDA(cudaStreamWaitEvent(hp.s_run, hp.out_done[buf], 0));
+        }
+        SALSA_CUDA(cudaMemcpyAsync(hp.d_audio[buf], audio_host + (size_t)first * audio_elems,
+                                   (size_t)n * audio_elems * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
+        SALSA_CUDA(cudaEventRecord(hp.in_done[buf], hp.s_in));
+        SALSA_CUDA(cudaStreamWaitEvent(hp.s_run, hp.in_done[buf], 0));
+        salsa_params_t pc = *p;
+        pc.n_clips = n;
+        int rc = run(&pc, hp.d_audio[buf], hp.d_feat[buf], hp.d_work, work_bytes, hp.s_run);
+        if (rc) return rc;
+        SALSA_CUDA(cudaEventRecord(hp.run_done[buf], hp.s_run));
+        SALSA_CUDA(cudaStreamWaitEvent(hp.s_out, hp.run_done[buf], 0));
+        SALSA_CUDA(cudaMemcpyAsync(feature_host + (size_t)first * feat_elems_per_clip, hp.d_feat[buf],
+                                   (size_t)n * feat_elems_per_clip * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+        SALSA_CUDA(cudaEventRecord(hp.out_done[buf], hp.s_out));
+    }
+    SALSA_CUDA(cudaStreamSynchronize(hp.s_out));
+    SALSA_CUDA(cudaStreamSynchronize(hp.s_run));
+    return SALSA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int salsa_extract_host(const salsa_params_t* p, const float* audio_host, float* feature_host,
+                       int32_t clips_per_chunk) {
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (!audio_host || !feature_host) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    const size_t n_frames = (size_t)salsa_n_frames(p->n_samples, p->hop_len);
+    const size_t feat = 7 * n_frames * (size_t)band_layout(p).n_out;
+    salsa_params_t pc = *p;
+    pc.n_clips = std::min(p->n_clips, clips_per_chunk > 0 ? clips_per_chunk : 16);
+    const size_t work = salsa_workspace_bytes(&pc);
+    return run_host_pipeline(p, feat, work, audio_host, feature_host, clips_per_chunk,
+                             [](const salsa_params_t* q, const float* a, float* f, void* w, size_t wb, cudaStream_t s) {
+                                 return salsa_extract(q, a, f, w, wb, (void*)s);
+                             });
+}
+
+int salsa_lite_extract_host(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode, const float* audio_host,
+                            float* feature_host, int32_t clips_per_chunk) {
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (!audio_host || !feature_host) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    if (cutoff_bin <= p->lower_bin) return fail(SALSA_EINVAL, "cutoff_bin must exceed lower_bin");
+    const size_t n_frames = (size_t)salsa_n_frames(p->n_samples, p->hop_len);
+    const size_t feat = 7 * n_frames * (size_t)(cutoff_bin - p->lower_bin);
+    return run_host_pipeline(
+        p, feat, 0, audio_host, feature_host, clips_per_chunk,
+        [=](const salsa_params_t* q, const float* a, float* f, void*, size_t, cudaStream_t s) {
+            return salsa_lite_extract(q, cutoff_bin, mode, a, f, (void*)s);
+        });
+}
+
+}  // extern "C"

@@ -1,0 +1,506 @@
+// SALSA / SALSA-Lite feature kernels for sm_100a.
+//
+//   stft_kernel          a1 + a3  librosa.stft (+ MagStftExtractor.extract, + |X0|^2 for the tracker)
+//   tracker_kernel       a4 + a5  noise-floor tracker (float64 recurrence over frames)
+//   eig_kernel           a6 - a8  covariance / eigenvector / coherence / normalisation from X in HBM
+//   salsa_fused_kernel   a1, a3, a6 - a9 in one pass: STFT -> shared-memory ring of frames ->
+//                        eigenvector step -> (7, T, F) feature rows; X never touches HBM
+//   lite_kernel          a10      SALSA-Lite / SALSA-IPD
+//
+// (row numbers: SURVEY.md section 8a; reference lines are cited at each function.)
+#pragma once
+#include "eig.cuh"
+#include "fft.cuh"
+
+namespace salsa {
+
+constexpr int kWarps = 8;                // warps per CTA in the STFT-bearing kernels
+constexpr int kThreads = kWarps * 32;
+constexpr int kHop = 3;                  // n_hopframes of the reference ("do not change")
+constexpr int kWin = 2 * kHop + 1;       // 7 frames per covariance
+constexpr float kAmin = 1e-10f;          // power_to_db amin (salsa_feature_extraction.py:195)
+
+// Layout of the log-linear bands (MagStftExtractor.__init__, :153-175):
+// band < n_lin -> bin band+1 (weight 1); n_lin <= band < n_out -> 8 bins (the last one fewer,
+// clipped at n_fft/2) starting at n_lin+1+8*(band-n_lin), weight 1/8.
+struct BandLayout {
+    int n_lin;
+    int n_out;
+};
+
+struct StftArgs {
+    const float* audio;   // [clip][n_chans][n_samples]
+    int n_chans;
+    int n_samples;
+    int hop;
+    int n_frames;
+    int lower;            // spatial bins lower..upper-1
+    int upper;
+    int ch_count;         // channels 0..ch_count-1 are transformed
+    int frames_per_block;
+    BandLayout bands;
+    float2* X;            // [clip][frame][n_chans][upper-lower] or null
+    float* spec;          // log-linear spectrogram or null
+    long long spec_clip_stride;
+    long long spec_chan_stride;   // row (frame) stride is bands.n_out
+    double* power0;       // [clip][frame][upper-lower] or null
+};
+
+template <typename T>
+struct FftSmem {
+    T win[kNfft];
+    Cx<T> tw_r[kHalf];
+    Cx<T> scratch[kWarps][kScratchElems];
+};
+
+template <typename T>
+__device__ __forceinline__ void load_fft_smem(FftSmem<T>& s, const FftTables<T>& tb) {
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s.win[i] = tb.window[i];
+    for (int i = threadIdx.x; i < kHalf; i += blockDim.x) s.tw_r[i] = tb.tw_r[i];
+}
+
+__device__ __forceinline__ float power_db(float p) { return 10.0f * log10f(fmaxf(kAmin, p)); }
+
+// |X|^2 as the reference computes it for the spectrogram: np.abs(complex64)**2 in float32 (:186-194).
+__device__ __forceinline__ float power_f32(float re, float im) {
+    const float m = hypotf(re, im);
+    return m * m;
+}
+
+// One warp, after warp_fft256_frame: writes the log-linear spectrogram row of this (frame, channel).
+// `pw` = 256 floats of per-warp scratch (aliasing the FFT scratch is fine after a __syncwarp).
+// p[j] is the power of bin lane + 32 j, p_nyq the power of the Nyquist bin (only the uncompressed
+// layout reaches it: its last band is bin n_fft/2, :172-175).
+__device__ __forceinline__ void write_logspec_row(const float (&p)[8], float p_nyq, float* pw, float* row,
+                                                  BandLayout bands, int lane) {
+    // linear part: band = bin - 1
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int band = lane + 32 * j - 1;
+        if (band >= 0 && band < bands.n_lin) row[band] = power_db(p[j]);
+    }
+    if (bands.n_lin == kHalf && lane == 0) row[kHalf - 1] = power_db(p_nyq);
+    if (bands.n_out > bands.n_lin) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pw[lane + 32 * j] = p[j];
+        __syncwarp();
+        const int band = bands.n_lin + lane;
+        if (band < bands.n_out) {
+            const int first = bands.n_lin + 1 + 8 * lane;
+            const int count = min(8, kHalf - first);
+            float acc = 0.0f;
+            for (int m = 0; m < count; ++m) acc = fmaf(0.125f, pw[first + m], acc);
+            row[band] = power_db(acc);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stft_kernel: grid (frame blocks, clips); one warp per (frame, channel) item.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T> tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
+    load_fft_smem(s, tb);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int clip = blockIdx.y;
+    const int f0 = blockIdx.x * a.frames_per_block;
+    const int f1 = min(a.n_frames, f0 + a.frames_per_block);
+    const int nb = a.upper - a.lower;
+    const float* clip_audio = a.audio + (long long)clip * a.n_chans * a.n_samples;
+    Cx<T>* scratch = s.scratch[warp];
+    for (int item = warp; item < (f1 - f0) * a.ch_count; item += kWarps) {
+        const int t = f0 + item / a.ch_count;
+        const int ch = item % a.ch_count;
+        warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, tb,
+                             scratch, lane);
+        float p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = lane + 32 * j;
+            const Cx<T> x = real_bin(scratch, s.tw_r, k);
+            const float re = (float)x.re, im = (float)x.im;     // librosa stores complex64
+            p[j] = power_f32(re, im);
+            if (k >= a.lower && k < a.upper) {
+                const long long o = ((long long)clip * a.n_frames + t);
+                if (a.X) a.X[(o * a.n_chans + ch) * nb + (k - a.lower)] = make_float2(re, im);
+                if (a.power0 && ch == 0) {
+                    const double m = hypot((double)re, (double)im);    // np.abs(complex128) ** 2 (:53-55)
+                    a.power0[o * nb + (k - a.lower)] = m * m;
+                }
+            }
+        }
+        const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
+        const float p_nyq = power_f32((float)xn.re, 0.0f);
+        __syncwarp();
+        if (a.spec) {
+            float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
+            write_logspec_row(p, p_nyq, reinterpret_cast<float*>(scratch), row, a.bands, lane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tracker_kernel: one thread per (clip, bin), one warp per 32-bin mask word; sequential over frames.
+// Reference: salsa_feature_extraction.py:26-36 (constants), :49-58 (signal, initial floor), :63-87.
+// ------------------------------------------------------------------------------------------------
+struct TrackerConsts {
+    double floor_up, floor_up_slow, floor_down, snr_ratio, floor_min;
+    int n_sig_frames, n_init_frames;
+};
+
+__global__ void tracker_kernel(const double* __restrict__ power0, uint32_t* __restrict__ mask, int n_frames,
+                               int n_bins, TrackerConsts c) {
+    const int clip = blockIdx.y;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int word = b >> 5, n_words = (n_bins + 31) >> 5;
+    const bool live = b < n_bins;
+    const double* a = power0 + (long long)clip * n_frames * n_bins + (live ? b : 0);
+    uint32_t* mrow = mask + (long long)clip * n_frames * n_words + word;
+    auto at = [&](int t) -> double {   // wrapped frame access (np.pad 'wrap', :43)
+        t %= n_frames;
+        if (t < 0) t += n_frames;
+        return live ? a[(long long)t * n_bins] : 0.0;
+    };
+    auto rms3 = [](double a0, double a1, double a2) { return sqrt(((a0 + a1) + a2) / 3.0); };
+    // initial floor: 0.5 * mean(sig[0:5])
+    const int n_init = min(c.n_init_frames, n_frames);
+    double acc = 0.0;
+    for (int t = 0; t < n_init; ++t) acc += rms3(at(t), at(t - 1), at(t - 2));
+    double nf = 0.5 * (acc / (double)n_init);
+    int cd = c.n_sig_frames;
+    double a1 = at(-1), a2 = at(-2);
+    constexpr int kChunk = 8;
+    for (int t0 = 0; t0 < n_frames; t0 += kChunk) {
+        double buf[kChunk];
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) buf[i] = (t0 + i < n_frames && live) ? a[(long long)(t0 + i) * n_bins] : 0.0;
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {
+            if (t0 + i < n_frames) {
+                const double a0 = buf[i];
+                const double x = rms3(a0, a1, a2);
+                a2 = a1;
+                a1 = a0;
+                const bool above = x > nf;
+                if (above) {
+                    cd -= 1;
+                    nf *= (cd < 0) ? c.floor_up_slow : c.floor_up;
+                } else {
+                    cd = c.n_sig_frames;
+                    nf *= c.floor_down;
+                }
+                if (nf < c.floor_min) nf = c.floor_min;
+                const bool sel = live && (x > c.snr_ratio * nf);
+                const uint32_t bits = __ballot_sync(0xffffffffu, sel);
+                if ((threadIdx.x & 31) == 0) mrow[(long long)(t0 + i) * n_words] = bits;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The eigenvector step for one TF bin.  `load(f, ch)` returns X[frame offset f in -3..3][ch].
+// ------------------------------------------------------------------------------------------------
+struct EigArgs {
+    int format;          // SALSA_FORMAT_*
+    int test;            // apply the coherence test (is_tracking)
+    int n_sq;            // squarings, float32 path
+    float cond;
+    double cond_d;
+    double inv_delta;    // 1 / delta, delta = 2 pi fs / (n_fft c)   (:38-40)
+    int lower;           // absolute index of spatial bin 0
+};
+
+template <typename T, typename Load>
+__device__ __forceinline__ void accumulate_cov(Herm4<T>& R, Load load) {
+    herm_zero(R);
+#pragma unroll
+    for (int f = -kHop; f <= kHop; ++f) {
+        Cx<T> x[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const float2 v = load(f, ch);
+            x[ch] = {(T)v.x, (T)v.y};
+        }
+        herm_rank1(R, x);
+    }
+}
+
+// float64 re-evaluation of a bin whose float32 verdict could not be certified
+template <typename Load>
+__device__ __noinline__ int eig_bin_f64(Load load, const EigArgs& e, float (&out)[3], int b) {
+    Herm4<double> R;
+    accumulate_cov<double>(R, load);
+    Cx<double> v[4];
+    int verdict = principal_eigenvector<double>(R, e.n_sq + 2, e.test != 0, e.cond_d, 0.0, v);
+    if (verdict == kEigAmbiguous) verdict = kEigFail;
+    if (verdict == kEigPass) {
+        if (e.format == SALSA_FORMAT_FOA) {
+            normalise_foa(v, out);
+        } else {
+            const double s = e.inv_delta / (double)(b + e.lower);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const Cx<double> p = cmulc(v[i + 1], v[0]);
+                out[i] = (float)(atan2(p.im, p.re) * s);
+            }
+        }
+    }
+    return verdict;
+}
+
+// Returns true when the bin is valid; out[] holds the three spatial features (zeros otherwise).
+template <typename Load>
+__device__ __forceinline__ bool eig_bin(Load load, const EigArgs& e, int b, float (&out)[3]) {
+    out[0] = out[1] = out[2] = 0.0f;
+    Herm4<float> R;
+    accumulate_cov<float>(R, load);
+    Cx<float> v[4];
+    int verdict = principal_eigenvector<float>(R, e.n_sq, e.test != 0, e.cond, 1e-4f, v);
+    if (verdict == kEigAmbiguous) {
+        verdict = eig_bin_f64(load, e, out, b);
+        return verdict == kEigPass;
+    }
+    if (!e.test && !(herm_trace(R) > 0.0f)) {
+        // is_tracking=False on an all-zero bin: svd gives u = I, so FOA divides 0 by 0 (NaN) and
+        // MIC yields angle(0) = 0, exactly as the reference does.
+        if (e.format == SALSA_FORMAT_FOA) out[0] = out[1] = out[2] = __int_as_float(0x7fc00000);
+        return true;
+    }
+    if (verdict != kEigPass) return false;
+    if (e.format == SALSA_FORMAT_FOA) {
+        normalise_foa(v, out);
+    } else {
+        const float s = (float)(e.inv_delta / (double)(b + e.lower));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const Cx<float> p = cmulc(v[i + 1], v[0]);
+            out[i] = atan2f(p.im, p.re) * s;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// from_reference_kernel: the reference hands extract_normalized_eigenvector a complex128 array laid
+// out (n_bins, n_frames, n_chans) (:20); convert one clip of it to the internal complex64
+// [frame][ch][bin] layout and emit |X[:, :, 0]|^2 in float64 for the tracker.
+// ------------------------------------------------------------------------------------------------
+__global__ void from_reference_kernel(const double2* __restrict__ Xref, float2* __restrict__ X,
+                                      double* __restrict__ power0, int n_bins, int n_frames) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_bins * n_frames) return;
+    const int t = (int)(i / n_bins), b = (int)(i % n_bins);
+    const double2* src = Xref + ((long long)b * n_frames + t) * 4;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        const double2 v = src[ch];
+        X[((long long)t * 4 + ch) * n_bins + b] = make_float2((float)v.x, (float)v.y);
+        if (ch == 0 && power0) {
+            const double m = hypot(v.x, v.y);
+            power0[(long long)t * n_bins + b] = m * m;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// eig_kernel: X resident in HBM ([clip][frame][ch][bin] complex64); thread per (frame, bin).
+// Used by the op-level seam extract_normalized_eigenvector (arbitrary caller-provided X).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eig_kernel(const float2* __restrict__ X, const uint32_t* __restrict__ mask,
+                                                  float* __restrict__ out, int n_frames, int n_bins, EigArgs e) {
+    const int clip = blockIdx.z;
+    const int t = blockIdx.y;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bins) return;
+    const int n_words = (n_bins + 31) >> 5;
+    bool sel = true;
+    if (mask) sel = (mask[((long long)clip * n_frames + t) * n_words + (b >> 5)] >> (b & 31)) & 1u;
+    float o[3] = {0.0f, 0.0f, 0.0f};
+    if (sel) {
+        const float2* base = X + (long long)clip * n_frames * 4 * n_bins + b;
+        auto load = [&](int f, int ch) -> float2 {
+            int tt = (t + f) % n_frames;
+            if (tt < 0) tt += n_frames;
+            return __ldg(base + ((long long)tt * 4 + ch) * n_bins);
+        };
+        eig_bin(load, e, b, o);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[(((long long)clip * 3 + i) * n_frames + t) * n_bins + b] = o[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// salsa_fused_kernel: grid (segments, clips).  A CTA walks `seg_len` consecutive frames of one clip
+// in steps of FT frames.  Per step: FT*4 warp-FFTs (new frames only) into a ring of FT+6 frames of
+// X in shared memory ([slot][ch][bin] complex64), log-spectrogram rows straight to HBM, then one
+// thread per (frame, bin) does the eigenvector step from the ring and writes the 3 spatial rows.
+// HBM traffic per clip = audio once (+ halo re-reads served by L2) + feature once + mask bits.
+// ------------------------------------------------------------------------------------------------
+struct FusedArgs {
+    const float* audio;
+    float* feature;          // [clip][7][n_frames][feat_dim]
+    const uint32_t* mask;    // tracker selection or null (is_tracking = false)
+    int n_samples;
+    int hop;
+    int n_frames;
+    int lower, upper;
+    int nbp;                 // ring row length in bins (n_bins rounded up to 32)
+    int seg_len;
+    BandLayout bands;
+    EigArgs eig;
+};
+
+template <typename T, int FT>
+__global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, FftTables<T> tb) {
+    constexpr int R = FT + 2 * kHop;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
+    float2* ring = reinterpret_cast<float2*>(smem_raw + sizeof(FftSmem<T>));   // [R][4][nbp]
+    load_fft_smem(s, tb);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int clip = blockIdx.y;
+    const int s0 = blockIdx.x * a.seg_len;
+    const int s1 = min(a.n_frames, s0 + a.seg_len);
+    const int n_bins = a.upper - a.lower;
+    const int n_words = (n_bins + 31) >> 5;
+    const int feat_dim = a.bands.n_out;
+    const long long chan_stride = (long long)a.n_frames * feat_dim;
+    const float* clip_audio = a.audio + (long long)clip * 4 * a.n_samples;
+    float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
+    Cx<T>* scratch = s.scratch[warp];
+    const int row = 4 * a.nbp;    // float2 per ring slot
+
+    // transforms frames [fa, fb) (un-wrapped indices relative to the clip) into the ring
+    auto transform = [&](int fa, int fb) {
+        for (int item = warp; item < (fb - fa) * 4; item += kWarps) {
+            const int f = fa + (item >> 2), ch = item & 3;
+            int fw = f % a.n_frames;                       // wrap padding of the frame axis (:43)
+            if (fw < 0) fw += a.n_frames;
+            warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, fw * a.hop - kNfft / 2,
+                                 s.win, tb, scratch, lane);
+            float2* dst = ring + ((f - (s0 - kHop)) % R) * row + ch * a.nbp;
+            float p[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = lane + 32 * j;
+                const Cx<T> x = real_bin(scratch, s.tw_r, k);
+                const float re = (float)x.re, im = (float)x.im;
+                p[j] = power_f32(re, im);
+                if (k >= a.lower && k < a.upper) dst[k - a.lower] = make_float2(re, im);
+            }
+            const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
+            const float p_nyq = power_f32((float)xn.re, 0.0f);
+            __syncwarp();
+            if (f >= s0 && f < s1) {
+                float* rowp = clip_feat + ch * chan_stride + (long long)f * feat_dim;
+                write_logspec_row(p, p_nyq, reinterpret_cast<float*>(scratch), rowp, a.bands, lane);
+                if (ch > 0) {   // zero padding of spatial channel ch-1 above the last spatial bin (:373-374)
+                    float* z = clip_feat + (3 + ch) * chan_stride + (long long)f * feat_dim;
+                    for (int k = n_bins + lane; k < feat_dim; k += 32) z[k] = 0.0f;
+                }
+            }
+        }
+    };
+
+    transform(s0 - kHop, s0 + kHop);
+    for (int t0 = s0; t0 < s1; t0 += FT) {
+        transform(t0 + kHop, min(t0 + FT, s1) + kHop);
+        __syncthreads();
+        const int nt = min(FT, s1 - t0);
+        for (int item = threadIdx.x; item < nt * a.nbp; item += kThreads) {
+            const int tl = item / a.nbp, b = item - tl * a.nbp;
+            if (b >= n_bins) continue;
+            const int t = t0 + tl;
+            bool sel = true;
+            if (a.mask) sel = (a.mask[((long long)clip * a.n_frames + t) * n_words + (b >> 5)] >> (b & 31)) & 1u;
+            float o[3] = {0.0f, 0.0f, 0.0f};
+            if (sel) {
+                const int rel = t - s0 + kHop;             // ring-relative index of frame t
+                auto load = [&](int f, int ch) -> float2 { return ring[((rel + f) % R) * row + ch * a.nbp + b]; };
+                eig_bin(load, a.eig, b, o);
+            }
+            float* dst = clip_feat + 4 * chan_stride + (long long)t * feat_dim + b;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dst[i * chan_stride] = o[i];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lite_kernel: SALSA-Lite / SALSA-IPD (salsa_lite_feature_extraction.py:94-123).
+// One warp per frame: the four channel transforms run back to back, channel 0 stays in registers.
+// ------------------------------------------------------------------------------------------------
+struct LiteArgs {
+    const float* audio;
+    float* feature;      // [clip][7][n_frames][cutoff - lower]
+    int n_samples;
+    int hop;
+    int n_frames;
+    int lower, cutoff;   // spectrogram bins lower..cutoff-1
+    int upper_cropped;   // spatial values at cropped index >= upper_cropped are zero (:120)
+    int mode;            // SALSA_LITE_*
+    double inv_delta;    // 1 / delta
+    int frames_per_block;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T> tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
+    load_fft_smem(s, tb);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int clip = blockIdx.y;
+    const int f0 = blockIdx.x * a.frames_per_block;
+    const int f1 = min(a.n_frames, f0 + a.frames_per_block);
+    const int width = a.cutoff - a.lower;
+    const long long chan_stride = (long long)a.n_frames * width;
+    const float* clip_audio = a.audio + (long long)clip * 4 * a.n_samples;
+    float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
+    Cx<T>* scratch = s.scratch[warp];
+    const float inv_pi = 0.318309886183790671538f;
+    for (int t = f0 + warp; t < f1; t += kWarps) {
+        float2 x0[8];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win,
+                                 tb, scratch, lane);
+            float* srow = clip_feat + ch * chan_stride + (long long)t * width;
+            float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width;   // used for ch >= 1
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = lane + 32 * j;
+                const Cx<T> x = real_bin(scratch, s.tw_r, k);
+                const float re = (float)x.re, im = (float)x.im;
+                if (ch == 0) x0[j] = make_float2(re, im);
+                const int c = k - a.lower;            // cropped index
+                if (c >= 0 && c < width) {
+                    srow[c] = power_db(power_f32(re, im));     // (np.abs(stft) ** 2).T -> power_to_db (:104-105)
+                    if (ch > 0) {
+                        float ph = 0.0f;
+                        if (c < a.upper_cropped) {
+                            // X_ch conj(X_0) with exact float64 products (:111), angle in float32
+                            const double pr = (double)re * x0[j].x + (double)im * x0[j].y;
+                            const double pi = (double)im * x0[j].x - (double)re * x0[j].y;
+                            const float ang = atan2f((float)pi, (float)pr);
+                            ph = a.mode == SALSA_LITE_IPD ? ang * inv_pi
+                                                          : ang * (float)(a.inv_delta / (double)max(k, 1));
+                        }
+                        prow[c] = ph;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace salsa

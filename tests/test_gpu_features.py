@@ -1,0 +1,231 @@
+"""Parity of the CUDA feature path (through the C ABI) against the oracle and the golden vectors
+frozen from the reference.  Needs a B200: run with `-m gpu`.
+
+Tolerances (BASELINE.json north_star: bit-exact for indexing, 1e-4 relative for floats):
+  * index maps / valid-bin masks: exact (mismatch count must be 0);
+  * log spectrogram (dB, |values| up to 100): |a-b| <= 1e-4 * max(1, |b|);
+  * spatial channels (unit vectors / normalised phases, |values| <= ~4): |a-b| <= 1e-4 * max(1, |b|),
+    compared on the bins both sides mark valid.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def close(a, b, what):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    assert np.all(np.isfinite(a) == np.isfinite(b)), what
+    err = np.where(np.isfinite(err), err, 0.0)
+    assert err.max() <= RTOL, '{}: max rel err {:.3e} at {}'.format(what, err.max(), np.unravel_index(err.argmax(), err.shape))
+    return err.max()
+
+
+def check_feature(out, ref, n_spec=4, what='feature'):
+    """spectrogram channels close; spatial channels: identical support, close values."""
+    assert out.shape == ref.shape and out.dtype == np.float32
+    close(out[:n_spec], ref[:n_spec], what + ' spectrogram')
+    sup_a, sup_b = out[n_spec:] != 0, ref[n_spec:] != 0
+    mismatch = int(np.count_nonzero(sup_a != sup_b))
+    assert mismatch == 0, '{}: {} valid-bin mask mismatches out of {}'.format(what, mismatch, sup_a.size)
+    close(out[n_spec:], ref[n_spec:], what + ' spatial')
+
+
+@pytest.fixture(scope='module')
+def sb():
+    import salsa_b200
+    assert torch.cuda.is_available()
+    return salsa_b200
+
+
+# ------------------------------------------------------------------------------------------------
+# op level seams
+# ------------------------------------------------------------------------------------------------
+def test_stft_matches_oracle(sb, golden):
+    from oracle import salsa as osalsa
+    audio = golden('clip_cases')['audio_foa']
+    ref = osalsa.multichannel_stft(audio, 512, 300)[1:256].astype(np.complex64)     # (255, T, 4)
+    out = sb.stft(audio, n_fft=512, hop_length=300, lower_bin=1, upper_bin=256)
+    assert out.shape == ref.shape and out.dtype == np.complex64
+    # float64 transform rounded to float32 on both sides: every complex value within one float32 ulp
+    assert np.all(np.abs(out - ref) <= 1.2e-7 * np.abs(ref))
+    # ... and bit-identical almost everywhere.  Frame 0 is excluded from the count: its reflected
+    # frame is symmetric, so its imaginary parts are pure float64 rounding noise (~1e-17) on both sides.
+    exact = np.mean(out[:, 1:] == ref[:, 1:])
+    assert exact > 0.9999, 'only {:.6f} of the complex64 values are bit-identical'.format(exact)
+
+
+def test_stft_float32_variant(sb, golden):
+    from oracle import salsa as osalsa
+    audio = golden('clip_cases')['audio_mic']
+    ref = osalsa.multichannel_stft(audio, 512, 300)[1:256]
+    out = sb.stft(audio, n_fft=512, hop_length=300, lower_bin=1, upper_bin=256, stft_precision=32)
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('compress,key', [(True, 'logspec_foa'), (False, 'logspec_foa_nocompress')])
+def test_logspec_matches_golden(sb, golden, compress, key):
+    g = golden('clip_cases')
+    out = sb.MagStftExtractor(n_fft=512, hop_length=300, win_length=512, is_compress_high_freq=compress).extract(
+        g['audio_foa'])
+    assert out.dtype == np.float32
+    close(out, g[key], key)
+
+
+def test_logspec_other_window(sb, golden):
+    from oracle import salsa as osalsa
+    audio = golden('clip_cases')['audio_foa']
+    ref = osalsa.MagStftExtractor(512, 300, 400, window='hamming').extract(audio)
+    out = sb.MagStftExtractor(512, 300, 400, window='hamming').extract(audio)
+    close(out, ref, 'hamming/400 window')
+
+
+def test_extractor_asserts_like_reference(sb):
+    with pytest.raises(AssertionError):
+        sb.MagStftExtractor(n_fft=1024, hop_length=300)
+    with pytest.raises(AssertionError):
+        sb.MagStftExtractor(n_fft=512, hop_length=300, win_length=1024)
+
+
+EIG_CASES = [(fmt, tag, trk, cond) for fmt in ('foa', 'mic')
+             for tag, trk, cond in (('t5', True, 5.0), ('t2', True, 2.0), ('t0', True, 0.0), ('n5', False, 5.0))]
+
+
+@pytest.mark.parametrize('fmt,tag,trk,cond', EIG_CASES)
+def test_eigenvector_matches_golden(sb, golden, fmt, tag, trk, cond):
+    from oracle import salsa as osalsa
+    g = golden('eigvec_cases')
+    X = g['X']
+    ref = g['{}_{}'.format(fmt, tag)]
+    out = sb.extract_normalized_eigenvector(X.copy(), condition_number=cond, n_hopframes=3, is_tracking=trk,
+                                            audio_format=fmt, fs=24000, n_fft=512, lower_bin=1)
+    assert out.shape == ref.shape and out.dtype == np.float64
+    assert np.array_equal(out != 0, ref != 0), 'valid-bin mask differs'
+    # Where the two largest eigenvalues are nearly equal the principal eigenvector is not determined
+    # by the data (the reference returns whatever LAPACK's rotation is); compare where the gap is >= 2.
+    _, aux = osalsa.extract_normalized_eigenvector_batched(
+        X.copy(), condition_number=cond, is_tracking=trk, audio_format=fmt, fs=24000, n_fft=512, lower_bin=1,
+        return_aux=True)
+    s = aux['s']
+    gap_ok = s[..., 0] >= 2.0 * s[..., 1]
+    sel = np.broadcast_to(gap_ok[None], ref.shape) & (ref != 0)
+    assert sel.sum() > 500
+    if fmt == 'mic':
+        # phases within 1e-3 rad of +-pi may legitimately wrap to the other sign
+        delta = 2 * np.pi * 24000 / (512 * 343.0)
+        k = (np.arange(X.shape[0]) + 1)[None, :, None]
+        near_cut = np.abs(np.abs(ref * delta * k) - np.pi) < 1e-3
+        sel &= ~near_cut
+    close(out[sel], ref[sel], 'eigenvector {} {}'.format(fmt, tag))
+
+
+def test_eigenvector_bad_format(sb):
+    X = np.ones((2, 8, 4), dtype=complex)
+    with pytest.raises(ValueError):
+        sb.extract_normalized_eigenvector(X, audio_format='xyz', fs=24000, n_fft=512, lower_bin=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# clip level
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('key,fmt,fmax,trk', [('salsa_foa', 'foa', 9000, True), ('salsa_mic', 'mic', 4000, True)])
+def test_salsa_clip_matches_golden(sb, golden, key, fmt, fmax, trk):
+    g = golden('clip_cases')
+    ex = sb.SalsaExtractor(audio_format=fmt, fmax_doa=fmax, is_tracking=trk)
+    audio = torch.from_numpy(g['audio_' + fmt])[None].cuda()
+    out = ex.extract(audio).cpu().numpy()[0]
+    check_feature(out, g[key], what=key)
+
+
+def test_salsa_lite_matches_golden(sb, golden):
+    g = golden('clip_cases')
+    audio = torch.from_numpy(g['audio_mic'])[None].cuda()
+    for ft in ('salsa_lite', 'salsa_ipd'):
+        out = sb.SalsaLiteExtractor(feature_type=ft).extract(audio).cpu().numpy()[0]
+        ref = g[ft]
+        assert out.shape == ref.shape == (7, 81, 191)
+        close(out[:4], ref[:4], ft + ' spectrogram')
+        assert np.all(out[4:, :, 42:] == 0)
+        scale = np.pi if ft == 'salsa_ipd' else 1.0
+        if ft == 'salsa_lite':
+            delta = 2 * np.pi * 24000 / (512 * 343.0)
+            ang_ref = ref[4:, :, :42] * delta * np.arange(1, 43)
+        else:
+            ang_ref = ref[4:, :, :42] * np.pi
+        near_cut = np.abs(np.abs(ang_ref) - np.pi) < 1e-3
+        close(out[4:, :, :42][~near_cut], ref[4:, :, :42][~near_cut], ft + ' phase')
+
+
+@pytest.mark.parametrize('fmt,fmax', [('foa', 9000), ('mic', 4000)])
+def test_salsa_clip_matches_oracle_5s(sb, fmt, fmax):
+    """A longer clip than the golden one, oracle computed on the spot (batched LAPACK form)."""
+    from oracle import salsa as osalsa, synth
+    audio = synth.make_clip(11, fmt, seconds=5.0)
+    ref = osalsa.salsa_clip(audio, fmt, fmax_doa=fmax)
+    out = sb.SalsaExtractor(audio_format=fmt, fmax_doa=fmax).extract(torch.from_numpy(audio)[None].cuda())
+    check_feature(out.cpu().numpy()[0], ref, what='5 s {}'.format(fmt))
+
+
+def test_salsa_no_tracking_matches_oracle(sb, golden):
+    from oracle import salsa as osalsa
+    g = golden('clip_cases')
+    audio = g['audio_foa']
+    ref, aux = osalsa.salsa_clip(audio, 'foa', is_tracking=False, return_aux=True)
+    np.testing.assert_allclose(ref, g['salsa_foa_notracking'], rtol=0, atol=1e-6)
+    out = sb.SalsaExtractor('foa', is_tracking=False).extract(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
+    close(out[:4], ref[:4], 'no-tracking spectrogram')
+    assert np.array_equal(out[4:] != 0, ref[4:] != 0)
+    gap_ok = (aux['s'][..., 0] >= 2.0 * aux['s'][..., 1]).T                  # (T, n_bins)
+    sel = np.zeros(ref[4:].shape, dtype=bool)
+    sel[:, :, :gap_ok.shape[1]] = gap_ok[None]
+    close(out[4:][sel], ref[4:][sel], 'no-tracking spatial (gap >= 2)')
+
+
+def test_batch_equals_single_and_host_path(sb):
+    """Clips are independent: a batch gives bit-identical rows to one-by-one calls, and the
+    host-buffer entry point (chunked, 3 streams) gives bit-identical results to the device one."""
+    from oracle import synth
+    clips = np.stack([synth.make_clip(20 + i, 'foa', seconds=1.0 + 0.0 * i) for i in range(5)])
+    ex = sb.SalsaExtractor('foa')
+    batch = ex.extract(torch.from_numpy(clips).cuda()).cpu().numpy()
+    for i in range(5):
+        one = ex.extract(torch.from_numpy(clips[i:i + 1]).cuda()).cpu().numpy()[0]
+        assert np.array_equal(one, batch[i], equal_nan=True)
+    host = ex.extract_host(clips, clips_per_chunk=2)
+    assert np.array_equal(host, batch, equal_nan=True)
+    lite = sb.SalsaLiteExtractor()
+    lb = lite.extract(torch.from_numpy(clips).cuda()).cpu().numpy()
+    assert np.array_equal(lite.extract_host(clips, clips_per_chunk=3), lb)
+
+
+def test_empty_batch_and_bad_shapes(sb):
+    ex = sb.SalsaExtractor('foa')
+    out = ex.extract(torch.empty((0, 4, 24000), device='cuda'))
+    assert tuple(out.shape) == (0, 7, 81, 200)
+    with pytest.raises(ValueError):
+        ex.extract(torch.zeros((1, 3, 24000), device='cuda'))
+    with pytest.raises(ValueError):
+        ex.extract(torch.zeros((1, 4, 100), device='cuda'))       # shorter than the reflect padding
+    with pytest.raises(ValueError):
+        sb.SalsaExtractor('xyz')
+
+
+def test_silence_and_ragged_lengths(sb):
+    """Digital silence: spectrogram at the -100 dB floor, no valid bins; odd lengths (frame count
+    1 + N // hop, last frame reflected) agree with the oracle."""
+    from oracle import salsa as osalsa, synth
+    ex = sb.SalsaExtractor('foa')
+    out = ex.extract(torch.zeros((1, 4, 12000), device='cuda')).cpu().numpy()[0]
+    assert np.all(out[:4] == -100.0) and np.all(out[4:] == 0)
+    for n in (7321, 9000, 8999):
+        audio = synth.make_clip(31, 'foa', seconds=1.0)[:, :n].copy()
+        ref = osalsa.salsa_clip(audio, 'foa')
+        got = ex.extract(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
+        assert got.shape == ref.shape == (7, 1 + n // 300, 200)
+        check_feature(got, ref, what='ragged n={}'.format(n))
