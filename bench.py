@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- SALSA feature extraction throughput on B200 (audio-minutes / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                           # the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[1]): SALSA FOA, 600 synthetic 4-channel 24 kHz 60 s clips per GPU,
+n_fft 512, hop 300.  One "step" = one pass of the hot path (audio -> (7, 4801, 200) features) over
+that batch.  1 clip = 1 audio-minute, so clips/s == audio-minutes/s.
+
+* `value`      : device-resident (audio and features stay in HBM), CUDA events, max over ranks.
+* `e2e`        : the same metric through the host-buffer C-ABI entry point `salsa_extract_host`
+                 (pinned host audio in, pinned host features out, H2D / kernels / D2H pipelined).
+* `roofline`   : dominant kernel (salsa_fused_kernel) against the measured HBM copy bandwidth in
+                 MEASURED_PEAKS.json, algorithmic bytes = audio read once + features written once.
+* `cpu_baseline`: the oracle (a line-by-line port of the reference's per-bin LAPACK loop) on all
+                 host cores over a bounded sample of the same clips.
+
+Under torchrun (N > 1) every rank processes its own 600 clips (weak scaling, clips are independent,
+no data-path collective); NCCL is used for the barrier and the max-over-ranks time only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS, N_FFT, HOP = 24000, 512, 300
+CLIP_SECONDS = 60
+N_SAMPLES = FS * CLIP_SECONDS
+N_FRAMES = 1 + N_SAMPLES // HOP
+AUDIO_BYTES_PER_CLIP = 4 * N_SAMPLES * 4                    # 23 040 000
+METRIC = 'audio-minutes/sec SALSA feature extraction'
+UNIT = 'audio-min/s'
+
+
+def feature_bytes_per_clip(freq_dim):
+    return 7 * N_FRAMES * freq_dim * 4                       # 26 885 600 for F = 200
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic clips, generated on the device (recipe of SURVEY.md section 8d / oracle/synth.py:
+# two band-passed (300-6000 Hz) gated noise sources, amplitude 0.1, FOA gains or tetrahedral-array
+# delays, 1e-3 sensor noise)
+# ------------------------------------------------------------------------------------------------
+def make_clips(torch, n_clips, audio_format, device, seed, n_samples=N_SAMPLES, chunk=40):
+    out = torch.empty((n_clips, 4, n_samples), dtype=torch.float32, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(2021 + seed)
+    f = torch.fft.rfftfreq(n_samples, 1.0 / FS).to(device)
+    # magnitude of a 4th-order Butterworth band-pass 300-6000 Hz (zero phase)
+    band = 1.0 / torch.sqrt(1.0 + (f / 6000.0) ** 8) * (1.0 / torch.sqrt(1.0 + (300.0 / f.clamp(min=1e-3)) ** 8))
+    t = torch.arange(n_samples, device=device, dtype=torch.float32)
+    ramp = 0.005 * FS
+    mic_dirs = torch.tensor([[45, 35], [-45, -35], [135, -35], [-135, 35]], dtype=torch.float32, device=device)
+    mic_dirs = torch.deg2rad(mic_dirs)
+    mic_unit = torch.stack([torch.cos(mic_dirs[:, 0]) * torch.cos(mic_dirs[:, 1]),
+                            torch.sin(mic_dirs[:, 0]) * torch.cos(mic_dirs[:, 1]), torch.sin(mic_dirs[:, 1])], dim=1)
+    for c0 in range(0, n_clips, chunk):
+        b = min(chunk, n_clips - c0)
+        mix = torch.zeros((b, 4, n_samples), dtype=torch.float32, device=device)
+        for _src in range(2):
+            S = torch.fft.rfft(torch.randn((b, n_samples), generator=g, device=device)) * band
+            s = torch.fft.irfft(S, n_samples)
+            s = s * (0.1 / s.std(dim=1, keepdim=True).clamp(min=1e-12))
+            gate = torch.zeros((b, n_samples), device=device)
+            for _seg in range(3):
+                a = torch.rand((b, 1), generator=g, device=device) * (n_samples * 7 / 8)
+                ln = n_samples / 8 + torch.rand((b, 1), generator=g, device=device) * (n_samples * 3 / 8)
+                on = (torch.rand((b, 1), generator=g, device=device) < (1.0 if _seg == 0 else 0.5)).float()
+                seg = torch.minimum((t[None] - a) / ramp, (a + ln - t[None]) / ramp).clamp(0.0, 1.0)
+                gate = torch.maximum(gate, seg * on)
+            s = s * gate
+            az = (torch.rand((b,), generator=g, device=device) * 360.0 - 180.0) * (3.141592653589793 / 180.0)
+            el = (torch.rand((b,), generator=g, device=device) * 90.0 - 45.0) * (3.141592653589793 / 180.0)
+            if audio_format == 'foa':
+                gains = torch.stack([torch.ones_like(az), torch.sin(az) * torch.cos(el), torch.sin(el),
+                                     torch.cos(az) * torch.cos(el)], dim=1)             # W, Y, Z, X
+                mix += gains[:, :, None] * s[:, None, :]
+            else:
+                u = torch.stack([torch.cos(az) * torch.cos(el), torch.sin(az) * torch.cos(el), torch.sin(el)], dim=1)
+                tau = -0.042 * (u @ mic_unit.T) / 343.0                                  # (b, 4) seconds
+                S = torch.fft.rfft(s)
+                for m in range(4):
+                    ph = torch.exp(-2j * 3.141592653589793 * f[None] * tau[:, m:m + 1])
+                    mix[:, m] += torch.fft.irfft(S * ph, n_samples)
+        mix += 1e-3 * torch.randn(mix.shape, generator=g, device=device)
+        out[c0:c0 + b] = mix
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix='clocks_', suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, reasons, power = [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        with open(self.path) as fh:
+            for line in fh:
+                parts = [p.strip() for p in line.split(',')]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    out['sm_max_mhz'] = float(parts[2])
+                    power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out['sm_mhz'] = sm[len(sm) // 2]
+            out['power_w_max'] = max(power)
+        out['reasons'] = sorted(reasons)
+        out['samples'] = len(sm)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's faithful port of the reference loop (one LAPACK SVD per selected bin)
+# ------------------------------------------------------------------------------------------------
+def _cpu_init():
+    from oracle import salsa as osalsa  # noqa: F401  (import cost outside the clock)
+
+
+def _cpu_worker(args):
+    audio, fmt, fmax, batched = args
+    from oracle import salsa as osalsa
+    t0 = time.perf_counter()
+    feat = osalsa.salsa_clip(audio, fmt, fmax_doa=fmax, batched=batched)
+    return time.perf_counter() - t0, float(feat[4:].astype(bool).mean())
+
+
+def cpu_baseline(clips, audio_format, fmax_doa, batched=False, cores=None):
+    """clips: list of (4, n) float32 arrays (one per worker).  Returns audio-min/s over all workers."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = '1'
+    ctx = mp.get_context('spawn')
+    jobs = [(c, audio_format, fmax_doa, batched) for c in clips]
+    with ctx.Pool(min(cores, len(jobs)), initializer=_cpu_init) as pool:
+        pool.map(abs, range(4 * cores))                              # workers up, imports done
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    minutes = sum(c.shape[1] for c in clips) / FS / 60.0
+    return minutes / wall, wall, min(cores, len(jobs)), sum(r[1] for r in res) / len(res)
+
+
+def host_sample_clips(n_workers, seconds, audio_format, seed=0):
+    """The same recipe as the device generator, drawn on the host by oracle.synth (bounded sample)."""
+    from oracle import synth
+    return [synth.make_clip(seed * 1000 + i, audio_format, seconds=seconds) for i in range(n_workers)]
+
+
+# ------------------------------------------------------------------------------------------------
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python
+    that cannot travel to the GPU box) on all host cores.  Each step = one bounded sample."""
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    seconds = args.cpu_seconds
+    fmax = 9000 if args.format == 'foa' else 4000
+    clips = host_sample_clips(cores, seconds, args.format)
+    vals = []
+    for step in range(args.warmup + args.steps):
+        v, wall, used, valid = cpu_baseline(clips, args.format, fmax, batched=False, cores=cores)
+        if step >= args.warmup:
+            vals.append((v, wall))
+    value = sum(v for v, _ in vals) / len(vals)
+    ms = 1e3 * sum(w for _, w in vals) / len(vals)
+    sample = '{} clips x {} s per step (one per core), oracle loop form = reference algorithm (1 LAPACK SVD per bin)'.format(
+        len(clips), seconds)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, world, None),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world, valid_frac):
+    cfg = {
+        'workload': 'SALSA {} batch: {} synthetic 4-ch 24 kHz 60 s clips per GPU, n_fft=512 hop=300 '
+                    '(BASELINE.json configs[1])'.format(args.format.upper(), args.clips),
+        'clips_per_gpu': args.clips, 'clips_total': args.clips * world, 'audio_format': args.format,
+        'stft_precision': args.stft_precision,
+        'l2_policy': 'inputs larger than L2 ({:.1f} GB audio per GPU per step)'.format(
+            args.clips * AUDIO_BYTES_PER_CLIP / 1e9),
+        'parallelism': 'clips sharded over {} GPU(s), no data-path collective'.format(world),
+    }
+    if valid_frac is not None:
+        cfg['valid_bin_fraction'] = round(valid_frac, 4)
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--clips', type=int, default=600, help='clips per GPU per step')
+    ap.add_argument('--format', default='foa', choices=['foa', 'mic'])
+    ap.add_argument('--stft-precision', type=int, default=64, choices=[32, 64])
+    ap.add_argument('--e2e-clips', type=int, default=120, help='clips per GPU per end-to-end step (host buffers)')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--cpu-seconds', type=float, default=5.0, help='clip length of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+
+    rank, world, local_rank = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import salsa_b200
+    from salsa_b200 import _native
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    fmax = 9000 if args.format == 'foa' else 4000
+    ex = salsa_b200.SalsaExtractor(args.format, fmax_doa=fmax, stft_precision=args.stft_precision)
+    n_clips = args.clips
+    audio = make_clips(torch, n_clips, args.format, dev, seed=1000 * rank)
+    feat = torch.empty((n_clips, 7, N_FRAMES, ex.freq_dim), dtype=torch.float32, device=dev)
+    feat_bytes = feature_bytes_per_clip(ex.freq_dim)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident: W warm-up steps, K timed steps --------------------------------------
+    for _ in range(args.warmup):
+        ex.extract(audio, out=feat)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _native.lib().salsa_launch_count(1)
+    _native.profile_enable(True)
+    _native.profile_read()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        ex.extract(audio, out=feat)
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = int(_native.lib().salsa_launch_count(0))
+    kernels = _native.profile_read()
+    _native.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = n_clips * world / (ms_per_step / 1e3)
+    valid_frac = float((feat[: min(n_clips, 8), 4:, :, :ex.upper_bin - ex.lower_bin] != 0).float().mean().item())
+
+    # ---- end to end through the host-buffer entry point ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_clips, n_clips)
+        h_audio = torch.empty((ne, 4, N_SAMPLES), dtype=torch.float32, pin_memory=True)
+        h_audio.copy_(audio[:ne])
+        h_feat = torch.empty((ne, 7, N_FRAMES, ex.freq_dim), dtype=torch.float32, pin_memory=True)
+        ex.extract_host(h_audio, out=h_feat, clips_per_chunk=8)             # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            ex.extract_host(h_audio, out=h_feat, clips_per_chunk=8)        # synchronous
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(h_feat[0].to(dev), feat[0]) or
+                    torch.allclose(h_feat[0].to(dev), feat[0], equal_nan=True))
+        e2e = {'value': ne * world * args.e2e_steps / float(te.item()), 'unit': UNIT,
+               'h2d_bytes_per_step': ne * AUDIO_BYTES_PER_CLIP, 'd2h_bytes_per_step': ne * feat_bytes,
+               'clips_per_step_per_gpu': ne, 'steps': args.e2e_steps, 'matches_device_path': same,
+               'api': 'SalsaExtractor.extract_host -> salsa_extract_host (pinned host buffers, 3-stream pipeline)'}
+        del h_audio, h_feat
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    dom = max(kernels.items(), key=lambda kv: kv[1][0]) if kernels else (None, (0.0, 0))
+    total_kernel_ms = sum(v[0] for v in kernels.values())
+    algo_bytes = n_clips * (AUDIO_BYTES_PER_CLIP + feat_bytes)
+    roofline = None
+    if dom[0]:
+        avg_ms = dom[1][0] / dom[1][1]
+        achieved = algo_bytes / (avg_ms / 1e3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': dom[0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': avg_ms,
+                    'share_of_step': dom[1][0] / total_kernel_ms,
+                    'kernels_ms_per_step': {k: v[0] / args.steps for k, v in kernels.items()}}
+        traffic_path = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.isfile(traffic_path):
+            try:
+                tr = json.load(open(traffic_path)).get(dom[0])
+                if tr:
+                    # ncu measured bytes per clip at its own (smaller) batch; scaled to this launch
+                    roofline['traffic'] = tr['dram_bytes_per_clip'] * n_clips
+                    roofline['traffic_source'] = tr.get('source')
+            except (ValueError, KeyError):
+                pass
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_audio = audio[:cores, :, :int(args.cpu_seconds * FS)].cpu().numpy()
+        clips = [np.ascontiguousarray(sample_audio[i]) for i in range(sample_audio.shape[0])]
+        v, wall, used, _ = cpu_baseline(clips, args.format, fmax, batched=False, cores=cores)
+        vb, wallb, _, _ = cpu_baseline(clips, args.format, fmax, batched=True, cores=cores)
+        cpu = {'value': v, 'unit': UNIT, 'cores': used, 'kind': 'port',
+               'sample': 'first {:.0f} s of {} of the benchmark clips, one per core, {:.1f} s wall; oracle loop form '
+                         '(1 LAPACK SVD per selected bin, as the reference)'.format(args.cpu_seconds, len(clips), wall),
+               'value_stacked_lapack': vb}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (covariance/eigenvector) + f64 (STFT, tracker)' if args.stft_precision == 64 else 'f32 (+ f64 tracker)',
+        'data': 'synthetic', 'config': workload_config(args, world, valid_frac),
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

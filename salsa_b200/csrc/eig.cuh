@@ -6,9 +6,10 @@
 // Design (everything lives in registers of ONE thread, no LAPACK-style iteration to convergence):
 //  * R is 4x4 Hermitian PSD: 4 real + 6 complex numbers.  It is accumulated from the 7 frames and
 //    scaled by 1/trace (eigenvectors and the ratio test are scale invariant).
-//  * principal eigenvector: n_sq matrix squarings B <- B*B/trace (power iteration with exponent
-//    2^n_sq).  A bin can only be kept when lambda1 > cond * lambda2, so the contamination of the
-//    eigenvector is <= cond^-(2^n_sq)  (5^-16 = 6.6e-12 for the default cond = 5, n_sq = 4).
+//  * principal eigenvector: n_sq matrix squarings B <- B*B, then one product of B with its dominant
+//    column (power iteration with exponent 2^(n_sq+1)).  A bin can only be kept when
+//    lambda1 > cond * lambda2, so the contamination of the eigenvector is <= cond^-(2^(n_sq+1))
+//    (5^-16 = 6.6e-12 for the default cond = 5, n_sq = 3).
 //  * lambda1 = Rayleigh quotient of R at that vector.
 //  * rank-1 test  lambda2 < mu := lambda1 / cond  without computing lambda2: a Householder reflector
 //    built from the eigenvector deflates R to the 3x3 Hermitian block R3 whose eigenvalues are
@@ -82,7 +83,9 @@ __device__ __forceinline__ void herm_scale(Herm4<T>& A, T s) {
 template <typename T>
 __device__ __forceinline__ T herm_trace(const Herm4<T>& A) { return (A.d[0] + A.d[1]) + (A.d[2] + A.d[3]); }
 
-// B = A * A (Hermitian)
+// B = A * A (Hermitian).  Written out so that the real diagonal never enters a complex product:
+//   B_ii = d_i^2 + sum_{k != i} |a_ik|^2
+//   B_ij = (d_i + d_j) a_ij + sum_{k != i,j} a_ik a_kj
 template <typename T>
 __device__ __forceinline__ Herm4<T> herm_square(const Herm4<T>& A) {
     Herm4<T> B;
@@ -95,9 +98,12 @@ __device__ __forceinline__ Herm4<T> herm_square(const Herm4<T>& A) {
         B.d[i] = s;
 #pragma unroll
         for (int j = i + 1; j < 4; ++j) {
-            Cx<T> acc = {(T)0, (T)0};
+            const Cx<T> aij = A.o[herm_idx(i, j)];
+            const T dd = A.d[i] + A.d[j];
+            Cx<T> acc = {dd * aij.re, dd * aij.im};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+                if (k == i || k == j) continue;
                 const Cx<T> p = cmul(herm_at(A, i, k), herm_at(A, k, j));
                 acc.re += p.re;
                 acc.im += p.im;
@@ -113,9 +119,10 @@ template <typename T>
 __device__ __forceinline__ void herm_matvec(const Herm4<T>& A, const Cx<T> (&x)[4], Cx<T> (&y)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        Cx<T> acc = {(T)0, (T)0};
+        Cx<T> acc = {A.d[i] * x[i].re, A.d[i] * x[i].im};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            if (k == i) continue;
             const Cx<T> p = cmul(herm_at(A, i, k), x[k]);
             acc.re += p.re;
             acc.im += p.im;
@@ -146,21 +153,31 @@ __device__ __forceinline__ int principal_eigenvector(const Herm4<T>& Rin, int n_
         return kEigFail;
     }
     herm_scale(R, (T)1 / tr);
+    // B = R^(2^n_sq); entries stay in range for two squarings of a trace-1 matrix (trace >= 1/64),
+    // so the trace is renormalised every second squaring only
     Herm4<T> B = R;
     for (int it = 0; it < n_sq; ++it) {
         B = herm_square(B);
-        herm_scale(B, (T)1 / herm_trace(B));
+        if (it & 1) herm_scale(B, (T)1 / herm_trace(B));
     }
-    // column with the largest diagonal entry of B ~ v v^H
+    // column with the largest diagonal entry of B ~ lambda^m v v^H, multiplied by B once more:
+    // v ~ R^(2^(n_sq+1)) e_p
     int p = 0;
     T best = B.d[0];
 #pragma unroll
     for (int i = 1; i < 4; ++i)
         if (B.d[i] > best) { best = B.d[i]; p = i; }
+    {
+        Cx<T> c[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        Cx<T> c0 = herm_at(B, i, 0), c1 = herm_at(B, i, 1), c2 = herm_at(B, i, 2), c3 = herm_at(B, i, 3);
-        v[i] = p == 0 ? c0 : (p == 1 ? c1 : (p == 2 ? c2 : c3));
+        for (int i = 0; i < 4; ++i) {
+            Cx<T> c0 = herm_at(B, i, 0), c1 = herm_at(B, i, 1), c2 = herm_at(B, i, 2), c3 = herm_at(B, i, 3);
+            c[i] = p == 0 ? c0 : (p == 1 ? c1 : (p == 2 ? c2 : c3));
+        }
+        const T cs = (T)1 / best;            // keeps the product in range: |c_i| <= 1 afterwards
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { c[i].re *= cs; c[i].im *= cs; }
+        herm_matvec(B, c, v);
     }
     T nv = (cabs2(v[0]) + cabs2(v[1])) + (cabs2(v[2]) + cabs2(v[3]));
     const T inv = rsqrt_t<T>(nv);

@@ -184,12 +184,13 @@ static EigArgs eig_args(const salsa_params_t* p) {
     e.test = p->is_tracking ? 1 : 0;
     e.cond = (float)p->cond_num;
     e.cond_d = p->cond_num;
-    // squarings so that cond^-(2^n) < 1e-7; without a usable gap (no test, cond <= 1) iterate longer
+    // n squarings + one matrix-vector product give the exponent 2^(n+1); choose n so that
+    // cond^-(2^(n+1)) < 1e-7.  Without a usable gap (no test, cond <= 1) iterate longer.
     int n_sq = 10;
     if (e.test && p->cond_num > 1.0) {
         const double need = log(1e7) / log(p->cond_num);
-        n_sq = (int)ceil(log2(need));
-        n_sq = std::max(3, std::min(10, n_sq));
+        n_sq = (int)ceil(log2(need)) - 1;
+        n_sq = std::max(2, std::min(10, n_sq));
     }
     e.n_sq = n_sq;
     const double delta = 2.0 * M_PI * (double)p->fs / ((double)p->n_fft * 343.0);
@@ -299,15 +300,15 @@ static int launch_fused(const salsa_params_t* p, const DeviceTables& tb, const f
     a.bands = band_layout(p);
     a.eig = eig_args(p);
     dim3 grid((a.n_frames + a.seg_len - 1) / a.seg_len, p->n_clips);
-    const size_t ring = (size_t)(kFusedFT + 2 * kHop) * 4 * a.nbp * sizeof(float2);
+    if (a.nbp > 256) return fail(SALSA_EINVAL, "more than 256 spatial bins");
     ProfScope prof("salsa_fused_kernel", st);
     if (p->stft_precision == 64) {
-        const size_t smem = sizeof(FftSmem<double>) + ring;
+        const size_t smem = fused_smem_bytes<double, kFusedFT>(a.nbp);
         int rc = set_smem(salsa_fused_kernel<double, kFusedFT>, smem);
         if (rc) return rc;
         salsa_fused_kernel<double, kFusedFT><<<grid, kThreads, smem, st>>>(a, tb.d);
     } else {
-        const size_t smem = sizeof(FftSmem<float>) + ring;
+        const size_t smem = fused_smem_bytes<float, kFusedFT>(a.nbp);
         int rc = set_smem(salsa_fused_kernel<float, kFusedFT>, smem);
         if (rc) return rc;
         salsa_fused_kernel<float, kFusedFT><<<grid, kThreads, smem, st>>>(a, tb.f);

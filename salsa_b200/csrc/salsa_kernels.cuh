@@ -61,11 +61,10 @@ __device__ __forceinline__ void load_fft_smem(FftSmem<T>& s, const FftTables<T>&
 
 __device__ __forceinline__ float power_db(float p) { return 10.0f * log10f(fmaxf(kAmin, p)); }
 
-// |X|^2 as the reference computes it for the spectrogram: np.abs(complex64)**2 in float32 (:186-194).
-__device__ __forceinline__ float power_f32(float re, float im) {
-    const float m = hypotf(re, im);
-    return m * m;
-}
+// |X|^2 for the spectrogram.  The reference takes np.abs(complex64)**2 in float32 (:186-194); the
+// sum of squares differs from hypot()^2 by about one float32 ulp (5e-7 dB) and can neither overflow
+// nor matter below the 1e-10 amin clamp for audio-range spectra.
+__device__ __forceinline__ float power_f32(float re, float im) { return fmaf(re, re, im * im); }
 
 // One warp, after warp_fft256_frame: writes the log-linear spectrogram row of this (frame, channel).
 // `pw` = 256 floats of per-warp scratch (aliasing the FFT scratch is fine after a __syncwarp).
@@ -127,16 +126,15 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
             if (k >= a.lower && k < a.upper) {
                 const long long o = ((long long)clip * a.n_frames + t);
                 if (a.X) a.X[(o * a.n_chans + ch) * nb + (k - a.lower)] = make_float2(re, im);
-                if (a.power0 && ch == 0) {
-                    const double m = hypot((double)re, (double)im);    // np.abs(complex128) ** 2 (:53-55)
-                    a.power0[o * nb + (k - a.lower)] = m * m;
-                }
+                // np.abs(complex128) ** 2 (:53-55) up to one float64 ulp
+                if (a.power0 && ch == 0) a.power0[o * nb + (k - a.lower)] = fma((double)re, (double)re, (double)im * (double)im);
             }
         }
-        const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
-        const float p_nyq = power_f32((float)xn.re, 0.0f);
         __syncwarp();
         if (a.spec) {
+            const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
+            const float p_nyq = power_f32((float)xn.re, 0.0f);
+            __syncwarp();
             float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
             write_logspec_row(p, p_nyq, reinterpret_cast<float*>(scratch), row, a.bands, lane);
         }
@@ -152,8 +150,8 @@ struct TrackerConsts {
     int n_sig_frames, n_init_frames;
 };
 
-__global__ void tracker_kernel(const double* __restrict__ power0, uint32_t* __restrict__ mask, int n_frames,
-                               int n_bins, TrackerConsts c) {
+__global__ void __launch_bounds__(256) tracker_kernel(const double* __restrict__ power0, uint32_t* __restrict__ mask,
+                                                      int n_frames, int n_bins, TrackerConsts c) {
     const int clip = blockIdx.y;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int word = b >> 5, n_words = (n_bins + 31) >> 5;
@@ -165,27 +163,39 @@ __global__ void tracker_kernel(const double* __restrict__ power0, uint32_t* __re
         if (t < 0) t += n_frames;
         return live ? a[(long long)t * n_bins] : 0.0;
     };
-    auto rms3 = [](double a0, double a1, double a2) { return sqrt(((a0 + a1) + a2) / 3.0); };
-    // initial floor: 0.5 * mean(sig[0:5])
+    // initial floor: 0.5 * mean(sig[0:5]), sig = sqrt(mean of three powers)   (:53-58)
     const int n_init = min(c.n_init_frames, n_frames);
     double acc = 0.0;
-    for (int t = 0; t < n_init; ++t) acc += rms3(at(t), at(t - 1), at(t - 2));
+    for (int t = 0; t < n_init; ++t) acc += sqrt(((at(t) + at(t - 1)) + at(t - 2)) / 3.0);
     double nf = 0.5 * (acc / (double)n_init);
     int cd = c.n_sig_frames;
     double a1 = at(-1), a2 = at(-2);
+    // The frame loop compares SQUARES: sig > floor  <=>  sig^2 = (a0+a1+a2)/3 > floor^2.  That removes
+    // the float64 sqrt and division (about 90 % of this kernel's float64 work) and moves the two
+    // comparisons by a few 1e-16 relative, far inside what hypot()'s last bit already leaves open.
+    const double third = 1.0 / 3.0;
+    const double snr2 = c.snr_ratio * c.snr_ratio;
     constexpr int kChunk = 8;
+    double nxt[kChunk];
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) nxt[i] = (i < n_frames && live) ? a[(long long)i * n_bins] : 0.0;
     for (int t0 = 0; t0 < n_frames; t0 += kChunk) {
         double buf[kChunk];
 #pragma unroll
-        for (int i = 0; i < kChunk; ++i) buf[i] = (t0 + i < n_frames && live) ? a[(long long)(t0 + i) * n_bins] : 0.0;
+        for (int i = 0; i < kChunk; ++i) buf[i] = nxt[i];
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {   // prefetch of the next chunk overlaps the recurrence below
+            const int t = t0 + kChunk + i;
+            nxt[i] = (t < n_frames && live) ? a[(long long)t * n_bins] : 0.0;
+        }
 #pragma unroll
         for (int i = 0; i < kChunk; ++i) {
             if (t0 + i < n_frames) {
                 const double a0 = buf[i];
-                const double x = rms3(a0, a1, a2);
+                const double q = ((a0 + a1) + a2) * third;
                 a2 = a1;
                 a1 = a0;
-                const bool above = x > nf;
+                const bool above = q > nf * nf;
                 if (above) {
                     cd -= 1;
                     nf *= (cd < 0) ? c.floor_up_slow : c.floor_up;
@@ -194,7 +204,7 @@ __global__ void tracker_kernel(const double* __restrict__ power0, uint32_t* __re
                     nf *= c.floor_down;
                 }
                 if (nf < c.floor_min) nf = c.floor_min;
-                const bool sel = live && (x > c.snr_ratio * nf);
+                const bool sel = live && (q > snr2 * (nf * nf));
                 const uint32_t bits = __ballot_sync(0xffffffffu, sel);
                 if ((threadIdx.x & 31) == 0) mrow[(long long)(t0 + i) * n_words] = bits;
             }
@@ -336,9 +346,15 @@ __global__ void __launch_bounds__(256) eig_kernel(const float2* __restrict__ X, 
 
 // ------------------------------------------------------------------------------------------------
 // salsa_fused_kernel: grid (segments, clips).  A CTA walks `seg_len` consecutive frames of one clip
-// in steps of FT frames.  Per step: FT*4 warp-FFTs (new frames only) into a ring of FT+6 frames of
-// X in shared memory ([slot][ch][bin] complex64), log-spectrogram rows straight to HBM, then one
-// thread per (frame, bin) does the eigenvector step from the ring and writes the 3 spatial rows.
+// in steps of FT frames.  Per step:
+//   phase 1  FT*4 warp-FFTs (new frames only) into a ring of FT+6 frames of X in shared memory
+//            ([slot][ch][bin] complex64); log-spectrogram rows go straight to HBM.  Meanwhile the
+//            tracker mask words of the step are compacted into a dense list of selected (frame, bin)
+//            items, so that phase 2 runs with full warps whatever the selection looks like.
+//   phase 2  one thread per list item: covariance over 7 ring frames, eigenvector, coherence test,
+//            normalisation -> staging tile in shared memory (aliases the FFT scratch).
+//   phase 3  the 3 x FT spatial rows are written to HBM as whole rows (float4), zeros where the
+//            bin was not selected / not valid / above the last spatial bin (:373-374).
 // HBM traffic per clip = audio once (+ halo re-reads served by L2) + feature once + mask bits.
 // ------------------------------------------------------------------------------------------------
 struct FusedArgs {
@@ -349,19 +365,35 @@ struct FusedArgs {
     int hop;
     int n_frames;
     int lower, upper;
-    int nbp;                 // ring row length in bins (n_bins rounded up to 32)
+    int nbp;                 // ring row length in bins (n_bins rounded up to 32, <= 256)
     int seg_len;
     BandLayout bands;
     EigArgs eig;
 };
 
+template <int FT>
+__host__ __device__ constexpr int fused_max_words() { return FT * 8; }
+
+// shared memory after FftSmem<T>: ring, item list, mask words, item count
+template <typename T, int FT>
+__host__ __device__ inline size_t fused_smem_bytes(int nbp) {
+    return sizeof(FftSmem<T>) + (size_t)(FT + 2 * kHop) * 4 * nbp * sizeof(float2) + (size_t)FT * nbp * sizeof(uint16_t) +
+           fused_max_words<FT>() * sizeof(uint32_t) + 16;
+}
+
 template <typename T, int FT>
 __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, FftTables<T> tb) {
     constexpr int R = FT + 2 * kHop;
+    static_assert(sizeof(Cx<T>) * kScratchElems * kWarps >= 3 * FT * 256 * sizeof(float), "staging tile must fit in the FFT scratch");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
-    float2* ring = reinterpret_cast<float2*>(smem_raw + sizeof(FftSmem<T>));   // [R][4][nbp]
+    float2* ring = reinterpret_cast<float2*>(smem_raw + sizeof(FftSmem<T>));                 // [R][4][nbp]
+    uint16_t* list = reinterpret_cast<uint16_t*>(ring + (size_t)R * 4 * a.nbp);               // [FT * nbp]
+    uint32_t* smask = reinterpret_cast<uint32_t*>(list + (size_t)FT * a.nbp);                 // [FT][n_words]
+    int* n_items = reinterpret_cast<int*>(smask + fused_max_words<FT>());
+    float* stage = reinterpret_cast<float*>(&s.scratch[0][0]);                                 // [3][FT][nbp]
     load_fft_smem(s, tb);
+    if (threadIdx.x == 0) *n_items = 0;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
     float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
     Cx<T>* scratch = s.scratch[warp];
     const int row = 4 * a.nbp;    // float2 per ring slot
+    const uint32_t tail_bits = (n_bins & 31) ? ((1u << (n_bins & 31)) - 1u) : 0xffffffffu;
 
     // transforms frames [fa, fb) (un-wrapped indices relative to the clip) into the ring
     auto transform = [&](int fa, int fb) {
@@ -401,34 +434,72 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
             if (f >= s0 && f < s1) {
                 float* rowp = clip_feat + ch * chan_stride + (long long)f * feat_dim;
                 write_logspec_row(p, p_nyq, reinterpret_cast<float*>(scratch), rowp, a.bands, lane);
-                if (ch > 0) {   // zero padding of spatial channel ch-1 above the last spatial bin (:373-374)
-                    float* z = clip_feat + (3 + ch) * chan_stride + (long long)f * feat_dim;
-                    for (int k = n_bins + lane; k < feat_dim; k += 32) z[k] = 0.0f;
-                }
             }
+        }
+    };
+
+    // compacts the selected (frame, bin) items of frames [t0, t0 + nt) into `list`
+    auto compact = [&](int t0, int nt) {
+        for (int w = warp; w < nt * n_words; w += kWarps) {
+            const int tl = w / n_words, wi = w - tl * n_words;
+            uint32_t bits = a.mask ? a.mask[((long long)clip * a.n_frames + t0 + tl) * n_words + wi] : 0xffffffffu;
+            if (wi == n_words - 1) bits &= tail_bits;
+            int base = 0;
+            if (lane == 0) {
+                smask[tl * n_words + wi] = bits;
+                base = atomicAdd(n_items, __popc(bits));
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((bits >> lane) & 1u) list[base + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((tl << 8) | (wi * 32 + lane));
         }
     };
 
     transform(s0 - kHop, s0 + kHop);
     for (int t0 = s0; t0 < s1; t0 += FT) {
-        transform(t0 + kHop, min(t0 + FT, s1) + kHop);
-        __syncthreads();
         const int nt = min(FT, s1 - t0);
-        for (int item = threadIdx.x; item < nt * a.nbp; item += kThreads) {
-            const int tl = item / a.nbp, b = item - tl * a.nbp;
-            if (b >= n_bins) continue;
-            const int t = t0 + tl;
-            bool sel = true;
-            if (a.mask) sel = (a.mask[((long long)clip * a.n_frames + t) * n_words + (b >> 5)] >> (b & 31)) & 1u;
-            float o[3] = {0.0f, 0.0f, 0.0f};
-            if (sel) {
-                const int rel = t - s0 + kHop;             // ring-relative index of frame t
-                auto load = [&](int f, int ch) -> float2 { return ring[((rel + f) % R) * row + ch * a.nbp + b]; };
-                eig_bin(load, a.eig, b, o);
-            }
-            float* dst = clip_feat + 4 * chan_stride + (long long)t * feat_dim + b;
+        // ---- phase 1
+        compact(t0, nt);
+        transform(t0 + kHop, t0 + nt + kHop);
+        __syncthreads();
+        // ---- phase 2
+        const int count = *n_items;
+        for (int item = threadIdx.x; item < count; item += kThreads) {
+            const int code = list[item];
+            const int tl = code >> 8, b = code & 255;
+            const int rel = t0 + tl - s0 + kHop;           // ring-relative index of the frame
+            float o[3];
+            auto load = [&](int f, int ch) -> float2 { return ring[((rel + f) % R) * row + ch * a.nbp + b]; };
+            eig_bin(load, a.eig, b, o);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) dst[i * chan_stride] = o[i];
+            for (int i = 0; i < 3; ++i) stage[(i * FT + tl) * a.nbp + b] = o[i];
+        }
+        __syncthreads();
+        // ---- phase 3
+        if (threadIdx.x == 0) *n_items = 0;
+        if ((feat_dim & 3) == 0) {
+            const int groups = feat_dim >> 2;
+            for (int g = threadIdx.x; g < 3 * nt * groups; g += kThreads) {
+                const int r = g / groups, k = (g - r * groups) * 4;      // r = channel * nt + frame
+                const int i = r / nt, tl = r - i * nt;
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (k < n_bins) {
+                    const uint32_t bits = smask[tl * n_words + (k >> 5)] >> (k & 31);
+                    const float* sp = stage + (i * FT + tl) * a.nbp + k;
+                    if (bits & 1u) v.x = sp[0];
+                    if (bits & 2u) v.y = sp[1];
+                    if (bits & 4u) v.z = sp[2];
+                    if (bits & 8u) v.w = sp[3];
+                }
+                *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * feat_dim + k) = v;
+            }
+        } else {
+            for (int g = threadIdx.x; g < 3 * nt * feat_dim; g += kThreads) {
+                const int r = g / feat_dim, k = g - r * feat_dim;
+                const int i = r / nt, tl = r - i * nt;
+                float v = 0.0f;
+                if (k < n_bins && ((smask[tl * n_words + (k >> 5)] >> (k & 31)) & 1u)) v = stage[(i * FT + tl) * a.nbp + k];
+                clip_feat[(4 + i) * chan_stride + (long long)(t0 + tl) * feat_dim + k] = v;
+            }
         }
         __syncthreads();
     }
