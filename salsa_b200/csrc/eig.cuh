@@ -131,6 +131,9 @@ __device__ __forceinline__ void herm_matvec(const Herm4<T>& A, const Cx<T> (&x)[
     }
 }
 
+template <typename T> __device__ __forceinline__ T eps_of();
+template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920929e-7f; }
+template <> __device__ __forceinline__ double eps_of<double>() { return 2.220446049250313e-16; }
 template <typename T> __device__ __forceinline__ T rsqrt_t(T x);
 template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return rsqrtf(x); }
 template <> __device__ __forceinline__ double rsqrt_t<double>(double x) { return 1.0 / sqrt(x); }
@@ -193,6 +196,10 @@ __device__ __forceinline__ int principal_eigenvector(const Herm4<T>& Rin, int n_
     for (int i = 0; i < 4; ++i) lam1 += v[i].re * rv[i].re + v[i].im * rv[i].im;   // Re(v^H R v), |v| = 1
     if (cond < (T)1) return lam1 > (T)0 ? kEigPass : kEigFail;                      // s1*cond < s0 always
     const T mu = lam1 / cond;
+    // Shortcut: R has trace 1 and is PSD, so lambda2 <= 1 - lambda1, and the Rayleigh quotient lam1 is
+    // a lower bound of lambda1 (exact to O(eps^2) at the converged vector).  A bin dominated by one
+    // source passes here without the deflation below: lambda2 <= 1 - lam1 <= (1 - tau) mu.
+    if (((T)1 - lam1) <= ((T)1 - (T)4 * tau) * mu - (T)8 * eps_of<T>()) return kEigPass;
 
     // Householder w = v - alpha e0, alpha = -exp(i arg v0) |v| = -exp(i arg v0)
     const T a0 = sqrt(cabs2(v[0]));

@@ -83,34 +83,38 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
     return i >= n ? 2 * (n - 1) - i : i;
 }
 
-// One warp: 256-point complex FFT of the windowed frame starting at sample `start`
-// (in un-padded coordinates, may be negative / run past the end -> reflection) of channel
-// signal `x` of length n.  Result Z[0..255] is left in `scratch` in natural order
-// (scratch must hold kScratchElems complex values).  `win` points to the window in shared memory.
-template <typename T>
-__device__ __forceinline__ void warp_fft256_frame(const float* __restrict__ x, int n, int start,
-                                                  const T* __restrict__ win, const FftTables<T>& tb,
-                                                  Cx<T>* scratch, int lane) {
-    Cx<T> v[8];
-    // ---- load + window: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1],  m = lane + 32 n1
+// One warp: loads the 512 samples of the frame starting at sample `start` (in un-padded coordinates,
+// may be negative / run past the end -> reflection) of channel signal `x` of length n.
+// raw[n1] = (x[2m], x[2m+1]) for m = lane + 32 n1.  Split from the transform so that callers can
+// issue the loads of the next frame before transforming the current one.
+__device__ __forceinline__ void load_frame(const float* __restrict__ x, int n, int start, int lane, float2 (&raw)[8]) {
     const bool interior = (start >= 0) && (start + kNfft <= n) &&
                           ((reinterpret_cast<uintptr_t>(x + start) & 7) == 0);
     if (interior) {
         const float2* xp = reinterpret_cast<const float2*>(x + start);
 #pragma unroll
-        for (int n1 = 0; n1 < 8; ++n1) {
-            const int m = lane + 32 * n1;
-            const float2 s = __ldg(xp + m);
-            v[n1] = {(T)s.x * win[2 * m], (T)s.y * win[2 * m + 1]};
-        }
+        for (int n1 = 0; n1 < 8; ++n1) raw[n1] = __ldg(xp + lane + 32 * n1);
     } else {
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
             const int m = lane + 32 * n1;
-            const float s0 = x[reflect_index(start + 2 * m, n)];
-            const float s1 = x[reflect_index(start + 2 * m + 1, n)];
-            v[n1] = {(T)s0 * win[2 * m], (T)s1 * win[2 * m + 1]};
+            raw[n1] = make_float2(x[reflect_index(start + 2 * m, n)], x[reflect_index(start + 2 * m + 1, n)]);
         }
+    }
+}
+
+// One warp: 256-point complex FFT of the windowed frame in `raw` (see load_frame).  Result Z[0..255]
+// is left in `scratch` in natural order (scratch must hold kScratchElems complex values).  `win`
+// points to the window in shared memory.
+template <typename T>
+__device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __restrict__ win, const FftTables<T>& tb,
+                                            Cx<T>* scratch, int lane) {
+    Cx<T> v[8];
+    // ---- window: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1],  m = lane + 32 n1
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) {
+        const int m = lane + 32 * n1;
+        v[n1] = {(T)raw[n1].x * win[2 * m], (T)raw[n1].y * win[2 * m + 1]};
     }
     // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1)
     dft8(v);
@@ -148,6 +152,16 @@ __device__ __forceinline__ void warp_fft256_frame(const float* __restrict__ x, i
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) scratch[lane + 32 * p + 64 * j2] = w[p][j2];
     __syncwarp();
+}
+
+// load + transform in one call
+template <typename T>
+__device__ __forceinline__ void warp_fft256_frame(const float* __restrict__ x, int n, int start,
+                                                  const T* __restrict__ win, const FftTables<T>& tb,
+                                                  Cx<T>* scratch, int lane) {
+    float2 raw[8];
+    load_frame(x, n, start, lane, raw);
+    warp_fft256<T>(raw, win, tb, scratch, lane);
 }
 
 // Bin k (0..256) of the 512-point real transform from the packed spectrum Z (natural order).

@@ -59,40 +59,51 @@ __device__ __forceinline__ void load_fft_smem(FftSmem<T>& s, const FftTables<T>&
     for (int i = threadIdx.x; i < kHalf; i += blockDim.x) s.tw_r[i] = tb.tw_r[i];
 }
 
-__device__ __forceinline__ float power_db(float p) { return 10.0f * log10f(fmaxf(kAmin, p)); }
+// power_to_db(ref=1, amin=1e-10, top_db=None): 10 log10(max(amin, p)) (:195).  The argument is never
+// denormal (>= amin), so the MUFU.LG2 approximation applies directly; its error (<= 2^-22 absolute
+// plus 2 ulp) is below 2e-5 dB over the whole [-100, +100] dB range.
+__device__ __forceinline__ float power_db(float p) { return 3.01029995663981195f * __log2f(fmaxf(kAmin, p)); }
+
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
 
 // |X|^2 for the spectrogram.  The reference takes np.abs(complex64)**2 in float32 (:186-194); the
 // sum of squares differs from hypot()^2 by about one float32 ulp (5e-7 dB) and can neither overflow
 // nor matter below the 1e-10 amin clamp for audio-range spectra.
 __device__ __forceinline__ float power_f32(float re, float im) { return fmaf(re, re, im * im); }
 
-// One warp, after warp_fft256_frame: writes the log-linear spectrogram row of this (frame, channel).
-// `pw` = 256 floats of per-warp scratch (aliasing the FFT scratch is fine after a __syncwarp).
+// One warp, after the transform: writes the log-linear spectrogram row of this (frame, channel).
 // p[j] is the power of bin lane + 32 j, p_nyq the power of the Nyquist bin (only the uncompressed
-// layout reaches it: its last band is bin n_fft/2, :172-175).
-__device__ __forceinline__ void write_logspec_row(const float (&p)[8], float p_nyq, float* pw, float* row,
-                                                  BandLayout bands, int lane) {
+// layout reaches it: its last band is bin n_fft/2, :172-175).  The compressed layout is the
+// n_fft = 512 one: 192 linear bands, then 8 bands of 8 bins (the last of 7) weighted 1/8 (:153-162).
+__device__ __forceinline__ void write_logspec_row(const float (&p)[8], float p_nyq, float* row, BandLayout bands,
+                                                  int lane) {
+    const bool compress = bands.n_out > bands.n_lin;
     // linear part: band = bin - 1
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int band = lane + 32 * j - 1;
         if (band >= 0 && band < bands.n_lin) row[band] = power_db(p[j]);
     }
-    if (bands.n_lin == kHalf && lane == 0) row[kHalf - 1] = power_db(p_nyq);
-    if (bands.n_out > bands.n_lin) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pw[lane + 32 * j] = p[j];
-        __syncwarp();
-        const int band = bands.n_lin + lane;
-        if (band < bands.n_out) {
-            const int first = bands.n_lin + 1 + 8 * lane;
-            const int count = min(8, kHalf - first);
-            float acc = 0.0f;
-            for (int m = 0; m < count; ++m) acc = fmaf(0.125f, pw[first + m], acc);
-            row[band] = power_db(acc);
-        }
-        __syncwarp();
+    if (!compress) {
+        if (lane == 0) row[kHalf - 1] = power_db(p_nyq);
+        return;
     }
+    // r6 / r7[lane] = power of bin 193 + lane / 225 + lane (bin 256 is not part of the last band)
+    const float up6 = __shfl_down_sync(0xffffffffu, p[6], 1), up7 = __shfl_down_sync(0xffffffffu, p[7], 1);
+    const float first7 = __shfl_sync(0xffffffffu, p[7], 0);
+    float r6 = lane == 31 ? first7 : up6;
+    float r7 = lane == 31 ? 0.0f : up7;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+        r6 += __shfl_xor_sync(0xffffffffu, r6, m);
+        r7 += __shfl_xor_sync(0xffffffffu, r7, m);
+    }
+    const float v6 = __shfl_sync(0xffffffffu, r6, 8 * (lane & 3)), v7 = __shfl_sync(0xffffffffu, r7, 8 * (lane & 3));
+    if (lane < 8) row[bands.n_lin + lane] = power_db(0.125f * (lane < 4 ? v6 : v7));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
             const float p_nyq = power_f32((float)xn.re, 0.0f);
             __syncwarp();
             float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
-            write_logspec_row(p, p_nyq, reinterpret_cast<float*>(scratch), row, a.bands, lane);
+            write_logspec_row(p, p_nyq, row, a.bands, lane);
         }
     }
 }
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(256) tracker_kernel(const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// The eigenvector step for one TF bin.  `load(f, ch)` returns X[frame offset f in -3..3][ch].
+// The eigenvector step for one TF bin.  `load(k, ch)` returns X[frame t - 3 + k][ch], k = 0..6.
 // ------------------------------------------------------------------------------------------------
 struct EigArgs {
     int format;          // SALSA_FORMAT_*
@@ -229,7 +240,7 @@ template <typename T, typename Load>
 __device__ __forceinline__ void accumulate_cov(Herm4<T>& R, Load load) {
     herm_zero(R);
 #pragma unroll
-    for (int f = -kHop; f <= kHop; ++f) {
+    for (int f = 0; f < kWin; ++f) {
         Cx<T> x[4];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -333,11 +344,14 @@ __global__ void __launch_bounds__(256) eig_kernel(const float2* __restrict__ X, 
     float o[3] = {0.0f, 0.0f, 0.0f};
     if (sel) {
         const float2* base = X + (long long)clip * n_frames * 4 * n_bins + b;
-        auto load = [&](int f, int ch) -> float2 {
-            int tt = (t + f) % n_frames;
+        const float2* fp[kWin];
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            int tt = (t - kHop + k) % n_frames;              // wrap padding of the frame axis (:43)
             if (tt < 0) tt += n_frames;
-            return __ldg(base + ((long long)tt * 4 + ch) * n_bins);
-        };
+            fp[k] = base + (long long)tt * 4 * n_bins;
+        }
+        auto load = [&](int k, int ch) -> float2 { return __ldg(fp[k] + ch * n_bins); };
         eig_bin(load, e, b, o);
     }
 #pragma unroll
@@ -409,16 +423,32 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
     Cx<T>* scratch = s.scratch[warp];
     const int row = 4 * a.nbp;    // float2 per ring slot
     const uint32_t tail_bits = (n_bins & 31) ? ((1u << (n_bins & 31)) - 1u) : 0xffffffffu;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t ch_bytes = (uint32_t)(a.nbp * sizeof(float2));
 
-    // transforms frames [fa, fb) (un-wrapped indices relative to the clip) into the ring
+    // transforms frames [fa, fb) (un-wrapped indices relative to the clip) into the ring; the samples
+    // of a warp's next (frame, channel) item are requested before the current one is transformed
+    auto frame_start = [&](int f) {
+        f %= a.n_frames;                                   // wrap padding of the frame axis (:43)
+        if (f < 0) f += a.n_frames;
+        return f * a.hop - kNfft / 2;
+    };
     auto transform = [&](int fa, int fb) {
-        for (int item = warp; item < (fb - fa) * 4; item += kWarps) {
+        const int n_items = (fb - fa) * 4;
+        float2 raw[8];
+        if (warp < n_items) load_frame(clip_audio + (long long)(warp & 3) * a.n_samples, a.n_samples,
+                                       frame_start(fa + (warp >> 2)), lane, raw);
+        for (int item = warp; item < n_items; item += kWarps) {
             const int f = fa + (item >> 2), ch = item & 3;
-            int fw = f % a.n_frames;                       // wrap padding of the frame axis (:43)
-            if (fw < 0) fw += a.n_frames;
-            warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, fw * a.hop - kNfft / 2,
-                                 s.win, tb, scratch, lane);
-            float2* dst = ring + ((f - (s0 - kHop)) % R) * row + ch * a.nbp;
+            float2 cur[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = raw[i];
+            const int nxt = item + kWarps;
+            if (nxt < n_items) load_frame(clip_audio + (long long)(nxt & 3) * a.n_samples, a.n_samples,
+                                          frame_start(fa + (nxt >> 2)), lane, raw);
+            warp_fft256<T>(cur, s.win, tb, scratch, lane);
+            const int slot = (f - (s0 - kHop)) % R;
+            float2* dst = ring + slot * row + ch * a.nbp;
             float p[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -428,13 +458,13 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
                 p[j] = power_f32(re, im);
                 if (k >= a.lower && k < a.upper) dst[k - a.lower] = make_float2(re, im);
             }
-            const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
-            const float p_nyq = power_f32((float)xn.re, 0.0f);
-            __syncwarp();
-            if (f >= s0 && f < s1) {
-                float* rowp = clip_feat + ch * chan_stride + (long long)f * feat_dim;
-                write_logspec_row(p, p_nyq, reinterpret_cast<float*>(scratch), rowp, a.bands, lane);
+            float p_nyq = 0.0f;
+            if (a.bands.n_out == a.bands.n_lin) {
+                const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
+                p_nyq = power_f32((float)xn.re, 0.0f);
             }
+            __syncwarp();
+            if (f >= s0 && f < s1) write_logspec_row(p, p_nyq, clip_feat + ch * chan_stride + (long long)f * feat_dim, a.bands, lane);
         }
     };
 
@@ -466,9 +496,16 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
         for (int item = threadIdx.x; item < count; item += kThreads) {
             const int code = list[item];
             const int tl = code >> 8, b = code & 255;
-            const int rel = t0 + tl - s0 + kHop;           // ring-relative index of the frame
+            // shared-memory addresses of X[t - 3 + k][ch = 0][b], k = 0..6 (ring slots wrap at R)
+            int slot = (t0 + tl - s0) % R;                 // slot of frame t - 3
+            uint32_t fa[kWin];
+#pragma unroll
+            for (int k = 0; k < kWin; ++k) {
+                fa[k] = ring_addr + (uint32_t)((slot * row + b) * sizeof(float2));
+                slot = slot + 1 == R ? 0 : slot + 1;
+            }
             float o[3];
-            auto load = [&](int f, int ch) -> float2 { return ring[((rel + f) % R) * row + ch * a.nbp + b]; };
+            auto load = [&](int k, int ch) -> float2 { return lds_f2(fa[k] + ch * ch_bytes); };
             eig_bin(load, a.eig, b, o);
 #pragma unroll
             for (int i = 0; i < 3; ++i) stage[(i * FT + tl) * a.nbp + b] = o[i];
