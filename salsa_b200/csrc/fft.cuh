@@ -106,9 +106,10 @@ __device__ __forceinline__ void load_frame(const float* __restrict__ x, int n, i
 // One warp: 256-point complex FFT of the windowed frame in `raw` (see load_frame).  Result Z[0..255]
 // is left in `scratch` in natural order (scratch must hold kScratchElems complex values).  `win`
 // points to the window in shared memory.
+// `w1` = W256^lane (lane_twiddle()), `tw_r` = the real-split table W512^k in shared memory.
 template <typename T>
-__device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __restrict__ win, const FftTables<T>& tb,
-                                            Cx<T>* scratch, int lane) {
+__device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __restrict__ win, const Cx<T> w1,
+                                            const Cx<T>* __restrict__ tw_r, Cx<T>* scratch, int lane) {
     Cx<T> v[8];
     // ---- window: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1],  m = lane + 32 n1
 #pragma unroll
@@ -116,10 +117,20 @@ __device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __r
         const int m = lane + 32 * n1;
         v[n1] = {(T)raw[n1].x * win[2 * m], (T)raw[n1].y * win[2 * m + 1]};
     }
-    // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1)
+    // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1) = w1^k1.  Only w1 comes
+    //      from memory (a per-lane constant the caller keeps in registers); the powers cost six
+    //      complex products and are good to a few ulp of T.
     dft8(v);
-#pragma unroll
-    for (int k1 = 1; k1 < 8; ++k1) v[k1] = cmul(v[k1], tb.tw_a[k1 * 32 + lane]);
+    {
+        const Cx<T> w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1));
+        v[6] = cmul(v[6], cmul(w4, w2));
+        v[7] = cmul(v[7], cmul(w4, w3));
+    }
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) scratch[k1 * kScratchPad + lane] = v[k1];
     __syncwarp();
@@ -129,8 +140,15 @@ __device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __r
     for (int m1 = 0; m1 < 8; ++m1) v[m1] = scratch[k1 * kScratchPad + 4 * m1 + m2];
     __syncwarp();
     dft8(v);
+    // twiddle W32^(m2*j1) = W512^(16 m2 j1) from the real-split table in shared memory (four distinct
+    // addresses per warp, all broadcasts); W512^(256 + x) = -W512^x
 #pragma unroll
-    for (int j1 = 1; j1 < 8; ++j1) v[j1] = cmul(v[j1], tb.tw_b[j1 * 32 + lane]);
+    for (int j1 = 1; j1 < 8; ++j1) {
+        const int x = 16 * m2 * j1;
+        Cx<T> w = tw_r[x & (kHalf - 1)];
+        if (x & kHalf) w = {-w.re, -w.im};
+        v[j1] = cmul(v[j1], w);
+    }
     // u[k1][m2][j1] at k1*kUStrideK + m2*kUStrideM + j1  (strides chosen bank-conflict free)
 #pragma unroll
     for (int j1 = 0; j1 < 8; ++j1) scratch[k1 * kUStrideK + m2 * kUStrideM + j1] = v[j1];
@@ -154,14 +172,18 @@ __device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __r
     __syncwarp();
 }
 
+// W256^lane, the per-lane constant of pass 1
+template <typename T>
+__device__ __forceinline__ Cx<T> lane_twiddle(const FftTables<T>& tb, int lane) { return tb.tw_a[32 + lane]; }
+
 // load + transform in one call
 template <typename T>
 __device__ __forceinline__ void warp_fft256_frame(const float* __restrict__ x, int n, int start,
-                                                  const T* __restrict__ win, const FftTables<T>& tb,
-                                                  Cx<T>* scratch, int lane) {
+                                                  const T* __restrict__ win, const Cx<T> w1,
+                                                  const Cx<T>* __restrict__ tw_r, Cx<T>* scratch, int lane) {
     float2 raw[8];
     load_frame(x, n, start, lane, raw);
-    warp_fft256<T>(raw, win, tb, scratch, lane);
+    warp_fft256<T>(raw, win, w1, tw_r, scratch, lane);
 }
 
 // Bin k (0..256) of the 512-point real transform from the packed spectrum Z (natural order).

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
     load_fft_smem(s, tb);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Cx<T> w1 = lane_twiddle(tb, lane);
     const int clip = blockIdx.y;
     const int f0 = blockIdx.x * a.frames_per_block;
     const int f1 = min(a.n_frames, f0 + a.frames_per_block);
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
     for (int item = warp; item < (f1 - f0) * a.ch_count; item += kWarps) {
         const int t = f0 + item / a.ch_count;
         const int ch = item % a.ch_count;
-        warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, tb,
-                             scratch, lane);
+        warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, w1,
+                             s.tw_r, scratch, lane);
         float p[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -253,7 +254,7 @@ __device__ __forceinline__ void accumulate_cov(Herm4<T>& R, Load load) {
 
 // float64 re-evaluation of a bin whose float32 verdict could not be certified
 template <typename Load>
-__device__ __noinline__ int eig_bin_f64(Load load, const EigArgs& e, float (&out)[3], int b) {
+__device__ __forceinline__ int eig_bin_f64(Load load, const EigArgs& e, float (&out)[3], int b) {
     Herm4<double> R;
     accumulate_cov<double>(R, load);
     Cx<double> v[4];
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Cx<T> w1 = lane_twiddle(tb, lane);
     const int clip = blockIdx.y;
     const int s0 = blockIdx.x * a.seg_len;
     const int s1 = min(a.n_frames, s0 + a.seg_len);
@@ -426,6 +428,22 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t ch_bytes = (uint32_t)(a.nbp * sizeof(float2));
 
+    // compacts the selected (frame, bin) items of frames [t0, t0 + nt) into `list`
+    auto compact = [&](int t0, int nt) {
+        for (int w = warp; w < nt * n_words; w += kWarps) {
+            const int tl = w / n_words, wi = w - tl * n_words;
+            uint32_t bits = a.mask ? a.mask[((long long)clip * a.n_frames + t0 + tl) * n_words + wi] : 0xffffffffu;
+            if (wi == n_words - 1) bits &= tail_bits;
+            int base = 0;
+            if (lane == 0) {
+                smask[tl * n_words + wi] = bits;
+                base = atomicAdd(n_items, __popc(bits));
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((bits >> lane) & 1u) list[base + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((tl << 8) | (wi * 32 + lane));
+        }
+    };
+
     // transforms frames [fa, fb) (un-wrapped indices relative to the clip) into the ring; the samples
     // of a warp's next (frame, channel) item are requested before the current one is transformed
     auto frame_start = [&](int f) {
@@ -433,11 +451,12 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
         if (f < 0) f += a.n_frames;
         return f * a.hop - kNfft / 2;
     };
-    auto transform = [&](int fa, int fb) {
+    auto transform = [&](int fa, int fb, int ct0, int cnt) {
         const int n_items = (fb - fa) * 4;
         float2 raw[8];
         if (warp < n_items) load_frame(clip_audio + (long long)(warp & 3) * a.n_samples, a.n_samples,
                                        frame_start(fa + (warp >> 2)), lane, raw);
+        if (cnt > 0) compact(ct0, cnt);                    // overlaps the latency of the loads above
         for (int item = warp; item < n_items; item += kWarps) {
             const int f = fa + (item >> 2), ch = item & 3;
             float2 cur[8];
@@ -446,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
             const int nxt = item + kWarps;
             if (nxt < n_items) load_frame(clip_audio + (long long)(nxt & 3) * a.n_samples, a.n_samples,
                                           frame_start(fa + (nxt >> 2)), lane, raw);
-            warp_fft256<T>(cur, s.win, tb, scratch, lane);
+            warp_fft256<T>(cur, s.win, w1, s.tw_r, scratch, lane);
             const int slot = (f - (s0 - kHop)) % R;
             float2* dst = ring + slot * row + ch * a.nbp;
             float p[8];
@@ -468,28 +487,11 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
         }
     };
 
-    // compacts the selected (frame, bin) items of frames [t0, t0 + nt) into `list`
-    auto compact = [&](int t0, int nt) {
-        for (int w = warp; w < nt * n_words; w += kWarps) {
-            const int tl = w / n_words, wi = w - tl * n_words;
-            uint32_t bits = a.mask ? a.mask[((long long)clip * a.n_frames + t0 + tl) * n_words + wi] : 0xffffffffu;
-            if (wi == n_words - 1) bits &= tail_bits;
-            int base = 0;
-            if (lane == 0) {
-                smask[tl * n_words + wi] = bits;
-                base = atomicAdd(n_items, __popc(bits));
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if ((bits >> lane) & 1u) list[base + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((tl << 8) | (wi * 32 + lane));
-        }
-    };
-
-    transform(s0 - kHop, s0 + kHop);
+    transform(s0 - kHop, s0 + kHop, 0, 0);
     for (int t0 = s0; t0 < s1; t0 += FT) {
         const int nt = min(FT, s1 - t0);
         // ---- phase 1
-        compact(t0, nt);
-        transform(t0 + kHop, t0 + nt + kHop);
+        transform(t0 + kHop, t0 + nt + kHop, t0, nt);
         __syncthreads();
         // ---- phase 2
         const int count = *n_items;
@@ -566,6 +568,7 @@ __global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T>
     load_fft_smem(s, tb);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Cx<T> w1 = lane_twiddle(tb, lane);
     const int clip = blockIdx.y;
     const int f0 = blockIdx.x * a.frames_per_block;
     const int f1 = min(a.n_frames, f0 + a.frames_per_block);
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T>
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
             warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win,
-                                 tb, scratch, lane);
+                                 w1, s.tw_r, scratch, lane);
             float* srow = clip_feat + ch * chan_stride + (long long)t * width;
             float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width;   // used for ch >= 1
 #pragma unroll
