@@ -1,4 +1,4 @@
-"""ctypes binding of libsalsa_b200.so (C ABI declared in include/salsa_b200.h).
+"""ctypes binding of libsalsa_b200.so (C ABI declared in include/salsa_b200.h and include/salsa_crnn.h).
 
 The library is the product; there is no Python / CPU fallback: loading fails loudly when the
 shared object has not been built (`python -c "import __graft_entry__ as g; g.build()"`).
@@ -54,6 +54,15 @@ SIGNATURES = {
     'salsa_launch_count': (_u64, [ctypes.c_int]),
     'salsa_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'salsa_profile_read': (ctypes.c_int, [_i32, _vp, _vp, _vp]),
+    # include/salsa_crnn.h
+    'crnn_conv2d': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_pack_input': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_avgpool2': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_freq_mean': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    'crnn_gru_layer': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    'crnn_head_finish': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    'crnn_gather_time': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
 
 

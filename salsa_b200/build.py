@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libsalsa_b200.so')
-SOURCES = ['salsa_abi.cu']
+SOURCES = ['salsa_abi.cu', 'crnn_abi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
 
@@ -20,7 +20,7 @@ def _newest(paths):
 def build(force=False, verbose=False):
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, 'include', 'salsa_b200.h')]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, 'include', f) for f in os.listdir(os.path.join(ROOT, 'include'))]
     if not force and os.path.isfile(OUT) and os.path.getmtime(OUT) >= _newest(deps):
         return OUT
     objs = []

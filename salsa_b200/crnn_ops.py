@@ -1,0 +1,131 @@
+"""Thin torch-tensor wrappers over the CRNN entry points of libsalsa_b200.so (include/salsa_crnn.h).
+
+Tensors are only device memory here: every function passes raw pointers and sizes through the C ABI.
+Activations are bf16 NHWC, see the header for layouts.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_act(x):
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()):
+        raise ValueError('activation must be a contiguous CUDA bf16 tensor')
+
+
+def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False):
+    """x (B,H,W,Cin) bf16 NHWC, w (k*k,Cout,Cin) bf16, bias (Cout,) fp32 -> (B,H,W,Cout) bf16 (or fp32)."""
+    _check_act(x)
+    B, H, W, Cin = x.shape
+    taps, Cout, Cin2 = w.shape
+    if Cin2 != Cin or taps not in (1, 9) or w.dtype != torch.bfloat16 or not w.is_contiguous():
+        raise ValueError('weights must be contiguous bf16 (k*k, Cout, Cin)')
+    if residual is not None:
+        _check_act(residual)
+        if tuple(residual.shape) != (B, H, W, Cout):
+            raise ValueError('residual shape mismatch')
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    o16, o32 = (None, out) if out.dtype == torch.float32 else (out, None)
+    _native.check(_native.lib().crnn_conv2d(_p(x), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), B, H, W, Cin, Cout,
+                                            3 if taps == 9 else 1, int(bool(relu)), _st()))
+    return out
+
+
+def pad_rows(n):
+    """GEMM inputs are allocated with their row count rounded up to a multiple of 8."""
+    return (n + 7) // 8 * 8
+
+
+def gemm(a, w, bias=None, relu=False, M=None, out_f32=False, out=None):
+    """a (Mpad,K) bf16 with Mpad % 8 == 0, w (N,K) bf16 -> (Mpad,N); rows >= M are left untouched."""
+    _check_act(a)
+    Mpad, K = a.shape
+    M = Mpad if M is None else M
+    if Mpad % 8 != 0 or M > Mpad:
+        raise ValueError('a must have a multiple of 8 rows (pad_rows)')
+    N, K2 = w.shape
+    if K2 != K or w.dtype != torch.bfloat16 or not w.is_contiguous():
+        raise ValueError('w must be contiguous bf16 (N, K)')
+    if out is None:
+        out = torch.zeros((Mpad, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+    o16, o32 = (None, out) if out.dtype == torch.float32 else (out, None)
+    _native.check(_native.lib().crnn_gemm(_p(a), _p(w), _p(bias), _p(o16), _p(o32), M, N, K, int(bool(relu)), _st()))
+    return out
+
+
+def pack_input(x, t_use=None, c_pad=64):
+    """(B,C,T,F) fp32 NCHW -> (B,t_use,F,c_pad) bf16 NHWC."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        raise ValueError('x must be a CUDA float32 tensor (B, C, T, F)')
+    x = x.contiguous()
+    B, C, T, F = x.shape
+    t_use = T if t_use is None else t_use
+    y = torch.empty((B, t_use, F, c_pad), dtype=torch.bfloat16, device=x.device)
+    _native.check(_native.lib().crnn_pack_input(_p(x), _p(y), B, C, T, F, t_use, c_pad, _st()))
+    return y
+
+
+def avgpool2(x):
+    _check_act(x)
+    B, H, W, C = x.shape
+    y = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
+    _native.check(_native.lib().crnn_avgpool2(_p(x), _p(y), B, H, W, C, _st()))
+    return y
+
+
+def freq_mean(x):
+    """(B,H,W,C) -> (pad_rows(B*H), C), mean over W; padding rows are zero."""
+    _check_act(x)
+    B, H, W, C = x.shape
+    y = torch.zeros((pad_rows(B * H), C), dtype=torch.bfloat16, device=x.device)
+    _native.check(_native.lib().crnn_freq_mean(_p(x), _p(y), B * H, W, C, _st()))
+    return y
+
+
+def gru_layer(xproj, w_hh, b_hh, B, T):
+    """xproj (>=B*T, 1536) fp32, w_hh (2,768,256) fp32, b_hh (2,768) fp32 -> y (pad_rows(B*T), 512) bf16."""
+    if xproj.dtype != torch.float32 or xproj.shape[1] != 1536 or not xproj.is_contiguous():
+        raise ValueError('xproj must be contiguous fp32 (rows, 1536)')
+    y = torch.zeros((pad_rows(B * T), 512), dtype=torch.bfloat16, device=xproj.device)
+    _native.check(_native.lib().crnn_gru_layer(_p(xproj), _p(w_hh), _p(b_hh), _p(y), B, T, _st()))
+    return y
+
+
+def head_finish(z, rows, n_classes):
+    logits = torch.empty((rows, n_classes), dtype=torch.float32, device=z.device)
+    doa = torch.empty((rows, 3 * n_classes), dtype=torch.float32, device=z.device)
+    _native.check(_native.lib().crnn_head_finish(_p(z), _p(logits), _p(doa), rows, n_classes, _st()))
+    return logits, doa
+
+
+def interpolate_index(n_in, ratio):
+    """Index map of interpolate_tensor (models/model_utils.py:66-70): floor(arange(n_out) / ratio) with the
+    division carried out in float32, as torch does for an int64 tensor divided by a Python float."""
+    ratio = float(ratio)
+    n_out = int(round(n_in * ratio))
+    idx = np.floor(np.arange(n_out).astype(np.float32) / np.float32(ratio)).astype(np.int64)
+    return idx
+
+
+def gather_time(x, idx):
+    """x (B,n_in,width) fp32 CUDA, idx int array -> (B,len(idx),width)."""
+    x = x.contiguous()
+    B, n_in, width = x.shape
+    if len(idx) and (idx.min() < 0 or idx.max() >= n_in):
+        raise IndexError('interpolation index out of range')
+    d_idx = torch.from_numpy(np.asarray(idx, dtype=np.int32)).to(x.device)
+    out = torch.empty((B, len(idx), width), dtype=torch.float32, device=x.device)
+    _native.check(_native.lib().crnn_gather_time(_p(x), _p(d_idx), _p(out), B, n_in, len(idx), width, _st()))
+    return out

@@ -1,0 +1,195 @@
+// C ABI of the SELD CRNN operators (see include/salsa_crnn.h).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "crnn_conv.cuh"
+#include "crnn_kernels.cuh"
+#include "salsa_crnn.h"
+
+namespace salsa {
+namespace crnn {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(SALSA_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SALSA_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return SALSA_OK;
+}
+
+template <int N_TILE>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tw, const ConvArgs& a, cudaStream_t st) {
+    const size_t smem = ConvSmem<N_TILE>::total(a.taps);
+    SALSA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = std::min(a.n_tiles, sms);
+    conv_tc_kernel<N_TILE><<<grid, kConvThreads, smem, st>>>(ta, tw, a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "conv_tc_kernel");
+}
+
+// x: NHWC bf16 [B][H][W][Cin]; for a GEMM: B = 1, W = 8, H = ceil(M / 8), pix_limit = M
+static int conv_generic(const void* x, const void* w, const float* bias, const void* residual, void* out, float* out_f32, int B,
+                        int H, int W, int Cin, int Cout, int taps, int relu, long long pix_limit, cudaStream_t st) {
+    if (!x || !w || (!out && !out_f32)) return fail(SALSA_EINVAL, "conv: null pointer");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv: bad dimensions");
+    if (Cin % kKC != 0 || Cin <= 0) return fail(SALSA_EINVAL, "conv: Cin must be a multiple of 64");
+    if (Cout % 64 != 0 || Cout <= 0) return fail(SALSA_EINVAL, "conv: Cout must be a multiple of 64");
+    if (taps != 1 && taps != 9) return fail(SALSA_EINVAL, "conv: kernel size must be 1 or 3");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return fail(SALSA_EINVAL, "conv: unaligned pointer");
+    const int n_tile = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    CUtensorMap ta, tw;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)kTileW, (cuuint32_t)(taps == 9 ? kTileH + 2 : kTileH), 1};
+        int rc = make_tmap(&ta, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)taps * Cout};
+        cuuint64_t str[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)n_tile};
+        int rc = make_tmap(&tw, w, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    ConvArgs a;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+    a.taps = taps;
+    a.tiles_w = (W + kTileW - 1) / kTileW;
+    a.tiles_h = (H + kTileH - 1) / kTileH;
+    a.n_tiles = B * a.tiles_h * a.tiles_w * (Cout / n_tile);
+    a.relu = relu;
+    a.pix_limit = pix_limit;
+    a.bias = bias;
+    a.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    a.out = reinterpret_cast<__nv_bfloat16*>(out);
+    a.out_f32 = out_f32;
+    if (n_tile == 256) return launch_conv<256>(ta, tw, a, st);
+    if (n_tile == 128) return launch_conv<128>(ta, tw, a, st);
+    return launch_conv<64>(ta, tw, a, st);
+}
+
+static int grid_for(long long total, int block) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (total + block - 1) / block;
+    return (int)std::max(1LL, std::min<long long>(want, (long long)sms * 16));
+}
+
+}  // namespace crnn
+}  // namespace salsa
+
+using namespace salsa;
+using namespace salsa::crnn;
+
+extern "C" {
+
+int crnn_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* out, float* out_f32, int32_t B,
+                int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, void* stream) {
+    if (ksize != 1 && ksize != 3) return fail(SALSA_EINVAL, "conv: kernel size must be 1 or 3");
+    return conv_generic(x, w, bias, residual, out, out_f32, B, H, W, Cin, Cout, ksize * ksize, relu, (long long)B * H * W,
+                        (cudaStream_t)stream);
+}
+
+int crnn_gemm(const void* a, const void* w, const float* bias, void* out, float* out_f32, int32_t M, int32_t N, int32_t K,
+              int32_t relu, void* stream) {
+    if (M <= 0) return fail(SALSA_EINVAL, "gemm: M must be positive");
+    return conv_generic(a, w, bias, nullptr, out, out_f32, 1, (M + 7) / 8, 8, K, N, 1, relu, M, (cudaStream_t)stream);
+}
+
+int crnn_pack_input(const float* x, void* y, int32_t B, int32_t C, int32_t T, int32_t F, int32_t T_use, int32_t Cpad,
+                    void* stream) {
+    if (!x || !y) return fail(SALSA_EINVAL, "pack_input: null pointer");
+    if (Cpad % 8 != 0 || C > Cpad || T_use > T || B <= 0) return fail(SALSA_EINVAL, "pack_input: bad dimensions");
+    const long long n = (long long)B * T_use * F;
+    pack_input_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, C, T, F, T_use, Cpad);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "pack_input_kernel");
+}
+
+int crnn_avgpool2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+    if (!x || !y) return fail(SALSA_EINVAL, "avgpool2: null pointer");
+    if (C % 8 != 0 || H < 2 || W < 2) return fail(SALSA_EINVAL, "avgpool2: bad dimensions");
+    const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+    avgpool2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                         reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "avgpool2_kernel");
+}
+
+int crnn_freq_mean(const void* x, void* y, int32_t BH, int32_t W, int32_t C, void* stream) {
+    if (!x || !y) return fail(SALSA_EINVAL, "freq_mean: null pointer");
+    if (C % 8 != 0 || W <= 0) return fail(SALSA_EINVAL, "freq_mean: bad dimensions");
+    const long long n = (long long)BH * (C / 8);
+    freq_mean_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                          reinterpret_cast<__nv_bfloat16*>(y), BH, W, C);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "freq_mean_kernel");
+}
+
+int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, void* y, int32_t B, int32_t T, void* stream) {
+    if (!xproj || !w_hh || !b_hh || !y) return fail(SALSA_EINVAL, "gru_layer: null pointer");
+    if (B <= 0 || T <= 0) return fail(SALSA_EINVAL, "gru_layer: bad dimensions");
+    SALSA_CUDA(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmemBytes));
+    GruArgs a;
+    a.xproj = xproj;
+    a.w_hh = w_hh;
+    a.b_hh = b_hh;
+    a.y = reinterpret_cast<__nv_bfloat16*>(y);
+    a.B = B;
+    a.T = T;
+    const int groups = (B + kGruClips - 1) / kGruClips;
+    gru_layer_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruSmemBytes, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gru_layer_kernel");
+}
+
+int crnn_head_finish(const float* z, float* logits, float* doa, int32_t rows, int32_t n_classes, void* stream) {
+    if (!z || !logits || !doa) return fail(SALSA_EINVAL, "head_finish: null pointer");
+    if (4 * n_classes > 64 || rows <= 0) return fail(SALSA_EINVAL, "head_finish: bad dimensions");
+    head_finish_kernel<<<grid_for((long long)rows * 4 * n_classes, 256), 256, 0, (cudaStream_t)stream>>>(z, logits, doa, rows, n_classes);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "head_finish_kernel");
+}
+
+int crnn_gather_time(const float* in, const int32_t* idx, float* out, int32_t B, int32_t n_in, int32_t n_out, int32_t width,
+                     void* stream) {
+    if (!in || !idx || !out) return fail(SALSA_EINVAL, "gather_time: null pointer");
+    if (B <= 0 || n_out <= 0) return SALSA_OK;
+    gather_time_kernel<<<grid_for((long long)B * n_out * width, 256), 256, 0, (cudaStream_t)stream>>>(in, idx, out, B, n_in, n_out, width);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gather_time_kernel");
+}
+
+}  // extern "C"

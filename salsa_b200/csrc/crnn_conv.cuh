@@ -1,0 +1,256 @@
+// Implicit-GEMM convolution (3x3 pad 1 / 1x1) and plain GEMM on the Blackwell tensor cores.
+//
+// Replaces the cuDNN / cuBLAS call sites of the reference CRNN: nn.Conv2d 3x3 of ConvBlock and
+// _ResnetBasicBlock (models/model_utils.py:192-200, :301-304), the 1x1 downsample convolutions
+// (:307-309), and the nn.Linear / GRU input projections of the decoder (models/decoders.py:44-46,
+// :75-92) -- the last two as "1x1 convolutions over an image 8 pixels wide".
+//
+// Data layout: activations NHWC bf16 with C a multiple of 64; weights [tap][Cout][Cin] bf16 with the
+// BatchNorm scale folded in; bias = folded BatchNorm shift (fp32).
+//
+// One CTA computes tiles of 16 x 8 = 128 output pixels (UMMA M) x N_TILE output channels (UMMA N),
+// fp32 accumulators in TMEM (two stages, so the epilogue of tile i overlaps the MMAs of tile i+1):
+//   warp 0     TMA producer.  Per 64-channel chunk of Cin it loads three column-shifted halo tiles
+//              (18 rows x 8 pixels x 64 ch, 128-byte swizzle; out-of-image pixels are zero-filled by
+//              TMA = the convolution's zero padding), from which all nine taps are addressed by a
+//              1024-byte-aligned row offset; per (chunk, tap) it loads the [N_TILE][64] weight tile.
+//   warp 1     MMA issuer: 4 x tcgen05.mma (K = 16) per (chunk, tap); tcgen05.commit releases the
+//              shared-memory stages and finally publishes the accumulator.
+//   warp 2     TMEM allocation.
+//   warps 4-7  epilogue: tcgen05.ld -> + bias (+ residual) -> ReLU -> bf16 / fp32 NHWC stores.
+// Persistent: grid = min(tiles, SMs), static round-robin over tiles.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "tc_ptx.cuh"
+
+namespace salsa {
+namespace crnn {
+
+constexpr int kTileH = 16, kTileW = 8;       // 128 output pixels per tile
+constexpr int kKC = 64;                       // channels per K chunk = one 128-byte swizzle row
+constexpr int kConvThreads = 256;
+constexpr int kAStages = 2;
+constexpr int kHaloBytes = (kTileH + 2) * kTileW * 128;    // one column-shifted halo tile (3x3)
+constexpr int kPlainBytes = kTileH * kTileW * 128;         // A tile of a 1x1 convolution / GEMM
+
+struct ConvArgs {
+    int B, H, W, Cin, Cout;
+    int taps;                  // 9 (3x3, pad 1) or 1
+    int tiles_w, tiles_h;      // spatial tiles per image
+    int n_tiles;               // B * tiles_h * tiles_w * (Cout / N_TILE)
+    int relu;
+    long long pix_limit;       // pixels (rows of a GEMM) beyond this index are not written
+    const float* bias;                 // [Cout] or null
+    const __nv_bfloat16* residual;     // NHWC [B][H][W][Cout] or null
+    __nv_bfloat16* out;                // NHWC bf16 (or null)
+    float* out_f32;                    // NHWC fp32 (or null)
+};
+
+template <int N_TILE>
+struct ConvSmem {
+    static constexpr int kBStages = N_TILE >= 256 ? 3 : 4;
+    static constexpr int kBBytes = N_TILE * 128;
+    static constexpr int a_bytes(int taps) { return taps == 9 ? 3 * kHaloBytes : kPlainBytes; }
+    static constexpr size_t total(int taps) {
+        return 1024 /* alignment slack */ + (size_t)kAStages * a_bytes(taps) + (size_t)kBStages * kBBytes + 256 /* barriers */;
+    }
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
+    using S = ConvSmem<N_TILE>;
+    constexpr int NB = S::kBStages;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = a.taps == 9 ? 3 * kHaloBytes : kPlainBytes;
+    unsigned char* a_smem = smem;
+    unsigned char* b_smem = smem + kAStages * a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + NB * S::kBBytes);
+    uint64_t* a_full = bars;                  // [kAStages]
+    uint64_t* a_empty = a_full + kAStages;    // [kAStages]
+    uint64_t* b_full = a_empty + kAStages;    // [NB]
+    uint64_t* b_empty = b_full + NB;          // [NB]
+    uint64_t* acc_full = b_empty + NB;        // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tm_act);
+        tc::prefetch_tmap(&tm_wgt);
+        for (int i = 0; i < kAStages; ++i) {
+            tc::mbar_init(a_full + i, 1);
+            tc::mbar_init(a_empty + i, 1);
+        }
+        for (int i = 0; i < NB; ++i) {
+            tc::mbar_init(b_full + i, 1);
+            tc::mbar_init(b_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(acc_full + i, 1);
+            tc::mbar_init(acc_empty + i, 4);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, 2 * N_TILE);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_chunks = a.Cin / kKC;
+    const int n_nt = a.Cout / N_TILE;
+    const int pad = a.taps == 9 ? 1 : 0;
+    auto decode = [&](int tile, int& n0, int& b, int& h0, int& w0) {
+        const int nt = tile % n_nt;
+        int sp = tile / n_nt;
+        const int tw = sp % a.tiles_w;
+        sp /= a.tiles_w;
+        const int th = sp % a.tiles_h;
+        b = sp / a.tiles_h;
+        n0 = nt * N_TILE;
+        h0 = th * kTileH;
+        w0 = tw * kTileW;
+    };
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (tc::elect_one()) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                int n0, b, h0, w0;
+                decode(tile, n0, b, h0, w0);
+                for (int c = 0; c < n_chunks; ++c) {
+                    tc::mbar_wait(a_empty + sa, pa ^ 1);
+                    tc::mbar_expect_tx(a_full + sa, (uint32_t)a_bytes);
+                    unsigned char* dst = a_smem + sa * a_bytes;
+                    if (a.taps == 9) {
+                        for (int kw = 0; kw < 3; ++kw)
+                            tc::tma_load_4d(dst + kw * kHaloBytes, &tm_act, a_full + sa, c * kKC, w0 - 1 + kw, h0 - 1, b);
+                    } else {
+                        tc::tma_load_4d(dst, &tm_act, a_full + sa, c * kKC, w0, h0, b);
+                    }
+                    if (++sa == kAStages) { sa = 0; pa ^= 1; }
+                    for (int t = 0; t < a.taps; ++t) {
+                        tc::mbar_wait(b_empty + sb, pb ^ 1);
+                        tc::mbar_expect_tx(b_full + sb, (uint32_t)S::kBBytes);
+                        tc::tma_load_2d(b_smem + sb * S::kBBytes, &tm_wgt, b_full + sb, c * kKC, t * a.Cout + n0);
+                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_bf16_m128(N_TILE);
+            int sa = 0, sb = 0, as = 0;
+            uint32_t pa = 0, pb = 0, pacc = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                tc::mbar_wait(acc_empty + as, pacc ^ 1);
+                tc::fence_after_sync();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * N_TILE);
+                for (int c = 0; c < n_chunks; ++c) {
+                    tc::mbar_wait(a_full + sa, pa);
+                    const uint32_t a_addr = tc::smem_u32(a_smem + sa * a_bytes);
+                    for (int t = 0; t < a.taps; ++t) {
+                        tc::mbar_wait(b_full + sb, pb);
+                        tc::fence_after_sync();
+                        const int kh = a.taps == 9 ? t / 3 : 0, kw = a.taps == 9 ? t % 3 : 0;
+                        const uint32_t a_tap = a_addr + (uint32_t)(kw * kHaloBytes + kh * kTileW * 128);
+                        const uint32_t b_addr = tc::smem_u32(b_smem + sb * S::kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kKC / 16; ++k) {
+                            const uint64_t da = tc::smem_desc_sw128(a_tap + k * 32, 1024);
+                            const uint64_t db = tc::smem_desc_sw128(b_addr + k * 32, 1024);
+                            tc::mma_bf16(tmem_d, da, db, idesc, (uint32_t)((c | t | k) != 0));
+                        }
+                        tc::mma_commit(b_empty + sb);
+                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    }
+                    tc::mma_commit(a_empty + sa);
+                    if (++sa == kAStages) { sa = 0; pa ^= 1; }
+                }
+                tc::mma_commit(acc_full + as);
+                if (++as == 2) { as = 0; pacc ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue ===========================
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;           // tile row = output pixel
+        const int hl = row / kTileW, wl = row % kTileW;
+        int as = 0;
+        uint32_t pacc = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            int n0, b, h0, w0;
+            decode(tile, n0, b, h0, w0);
+            const int h = h0 + hl, w = w0 + wl;
+            const size_t pix = ((size_t)b * a.H + h) * a.W + w;
+            const bool valid = h < a.H && w < a.W && (long long)pix < a.pix_limit;
+            tc::mbar_wait(acc_full + as, pacc);
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int j = 0; j < N_TILE / 32; ++j) {
+                uint32_t r[32];
+                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N_TILE + j * 32), r);
+                tc::tmem_ld_wait();
+                if (valid) {
+                    const int n = n0 + j * 32;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (a.bias ? __ldg(a.bias + n + i) : 0.0f);
+                    if (a.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.Cout + n);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 u = __ldg(rp + i);
+                            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                                v[i * 8 + e * 2] += __low2float(h2);
+                                v[i * 8 + e * 2 + 1] += __high2float(h2);
+                            }
+                        }
+                    }
+                    if (a.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+                    }
+                    if (a.out) {
+                        uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.Cout + n);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            op[i] = make_uint4(pack_bf16(v[i * 8], v[i * 8 + 1]), pack_bf16(v[i * 8 + 2], v[i * 8 + 3]),
+                                               pack_bf16(v[i * 8 + 4], v[i * 8 + 5]), pack_bf16(v[i * 8 + 6], v[i * 8 + 7]));
+                    }
+                    if (a.out_f32) {
+                        float4* op = reinterpret_cast<float4*>(a.out_f32 + pix * a.Cout + n);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + as);
+            if (++as == 2) { as = 0; pacc ^= 1; }
+        }
+    }
+    // teardown
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 2 * N_TILE);
+}
+
+}  // namespace crnn
+}  // namespace salsa

@@ -1,0 +1,236 @@
+// Element-wise / recurrent kernels around the tensor-core convolutions of the SELD CRNN.
+//
+//   pack_input_kernel     (B,7,T,F) fp32 NCHW -> (B,T,F,64) bf16 NHWC, zero-padded channels
+//   avgpool2_kernel       F.avg_pool2d(kernel 2x2), floor mode   (model_utils.py:220, :349, :476)
+//   freq_mean_kernel      torch.mean(x, dim=3)                   (decoders.py:111)
+//   gru_layer_kernel      one bidirectional GRU layer, recurrent part (decoders.py:44-46, :126)
+//   head_finish_kernel    split of the fused head GEMM, tanh on the DOA part (decoders.py:137-147)
+//   gather_time_kernel    interpolate_tensor's index gather      (model_utils.py:57-75)
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace salsa {
+namespace crnn {
+
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C, int T, int F,
+                                  int T_use, int Cpad) {
+    // one thread per output pixel; reads are coalesced along F, each thread writes Cpad bf16
+    const long long n_pix = (long long)B * T_use * F;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(p % F);
+        const long long bt = p / F;
+        const int t = (int)(bt % T_use), b = (int)(bt / T_use);
+        const float* src = x + ((long long)b * C * T + t) * F + f;
+        uint4* dst = reinterpret_cast<uint4*>(y + p * Cpad);
+        for (int c0 = 0; c0 < Cpad; c0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (c0 + i < C) ? __ldg(src + (long long)(c0 + i) * T * F) : 0.0f;
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            dst[c0 / 8] = *reinterpret_cast<uint4*>(h);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __low2float(h[i]);
+        f[2 * i + 1] = __high2float(h[i]);
+    }
+}
+
+__global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+    const long long total = (long long)B * Ho * Wo * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        long long p = i / C8;
+        const int wo = (int)(p % Wo);
+        p /= Wo;
+        const int ho = (int)(p % Ho), b = (int)(p / Ho);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + 2 * ho + dh) * W + 2 * wo + dw) * C) + c8);
+                float f[8];
+                bf16x8_to_float(u, f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            }
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(0.25f * acc[2 * k], 0.25f * acc[2 * k + 1]);
+        reinterpret_cast<uint4*>(y + (((long long)b * Ho + ho) * Wo + wo) * C)[c8] = *reinterpret_cast<uint4*>(h);
+    }
+}
+
+// (B,H,W,C) bf16 -> (B*H, C) bf16, mean over W
+__global__ void freq_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int BH, int W, int C) {
+    const int C8 = C / 8;
+    const long long total = (long long)BH * C8;
+    const float inv = 1.0f / (float)W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const long long r = i / C8;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int w = 0; w < W; ++w) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (r * W + w) * C) + c8);
+            float f[8];
+            bf16x8_to_float(u, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        }
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[2 * k] * inv, acc[2 * k + 1] * inv);
+        reinterpret_cast<uint4*>(y + r * C)[c8] = *reinterpret_cast<uint4*>(h);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gru_layer_kernel: recurrent part of one bidirectional GRU layer, hidden size 256 (nn.GRU gate
+// order r, z, n; n = tanh(W_in x + b_in + r * (W_hn h + b_hn))).
+//
+// A thread-block cluster of 8 CTAs owns one (direction, group of 8 clips): CTA c keeps the 96 rows of
+// W_hh that belong to hidden units 32c .. 32c+31 (fp32, 96 KB of shared memory, loaded once) and the
+// full hidden state of its 8 clips.  Per time step every CTA computes its 32 x 8 new hidden values
+// and writes them into the shared memory of all 8 CTAs (DSMEM); one cluster barrier per step.
+// The input projections W_ih x + b_ih come from the tensor-core GEMM (xproj, fp32).
+// ------------------------------------------------------------------------------------------------
+constexpr int kGruHidden = 256;
+constexpr int kGruCluster = 8;
+constexpr int kGruUnits = kGruHidden / kGruCluster;    // hidden units per CTA (32)
+constexpr int kGruClips = 8;                            // clips per cluster
+constexpr int kGruThreads = 256;
+
+struct GruArgs {
+    const float* xproj;        // [B*T][2*768]   (direction-major: fwd r,z,n | bwd r,z,n)
+    const float* w_hh;         // [2][768][256]
+    const float* b_hh;         // [2][768]
+    __nv_bfloat16* y;          // [B*T][512]  (fwd | bwd)
+    int B, T;
+};
+
+constexpr size_t kGruSmemBytes = (size_t)(3 * kGruUnits * kGruHidden + 2 * kGruHidden * kGruClips + 3 * kGruUnits * kGruClips) * sizeof(float);
+
+__global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1) gru_layer_kernel(GruArgs a) {
+    extern __shared__ __align__(16) float gsm[];
+    float* wT = gsm;                                             // [256 k][96 rows]   (k-major: conflict-free)
+    float* hbuf = wT + 3 * kGruUnits * kGruHidden;               // [2][256 k][8 clips]
+    float* gates = hbuf + 2 * kGruHidden * kGruClips;            // [96 rows][8 clips]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / kGruCluster;                    // cluster index
+    const int dir = cid & 1, grp = cid >> 1;
+    const int b0 = grp * kGruClips;
+    const int tid = threadIdx.x;
+    constexpr int R = 3 * kGruUnits;                             // 96 rows per CTA
+
+    // W_hh slice: local row lr = g*32 + jl  <-  global row g*256 + rank*32 + jl
+    const float* w = a.w_hh + (size_t)dir * 3 * kGruHidden * kGruHidden;
+    for (int i = tid; i < R * kGruHidden; i += kGruThreads) {
+        const int lr = i / kGruHidden, k = i - lr * kGruHidden;
+        const int g = lr / kGruUnits, jl = lr - g * kGruUnits;
+        wT[k * R + lr] = w[(size_t)(g * kGruHidden + rank * kGruUnits + jl) * kGruHidden + k];
+    }
+    for (int i = tid; i < 2 * kGruHidden * kGruClips; i += kGruThreads) hbuf[i] = 0.0f;
+    cluster.sync();
+
+    // matvec mapping: threads 0..191: row lr = tid % 96, clip half = tid / 96 (4 clips each)
+    const int lr = tid % R, half = tid / R;
+    // gate mapping: thread -> (unit jl = tid % 32, clip bl = tid / 32)
+    const int jl = tid & 31, bl = tid >> 5;
+    const int j = rank * kGruUnits + jl;
+    const float* bh = a.b_hh + (size_t)dir * 3 * kGruHidden;
+    const float b_hr = bh[j], b_hz = bh[kGruHidden + j], b_hn = bh[2 * kGruHidden + j];
+    const int b = b0 + bl;
+    const bool live = b < a.B;
+    float h_prev = 0.0f;
+
+    for (int s = 0; s < a.T; ++s) {
+        const int t = dir ? a.T - 1 - s : s;
+        const float* hc = hbuf + (s & 1) * kGruHidden * kGruClips;
+        float* hn = hbuf + ((s + 1) & 1) * kGruHidden * kGruClips;
+        // the three input projections of this thread's (unit, clip): issued early, used after the matvec
+        float xr = 0.0f, xz = 0.0f, xn = 0.0f;
+        if (live) {
+            const float* xp = a.xproj + ((size_t)b * a.T + t) * (2 * 3 * kGruHidden) + dir * 3 * kGruHidden + j;
+            xr = __ldg(xp);
+            xz = __ldg(xp + kGruHidden);
+            xn = __ldg(xp + 2 * kGruHidden);
+        }
+        if (tid < 2 * R) {
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const float4* h4 = reinterpret_cast<const float4*>(hc) + half;     // [k][2 halves] of float4
+#pragma unroll 8
+            for (int k = 0; k < kGruHidden; ++k) {
+                const float wv = wT[k * R + lr];
+                const float4 hv = h4[k * 2];
+                acc[0] = fmaf(wv, hv.x, acc[0]);
+                acc[1] = fmaf(wv, hv.y, acc[1]);
+                acc[2] = fmaf(wv, hv.z, acc[2]);
+                acc[3] = fmaf(wv, hv.w, acc[3]);
+            }
+            *reinterpret_cast<float4*>(gates + lr * kGruClips + half * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+        __syncthreads();
+        {
+            const float ar = gates[jl * kGruClips + bl];
+            const float az = gates[(kGruUnits + jl) * kGruClips + bl];
+            const float an = gates[(2 * kGruUnits + jl) * kGruClips + bl];
+            const float r = 1.0f / (1.0f + __expf(-(xr + ar + b_hr)));
+            const float z = 1.0f / (1.0f + __expf(-(xz + az + b_hz)));
+            const float n = tanhf(xn + r * (an + b_hn));
+            const float h_new = (1.0f - z) * n + z * h_prev;
+            h_prev = h_new;
+            // publish to every CTA of the cluster (including this one)
+#pragma unroll
+            for (int c = 0; c < kGruCluster; ++c) {
+                float* remote = cluster.map_shared_rank(hn, c);
+                remote[j * kGruClips + bl] = h_new;
+            }
+            if (live) a.y[((size_t)b * a.T + t) * (2 * kGruHidden) + dir * kGruHidden + j] = __float2bfloat16(h_new);
+        }
+        cluster.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head GEMM output (rows, 64) fp32: cols 0..11 SED logits, 12..47 x|y|z before tanh
+__global__ void head_finish_kernel(const float* __restrict__ z, float* __restrict__ logits, float* __restrict__ doa, int rows,
+                                   int n_classes) {
+    const int total = rows * 4 * n_classes;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / (4 * n_classes), c = i - r * 4 * n_classes;
+        const float v = z[(size_t)r * 64 + c];
+        if (c < n_classes) logits[(size_t)r * n_classes + c] = v;
+        else doa[(size_t)r * 3 * n_classes + (c - n_classes)] = tanhf(v);
+    }
+}
+
+// out[b][i][:] = in[b][idx[i]][:]
+__global__ void gather_time_kernel(const float* __restrict__ in, const int* __restrict__ idx, float* __restrict__ out, int B,
+                                   int n_in, int n_out, int width) {
+    const long long total = (long long)B * n_out * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % width);
+        const long long r = i / width;
+        const int o = (int)(r % n_out), b = (int)(r / n_out);
+        out[i] = in[((long long)b * n_in + idx[o]) * width + c];
+    }
+}
+
+}  // namespace crnn
+}  // namespace salsa

@@ -1,0 +1,108 @@
+"""CRNN operators (C ABI of include/salsa_crnn.h) against plain PyTorch fp32 references of the same op.
+
+Inputs and weights are rounded to bf16 first, so the only differences are the accumulation order
+(fp32 in both) and the bf16 rounding of the output: tolerance 1e-2 relative to the output scale for
+bf16 outputs, 2e-3 for fp32 outputs.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from salsa_b200 import crnn_ops
+    assert torch.cuda.is_available()
+    return crnn_ops
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-6))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 64, 64), (300, 1536, 512), (1000, 256, 1024), (8, 64, 128), (2400, 128, 64)])
+def test_gemm(ops, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, generator=g)
+    ref = a.float() @ w.float().T + bias
+    a_pad = torch.zeros(ops.pad_rows(M), K, dtype=torch.bfloat16)
+    a_pad[:M] = a
+    out = ops.gemm(a_pad.cuda(), w.cuda(), bias.cuda(), M=M, out_f32=True)[:M].cpu()
+    assert rel_err(out, ref) < 2e-3
+    out16 = ops.gemm(a_pad.cuda(), w.cuda(), bias.cuda(), relu=True, M=M)[:M].cpu().float()
+    assert rel_err(out16, ref.clamp(min=0)) < 1e-2
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k', [
+    (1, 16, 8, 64, 64, 3), (2, 40, 25, 64, 64, 3), (1, 33, 12, 128, 256, 3), (1, 20, 11, 256, 512, 3),
+    (2, 37, 50, 64, 128, 1), (1, 16, 200, 64, 64, 3), (1, 18, 6, 512, 512, 3)])
+def test_conv2d(ops, B, H, W, Cin, Cout, k):
+    g = torch.Generator().manual_seed(H * W + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, generator=g)
+    res = torch.randn(B, H, W, Cout, generator=g).bfloat16()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=k // 2) + bias[None, :, None, None]
+    ref = ref.permute(0, 2, 3, 1)
+    wp = w.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin).contiguous()
+    out = ops.conv2d(x.cuda(), wp.cuda(), bias.cuda(), out_f32=True).cpu()
+    assert rel_err(out, ref) < 2e-3
+    out2 = ops.conv2d(x.cuda(), wp.cuda(), bias.cuda(), residual=res.cuda(), relu=True).cpu().float()
+    assert rel_err(out2, (ref + res.float()).clamp(min=0)) < 1e-2
+
+
+def test_pack_pool_mean(ops):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 7, 33, 21, generator=g)
+    y = ops.pack_input(x.cuda(), t_use=32).cpu().float()
+    assert y.shape == (2, 32, 21, 64)
+    assert torch.equal(y[..., :7], x[:, :, :32].permute(0, 2, 3, 1).bfloat16().float())
+    assert torch.all(y[..., 7:] == 0)
+    a = torch.randn(2, 9, 25, 64, generator=g).bfloat16()
+    p = ops.avgpool2(a.cuda()).cpu().float()
+    ref = F.avg_pool2d(a.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert p.shape == (2, 4, 12, 64) and rel_err(p, ref) < 1e-2
+    m = ops.freq_mean(a.cuda()).cpu().float()
+    assert m.shape == (ops.pad_rows(18), 64)
+    assert rel_err(m[:18], a.float().mean(dim=2).reshape(18, 64)) < 1e-2
+    assert torch.all(m[18:] == 0)
+
+
+@pytest.mark.parametrize('B,T', [(1, 40), (3, 75), (9, 20)])
+def test_gru_layer(ops, B, T):
+    torch.manual_seed(B * 100 + T)
+    gru = torch.nn.GRU(input_size=512, hidden_size=256, num_layers=1, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, 512)
+    with torch.no_grad():
+        ref, _ = gru(x)
+        xproj = torch.cat([x @ gru.weight_ih_l0.T + gru.bias_ih_l0, x @ gru.weight_ih_l0_reverse.T + gru.bias_ih_l0_reverse], dim=-1)
+    w_hh = torch.stack([gru.weight_hh_l0, gru.weight_hh_l0_reverse]).detach().contiguous()
+    b_hh = torch.stack([gru.bias_hh_l0, gru.bias_hh_l0_reverse]).detach().contiguous()
+    y = ops.gru_layer(xproj.reshape(B * T, 1536).contiguous().cuda(), w_hh.cuda(), b_hh.cuda(), B, T)
+    y = y[:B * T].cpu().float().reshape(B, T, 512)
+    assert (y - ref).abs().max() < 1e-2           # bf16 output rounding of values in (-1, 1)
+
+
+def test_interpolate_index_and_gather(ops, golden):
+    assert np.array_equal(ops.interpolate_index(40, 2.0), np.repeat(np.arange(40), 2))
+    assert np.array_equal(ops.interpolate_index(8, 0.5), np.arange(0, 8, 2))
+    x = torch.arange(24, dtype=torch.float32).reshape(2, 4, 3)
+    for ratio in (0.5, 2.0, 1.5):
+        idx = ops.interpolate_index(4, ratio)
+        n_out = int(round(4 * ratio))
+        ref = x[:, torch.floor(torch.arange(n_out) / ratio).long()]
+        out = ops.gather_time(x.cuda(), idx).cpu()
+        assert torch.equal(out, ref)
+
+
+def test_head_finish(ops):
+    z = torch.randn(10, 64)
+    logits, doa = ops.head_finish(z.cuda(), 10, 12)
+    assert torch.equal(logits.cpu(), z[:, :12])
+    assert torch.allclose(doa.cpu(), torch.tanh(z[:, 12:48]), atol=1e-6)
