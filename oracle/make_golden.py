@@ -81,32 +81,26 @@ def model_cases():
     out['interp_double'] = interpolate_tensor(x, ratio=2.0).numpy()
     out['interp_40_to_80'] = interpolate_tensor(torch.arange(40).reshape(1, 40, 1), ratio=2.0).numpy().ravel()
 
-    torch.manual_seed(0)
+    # the reference modules, loaded with the deterministic random state dict of oracle/crnn.py (the
+    # reference's own init zeroes bn2.weight, which would switch every residual branch off)
+    from . import crnn as ocrnn
     model = ref_import.build_reference_seld_model()
-    # zero-init bn2 makes every residual branch vanish at init (model_utils.py:343): randomise the
-    # BN affine parameters and running statistics so the golden forward exercises every layer.
-    g = torch.Generator().manual_seed(1)
-    for m in model.modules():
-        if isinstance(m, torch.nn.BatchNorm2d):
-            m.weight.data = torch.empty_like(m.weight).uniform_(0.5, 1.5, generator=g)
-            m.bias.data = torch.empty_like(m.bias).uniform_(-0.2, 0.2, generator=g)
-            m.running_mean.data = torch.empty_like(m.running_mean).uniform_(-0.2, 0.2, generator=g)
-            m.running_var.data = torch.empty_like(m.running_var).uniform_(0.5, 1.5, generator=g)
-    for name, p in model.named_parameters():
-        if name.startswith('decoder.gru.bias') or (name.startswith('decoder.') and name.endswith('fc_1.bias')) \
-                or (name.startswith('decoder.') and name.endswith('fc_2.bias')):
-            p.data = torch.empty_like(p).uniform_(-0.1, 0.1, generator=g)
+    missing = model.load_state_dict(ocrnn.make_state_dict(0), strict=True)
     model.eval()
-    xin = torch.randn(2, 7, 128, 200, generator=torch.Generator().manual_seed(2))
+    xin = ocrnn.model_input(2, (2, 7, 128, 200))
     with torch.no_grad():
         y = model(xin)
         enc = model.encoder(xin)
-    out['model_in'] = xin.numpy()
-    out['model_encoder_out'] = enc.numpy()
+    out['model_encoder_out'] = enc.numpy().astype(np.float16)       # checked at 1e-3: float16 is enough
     out['model_event_frame_logit'] = y['event_frame_logit'].numpy()
     out['model_doa_frame_output'] = y['doa_frame_output'].numpy()
-    state = {k: v.numpy() for k, v in model.state_dict().items()}
-    return out, state
+    # a second, ragged case: F = 191 (SALSA-Lite), odd batch
+    xin2 = ocrnn.model_input(3, (1, 7, 96, 191))
+    with torch.no_grad():
+        y2 = model(xin2)
+    out['lite_event_frame_logit'] = y2['event_frame_logit'].numpy()
+    out['lite_doa_frame_output'] = y2['doa_frame_output'].numpy()
+    return out
 
 
 def main(argv=None):
@@ -114,14 +108,12 @@ def main(argv=None):
         print('reference checkout not found; golden vectors can only be generated in the build container')
         return 1
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    np.savez_compressed(os.path.join(GOLDEN_DIR, 'eigvec_cases.npz'), **eigvec_cases())
-    np.savez_compressed(os.path.join(GOLDEN_DIR, 'clip_cases.npz'), **clip_cases())
+    if not argv or 'features' in argv:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'eigvec_cases.npz'), **eigvec_cases())
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'clip_cases.npz'), **clip_cases())
     if argv and 'model' in argv:
-        cases, state = model_cases()
-        np.savez_compressed(os.path.join(GOLDEN_DIR, 'model_cases.npz'), **cases)
-        # weights are regenerated from the seed by tests (torch.manual_seed(0) + the BN recipe above)
-        # only when the reference is mounted; the frozen copy travels as float16-free npz
-        np.savez_compressed(os.path.join(GOLDEN_DIR, 'model_state.npz'), **state)
+        # inputs and weights are regenerated from their seeds (oracle/crnn.py); only outputs are stored
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'model_cases.npz'), **model_cases())
     for fn in sorted(os.listdir(GOLDEN_DIR)):
         print('{:32s} {:10d} B'.format(fn, os.path.getsize(os.path.join(GOLDEN_DIR, fn))))
     return 0

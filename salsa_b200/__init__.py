@@ -9,4 +9,7 @@ from . import _native  # noqa: F401
 from .features import (MagStftExtractor, SalsaExtractor, SalsaLiteExtractor, doa_bins,  # noqa: F401
                        extract_normalized_eigenvector, stft)
 
+from .crnn import PannResNet22, SeldDecoder, SeldModel  # noqa: F401
+from . import crnn_ops  # noqa: F401
+
 __version__ = '0.1.0'

@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference SELD CRNN (forward / inference path) on libsalsa_b200.so.
+
+Same class names, constructor arguments, attributes and state-dict keys as the reference:
+`models.encoders.PannResNet22` (encoders.py:26-56), `models.decoders.SeldDecoder` (decoders.py:13-154,
+`decoder_type='bigru'`, `freq_pool='avg'` -- the only combination the reference configs use,
+experiments/configs/seld.yml:30-32) and `models.seld_models.SeldModel.forward` (seld_models.py:39-49).
+`SeldModel.load_state_dict` takes a reference checkpoint's `['state_dict']` (inference.py:115-116).
+
+Eval mode only: BatchNorm uses running statistics (folded into the convolution weights when the state
+dict is loaded) and dropout is the identity.  All compute happens in the CUDA library; there is no
+PyTorch / CPU fallback.  Arithmetic: bf16 operands, fp32 accumulation (tensor cores), fp32 GRU state.
+"""
+import numpy as np
+import torch
+
+from . import crnn_ops as ops
+
+BN_EPS = 1e-5
+
+
+def _t(v):
+    return v.detach().float().cpu() if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v)).float()
+
+
+class PannResNet22:
+    """Encoder description (encoders.py:26-46).  Holds no parameters itself: `SeldModel` owns the packed weights."""
+
+    def __init__(self, n_input_channels: int = 1, p_dropout: float = 0.0, **kwargs):
+        self.n_input_channels = n_input_channels
+        self.p_dropout = p_dropout
+        self.n_output_channels = 512
+        self.time_downsample_ratio = 16
+
+
+class SeldDecoder:
+    """Decoder description (decoders.py:18-46)."""
+
+    def __init__(self, n_output_channels, n_classes: int = 12, output_format: str = 'reg_xyz', decoder_type: str = None,
+                 freq_pool: str = None, decoder_size: int = 128, **kwargs):
+        assert decoder_type in ['gru', 'bigru', 'lstm', 'bilstm', 'transformer'], 'Invalid decoder type {}'.format(decoder_type)
+        if decoder_type != 'bigru':
+            raise NotImplementedError('decoder type: {} is not implemented (salsa_b200 implements bigru)'.format(decoder_type))
+        if freq_pool != 'avg':
+            raise NotImplementedError('freq pooling {} is not implemented (salsa_b200 implements avg)'.format(freq_pool))
+        if decoder_size != 256 or n_output_channels != 512:
+            raise NotImplementedError('salsa_b200 implements decoder_size=256 on 512 encoder channels')
+        if 4 * n_classes > 64:
+            raise NotImplementedError('at most 16 classes')
+        self.n_classes = n_classes
+        self.decoder_type = decoder_type
+        self.freq_pool = freq_pool
+        self.doa_format = output_format
+        self.gru_size = decoder_size
+        self.fc_size = 2 * decoder_size
+
+
+class SeldModel:
+    """Inference counterpart of models.seld_models.SeldModel."""
+
+    def __init__(self, encoder: PannResNet22, decoder: SeldDecoder, label_rate: int = 10, feature_rate: float = None,
+                 device='cuda', **kwargs):
+        self.encoder, self.decoder = encoder, decoder
+        self.label_rate, self.feature_rate = label_rate, feature_rate
+        self.time_downsample_ratio = float(encoder.time_downsample_ratio)
+        self.n_classes = decoder.n_classes
+        self.doa_format = decoder.doa_format
+        self.device = torch.device(device)
+        self.training = False
+        self._w = None
+
+    # ---- nn.Module-like surface -----------------------------------------------------------------
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError('salsa_b200.SeldModel is the forward / inference path only')
+        return self.eval()
+
+    def __call__(self, x):
+        return self.forward(x)
+
+    # ---- weights ----------------------------------------------------------------------------------
+    def _fold(self, sd, conv_key, bn_prefix):
+        """conv weight (Cout,Cin,k,k) + eval BatchNorm -> bf16 (k*k, Cout, Cin_pad64), fp32 bias (Cout,)."""
+        w = _t(sd[conv_key])
+        scale = _t(sd[bn_prefix + '.weight']) / torch.sqrt(_t(sd[bn_prefix + '.running_var']) + BN_EPS)
+        bias = _t(sd[bn_prefix + '.bias']) - _t(sd[bn_prefix + '.running_mean']) * scale
+        w = w * scale[:, None, None, None]
+        cout, cin, k, _ = w.shape
+        cin_pad = (cin + 63) // 64 * 64
+        wp = torch.zeros((k * k, cout, cin_pad))
+        wp[:, :, :cin] = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
+        return wp.to(torch.bfloat16).contiguous().to(self.device), bias.contiguous().to(self.device)
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        sd = state_dict
+        W = {}
+        W['cb1'] = self._fold(sd, 'encoder.conv_block1.conv1.weight', 'encoder.conv_block1.bn1')
+        W['cb2'] = self._fold(sd, 'encoder.conv_block1.conv2.weight', 'encoder.conv_block1.bn2')
+        for li in range(1, 5):
+            for bi in range(2):
+                p = 'encoder.resnet.layer{}.{}'.format(li, bi)
+                W[(li, bi, 1)] = self._fold(sd, p + '.conv1.weight', p + '.bn1')
+                W[(li, bi, 2)] = self._fold(sd, p + '.conv2.weight', p + '.bn2')
+                if li > 1 and bi == 0:
+                    W[(li, bi, 'ds')] = self._fold(sd, p + '.downsample.1.weight', p + '.downsample.2')
+        dev = self.device
+        for layer in range(2):
+            w_ih = torch.cat([_t(sd['decoder.gru.weight_ih_l{}'.format(layer)]), _t(sd['decoder.gru.weight_ih_l{}_reverse'.format(layer)])])
+            b_ih = torch.cat([_t(sd['decoder.gru.bias_ih_l{}'.format(layer)]), _t(sd['decoder.gru.bias_ih_l{}_reverse'.format(layer)])])
+            w_hh = torch.stack([_t(sd['decoder.gru.weight_hh_l{}'.format(layer)]), _t(sd['decoder.gru.weight_hh_l{}_reverse'.format(layer)])])
+            b_hh = torch.stack([_t(sd['decoder.gru.bias_hh_l{}'.format(layer)]), _t(sd['decoder.gru.bias_hh_l{}_reverse'.format(layer)])])
+            W[('gru', layer)] = (w_ih.to(torch.bfloat16).contiguous().to(dev), b_ih.contiguous().to(dev),
+                                 w_hh.contiguous().to(dev), b_hh.contiguous().to(dev))
+        heads = ('event', 'x', 'y', 'z')
+        n = self.n_classes
+        w1 = torch.cat([_t(sd['decoder.{}_fc_1.weight'.format(h)]) for h in heads])            # (1024, 512)
+        b1 = torch.cat([_t(sd['decoder.{}_fc_1.bias'.format(h)]) for h in heads])
+        w2 = torch.zeros((64, 1024))                                                             # block diagonal
+        b2 = torch.zeros((64,))
+        for i, h in enumerate(heads):
+            w2[i * n:(i + 1) * n, i * 256:(i + 1) * 256] = _t(sd['decoder.{}_fc_2.weight'.format(h)])
+            b2[i * n:(i + 1) * n] = _t(sd['decoder.{}_fc_2.bias'.format(h)])
+        W['fc1'] = (w1.to(torch.bfloat16).contiguous().to(dev), b1.contiguous().to(dev))
+        W['fc2'] = (w2.to(torch.bfloat16).contiguous().to(dev), b2.contiguous().to(dev))
+        self._w = W
+        return self
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def encode(self, x):
+        """PannResNet22.forward: (B,7,T,F) fp32 CUDA -> (B, T/16, F/16, 512) bf16 NHWC."""
+        if self._w is None:
+            raise RuntimeError('load_state_dict() first')
+        if x.dim() != 4 or x.shape[1] != self.encoder.n_input_channels:
+            raise ValueError('x must be (batch_size, {}, n_timesteps, n_features)'.format(self.encoder.n_input_channels))
+        W = self._w
+        h = ops.pack_input(x.to(self.device, torch.float32))
+        h = ops.conv2d(h, *W['cb1'], relu=True)
+        h = ops.conv2d(h, *W['cb2'], relu=True)
+        h = ops.avgpool2(h)
+        for li in range(1, 5):
+            for bi in range(2):
+                if li > 1 and bi == 0:
+                    pooled = ops.avgpool2(h)
+                    identity = ops.conv2d(pooled, *W[(li, bi, 'ds')])
+                    out = ops.conv2d(pooled, *W[(li, bi, 1)], relu=True)
+                else:
+                    identity = h
+                    out = ops.conv2d(h, *W[(li, bi, 1)], relu=True)
+                h = ops.conv2d(out, *W[(li, bi, 2)], residual=identity, relu=True)
+        return h
+
+    def decode(self, enc):
+        """SeldDecoder.forward on the NHWC encoder output."""
+        W = self._w
+        B, T, _, _ = enc.shape
+        rows = B * T
+        h = ops.freq_mean(enc)                                              # (rows_pad, 512)
+        for layer in range(2):
+            w_ih, b_ih, w_hh, b_hh = W[('gru', layer)]
+            xproj = ops.gemm(h, w_ih, b_ih, M=rows, out_f32=True)
+            h = ops.gru_layer(xproj, w_hh, b_hh, B, T)
+        f1 = ops.gemm(h, *W['fc1'], relu=True, M=rows)
+        z = ops.gemm(f1, *W['fc2'], M=rows, out_f32=True)
+        logits, doa = ops.head_finish(z, rows, self.n_classes)
+        return {'event_frame_logit': logits.reshape(B, T, self.n_classes),
+                'doa_frame_output': doa.reshape(B, T, 3 * self.n_classes)}
+
+    def forward(self, x):
+        """x: (batch_size, n_channels, n_timesteps, n_features) -> the reference's output dict (seld_models.py:39-49)."""
+        return self.decode(self.encode(x))
+
+    def predict(self, x):
+        """forward + interpolate_tensor to the label rate, as `common_step` does (seld_models.py:58-64)."""
+        out = self.forward(x)
+        ratio = self.time_downsample_ratio * self.label_rate / self.feature_rate
+        idx = ops.interpolate_index(out['event_frame_logit'].shape[1], ratio)
+        return {k: ops.gather_time(v, idx) for k, v in out.items()}

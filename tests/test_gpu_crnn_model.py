@@ -1,0 +1,95 @@
+"""SELD CRNN forward through the C ABI against the oracle (plain PyTorch fp32 restatement pinned to the
+reference modules) and the golden outputs of the reference itself.
+
+Arithmetic is bf16 operands with fp32 accumulation, so the 1e-4 target of the float32 reference cannot
+hold for the logits; the tolerances below are the measured bf16 envelope (relative to the output
+scale): encoder activations 3e-2, logits / DOA 3e-2.  The index map of interpolate_tensor is exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def scale_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-6)
+
+
+@pytest.fixture(scope='module')
+def model():
+    import salsa_b200
+    from oracle import crnn as ocrnn
+    m = salsa_b200.SeldModel(salsa_b200.PannResNet22(n_input_channels=7),
+                             salsa_b200.SeldDecoder(512, n_classes=12, output_format='reg_xyz', decoder_type='bigru',
+                                                    freq_pool='avg', decoder_size=256),
+                             label_rate=10, feature_rate=80.0)
+    m.load_state_dict(ocrnn.make_state_dict(0))
+    return m.eval()
+
+
+def test_forward_matches_golden(model, golden):
+    from oracle import crnn as ocrnn
+    g = golden('model_cases')
+    x = ocrnn.model_input(2, (2, 7, 128, 200))
+    enc = model.encode(x.cuda()).float().cpu().permute(0, 3, 1, 2).numpy()
+    assert enc.shape == (2, 512, 8, 12)
+    assert scale_err(enc, g['model_encoder_out'].astype(np.float32)) < 3e-2
+    y = model(x.cuda())
+    assert tuple(y['event_frame_logit'].shape) == (2, 8, 12) and tuple(y['doa_frame_output'].shape) == (2, 8, 36)
+    assert y['event_frame_logit'].dtype == torch.float32
+    e1 = scale_err(y['event_frame_logit'].cpu().numpy(), g['model_event_frame_logit'])
+    e2 = scale_err(y['doa_frame_output'].cpu().numpy(), g['model_doa_frame_output'])
+    print('bf16 CRNN vs reference: logits {:.3e}, doa {:.3e} (relative to output scale)'.format(e1, e2))
+    assert e1 < 3e-2 and e2 < 3e-2
+
+
+def test_forward_lite_shape_matches_golden(model, golden):
+    from oracle import crnn as ocrnn
+    g = golden('model_cases')
+    y = model(ocrnn.model_input(3, (1, 7, 96, 191)).cuda())
+    assert tuple(y['event_frame_logit'].shape) == (1, 6, 12)
+    assert scale_err(y['event_frame_logit'].cpu().numpy(), g['lite_event_frame_logit']) < 3e-2
+    assert scale_err(y['doa_frame_output'].cpu().numpy(), g['lite_doa_frame_output']) < 3e-2
+
+
+def test_forward_matches_oracle_other_weights_and_batch_invariance():
+    import salsa_b200
+    from oracle import crnn as ocrnn
+    sd = ocrnn.make_state_dict(3)
+    m = salsa_b200.SeldModel(salsa_b200.PannResNet22(7), salsa_b200.SeldDecoder(512, decoder_type='bigru', freq_pool='avg', decoder_size=256))
+    m.load_state_dict(sd)
+    x = ocrnn.model_input(11, (3, 7, 80, 200))
+    ref = ocrnn.forward(sd, x)
+    y = m(x.cuda())
+    for k in ref:
+        assert scale_err(y[k].cpu().numpy(), ref[k].numpy()) < 3e-2
+    # clips are independent: one-by-one gives the same rows (bit-identical)
+    for i in range(3):
+        yi = m(x[i:i + 1].cuda())
+        for k in ref:
+            assert torch.equal(yi[k][0], y[k][i])
+
+
+def test_predict_interpolates_like_reference(model):
+    from oracle import crnn as ocrnn
+    x = ocrnn.model_input(5, (1, 7, 64, 200))
+    y = model(x.cuda())
+    p = model.predict(x.cuda())
+    for k in y:
+        ref = ocrnn.interpolate_tensor(y[k].cpu(), 16 * 10 / 80.0)
+        assert torch.equal(p[k].cpu(), ref)
+
+
+def test_interface_errors():
+    import salsa_b200
+    with pytest.raises(AssertionError):
+        salsa_b200.SeldDecoder(512, decoder_type='foo', freq_pool='avg', decoder_size=256)
+    with pytest.raises(NotImplementedError):
+        salsa_b200.SeldDecoder(512, decoder_type='transformer', freq_pool='avg', decoder_size=256)
+    m = salsa_b200.SeldModel(salsa_b200.PannResNet22(7), salsa_b200.SeldDecoder(512, decoder_type='bigru', freq_pool='avg', decoder_size=256))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 7, 32, 200).cuda())
+    with pytest.raises(NotImplementedError):
+        m.train()

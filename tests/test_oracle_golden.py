@@ -145,3 +145,50 @@ def test_live_reference_driver_bodies():
     for ft in ('salsa_lite', 'salsa_ipd'):
         a = ref_import.run_driver_body('salsa_lite', clip, DATA_CFG['lite'], feature_type=ft)
         np.testing.assert_array_equal(a, salsa.salsa_lite_clip(clip, ft))
+
+
+# --------------------------------------------------------------------------------------------------
+# CRNN oracle (oracle/crnn.py) against outputs of the unmodified reference modules
+# --------------------------------------------------------------------------------------------------
+def test_crnn_oracle_matches_golden(golden):
+    import torch
+    from oracle import crnn as ocrnn
+    g = golden('model_cases')
+    sd = ocrnn.make_state_dict(0)
+    x = ocrnn.model_input(2, (2, 7, 128, 200))
+    with torch.no_grad():
+        enc = ocrnn.encoder_forward(sd, x)
+    y = ocrnn.forward(sd, x)
+    assert tuple(enc.shape) == (2, 512, 8, 12)
+    np.testing.assert_allclose(enc.numpy(), g['model_encoder_out'].astype(np.float32), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(y['event_frame_logit'].numpy(), g['model_event_frame_logit'], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(y['doa_frame_output'].numpy(), g['model_doa_frame_output'], rtol=0, atol=2e-5)
+    y2 = ocrnn.forward(sd, ocrnn.model_input(3, (1, 7, 96, 191)))
+    assert tuple(y2['event_frame_logit'].shape) == (1, 6, 12)
+    np.testing.assert_allclose(y2['event_frame_logit'].numpy(), g['lite_event_frame_logit'], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(y2['doa_frame_output'].numpy(), g['lite_doa_frame_output'], rtol=0, atol=2e-5)
+
+
+def test_interpolate_matches_golden(golden):
+    import torch
+    from oracle import crnn as ocrnn
+    g = golden('model_cases')
+    x = torch.from_numpy(g['interp_in'])
+    assert np.array_equal(ocrnn.interpolate_tensor(x, 0.5).numpy(), g['interp_half'])
+    assert np.array_equal(ocrnn.interpolate_tensor(x, 2.0).numpy(), g['interp_double'])
+    assert np.array_equal(ocrnn.interpolate_tensor(torch.arange(40).reshape(1, 40, 1), 2.0).numpy().ravel(), g['interp_40_to_80'])
+
+
+@pytest.mark.reference
+def test_crnn_oracle_matches_live_reference():
+    import torch
+    from oracle import crnn as ocrnn, ref_import
+    model = ref_import.build_reference_seld_model()
+    model.load_state_dict(ocrnn.make_state_dict(1), strict=True)
+    model.eval()
+    x = ocrnn.model_input(7, (1, 7, 64, 200))
+    with torch.no_grad():
+        ref = model(x)
+    out = ocrnn.forward(ocrnn.make_state_dict(1), x)
+    for k in ref:
+        np.testing.assert_allclose(out[k].numpy(), ref[k].numpy(), rtol=0, atol=2e-5)
