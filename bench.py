@@ -245,6 +245,97 @@ def workload_config(args, world, valid_frac):
     return cfg
 
 
+# ------------------------------------------------------------------------------------------------
+# second metric of BASELINE.json: CRNN clips/sec (full-clip inference on the extracted features)
+# ------------------------------------------------------------------------------------------------
+CRNN_CONV_FLOP_PER_CLIP = 2 * 22.368e9 * 7.5            # SURVEY.md appendix A x (4800 / 640)
+
+
+def _crnn_cpu_chunk(_):
+    import torch
+    from oracle import crnn as ocrnn
+    sd = ocrnn.make_state_dict(0)
+    x = ocrnn.model_input(1, (1, 7, 640, 200))
+    t0 = time.perf_counter()
+    ocrnn.forward(sd, x)
+    return time.perf_counter() - t0
+
+
+def bench_crnn(args, torch, dist, feat, rank, world, dev, peaks):
+    import salsa_b200
+    from salsa_b200 import _native
+    B = min(args.crnn_batch, feat.shape[0])
+    model = salsa_b200.SeldModel(salsa_b200.PannResNet22(n_input_channels=7),
+                                 salsa_b200.SeldDecoder(512, n_classes=12, output_format='reg_xyz', decoder_type='bigru',
+                                                        freq_pool='avg', decoder_size=256), label_rate=10, feature_rate=80.0)
+    model.load_state_dict(salsa_b200.crnn.random_state_dict(0))
+    x = feat[:B]
+    T = (x.shape[2] // 16) * 16                           # 4801 -> 4800 (database.py:205-207)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = model.forward(x, n_frames=T)
+    barrier()
+    _native.lib().salsa_launch_count(1)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        out = model.forward(x, n_frames=T)
+    stop.record()
+    barrier()
+    launches = int(_native.lib().salsa_launch_count(0))
+    t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    value = B * world / (ms / 1e3)
+    # end to end: pinned host features in, host logits out
+    nb = min(B, 8)
+    h_x = torch.empty((nb,) + tuple(x.shape[1:]), dtype=torch.float32, pin_memory=True)
+    h_x.copy_(x[:nb])
+    d_x = torch.empty_like(x[:nb])
+    h_out = {k: torch.empty(v[:nb].shape, dtype=torch.float32, pin_memory=True) for k, v in out.items()}
+    d_x.copy_(h_x, non_blocking=True)
+    model.forward(d_x, n_frames=T)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        d_x.copy_(h_x, non_blocking=True)
+        o = model.forward(d_x, n_frames=T)
+        for k in o:
+            h_out[k].copy_(o[k], non_blocking=True)
+        torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = nb * world * args.e2e_steps / float(te.item())
+    achieved = value / world * CRNN_CONV_FLOP_PER_CLIP / 1e12
+    res = {
+        'metric': 'CRNN clips/sec (ResNet22 + BiGRU forward, full 60 s clips)', 'value': value, 'unit': 'clips/s',
+        'ms_per_step': ms, 'dtype': 'bf16', 'config': {'batch_per_gpu': B, 'input': [B, 7, T, int(x.shape[3])],
+                                                        'weights': 'random init (reference state-dict keys)'},
+        'gpu_launches': launches,
+        'e2e': {'value': e2e, 'unit': 'clips/s', 'h2d_bytes_per_step': int(h_x.numel() * 4),
+                'd2h_bytes_per_step': int(sum(v.numel() for v in h_out.values()) * 4), 'clips_per_step_per_gpu': nb},
+        'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (all 22 convolutions)', 'achieved': achieved,
+                     'peak': peaks.get('bf16_tflops_sustained', 1400.0), 'unit': 'TFLOP/s',
+                     'frac': achieved / peaks.get('bf16_tflops_sustained', 1400.0), 'traffic': None,
+                     'note': 'algorithmic conv FLOPs (335.5 GFLOP per clip) over the whole forward time, GRU and heads included in the time'},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        import torch as _t
+        tc = _crnn_cpu_chunk(None)
+        tc = min(tc, _crnn_cpu_chunk(None))
+        res['cpu_baseline'] = {'value': 1.0 / (7.5 * tc), 'unit': 'clips/s', 'cores': _t.get_num_threads(), 'kind': 'port',
+                               'sample': 'oracle fp32 forward (stock PyTorch CPU ops) of one (1,7,640,200) chunk, {:.2f} s; '
+                                         'a clip is 7.5 chunks'.format(tc)}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -259,6 +350,8 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=5.0, help='clip length of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-crnn', action='store_true')
+    ap.add_argument('--crnn-batch', type=int, default=32, help='clips per CRNN forward per GPU')
     args = ap.parse_args()
 
     rank, world, local_rank = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
@@ -343,6 +436,24 @@ def main():
                'api': 'SalsaExtractor.extract_host -> salsa_extract_host (pinned host buffers, 3-stream pipeline)'}
         del h_audio, h_feat
 
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    peaks = json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {}
+    cpu_clips = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # bounded CPU sample: one window of cpu_seconds per host core, taken at offsets spread over the
+        # clip length (clip starts are often silent, which would flatter the CPU's masked-bin loop)
+        cores = os.cpu_count() or 1
+        n_win = int(args.cpu_seconds * FS)
+        cpu_clips = []
+        for i in range(min(cores, n_clips)):
+            off = int((i + 0.5) / cores * max(1, N_SAMPLES - n_win))
+            cpu_clips.append(np.ascontiguousarray(audio[i, :, off:off + n_win].cpu().numpy()))
+    crnn = None
+    if not args.no_crnn:
+        del audio
+        torch.cuda.empty_cache()
+        crnn = bench_crnn(args, torch, dist, feat, rank, world, dev, peaks)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -350,9 +461,8 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.isfile(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy)'
+    if 'hbm_gbs' in peaks:
+        peak, peak_src = float(peaks['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     dom = max(kernels.items(), key=lambda kv: kv[1][0]) if kernels else (None, (0.0, 0))
@@ -381,13 +491,13 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample_audio = audio[:cores, :, :int(args.cpu_seconds * FS)].cpu().numpy()
-        clips = [np.ascontiguousarray(sample_audio[i]) for i in range(sample_audio.shape[0])]
-        v, wall, used, _ = cpu_baseline(clips, args.format, fmax, batched=False, cores=cores)
+        clips = cpu_clips
+        v, wall, used, vfrac = cpu_baseline(clips, args.format, fmax, batched=False, cores=cores)
         vb, wallb, _, _ = cpu_baseline(clips, args.format, fmax, batched=True, cores=cores)
         cpu = {'value': v, 'unit': UNIT, 'cores': used, 'kind': 'port',
-               'sample': 'first {:.0f} s of {} of the benchmark clips, one per core, {:.1f} s wall; oracle loop form '
-                         '(1 LAPACK SVD per selected bin, as the reference)'.format(args.cpu_seconds, len(clips), wall),
+               'sample': '{:.0f} s windows of {} of the benchmark clips (offsets spread over the clip), one per core, '
+                         '{:.1f} s wall, valid-bin fraction {:.2f}; oracle loop form (1 LAPACK SVD per selected bin, as the '
+                         'reference)'.format(args.cpu_seconds, len(clips), wall, vfrac),
                'value_stacked_lapack': vb}
 
     line = {
@@ -396,6 +506,7 @@ def main():
         'dtype': 'f32 (covariance/eigenvector) + f64 (STFT, tracker)' if args.stft_precision == 64 else 'f32 (+ f64 tracker)',
         'data': 'synthetic', 'config': workload_config(args, world, valid_frac),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+        'crnn': crnn,
     }
     print(json.dumps(line))
     if world > 1:

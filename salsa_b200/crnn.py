@@ -22,6 +22,44 @@ def _t(v):
     return v.detach().float().cpu() if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v)).float()
 
 
+def random_state_dict(seed: int = 0) -> dict:
+    """Random-init weights with the reference's state-dict keys and shapes (for benchmarks and smoke runs:
+    there are no checkpoints to download).  He-normal convolutions / linears, non-trivial BatchNorm
+    statistics, uniform(-1/16, 1/16) GRU weights (PyTorch's default for hidden size 256)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv_bn(wkey, bn, cout, cin, k):
+        sd[wkey] = torch.randn((cout, cin, k, k), generator=g) * (2.0 / (cin * k * k)) ** 0.5
+        sd[bn + '.weight'] = torch.empty(cout).uniform_(0.5, 1.5, generator=g)
+        sd[bn + '.bias'] = torch.empty(cout).uniform_(-0.2, 0.2, generator=g)
+        sd[bn + '.running_mean'] = torch.empty(cout).uniform_(-0.2, 0.2, generator=g)
+        sd[bn + '.running_var'] = torch.empty(cout).uniform_(0.5, 1.5, generator=g)
+        sd[bn + '.num_batches_tracked'] = torch.zeros((), dtype=torch.int64)
+
+    conv_bn('encoder.conv_block1.conv1.weight', 'encoder.conv_block1.bn1', 64, 7, 3)
+    conv_bn('encoder.conv_block1.conv2.weight', 'encoder.conv_block1.bn2', 64, 64, 3)
+    inpl = 64
+    for li, planes in zip(range(1, 5), (64, 128, 256, 512)):
+        for bi in range(2):
+            p = 'encoder.resnet.layer{}.{}'.format(li, bi)
+            conv_bn(p + '.conv1.weight', p + '.bn1', planes, inpl if bi == 0 else planes, 3)
+            conv_bn(p + '.conv2.weight', p + '.bn2', planes, planes, 3)
+            if li > 1 and bi == 0:
+                conv_bn(p + '.downsample.1.weight', p + '.downsample.2', planes, inpl, 1)
+        inpl = planes
+    for layer in range(2):
+        for suffix in ('', '_reverse'):
+            for name, shape in (('weight_ih', (768, 512)), ('weight_hh', (768, 256)), ('bias_ih', (768,)), ('bias_hh', (768,))):
+                sd['decoder.gru.{}_l{}{}'.format(name, layer, suffix)] = torch.empty(shape).uniform_(-1 / 16, 1 / 16, generator=g)
+    for head in ('event', 'x', 'y', 'z'):
+        sd['decoder.{}_fc_1.weight'.format(head)] = torch.randn((256, 512), generator=g) * (2.0 / 512) ** 0.5
+        sd['decoder.{}_fc_1.bias'.format(head)] = torch.zeros(256)
+        sd['decoder.{}_fc_2.weight'.format(head)] = torch.randn((12, 256), generator=g) * (2.0 / 256) ** 0.5
+        sd['decoder.{}_fc_2.bias'.format(head)] = torch.zeros(12)
+    return sd
+
+
 class PannResNet22:
     """Encoder description (encoders.py:26-46).  Holds no parameters itself: `SeldModel` owns the packed weights."""
 
@@ -129,14 +167,16 @@ class SeldModel:
         return self
 
     # ---- forward ----------------------------------------------------------------------------------
-    def encode(self, x):
-        """PannResNet22.forward: (B,7,T,F) fp32 CUDA -> (B, T/16, F/16, 512) bf16 NHWC."""
+    def encode(self, x, n_frames=None):
+        """PannResNet22.forward: (B,7,T,F) fp32 CUDA -> (B, T/16, F/16, 512) bf16 NHWC.
+        `n_frames` keeps only the first frames of x (the reference trims 4801 -> 4800 before the model,
+        database.py:205-207) without a copy."""
         if self._w is None:
             raise RuntimeError('load_state_dict() first')
         if x.dim() != 4 or x.shape[1] != self.encoder.n_input_channels:
             raise ValueError('x must be (batch_size, {}, n_timesteps, n_features)'.format(self.encoder.n_input_channels))
         W = self._w
-        h = ops.pack_input(x.to(self.device, torch.float32))
+        h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames)
         h = ops.conv2d(h, *W['cb1'], relu=True)
         h = ops.conv2d(h, *W['cb2'], relu=True)
         h = ops.avgpool2(h)
@@ -168,9 +208,9 @@ class SeldModel:
         return {'event_frame_logit': logits.reshape(B, T, self.n_classes),
                 'doa_frame_output': doa.reshape(B, T, 3 * self.n_classes)}
 
-    def forward(self, x):
+    def forward(self, x, n_frames=None):
         """x: (batch_size, n_channels, n_timesteps, n_features) -> the reference's output dict (seld_models.py:39-49)."""
-        return self.decode(self.encode(x))
+        return self.decode(self.encode(x, n_frames))
 
     def predict(self, x):
         """forward + interpolate_tensor to the label rate, as `common_step` does (seld_models.py:58-64)."""

@@ -1,0 +1,72 @@
+"""Multi-process sharding logic on CPU: world_size 2, gloo backend."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from salsa_b200 import sharding
+
+
+def test_clip_range_partitions():
+    for n in (0, 1, 7, 600, 4800, 4801):
+        for world in (1, 2, 3, 8):
+            ranges = [sharding.clip_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            for (a, b), (c, d) in zip(ranges, ranges[1:]):
+                assert b == c and a <= b
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.clip_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_clips, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        lo, hi = sharding.clip_range(n_clips, rank, world)
+        # per-clip "outputs": row i holds clip index i (what a rank would produce for its own clips)
+        local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None].expand(hi - lo, 3, 4).contiguous()
+        full = sharding.gather_clip_outputs(local, n_clips)
+        ok = full.shape == (n_clips, 3, 4) and torch.equal(full[:, 0, 0], torch.arange(n_clips, dtype=torch.float32))
+        # max-over-ranks timing reduction used by bench.py
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = ok and t.item() == world
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_clips', [5, 8])
+def test_gather_world_size_2(n_clips):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_clips, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == {0: True, 1: True}
+
+
+def test_gather_single_process():
+    x = torch.zeros(4, 2)
+    assert sharding.gather_clip_outputs(x, 4) is x
+    with pytest.raises(ValueError):
+        sharding.gather_clip_outputs(x, 5)
