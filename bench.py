@@ -326,6 +326,24 @@ def bench_crnn(args, torch, dist, feat, rank, world, dev, peaks):
                      'frac': achieved / peaks.get('bf16_tflops_sustained', 1400.0), 'traffic': None,
                      'note': 'algorithmic conv FLOPs (335.5 GFLOP per clip) over the whole forward time, GRU and heads included in the time'},
     }
+    # the float32-parity mode (three bf16 planes per operand, six plane products per MAC), for the record
+    del model, out
+    torch.cuda.empty_cache()
+    m3 = salsa_b200.SeldModel(salsa_b200.PannResNet22(n_input_channels=7),
+                              salsa_b200.SeldDecoder(512, n_classes=12, output_format='reg_xyz', decoder_type='bigru',
+                                                     freq_pool='avg', decoder_size=256), precision='bf16x3')
+    m3.load_state_dict(salsa_b200.crnn.random_state_dict(0))
+    b3 = min(B, 8)
+    m3.forward(x[:b3], n_frames=T)
+    barrier()
+    start.record()
+    for _ in range(2):
+        m3.forward(x[:b3], n_frames=T)
+    stop.record()
+    barrier()
+    res['bf16x3_parity_mode'] = {'value': b3 * world * 2 / (start.elapsed_time(stop) / 1e3), 'unit': 'clips/s', 'batch_per_gpu': b3,
+                                 'note': 'logits within 1e-4 of the float32 reference (tests/test_gpu_crnn_model.py), 6x the MMA work'}
+    del m3
     if rank == 0 and not args.no_cpu_baseline:
         import torch as _t
         tc = _crnn_cpu_chunk(None)

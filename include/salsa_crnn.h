@@ -11,6 +11,11 @@
  *   conv weights bf16       [kh*kw][Cout][Cin]  (BatchNorm scale already folded in)
  *   GEMM weights bf16       [N][K]              (nn.Linear.weight layout)
  *   bias         fp32       [Cout] / [N]        (folded BatchNorm shift or nn.Linear.bias)
+ *
+ * Precision: `planes` = 1 is plain bf16 operands with fp32 accumulation.  `planes` = 3 ("bf16x3") stores every
+ * activation and weight as the sum of three bf16 planes laid side by side along the channel axis
+ * ([..][3][C], hi | mid | lo) and accumulates the six plane products whose weight is above 2^-24 on the same
+ * tensor-core path: float32-grade results at six times the MMA work, used for parity with the reference.
  */
 #ifndef SALSA_CRNN_H
 #define SALSA_CRNN_H
@@ -27,30 +32,32 @@ extern "C" {
  * downsample branch (:474-481).  tcgen05 implicit GEMM, fp32 accumulation.
  * out (bf16) and/or out_f32 receive relu?(conv(x, w) + bias + residual). */
 int crnn_conv2d(const void *x, const void *w, const float *bias, const void *residual, void *out, float *out_f32,
-                int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, void *stream);
+                int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, int32_t planes,
+                void *stream);
 
 /* nn.Linear / GRU input projection (models/decoders.py:44-46, :75-92): out[M][N] = relu?(a[M][K] w[N][K]^T + bias).
  * `a` must be allocated with its row count rounded up to a multiple of 8. */
 int crnn_gemm(const void *a, const void *w, const float *bias, void *out, float *out_f32, int32_t M, int32_t N,
-              int32_t K, int32_t relu, void *stream);
+              int32_t K, int32_t relu, int32_t planes, void *stream);
 
 /* (B, C, T, F) fp32 NCHW feature batch (the tensor SeldModel.forward receives, models/seld_models.py:39-43)
  * -> bf16 NHWC [B][T_use][F][Cpad], channels C..Cpad-1 zero; frames >= T_use are dropped
  * (database.py:205-207 trims 4801 -> 4800). */
 int crnn_pack_input(const float *x, void *y, int32_t B, int32_t C, int32_t T, int32_t F, int32_t T_use, int32_t Cpad,
-                    void *stream);
+                    int32_t planes, void *stream);
 
 /* F.avg_pool2d(x, kernel_size=(2, 2)) (models/model_utils.py:220, :349; nn.AvgPool2d :476), floor mode. */
-int crnn_avgpool2(const void *x, void *y, int32_t B, int32_t H, int32_t W, int32_t C, void *stream);
+int crnn_avgpool2(const void *x, void *y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t planes, void *stream);
 
 /* torch.mean(x, dim=3) + transpose (models/decoders.py:111, :123): [B*H][W][C] -> [B*H][C]. */
-int crnn_freq_mean(const void *x, void *y, int32_t BH, int32_t W, int32_t C, void *stream);
+int crnn_freq_mean(const void *x, void *y, int32_t BH, int32_t W, int32_t C, int32_t planes, void *stream);
 
 /* Recurrent part of one bidirectional nn.GRU layer, hidden size 256 (models/decoders.py:44-46, :126).
  *   xproj fp32 [B*T][1536] = x W_ih^T + b_ih, forward direction in columns 0..767 (r|z|n), backward in 768..1535
  *   w_hh  fp32 [2][768][256], b_hh fp32 [2][768]   (weight_hh_l*, weight_hh_l*_reverse)
  *   y     bf16 [B*T][512]     forward | backward hidden states */
-int crnn_gru_layer(const float *xproj, const float *w_hh, const float *b_hh, void *y, int32_t B, int32_t T, void *stream);
+int crnn_gru_layer(const float *xproj, const float *w_hh, const float *b_hh, void *y, int32_t B, int32_t T, int32_t planes,
+                   void *stream);
 
 /* Output stage of SeldDecoder.forward (models/decoders.py:137-147): z fp32 [rows][64] holds the fused
  * event|x|y|z second-layer outputs in columns 0..4*n_classes-1; logits = z[:, :n], doa = tanh(z[:, n:4n]). */

@@ -55,12 +55,12 @@ SIGNATURES = {
     'salsa_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'salsa_profile_read': (ctypes.c_int, [_i32, _vp, _vp, _vp]),
     # include/salsa_crnn.h
-    'crnn_conv2d': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    'crnn_pack_input': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    'crnn_avgpool2': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    'crnn_freq_mean': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
-    'crnn_gru_layer': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    'crnn_conv2d': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_pack_input': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_avgpool2': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_freq_mean': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_gru_layer': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     'crnn_head_finish': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     'crnn_gather_time': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
 }

@@ -96,7 +96,14 @@ class SeldModel:
     """Inference counterpart of models.seld_models.SeldModel."""
 
     def __init__(self, encoder: PannResNet22, decoder: SeldDecoder, label_rate: int = 10, feature_rate: float = None,
-                 device='cuda', **kwargs):
+                 device='cuda', precision: str = 'bf16', **kwargs):
+        """precision: 'bf16' (bf16 operands, fp32 accumulation: the fast mode) or 'bf16x3' (every operand is the
+        sum of three bf16 planes, six plane products per MAC on the same tensor-core kernels: float32-grade
+        results, used for parity with the float32 reference)."""
+        if precision not in ('bf16', 'bf16x3'):
+            raise ValueError('precision must be bf16 or bf16x3')
+        self.precision = precision
+        self.planes = 3 if precision == 'bf16x3' else 1
         self.encoder, self.decoder = encoder, decoder
         self.label_rate, self.feature_rate = label_rate, feature_rate
         self.time_downsample_ratio = float(encoder.time_downsample_ratio)
@@ -130,7 +137,7 @@ class SeldModel:
         cin_pad = (cin + 63) // 64 * 64
         wp = torch.zeros((k * k, cout, cin_pad))
         wp[:, :, :cin] = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
-        return wp.to(torch.bfloat16).contiguous().to(self.device), bias.contiguous().to(self.device)
+        return ops.split_planes(wp, self.planes).to(self.device), bias.contiguous().to(self.device)
 
     def load_state_dict(self, state_dict, strict: bool = True):
         sd = state_dict
@@ -150,7 +157,7 @@ class SeldModel:
             b_ih = torch.cat([_t(sd['decoder.gru.bias_ih_l{}'.format(layer)]), _t(sd['decoder.gru.bias_ih_l{}_reverse'.format(layer)])])
             w_hh = torch.stack([_t(sd['decoder.gru.weight_hh_l{}'.format(layer)]), _t(sd['decoder.gru.weight_hh_l{}_reverse'.format(layer)])])
             b_hh = torch.stack([_t(sd['decoder.gru.bias_hh_l{}'.format(layer)]), _t(sd['decoder.gru.bias_hh_l{}_reverse'.format(layer)])])
-            W[('gru', layer)] = (w_ih.to(torch.bfloat16).contiguous().to(dev), b_ih.contiguous().to(dev),
+            W[('gru', layer)] = (ops.split_planes(w_ih, self.planes).to(dev), b_ih.contiguous().to(dev),
                                  w_hh.contiguous().to(dev), b_hh.contiguous().to(dev))
         heads = ('event', 'x', 'y', 'z')
         n = self.n_classes
@@ -161,49 +168,49 @@ class SeldModel:
         for i, h in enumerate(heads):
             w2[i * n:(i + 1) * n, i * 256:(i + 1) * 256] = _t(sd['decoder.{}_fc_2.weight'.format(h)])
             b2[i * n:(i + 1) * n] = _t(sd['decoder.{}_fc_2.bias'.format(h)])
-        W['fc1'] = (w1.to(torch.bfloat16).contiguous().to(dev), b1.contiguous().to(dev))
-        W['fc2'] = (w2.to(torch.bfloat16).contiguous().to(dev), b2.contiguous().to(dev))
+        W['fc1'] = (ops.split_planes(w1, self.planes).to(dev), b1.contiguous().to(dev))
+        W['fc2'] = (ops.split_planes(w2, self.planes).to(dev), b2.contiguous().to(dev))
         self._w = W
         return self
 
     # ---- forward ----------------------------------------------------------------------------------
     def encode(self, x, n_frames=None):
-        """PannResNet22.forward: (B,7,T,F) fp32 CUDA -> (B, T/16, F/16, 512) bf16 NHWC.
+        """PannResNet22.forward: (B,7,T,F) fp32 CUDA -> (B, T/16, F/16, planes*512) bf16 NHWC.
         `n_frames` keeps only the first frames of x (the reference trims 4801 -> 4800 before the model,
         database.py:205-207) without a copy."""
         if self._w is None:
             raise RuntimeError('load_state_dict() first')
         if x.dim() != 4 or x.shape[1] != self.encoder.n_input_channels:
             raise ValueError('x must be (batch_size, {}, n_timesteps, n_features)'.format(self.encoder.n_input_channels))
-        W = self._w
-        h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames)
-        h = ops.conv2d(h, *W['cb1'], relu=True)
-        h = ops.conv2d(h, *W['cb2'], relu=True)
-        h = ops.avgpool2(h)
+        W, P = self._w, self.planes
+        h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames, planes=P)
+        h = ops.conv2d(h, *W['cb1'], relu=True, planes=P)
+        h = ops.conv2d(h, *W['cb2'], relu=True, planes=P)
+        h = ops.avgpool2(h, planes=P)
         for li in range(1, 5):
             for bi in range(2):
                 if li > 1 and bi == 0:
-                    pooled = ops.avgpool2(h)
-                    identity = ops.conv2d(pooled, *W[(li, bi, 'ds')])
-                    out = ops.conv2d(pooled, *W[(li, bi, 1)], relu=True)
+                    pooled = ops.avgpool2(h, planes=P)
+                    identity = ops.conv2d(pooled, *W[(li, bi, 'ds')], planes=P)
+                    out = ops.conv2d(pooled, *W[(li, bi, 1)], relu=True, planes=P)
                 else:
                     identity = h
-                    out = ops.conv2d(h, *W[(li, bi, 1)], relu=True)
-                h = ops.conv2d(out, *W[(li, bi, 2)], residual=identity, relu=True)
+                    out = ops.conv2d(h, *W[(li, bi, 1)], relu=True, planes=P)
+                h = ops.conv2d(out, *W[(li, bi, 2)], residual=identity, relu=True, planes=P)
         return h
 
     def decode(self, enc):
         """SeldDecoder.forward on the NHWC encoder output."""
-        W = self._w
+        W, P = self._w, self.planes
         B, T, _, _ = enc.shape
         rows = B * T
-        h = ops.freq_mean(enc)                                              # (rows_pad, 512)
+        h = ops.freq_mean(enc, planes=P)                                    # (rows_pad, P*512)
         for layer in range(2):
             w_ih, b_ih, w_hh, b_hh = W[('gru', layer)]
-            xproj = ops.gemm(h, w_ih, b_ih, M=rows, out_f32=True)
-            h = ops.gru_layer(xproj, w_hh, b_hh, B, T)
-        f1 = ops.gemm(h, *W['fc1'], relu=True, M=rows)
-        z = ops.gemm(f1, *W['fc2'], M=rows, out_f32=True)
+            xproj = ops.gemm(h, w_ih, b_ih, M=rows, out_f32=True, planes=P)
+            h = ops.gru_layer(xproj, w_hh, b_hh, B, T, planes=P)
+        f1 = ops.gemm(h, *W['fc1'], relu=True, M=rows, planes=P)
+        z = ops.gemm(f1, *W['fc2'], M=rows, out_f32=True, planes=P)
         logits, doa = ops.head_finish(z, rows, self.n_classes)
         return {'event_frame_logit': logits.reshape(B, T, self.n_classes),
                 'doa_frame_output': doa.reshape(B, T, 3 * self.n_classes)}

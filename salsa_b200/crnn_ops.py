@@ -24,22 +24,43 @@ def _check_act(x):
         raise ValueError('activation must be a contiguous CUDA bf16 tensor')
 
 
-def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False):
-    """x (B,H,W,Cin) bf16 NHWC, w (k*k,Cout,Cin) bf16, bias (Cout,) fp32 -> (B,H,W,Cout) bf16 (or fp32)."""
+def split_planes(t, planes):
+    """float tensor (..., C) -> bf16 (..., planes*C): hi | mid | lo planes along the last axis (bf16x3 mode)."""
+    t = t.float()
+    parts = []
+    for _ in range(planes):
+        p = t.to(torch.bfloat16)
+        parts.append(p)
+        t = t - p.float()
+    return torch.cat(parts, dim=-1).contiguous()
+
+
+def merge_planes(t, planes):
+    """inverse of split_planes (as float32)."""
+    if planes == 1:
+        return t.float()
+    c = t.shape[-1] // planes
+    return sum(t[..., i * c:(i + 1) * c].float() for i in range(planes))
+
+
+def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, planes=1):
+    """x (B,H,W,planes*Cin) bf16 NHWC, w (k*k,Cout,planes*Cin) bf16, bias (Cout,) fp32
+    -> (B,H,W,planes*Cout) bf16, or (B,H,W,Cout) fp32 with out_f32."""
     _check_act(x)
-    B, H, W, Cin = x.shape
+    B, H, W, CinP = x.shape
     taps, Cout, Cin2 = w.shape
-    if Cin2 != Cin or taps not in (1, 9) or w.dtype != torch.bfloat16 or not w.is_contiguous():
-        raise ValueError('weights must be contiguous bf16 (k*k, Cout, Cin)')
+    if Cin2 != CinP or CinP % planes or taps not in (1, 9) or w.dtype != torch.bfloat16 or not w.is_contiguous():
+        raise ValueError('weights must be contiguous bf16 (k*k, Cout, planes*Cin)')
     if residual is not None:
         _check_act(residual)
-        if tuple(residual.shape) != (B, H, W, Cout):
+        if tuple(residual.shape) != (B, H, W, planes * Cout):
             raise ValueError('residual shape mismatch')
     if out is None:
-        out = torch.empty((B, H, W, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+        out = (torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device) if out_f32 else
+               torch.empty((B, H, W, planes * Cout), dtype=torch.bfloat16, device=x.device))
     o16, o32 = (None, out) if out.dtype == torch.float32 else (out, None)
-    _native.check(_native.lib().crnn_conv2d(_p(x), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), B, H, W, Cin, Cout,
-                                            3 if taps == 9 else 1, int(bool(relu)), _st()))
+    _native.check(_native.lib().crnn_conv2d(_p(x), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), B, H, W, CinP // planes, Cout,
+                                            3 if taps == 9 else 1, int(bool(relu)), planes, _st()))
     return out
 
 
@@ -48,8 +69,9 @@ def pad_rows(n):
     return (n + 7) // 8 * 8
 
 
-def gemm(a, w, bias=None, relu=False, M=None, out_f32=False, out=None):
-    """a (Mpad,K) bf16 with Mpad % 8 == 0, w (N,K) bf16 -> (Mpad,N); rows >= M are left untouched."""
+def gemm(a, w, bias=None, relu=False, M=None, out_f32=False, out=None, planes=1):
+    """a (Mpad,planes*K) bf16 with Mpad % 8 == 0, w (N,planes*K) bf16 -> (Mpad,planes*N) bf16 or (Mpad,N) fp32;
+    rows >= M are left untouched."""
     _check_act(a)
     Mpad, K = a.shape
     M = Mpad if M is None else M
@@ -59,47 +81,48 @@ def gemm(a, w, bias=None, relu=False, M=None, out_f32=False, out=None):
     if K2 != K or w.dtype != torch.bfloat16 or not w.is_contiguous():
         raise ValueError('w must be contiguous bf16 (N, K)')
     if out is None:
-        out = torch.zeros((Mpad, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+        out = (torch.zeros((Mpad, N), dtype=torch.float32, device=a.device) if out_f32 else
+               torch.zeros((Mpad, planes * N), dtype=torch.bfloat16, device=a.device))
     o16, o32 = (None, out) if out.dtype == torch.float32 else (out, None)
-    _native.check(_native.lib().crnn_gemm(_p(a), _p(w), _p(bias), _p(o16), _p(o32), M, N, K, int(bool(relu)), _st()))
+    _native.check(_native.lib().crnn_gemm(_p(a), _p(w), _p(bias), _p(o16), _p(o32), M, N, K // planes, int(bool(relu)), planes, _st()))
     return out
 
 
-def pack_input(x, t_use=None, c_pad=64):
-    """(B,C,T,F) fp32 NCHW -> (B,t_use,F,c_pad) bf16 NHWC."""
+def pack_input(x, t_use=None, c_pad=64, planes=1):
+    """(B,C,T,F) fp32 NCHW -> (B,t_use,F,planes*c_pad) bf16 NHWC."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
         raise ValueError('x must be a CUDA float32 tensor (B, C, T, F)')
     x = x.contiguous()
     B, C, T, F = x.shape
     t_use = T if t_use is None else t_use
-    y = torch.empty((B, t_use, F, c_pad), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().crnn_pack_input(_p(x), _p(y), B, C, T, F, t_use, c_pad, _st()))
+    y = torch.empty((B, t_use, F, planes * c_pad), dtype=torch.bfloat16, device=x.device)
+    _native.check(_native.lib().crnn_pack_input(_p(x), _p(y), B, C, T, F, t_use, c_pad, planes, _st()))
     return y
 
 
-def avgpool2(x):
+def avgpool2(x, planes=1):
     _check_act(x)
     B, H, W, C = x.shape
     y = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().crnn_avgpool2(_p(x), _p(y), B, H, W, C, _st()))
+    _native.check(_native.lib().crnn_avgpool2(_p(x), _p(y), B, H, W, C // planes, planes, _st()))
     return y
 
 
-def freq_mean(x):
+def freq_mean(x, planes=1):
     """(B,H,W,C) -> (pad_rows(B*H), C), mean over W; padding rows are zero."""
     _check_act(x)
     B, H, W, C = x.shape
     y = torch.zeros((pad_rows(B * H), C), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().crnn_freq_mean(_p(x), _p(y), B * H, W, C, _st()))
+    _native.check(_native.lib().crnn_freq_mean(_p(x), _p(y), B * H, W, C // planes, planes, _st()))
     return y
 
 
-def gru_layer(xproj, w_hh, b_hh, B, T):
-    """xproj (>=B*T, 1536) fp32, w_hh (2,768,256) fp32, b_hh (2,768) fp32 -> y (pad_rows(B*T), 512) bf16."""
+def gru_layer(xproj, w_hh, b_hh, B, T, planes=1):
+    """xproj (>=B*T, 1536) fp32, w_hh (2,768,256) fp32, b_hh (2,768) fp32 -> y (pad_rows(B*T), planes*512) bf16."""
     if xproj.dtype != torch.float32 or xproj.shape[1] != 1536 or not xproj.is_contiguous():
         raise ValueError('xproj must be contiguous fp32 (rows, 1536)')
-    y = torch.zeros((pad_rows(B * T), 512), dtype=torch.bfloat16, device=xproj.device)
-    _native.check(_native.lib().crnn_gru_layer(_p(xproj), _p(w_hh), _p(b_hh), _p(y), B, T, _st()))
+    y = torch.zeros((pad_rows(B * T), planes * 512), dtype=torch.bfloat16, device=xproj.device)
+    _native.check(_native.lib().crnn_gru_layer(_p(xproj), _p(w_hh), _p(b_hh), _p(y), B, T, planes, _st()))
     return y
 
 

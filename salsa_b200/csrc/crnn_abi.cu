@@ -59,25 +59,28 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tw, const ConvA
 
 // x: NHWC bf16 [B][H][W][Cin]; for a GEMM: B = 1, W = 8, H = ceil(M / 8), pix_limit = M
 static int conv_generic(const void* x, const void* w, const float* bias, const void* residual, void* out, float* out_f32, int B,
-                        int H, int W, int Cin, int Cout, int taps, int relu, long long pix_limit, cudaStream_t st) {
+                        int H, int W, int Cin, int Cout, int taps, int relu, int planes, long long pix_limit, cudaStream_t st) {
+    if (planes != 1 && planes != 3) return fail(SALSA_EINVAL, "conv: planes must be 1 (bf16) or 3 (bf16x3)");
     if (!x || !w || (!out && !out_f32)) return fail(SALSA_EINVAL, "conv: null pointer");
     if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv: bad dimensions");
     if (Cin % kKC != 0 || Cin <= 0) return fail(SALSA_EINVAL, "conv: Cin must be a multiple of 64");
     if (Cout % 64 != 0 || Cout <= 0) return fail(SALSA_EINVAL, "conv: Cout must be a multiple of 64");
     if (taps != 1 && taps != 9) return fail(SALSA_EINVAL, "conv: kernel size must be 1 or 3");
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return fail(SALSA_EINVAL, "conv: unaligned pointer");
-    const int n_tile = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    // bf16x3 needs two accumulators per stage: 4 * n_tile TMEM columns <= 512
+    const int n_tile = (Cout % 256 == 0 && planes == 1) ? 256 : (Cout % 128 == 0 ? 128 : 64);
     CUtensorMap ta, tw;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        const cuuint64_t cp = (cuuint64_t)Cin * planes;      // channels per pixel in memory
+        cuuint64_t dims[4] = {cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {cp * 2, (cuuint64_t)W * cp * 2, (cuuint64_t)H * W * cp * 2};
         cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)kTileW, (cuuint32_t)(taps == 9 ? kTileH + 2 : kTileH), 1};
         int rc = make_tmap(&ta, x, 4, dims, str, box);
         if (rc) return rc;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)taps * Cout};
-        cuuint64_t str[1] = {(cuuint64_t)Cin * 2};
+        cuuint64_t dims[2] = {(cuuint64_t)Cin * planes, (cuuint64_t)taps * Cout};
+        cuuint64_t str[1] = {(cuuint64_t)Cin * planes * 2};
         cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)n_tile};
         int rc = make_tmap(&tw, w, 2, dims, str, box);
         if (rc) return rc;
@@ -85,6 +88,7 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
     ConvArgs a;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
     a.taps = taps;
+    a.planes = planes;
     a.tiles_w = (W + kTileW - 1) / kTileW;
     a.tiles_h = (H + kTileH - 1) / kTileH;
     a.n_tiles = B * a.tiles_h * a.tiles_w * (Cout / n_tile);
@@ -116,49 +120,50 @@ using namespace salsa::crnn;
 extern "C" {
 
 int crnn_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* out, float* out_f32, int32_t B,
-                int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, void* stream) {
+                int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, int32_t planes, void* stream) {
     if (ksize != 1 && ksize != 3) return fail(SALSA_EINVAL, "conv: kernel size must be 1 or 3");
-    return conv_generic(x, w, bias, residual, out, out_f32, B, H, W, Cin, Cout, ksize * ksize, relu, (long long)B * H * W,
+    return conv_generic(x, w, bias, residual, out, out_f32, B, H, W, Cin, Cout, ksize * ksize, relu, planes, (long long)B * H * W,
                         (cudaStream_t)stream);
 }
 
 int crnn_gemm(const void* a, const void* w, const float* bias, void* out, float* out_f32, int32_t M, int32_t N, int32_t K,
-              int32_t relu, void* stream) {
+              int32_t relu, int32_t planes, void* stream) {
     if (M <= 0) return fail(SALSA_EINVAL, "gemm: M must be positive");
-    return conv_generic(a, w, bias, nullptr, out, out_f32, 1, (M + 7) / 8, 8, K, N, 1, relu, M, (cudaStream_t)stream);
+    return conv_generic(a, w, bias, nullptr, out, out_f32, 1, (M + 7) / 8, 8, K, N, 1, relu, planes, M, (cudaStream_t)stream);
 }
 
 int crnn_pack_input(const float* x, void* y, int32_t B, int32_t C, int32_t T, int32_t F, int32_t T_use, int32_t Cpad,
-                    void* stream) {
+                    int32_t planes, void* stream) {
     if (!x || !y) return fail(SALSA_EINVAL, "pack_input: null pointer");
     if (Cpad % 8 != 0 || C > Cpad || T_use > T || B <= 0) return fail(SALSA_EINVAL, "pack_input: bad dimensions");
     const long long n = (long long)B * T_use * F;
-    pack_input_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, C, T, F, T_use, Cpad);
+    pack_input_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, C, T, F, T_use, Cpad, planes);
     count_launch();
     return check_cuda(cudaGetLastError(), "pack_input_kernel");
 }
 
-int crnn_avgpool2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+int crnn_avgpool2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t planes, void* stream) {
     if (!x || !y) return fail(SALSA_EINVAL, "avgpool2: null pointer");
     if (C % 8 != 0 || H < 2 || W < 2) return fail(SALSA_EINVAL, "avgpool2: bad dimensions");
     const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
     avgpool2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                         reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+                                                                         reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C, planes);
     count_launch();
     return check_cuda(cudaGetLastError(), "avgpool2_kernel");
 }
 
-int crnn_freq_mean(const void* x, void* y, int32_t BH, int32_t W, int32_t C, void* stream) {
+int crnn_freq_mean(const void* x, void* y, int32_t BH, int32_t W, int32_t C, int32_t planes, void* stream) {
     if (!x || !y) return fail(SALSA_EINVAL, "freq_mean: null pointer");
     if (C % 8 != 0 || W <= 0) return fail(SALSA_EINVAL, "freq_mean: bad dimensions");
     const long long n = (long long)BH * (C / 8);
     freq_mean_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                          reinterpret_cast<__nv_bfloat16*>(y), BH, W, C);
+                                                                          reinterpret_cast<__nv_bfloat16*>(y), BH, W, C, planes);
     count_launch();
     return check_cuda(cudaGetLastError(), "freq_mean_kernel");
 }
 
-int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, void* y, int32_t B, int32_t T, void* stream) {
+int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, void* y, int32_t B, int32_t T, int32_t planes,
+                   void* stream) {
     if (!xproj || !w_hh || !b_hh || !y) return fail(SALSA_EINVAL, "gru_layer: null pointer");
     if (B <= 0 || T <= 0) return fail(SALSA_EINVAL, "gru_layer: bad dimensions");
     SALSA_CUDA(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmemBytes));
@@ -169,6 +174,7 @@ int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, voi
     a.y = reinterpret_cast<__nv_bfloat16*>(y);
     a.B = B;
     a.T = T;
+    a.planes = planes;
     const int groups = (B + kGruClips - 1) / kGruClips;
     gru_layer_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruSmemBytes, (cudaStream_t)stream>>>(a);
     count_launch();

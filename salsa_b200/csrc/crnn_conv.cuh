@@ -37,6 +37,7 @@ constexpr int kPlainBytes = kTileH * kTileW * 128;         // A tile of a 1x1 co
 struct ConvArgs {
     int B, H, W, Cin, Cout;
     int taps;                  // 9 (3x3, pad 1) or 1
+    int planes;                // 1: bf16 operands.  3: every operand is a sum of three bf16 planes (fp32-grade products)
     int tiles_w, tiles_h;      // spatial tiles per image
     int n_tiles;               // B * tiles_h * tiles_w * (Cout / N_TILE)
     int relu;
@@ -99,7 +100,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc(tmem_slot, 2 * N_TILE);
+    // planes == 3 keeps the small correction products in their own accumulator (see the MMA issuer)
+    const int acc_cols = a.planes == 3 ? 2 * N_TILE : N_TILE;      // TMEM columns per accumulator stage
+    if (warp == 2) tc::tmem_alloc(tmem_slot, (uint32_t)(2 * acc_cols));
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -107,7 +110,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
 
     const int n_chunks = a.Cin / kKC;
     const int n_nt = a.Cout / N_TILE;
-    const int pad = a.taps == 9 ? 1 : 0;
     auto decode = [&](int tile, int& n0, int& b, int& h0, int& w0) {
         const int nt = tile % n_nt;
         int sp = tile / n_nt;
@@ -129,21 +131,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 int n0, b, h0, w0;
                 decode(tile, n0, b, h0, w0);
                 for (int c = 0; c < n_chunks; ++c) {
-                    tc::mbar_wait(a_empty + sa, pa ^ 1);
-                    tc::mbar_expect_tx(a_full + sa, (uint32_t)a_bytes);
-                    unsigned char* dst = a_smem + sa * a_bytes;
-                    if (a.taps == 9) {
-                        for (int kw = 0; kw < 3; ++kw)
-                            tc::tma_load_4d(dst + kw * kHaloBytes, &tm_act, a_full + sa, c * kKC, w0 - 1 + kw, h0 - 1, b);
-                    } else {
-                        tc::tma_load_4d(dst, &tm_act, a_full + sa, c * kKC, w0, h0, b);
-                    }
-                    if (++sa == kAStages) { sa = 0; pa ^= 1; }
-                    for (int t = 0; t < a.taps; ++t) {
-                        tc::mbar_wait(b_empty + sb, pb ^ 1);
-                        tc::mbar_expect_tx(b_full + sb, (uint32_t)S::kBBytes);
-                        tc::tma_load_2d(b_smem + sb * S::kBBytes, &tm_wgt, b_full + sb, c * kKC, t * a.Cout + n0);
-                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    for (int ap = 0; ap < a.planes; ++ap) {
+                        tc::mbar_wait(a_empty + sa, pa ^ 1);
+                        tc::mbar_expect_tx(a_full + sa, (uint32_t)a_bytes);
+                        unsigned char* dst = a_smem + sa * a_bytes;
+                        const int ch0 = ap * a.Cin + c * kKC;
+                        if (a.taps == 9) {
+                            for (int kw = 0; kw < 3; ++kw)
+                                tc::tma_load_4d(dst + kw * kHaloBytes, &tm_act, a_full + sa, ch0, w0 - 1 + kw, h0 - 1, b);
+                        } else {
+                            tc::tma_load_4d(dst, &tm_act, a_full + sa, ch0, w0, h0, b);
+                        }
+                        if (++sa == kAStages) { sa = 0; pa ^= 1; }
+                        // activation plane ap meets weight planes 0 .. planes-1-ap (products below 2^-24 are dropped)
+                        for (int wp = 0; wp < a.planes - ap; ++wp) {
+                            for (int t = 0; t < a.taps; ++t) {
+                                tc::mbar_wait(b_empty + sb, pb ^ 1);
+                                tc::mbar_expect_tx(b_full + sb, (uint32_t)S::kBBytes);
+                                tc::tma_load_2d(b_smem + sb * S::kBBytes, &tm_wgt, b_full + sb, wp * a.Cin + c * kKC, t * a.Cout + n0);
+                                if (++sb == NB) { sb = 0; pb ^= 1; }
+                            }
+                        }
                     }
                 }
             }
@@ -157,27 +165,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 tc::mbar_wait(acc_empty + as, pacc ^ 1);
                 tc::fence_after_sync();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * N_TILE);
+                // The tensor core's fp32 accumulation loses about 2^-24 of the accumulator per instruction, whatever
+                // the size of the addend.  In bf16x3 mode the five correction products (2^-8 and below) therefore
+                // go to a second accumulator, so that the main one sees one sixth of the instructions; the
+                // epilogue adds the two.
+                const uint32_t tmem_main = tmem_base + (uint32_t)(as * acc_cols);
+                const uint32_t tmem_corr = tmem_main + (uint32_t)N_TILE;
+                uint32_t first_corr = 1;
+                uint32_t first = 1;
                 for (int c = 0; c < n_chunks; ++c) {
-                    tc::mbar_wait(a_full + sa, pa);
-                    const uint32_t a_addr = tc::smem_u32(a_smem + sa * a_bytes);
-                    for (int t = 0; t < a.taps; ++t) {
-                        tc::mbar_wait(b_full + sb, pb);
-                        tc::fence_after_sync();
-                        const int kh = a.taps == 9 ? t / 3 : 0, kw = a.taps == 9 ? t % 3 : 0;
-                        const uint32_t a_tap = a_addr + (uint32_t)(kw * kHaloBytes + kh * kTileW * 128);
-                        const uint32_t b_addr = tc::smem_u32(b_smem + sb * S::kBBytes);
+                    for (int ap = 0; ap < a.planes; ++ap) {
+                        tc::mbar_wait(a_full + sa, pa);
+                        const uint32_t a_addr = tc::smem_u32(a_smem + sa * a_bytes);
+                        for (int wp = 0; wp < a.planes - ap; ++wp) {
+                            for (int t = 0; t < a.taps; ++t) {
+                                tc::mbar_wait(b_full + sb, pb);
+                                tc::fence_after_sync();
+                                const int kh = a.taps == 9 ? t / 3 : 0, kw = a.taps == 9 ? t % 3 : 0;
+                                const uint32_t a_tap = a_addr + (uint32_t)(kw * kHaloBytes + kh * kTileW * 128);
+                                const uint32_t b_addr = tc::smem_u32(b_smem + sb * S::kBBytes);
 #pragma unroll
-                        for (int k = 0; k < kKC / 16; ++k) {
-                            const uint64_t da = tc::smem_desc_sw128(a_tap + k * 32, 1024);
-                            const uint64_t db = tc::smem_desc_sw128(b_addr + k * 32, 1024);
-                            tc::mma_bf16(tmem_d, da, db, idesc, (uint32_t)((c | t | k) != 0));
+                                for (int k = 0; k < kKC / 16; ++k) {
+                                    const uint64_t da = tc::smem_desc_sw128(a_tap + k * 32, 1024);
+                                    const uint64_t db = tc::smem_desc_sw128(b_addr + k * 32, 1024);
+                                    if (ap == 0 && wp == 0) {
+                                        tc::mma_bf16(tmem_main, da, db, idesc, first ? 0u : 1u);
+                                        first = 0;
+                                    } else {
+                                        tc::mma_bf16(tmem_corr, da, db, idesc, first_corr ? 0u : 1u);
+                                        first_corr = 0;
+                                    }
+                                }
+                                tc::mma_commit(b_empty + sb);
+                                if (++sb == NB) { sb = 0; pb ^= 1; }
+                            }
                         }
-                        tc::mma_commit(b_empty + sb);
-                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                        tc::mma_commit(a_empty + sa);
+                        if (++sa == kAStages) { sa = 0; pa ^= 1; }
                     }
-                    tc::mma_commit(a_empty + sa);
-                    if (++sa == kAStages) { sa = 0; pa ^= 1; }
                 }
                 tc::mma_commit(acc_full + as);
                 if (++as == 2) { as = 0; pacc ^= 1; }
@@ -201,24 +226,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
 #pragma unroll 1
             for (int j = 0; j < N_TILE / 32; ++j) {
                 uint32_t r[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N_TILE + j * 32), r);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols + j * 32);
+                tc::tmem_ld32(taddr, r);
                 tc::tmem_ld_wait();
+                if (a.planes == 3) {
+                    uint32_t r2[32];
+                    tc::tmem_ld32(taddr + (uint32_t)N_TILE, r2);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                }
                 if (valid) {
                     const int n = n0 + j * 32;
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (a.bias ? __ldg(a.bias + n + i) : 0.0f);
+                    const size_t ostride = (size_t)a.planes * a.Cout;      // channels per pixel in memory
                     if (a.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.Cout + n);
+                        for (int pl = 0; pl < a.planes; ++pl) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * ostride + (size_t)pl * a.Cout + n);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 u = __ldg(rp + i);
-                            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 u = __ldg(rp + i);
+                                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
-                                v[i * 8 + e * 2] += __low2float(h2);
-                                v[i * 8 + e * 2 + 1] += __high2float(h2);
+                                for (int e = 0; e < 4; ++e) {
+                                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                                    v[i * 8 + e * 2] += __low2float(h2);
+                                    v[i * 8 + e * 2 + 1] += __high2float(h2);
+                                }
                             }
                         }
                     }
@@ -226,17 +262,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
                     }
-                    if (a.out) {
-                        uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.Cout + n);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            op[i] = make_uint4(pack_bf16(v[i * 8], v[i * 8 + 1]), pack_bf16(v[i * 8 + 2], v[i * 8 + 3]),
-                                               pack_bf16(v[i * 8 + 4], v[i * 8 + 5]), pack_bf16(v[i * 8 + 6], v[i * 8 + 7]));
-                    }
                     if (a.out_f32) {
                         float4* op = reinterpret_cast<float4*>(a.out_f32 + pix * a.Cout + n);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+                    }
+                    if (a.out) {
+                        for (int pl = 0; pl < a.planes; ++pl) {
+                            uint4* op = reinterpret_cast<uint4*>(a.out + pix * ostride + (size_t)pl * a.Cout + n);
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                                pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                v[2 * i] -= __low2float(h2);              // remainder goes to the next plane
+                                v[2 * i + 1] -= __high2float(h2);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) op[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                        }
                     }
                 }
             }
@@ -249,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     // teardown
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem_base, 2 * N_TILE);
+    if (warp == 2) tc::tmem_dealloc(tmem_base, (uint32_t)(2 * acc_cols));
 }
 
 }  // namespace crnn

@@ -16,9 +16,27 @@ namespace crnn {
 
 namespace cg = cooperative_groups;
 
+// A float as the sum of up to three bf16 planes (the "bf16x3" precision mode): plane k holds the bf16
+// rounding of what the planes before it left over, so hi + mid + lo reproduces 24 mantissa bits.
+__device__ __forceinline__ void split_store8(const float (&v)[8], __nv_bfloat16* dst, int planes, size_t plane_stride) {
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = v[k];
+    for (int pl = 0; pl < planes; ++pl) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
+            r[2 * k] -= __low2float(h[k]);
+            r[2 * k + 1] -= __high2float(h[k]);
+        }
+        *reinterpret_cast<uint4*>(dst + pl * plane_stride) = *reinterpret_cast<uint4*>(h);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C, int T, int F,
-                                  int T_use, int Cpad) {
+                                  int T_use, int Cpad, int planes) {
     // one thread per output pixel; reads are coalesced along F, each thread writes Cpad bf16
     const long long n_pix = (long long)B * T_use * F;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
@@ -26,15 +44,12 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
         const long long bt = p / F;
         const int t = (int)(bt % T_use), b = (int)(bt / T_use);
         const float* src = x + ((long long)b * C * T + t) * F + f;
-        uint4* dst = reinterpret_cast<uint4*>(y + p * Cpad);
+        __nv_bfloat16* dst = y + p * Cpad * planes;
         for (int c0 = 0; c0 < Cpad; c0 += 8) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = (c0 + i < C) ? __ldg(src + (long long)(c0 + i) * T * F) : 0.0f;
-            __nv_bfloat162 h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            dst[c0 / 8] = *reinterpret_cast<uint4*>(h);
+            split_store8(v, dst + c0, planes, Cpad);
         }
     }
 }
@@ -49,7 +64,9 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
     }
 }
 
-__global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C) {
+__global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C,
+                                int planes) {
+    const int CP = C * planes;       // channels per pixel in memory
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
     const long long total = (long long)B * Ho * Wo * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -63,21 +80,25 @@ __global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
         for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
             for (int dw = 0; dw < 2; ++dw) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + 2 * ho + dh) * W + 2 * wo + dw) * C) + c8);
-                float f[8];
-                bf16x8_to_float(u, f);
+                const __nv_bfloat16* px = x + (((long long)b * H + 2 * ho + dh) * W + 2 * wo + dw) * CP + c8 * 8;
+                for (int pl = 0; pl < planes; ++pl) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(px + pl * C));
+                    float f[8];
+                    bf16x8_to_float(u, f);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+                    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+                }
             }
-        __nv_bfloat162 h[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(0.25f * acc[2 * k], 0.25f * acc[2 * k + 1]);
-        reinterpret_cast<uint4*>(y + (((long long)b * Ho + ho) * Wo + wo) * C)[c8] = *reinterpret_cast<uint4*>(h);
+        for (int k = 0; k < 8; ++k) acc[k] *= 0.25f;
+        split_store8(acc, y + (((long long)b * Ho + ho) * Wo + wo) * CP + c8 * 8, planes, C);
     }
 }
 
 // (B,H,W,C) bf16 -> (B*H, C) bf16, mean over W
-__global__ void freq_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int BH, int W, int C) {
+__global__ void freq_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int BH, int W, int C,
+                                 int planes) {
+    const int CP = C * planes;
     const int C8 = C / 8;
     const long long total = (long long)BH * C8;
     const float inv = 1.0f / (float)W;
@@ -86,16 +107,17 @@ __global__ void freq_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
         const long long r = i / C8;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int w = 0; w < W; ++w) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (r * W + w) * C) + c8);
-            float f[8];
-            bf16x8_to_float(u, f);
+            for (int pl = 0; pl < planes; ++pl) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (r * W + w) * CP + pl * C + c8 * 8));
+                float f[8];
+                bf16x8_to_float(u, f);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += f[k];
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            }
         }
-        __nv_bfloat162 h[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[2 * k] * inv, acc[2 * k + 1] * inv);
-        reinterpret_cast<uint4*>(y + r * C)[c8] = *reinterpret_cast<uint4*>(h);
+        for (int k = 0; k < 8; ++k) acc[k] *= inv;
+        split_store8(acc, y + r * CP + c8 * 8, planes, C);
     }
 }
 
@@ -119,8 +141,8 @@ struct GruArgs {
     const float* xproj;        // [B*T][2*768]   (direction-major: fwd r,z,n | bwd r,z,n)
     const float* w_hh;         // [2][768][256]
     const float* b_hh;         // [2][768]
-    __nv_bfloat16* y;          // [B*T][512]  (fwd | bwd)
-    int B, T;
+    __nv_bfloat16* y;          // [B*T][planes][512]  (fwd | bwd)
+    int B, T, planes;
 };
 
 constexpr size_t kGruSmemBytes = (size_t)(3 * kGruUnits * kGruHidden + 2 * kGruHidden * kGruClips + 3 * kGruUnits * kGruClips) * sizeof(float);
@@ -190,8 +212,8 @@ __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThread
             const float ar = gates[jl * kGruClips + bl];
             const float az = gates[(kGruUnits + jl) * kGruClips + bl];
             const float an = gates[(2 * kGruUnits + jl) * kGruClips + bl];
-            const float r = 1.0f / (1.0f + __expf(-(xr + ar + b_hr)));
-            const float z = 1.0f / (1.0f + __expf(-(xz + az + b_hz)));
+            const float r = 1.0f / (1.0f + expf(-(xr + ar + b_hr)));
+            const float z = 1.0f / (1.0f + expf(-(xz + az + b_hz)));
             const float n = tanhf(xn + r * (an + b_hn));
             const float h_new = (1.0f - z) * n + z * h_prev;
             h_prev = h_new;
@@ -201,7 +223,15 @@ __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThread
                 float* remote = cluster.map_shared_rank(hn, c);
                 remote[j * kGruClips + bl] = h_new;
             }
-            if (live) a.y[((size_t)b * a.T + t) * (2 * kGruHidden) + dir * kGruHidden + j] = __float2bfloat16(h_new);
+            if (live) {
+                __nv_bfloat16* yp = a.y + ((size_t)b * a.T + t) * (2 * kGruHidden) * a.planes + dir * kGruHidden + j;
+                float rem = h_new;
+                for (int pl = 0; pl < a.planes; ++pl) {
+                    const __nv_bfloat16 hb = __float2bfloat16(rem);
+                    yp[pl * 2 * kGruHidden] = hb;
+                    rem -= __bfloat162float(hb);
+                }
+            }
         }
         cluster.sync();
     }

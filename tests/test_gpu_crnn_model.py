@@ -45,6 +45,28 @@ def test_forward_matches_golden(model, golden):
     assert e1 < 3e-2 and e2 < 3e-2
 
 
+def test_forward_bf16x3_meets_float32_tolerance(golden):
+    """The parity mode: three bf16 planes per operand, six plane products per MAC on the same tcgen05 kernels.
+    Bar = the float32 target of BASELINE.json: 1e-4 relative (to the output scale) on logits and DOA."""
+    import salsa_b200
+    from oracle import crnn as ocrnn
+    g = golden('model_cases')
+    m = salsa_b200.SeldModel(salsa_b200.PannResNet22(7), salsa_b200.SeldDecoder(512, decoder_type='bigru', freq_pool='avg', decoder_size=256),
+                             precision='bf16x3')
+    m.load_state_dict(ocrnn.make_state_dict(0))
+    x = ocrnn.model_input(2, (2, 7, 128, 200))
+    enc = salsa_b200.crnn_ops.merge_planes(m.encode(x.cuda()).cpu(), 3).permute(0, 3, 1, 2).numpy()
+    assert scale_err(enc, g['model_encoder_out'].astype(np.float32)) < 1e-3            # golden copy is float16
+    y = m(x.cuda())
+    e1 = scale_err(y['event_frame_logit'].cpu().numpy(), g['model_event_frame_logit'])
+    e2 = scale_err(y['doa_frame_output'].cpu().numpy(), g['model_doa_frame_output'])
+    print('bf16x3 CRNN vs reference: logits {:.3e}, doa {:.3e} (relative to output scale)'.format(e1, e2))
+    assert e1 < 1e-4 and e2 < 1e-4
+    y2 = m(ocrnn.model_input(3, (1, 7, 96, 191)).cuda())
+    assert scale_err(y2['event_frame_logit'].cpu().numpy(), g['lite_event_frame_logit']) < 1e-4
+    assert scale_err(y2['doa_frame_output'].cpu().numpy(), g['lite_doa_frame_output']) < 1e-4
+
+
 def test_forward_lite_shape_matches_golden(model, golden):
     from oracle import crnn as ocrnn
     g = golden('model_cases')

@@ -106,3 +106,36 @@ def test_head_finish(ops):
     logits, doa = ops.head_finish(z.cuda(), 10, 12)
     assert torch.equal(logits.cpu(), z[:, :12])
     assert torch.allclose(doa.cpu(), torch.tanh(z[:, 12:48]), atol=1e-6)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k', [(1, 20, 9, 64, 64, 3), (1, 17, 12, 128, 256, 3), (2, 16, 8, 64, 128, 1)])
+def test_conv2d_bf16x3_is_float32_grade(ops, B, H, W, Cin, Cout, k):
+    """planes = 3: operands are NOT rounded to bf16 first; the result must match an fp64 reference of the
+    float32 inputs to float32 accuracy."""
+    g = torch.Generator().manual_seed(H * W + Cin + Cout + 1)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    res = torch.randn(B, H, W, Cout, generator=g)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), padding=k // 2) + bias.double()[None, :, None, None]
+    ref = ref.permute(0, 2, 3, 1)
+    wp = ops.split_planes(w.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin), 3)
+    xs, rs = ops.split_planes(x, 3), ops.split_planes(res, 3)
+    assert rel_err(ops.merge_planes(xs, 3), x) < 1e-7
+    out = ops.conv2d(xs.cuda(), wp.cuda(), bias.cuda(), out_f32=True, planes=3).cpu()
+    assert rel_err(out, ref) < 1e-5          # tensor-core fp32 accumulation: a few 1e-6
+    out2 = ops.conv2d(xs.cuda(), wp.cuda(), bias.cuda(), residual=rs.cuda(), relu=True, planes=3).cpu()
+    assert rel_err(ops.merge_planes(out2, 3), (ref + res.double()).clamp(min=0)) < 1e-5
+
+
+def test_gemm_pool_mean_gru_bf16x3(ops):
+    g = torch.Generator().manual_seed(77)
+    a = torch.randn(40, 128, generator=g)
+    w = torch.randn(192, 128, generator=g) / 128 ** 0.5
+    out = ops.gemm(ops.split_planes(a, 3).cuda(), ops.split_planes(w, 3).cuda(), None, out_f32=True, planes=3).cpu()
+    assert rel_err(out, a.double() @ w.double().T) < 1e-5
+    x = torch.randn(1, 8, 10, 64, generator=g)
+    p = ops.merge_planes(ops.avgpool2(ops.split_planes(x, 3).cuda(), planes=3).cpu(), 3)
+    assert rel_err(p, F.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)) < 1e-6
+    m = ops.merge_planes(ops.freq_mean(ops.split_planes(x, 3).cuda(), planes=3).cpu(), 3)
+    assert rel_err(m[:8], x.mean(dim=2).reshape(8, 64)) < 1e-6
