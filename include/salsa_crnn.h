@@ -35,6 +35,15 @@ int crnn_conv2d(const void *x, const void *w, const float *bias, const void *res
                 int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, int32_t planes,
                 void *stream);
 
+/* The first convolution of the encoder (conv_block1.conv1 + bn1 + ReLU, models/model_utils.py:213-215) on an input
+ * padded to 16 channels: x bf16 NHWC [B][H][W][planes*16], w bf16 [9][64][planes*16] -> out bf16 [B][H][W][planes*64]. */
+int crnn_conv_first(const void *x, const void *w, const float *bias, void *out, int32_t B, int32_t H, int32_t W,
+                    int32_t relu, int32_t planes, void *stream);
+
+/* Tuning knobs of the convolution kernels (not part of the reference surface): "resident_b" (0 / 1: weights resident
+ * in shared memory for 64 -> 64 convolutions); value -1 restores the built-in choice. */
+int crnn_set_option(const char *name, int32_t value);
+
 /* nn.Linear / GRU input projection (models/decoders.py:44-46, :75-92): out[M][N] = relu?(a[M][K] w[N][K]^T + bias).
  * `a` must be allocated with its row count rounded up to a multiple of 8. */
 int crnn_gemm(const void *a, const void *w, const float *bias, void *out, float *out_f32, int32_t M, int32_t N,

@@ -127,14 +127,14 @@ class SeldModel:
         return self.forward(x)
 
     # ---- weights ----------------------------------------------------------------------------------
-    def _fold(self, sd, conv_key, bn_prefix):
-        """conv weight (Cout,Cin,k,k) + eval BatchNorm -> bf16 (k*k, Cout, Cin_pad64), fp32 bias (Cout,)."""
+    def _fold(self, sd, conv_key, bn_prefix, pad_to=64):
+        """conv weight (Cout,Cin,k,k) + eval BatchNorm -> bf16 (k*k, Cout, planes*Cin_pad), fp32 bias (Cout,)."""
         w = _t(sd[conv_key])
         scale = _t(sd[bn_prefix + '.weight']) / torch.sqrt(_t(sd[bn_prefix + '.running_var']) + BN_EPS)
         bias = _t(sd[bn_prefix + '.bias']) - _t(sd[bn_prefix + '.running_mean']) * scale
         w = w * scale[:, None, None, None]
         cout, cin, k, _ = w.shape
-        cin_pad = (cin + 63) // 64 * 64
+        cin_pad = (cin + pad_to - 1) // pad_to * pad_to
         wp = torch.zeros((k * k, cout, cin_pad))
         wp[:, :, :cin] = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
         return ops.split_planes(wp, self.planes).to(self.device), bias.contiguous().to(self.device)
@@ -142,7 +142,7 @@ class SeldModel:
     def load_state_dict(self, state_dict, strict: bool = True):
         sd = state_dict
         W = {}
-        W['cb1'] = self._fold(sd, 'encoder.conv_block1.conv1.weight', 'encoder.conv_block1.bn1')
+        W['cb1'] = self._fold(sd, 'encoder.conv_block1.conv1.weight', 'encoder.conv_block1.bn1', pad_to=16)
         W['cb2'] = self._fold(sd, 'encoder.conv_block1.conv2.weight', 'encoder.conv_block1.bn2')
         for li in range(1, 5):
             for bi in range(2):
@@ -183,8 +183,10 @@ class SeldModel:
         if x.dim() != 4 or x.shape[1] != self.encoder.n_input_channels:
             raise ValueError('x must be (batch_size, {}, n_timesteps, n_features)'.format(self.encoder.n_input_channels))
         W, P = self._w, self.planes
-        h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames, planes=P)
-        h = ops.conv2d(h, *W['cb1'], relu=True, planes=P)
+        if self.encoder.n_input_channels > 16:
+            raise NotImplementedError('at most 16 input channels')
+        h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames, c_pad=16, planes=P)
+        h = ops.conv_first(h, *W['cb1'], relu=True, planes=P)
         h = ops.conv2d(h, *W['cb2'], relu=True, planes=P)
         h = ops.avgpool2(h, planes=P)
         for li in range(1, 5):

@@ -64,6 +64,17 @@ def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, 
     return out
 
 
+def conv_first(x, w, bias=None, relu=True, planes=1):
+    """First convolution: x (B,H,W,planes*16) bf16, w (9,64,planes*16) bf16 -> (B,H,W,planes*64) bf16."""
+    _check_act(x)
+    B, H, W, C = x.shape
+    if C != 16 * planes or tuple(w.shape) != (9, 64, 16 * planes) or w.dtype != torch.bfloat16 or not w.is_contiguous():
+        raise ValueError('conv_first expects 16 (padded) input channels and 64 output channels')
+    out = torch.empty((B, H, W, planes * 64), dtype=torch.bfloat16, device=x.device)
+    _native.check(_native.lib().crnn_conv_first(_p(x), _p(w), _p(bias), _p(out), B, H, W, int(bool(relu)), planes, _st()))
+    return out
+
+
 def pad_rows(n):
     """GEMM inputs are allocated with their row count rounded up to a multiple of 8."""
     return (n + 7) // 8 * 8

@@ -33,20 +33,23 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                     const cuuint32_t* box) {
+                     const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(SALSA_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SALSA_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
     return SALSA_OK;
 }
 
+// tuning knobs (crnn_set_option): -1 = automatic
+static int g_opt_resident = -1;
+
 template <int N_TILE>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tw, const ConvArgs& a, cudaStream_t st) {
-    const size_t smem = ConvSmem<N_TILE>::total(a.taps);
+    const size_t smem = ConvSmem<N_TILE>::total(a.taps, a.resident_b);
     SALSA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -69,6 +72,7 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return fail(SALSA_EINVAL, "conv: unaligned pointer");
     // bf16x3 needs two accumulators per stage: 4 * n_tile TMEM columns <= 512
     const int n_tile = (Cout % 256 == 0 && planes == 1) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    const int resident = (planes == 1 && Cin == 64 && Cout == 64 && taps == 9) && (g_opt_resident < 0 ? 1 : g_opt_resident);
     CUtensorMap ta, tw;
     {
         const cuuint64_t cp = (cuuint64_t)Cin * planes;      // channels per pixel in memory
@@ -93,6 +97,7 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
     a.tiles_h = (H + kTileH - 1) / kTileH;
     a.n_tiles = B * a.tiles_h * a.tiles_w * (Cout / n_tile);
     a.relu = relu;
+    a.resident_b = resident;
     a.pix_limit = pix_limit;
     a.bias = bias;
     a.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
@@ -101,6 +106,51 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
     if (n_tile == 256) return launch_conv<256>(ta, tw, a, st);
     if (n_tile == 128) return launch_conv<128>(ta, tw, a, st);
     return launch_conv<64>(ta, tw, a, st);
+}
+
+// first convolution: x NHWC bf16 [B][H][W][planes*16], w [9][64][planes*16]
+static int conv_first(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int relu, int planes,
+                      cudaStream_t st) {
+    if (!x || !w || !out) return fail(SALSA_EINVAL, "conv_first: null pointer");
+    if (planes != 1 && planes != 3) return fail(SALSA_EINVAL, "conv_first: planes must be 1 or 3");
+    CUtensorMap ta, tw;
+    {
+        const cuuint64_t cp = (cuuint64_t)kC1 * planes;
+        cuuint64_t dims[4] = {cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {cp * 2, (cuuint64_t)W * cp * 2, (cuuint64_t)H * W * cp * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kC1, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + 2), 1};
+        int rc = make_tmap(&ta, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)kC1 * planes, (cuuint64_t)9 * 64};
+        cuuint64_t str[1] = {(cuuint64_t)kC1 * planes * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kC1, 64};
+        int rc = make_tmap(&tw, w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
+        if (rc) return rc;
+    }
+    ConvArgs a;
+    a.B = B; a.H = H; a.W = W; a.Cin = kC1; a.Cout = 64;
+    a.taps = 9;
+    a.planes = planes;
+    a.tiles_w = (W + kTileW - 1) / kTileW;
+    a.tiles_h = (H + kTileH - 1) / kTileH;
+    a.n_tiles = B * a.tiles_h * a.tiles_w;
+    a.relu = relu;
+    a.resident_b = 1;
+    a.pix_limit = (long long)B * H * W;
+    a.bias = bias;
+    a.residual = nullptr;
+    a.out = reinterpret_cast<__nv_bfloat16*>(out);
+    a.out_f32 = nullptr;
+    const size_t smem = conv_first_smem(planes);
+    SALSA_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    conv_first_kernel<<<std::min(a.n_tiles, sms), kConvThreads, smem, st>>>(ta, tw, a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "conv_first_kernel");
 }
 
 static int grid_for(long long total, int block) {
@@ -126,10 +176,23 @@ int crnn_conv2d(const void* x, const void* w, const float* bias, const void* res
                         (cudaStream_t)stream);
 }
 
+int crnn_conv_first(const void* x, const void* w, const float* bias, void* out, int32_t B, int32_t H, int32_t W, int32_t relu,
+                    int32_t planes, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv_first: bad dimensions");
+    return conv_first(x, w, bias, out, B, H, W, relu, planes, (cudaStream_t)stream);
+}
+
 int crnn_gemm(const void* a, const void* w, const float* bias, void* out, float* out_f32, int32_t M, int32_t N, int32_t K,
               int32_t relu, int32_t planes, void* stream) {
     if (M <= 0) return fail(SALSA_EINVAL, "gemm: M must be positive");
     return conv_generic(a, w, bias, nullptr, out, out_f32, 1, (M + 7) / 8, 8, K, N, 1, relu, planes, M, (cudaStream_t)stream);
+}
+
+int crnn_set_option(const char* name, int32_t value) {
+    const std::string n = name ? name : "";
+    if (n == "resident_b") g_opt_resident = value;
+    else return fail(SALSA_EINVAL, "unknown option " + n);
+    return SALSA_OK;
 }
 
 int crnn_pack_input(const float* x, void* y, int32_t B, int32_t C, int32_t T, int32_t F, int32_t T_use, int32_t Cpad,

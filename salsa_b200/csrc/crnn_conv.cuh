@@ -41,6 +41,7 @@ struct ConvArgs {
     int tiles_w, tiles_h;      // spatial tiles per image
     int n_tiles;               // B * tiles_h * tiles_w * (Cout / N_TILE)
     int relu;
+    int resident_b;            // all weight tiles stay in shared memory for the whole kernel (Cin = Cout = 64)
     long long pix_limit;       // pixels (rows of a GEMM) beyond this index are not written
     const float* bias;                 // [Cout] or null
     const __nv_bfloat16* residual;     // NHWC [B][H][W][Cout] or null
@@ -52,15 +53,88 @@ template <int N_TILE>
 struct ConvSmem {
     static constexpr int kBStages = N_TILE >= 256 ? 3 : 4;
     static constexpr int kBBytes = N_TILE * 128;
-    static constexpr int a_bytes(int taps) { return taps == 9 ? 3 * kHaloBytes : kPlainBytes; }
-    static constexpr size_t total(int taps) {
-        return 1024 /* alignment slack */ + (size_t)kAStages * a_bytes(taps) + (size_t)kBStages * kBBytes + 256 /* barriers */;
+    __host__ __device__ static constexpr int a_bytes(int taps) { return taps == 9 ? 3 * kHaloBytes : kPlainBytes; }
+    __host__ __device__ static constexpr int b_tiles(int taps, int resident) { return resident ? taps : kBStages; }
+    static constexpr size_t total(int taps, int resident) {
+        return 1024 /* alignment slack */ + (size_t)kAStages * a_bytes(taps) + (size_t)b_tiles(taps, resident) * kBBytes +
+               256 /* barriers */;
     }
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Epilogue of one tile for one warp (32 output pixels): TMEM -> registers -> + bias (+ residual) -> ReLU ->
+// fp32 and / or bf16 (one or three planes) NHWC stores.  `taddr0` = accumulator stage address of this warp's
+// lane quarter; with planes == 3 the correction accumulator sits N_TILE columns further.
+// Epilogue of one tile for one warp (32 output pixels): TMEM -> registers -> + bias (+ residual) -> ReLU ->
+// fp32 and / or bf16 (one or three planes) NHWC stores.  `taddr0` = accumulator stage address of this warp's
+// lane quarter; with planes == 3 the correction accumulator sits N_TILE columns further.
+template <int N_TILE>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0, int n0, size_t pix, bool valid) {
+#pragma unroll 1
+    for (int j = 0; j < N_TILE / 32; ++j) {
+        uint32_t r[32];
+        const uint32_t taddr = taddr0 + (uint32_t)(j * 32);
+        tc::tmem_ld32(taddr, r);
+        tc::tmem_ld_wait();
+        if (a.planes == 3) {
+            uint32_t r2[32];
+            tc::tmem_ld32(taddr + (uint32_t)N_TILE, r2);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        }
+        if (valid) {
+            const int n = n0 + j * 32;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (a.bias ? __ldg(a.bias + n + i) : 0.0f);
+            const size_t ostride = (size_t)a.planes * a.Cout;      // channels per pixel in memory
+            if (a.residual) {
+                for (int pl = 0; pl < a.planes; ++pl) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * ostride + (size_t)pl * a.Cout + n);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 u = __ldg(rp + i);
+                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                            v[i * 8 + e * 2] += __low2float(h2);
+                            v[i * 8 + e * 2 + 1] += __high2float(h2);
+                        }
+                    }
+                }
+            }
+            if (a.relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+            if (a.out_f32) {
+                float4* op = reinterpret_cast<float4*>(a.out_f32 + pix * a.Cout + n);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+            }
+            if (a.out) {
+                for (int pl = 0; pl < a.planes; ++pl) {
+                    uint4* op = reinterpret_cast<uint4*>(a.out + pix * ostride + (size_t)pl * a.Cout + n);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                        v[2 * i] -= __low2float(h2);              // remainder goes to the next plane
+                        v[2 * i + 1] -= __high2float(h2);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) op[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+            }
+        }
+    }
 }
 
 template <int N_TILE>
@@ -70,10 +144,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     constexpr int NB = S::kBStages;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int a_bytes = a.taps == 9 ? 3 * kHaloBytes : kPlainBytes;
+    const int a_bytes = S::a_bytes(a.taps);
     unsigned char* a_smem = smem;
     unsigned char* b_smem = smem + kAStages * a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + NB * S::kBBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + S::b_tiles(a.taps, a.resident_b) * S::kBBytes);
     uint64_t* a_full = bars;                  // [kAStages]
     uint64_t* a_empty = a_full + kAStages;    // [kAStages]
     uint64_t* b_full = a_empty + kAStages;    // [NB]
@@ -127,6 +201,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (tc::elect_one()) {
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
+            if (a.resident_b) {     // every weight tile once, for the whole kernel
+                tc::mbar_expect_tx(b_full, (uint32_t)(a.taps * S::kBBytes));
+                for (int t = 0; t < a.taps; ++t) tc::tma_load_2d(b_smem + t * S::kBBytes, &tm_wgt, b_full, 0, t * a.Cout);
+            }
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 int n0, b, h0, w0;
                 decode(tile, n0, b, h0, w0);
@@ -144,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         }
                         if (++sa == kAStages) { sa = 0; pa ^= 1; }
                         // activation plane ap meets weight planes 0 .. planes-1-ap (products below 2^-24 are dropped)
-                        for (int wp = 0; wp < a.planes - ap; ++wp) {
+                        for (int wp = 0; wp < a.planes - ap && !a.resident_b; ++wp) {
                             for (int t = 0; t < a.taps; ++t) {
                                 tc::mbar_wait(b_empty + sb, pb ^ 1);
                                 tc::mbar_expect_tx(b_full + sb, (uint32_t)S::kBBytes);
@@ -162,6 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             constexpr uint32_t idesc = tc::idesc_bf16_m128(N_TILE);
             int sa = 0, sb = 0, as = 0;
             uint32_t pa = 0, pb = 0, pacc = 0;
+            if (a.resident_b) tc::mbar_wait(b_full, 0);
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 tc::mbar_wait(acc_empty + as, pacc ^ 1);
                 tc::fence_after_sync();
@@ -179,11 +258,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         const uint32_t a_addr = tc::smem_u32(a_smem + sa * a_bytes);
                         for (int wp = 0; wp < a.planes - ap; ++wp) {
                             for (int t = 0; t < a.taps; ++t) {
-                                tc::mbar_wait(b_full + sb, pb);
+                                if (!a.resident_b) tc::mbar_wait(b_full + sb, pb);
                                 tc::fence_after_sync();
                                 const int kh = a.taps == 9 ? t / 3 : 0, kw = a.taps == 9 ? t % 3 : 0;
                                 const uint32_t a_tap = a_addr + (uint32_t)(kw * kHaloBytes + kh * kTileW * 128);
-                                const uint32_t b_addr = tc::smem_u32(b_smem + sb * S::kBBytes);
+                                const uint32_t b_addr = tc::smem_u32(b_smem + (a.resident_b ? t : sb) * S::kBBytes);
 #pragma unroll
                                 for (int k = 0; k < kKC / 16; ++k) {
                                     const uint64_t da = tc::smem_desc_sw128(a_tap + k * 32, 1024);
@@ -196,8 +275,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                                         first_corr = 0;
                                     }
                                 }
-                                tc::mma_commit(b_empty + sb);
-                                if (++sb == NB) { sb = 0; pb ^= 1; }
+                                if (!a.resident_b) {
+                                    tc::mma_commit(b_empty + sb);
+                                    if (++sb == NB) { sb = 0; pb ^= 1; }
+                                }
                             }
                         }
                         tc::mma_commit(a_empty + sa);
@@ -223,67 +304,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const bool valid = h < a.H && w < a.W && (long long)pix < a.pix_limit;
             tc::mbar_wait(acc_full + as, pacc);
             tc::fence_after_sync();
-#pragma unroll 1
-            for (int j = 0; j < N_TILE / 32; ++j) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols + j * 32);
-                tc::tmem_ld32(taddr, r);
-                tc::tmem_ld_wait();
-                if (a.planes == 3) {
-                    uint32_t r2[32];
-                    tc::tmem_ld32(taddr + (uint32_t)N_TILE, r2);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
-                }
-                if (valid) {
-                    const int n = n0 + j * 32;
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (a.bias ? __ldg(a.bias + n + i) : 0.0f);
-                    const size_t ostride = (size_t)a.planes * a.Cout;      // channels per pixel in memory
-                    if (a.residual) {
-                        for (int pl = 0; pl < a.planes; ++pl) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * ostride + (size_t)pl * a.Cout + n);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 u = __ldg(rp + i);
-                                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
-                                    v[i * 8 + e * 2] += __low2float(h2);
-                                    v[i * 8 + e * 2 + 1] += __high2float(h2);
-                                }
-                            }
-                        }
-                    }
-                    if (a.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-                    }
-                    if (a.out_f32) {
-                        float4* op = reinterpret_cast<float4*>(a.out_f32 + pix * a.Cout + n);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-                    }
-                    if (a.out) {
-                        for (int pl = 0; pl < a.planes; ++pl) {
-                            uint4* op = reinterpret_cast<uint4*>(a.out + pix * ostride + (size_t)pl * a.Cout + n);
-                            uint32_t pk[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                                pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                                v[2 * i] -= __low2float(h2);              // remainder goes to the next plane
-                                v[2 * i + 1] -= __high2float(h2);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) op[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                        }
-                    }
-                }
-            }
+            epilogue_tile<N_TILE>(a, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols), n0, pix, valid);
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + as);
@@ -291,6 +312,154 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
     }
     // teardown
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, (uint32_t)(2 * acc_cols));
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_first_kernel: the first convolution of the network (conv_block1.conv1, 7 -> 64 channels, 3x3).
+// Its input has 7 channels, padded to 16 = ONE K = 16 step per tap, so the whole 3x3 x 16 filter bank
+// (9 x 2 KB per plane) stays resident in shared memory and a tile costs 9 MMAs.  Same tiling, TMA halo
+// trick (32-byte swizzle here: one pixel = one 32-byte row), accumulator staging and epilogue as
+// conv_tc_kernel; the kernel is bound by writing its 64-channel output.
+// ------------------------------------------------------------------------------------------------
+constexpr int kC1 = 16;                                        // padded input channels
+constexpr int kC1HaloBytes = (kTileH + 2) * kTileW * kC1 * 2;  // 4608: one column-shifted halo tile
+constexpr int kC1WBytes = 64 * kC1 * 2;                        // 2048: weight tile of one tap
+constexpr int kC1AStages = 4;
+
+__host__ __device__ constexpr size_t conv_first_smem(int planes) {
+    return 1024 + (size_t)planes * 9 * kC1WBytes + (size_t)kC1AStages * 3 * kC1HaloBytes + 256;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
+    constexpr int N_TILE = 64;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* w_smem = smem;                                         // [planes][9][64][16]
+    unsigned char* a_smem = w_smem + a.planes * 9 * kC1WBytes;            // [stages][3][18][8][16]
+    constexpr int a_bytes = 3 * kC1HaloBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + kC1AStages * a_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + kC1AStages;
+    uint64_t* w_full = a_empty + kC1AStages;
+    uint64_t* acc_full = w_full + 1;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tm_act);
+        tc::prefetch_tmap(&tm_wgt);
+        for (int i = 0; i < kC1AStages; ++i) {
+            tc::mbar_init(a_full + i, 1);
+            tc::mbar_init(a_empty + i, 1);
+        }
+        tc::mbar_init(w_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(acc_full + i, 1);
+            tc::mbar_init(acc_empty + i, 4);
+        }
+        tc::fence_barrier_init();
+    }
+    const int acc_cols = a.planes == 3 ? 2 * N_TILE : N_TILE;
+    if (warp == 2) tc::tmem_alloc(tmem_slot, (uint32_t)(2 * acc_cols));
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int tile, int& b, int& h0, int& w0) {
+        const int tw = tile % a.tiles_w;
+        tile /= a.tiles_w;
+        const int th = tile % a.tiles_h;
+        b = tile / a.tiles_h;
+        h0 = th * kTileH;
+        w0 = tw * kTileW;
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(w_full, (uint32_t)(a.planes * 9 * kC1WBytes));
+            for (int wp = 0; wp < a.planes; ++wp)
+                for (int t = 0; t < 9; ++t)
+                    tc::tma_load_2d(w_smem + (wp * 9 + t) * kC1WBytes, &tm_wgt, w_full, wp * kC1, t * a.Cout);
+            int sa = 0;
+            uint32_t pa = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                int b, h0, w0;
+                decode(tile, b, h0, w0);
+                for (int ap = 0; ap < a.planes; ++ap) {
+                    tc::mbar_wait(a_empty + sa, pa ^ 1);
+                    tc::mbar_expect_tx(a_full + sa, (uint32_t)a_bytes);
+                    for (int kw = 0; kw < 3; ++kw)
+                        tc::tma_load_4d(a_smem + sa * a_bytes + kw * kC1HaloBytes, &tm_act, a_full + sa, ap * kC1, w0 - 1 + kw, h0 - 1, b);
+                    if (++sa == kC1AStages) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_bf16_m128(N_TILE);
+            int sa = 0, as = 0;
+            uint32_t pa = 0, pacc = 0;
+            tc::mbar_wait(w_full, 0);
+            const uint32_t w_addr = tc::smem_u32(w_smem);
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                tc::mbar_wait(acc_empty + as, pacc ^ 1);
+                tc::fence_after_sync();
+                const uint32_t tmem_main = tmem_base + (uint32_t)(as * acc_cols);
+                const uint32_t tmem_corr = tmem_main + (uint32_t)N_TILE;
+                uint32_t first = 1, first_corr = 1;
+                for (int ap = 0; ap < a.planes; ++ap) {
+                    tc::mbar_wait(a_full + sa, pa);
+                    tc::fence_after_sync();
+                    const uint32_t a_addr = tc::smem_u32(a_smem + sa * a_bytes);
+                    for (int wp = 0; wp < a.planes - ap; ++wp) {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int kh = t / 3, kw = t % 3;
+                            const uint64_t da = tc::smem_desc_sw32(a_addr + (uint32_t)(kw * kC1HaloBytes + kh * kTileW * kC1 * 2), 256);
+                            const uint64_t db = tc::smem_desc_sw32(w_addr + (uint32_t)((wp * 9 + t) * kC1WBytes), 256);
+                            if (ap == 0 && wp == 0) {
+                                tc::mma_bf16(tmem_main, da, db, idesc, first ? 0u : 1u);
+                                first = 0;
+                            } else {
+                                tc::mma_bf16(tmem_corr, da, db, idesc, first_corr ? 0u : 1u);
+                                first_corr = 0;
+                            }
+                        }
+                    }
+                    tc::mma_commit(a_empty + sa);
+                    if (++sa == kC1AStages) { sa = 0; pa ^= 1; }
+                }
+                tc::mma_commit(acc_full + as);
+                if (++as == 2) { as = 0; pacc ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int hl = row / kTileW, wl = row % kTileW;
+        int as = 0;
+        uint32_t pacc = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            int b, h0, w0;
+            decode(tile, b, h0, w0);
+            const int h = h0 + hl, w = w0 + wl;
+            const size_t pix = ((size_t)b * a.H + h) * a.W + w;
+            const bool valid = h < a.H && w < a.W;
+            tc::mbar_wait(acc_full + as, pacc);
+            tc::fence_after_sync();
+            epilogue_tile<N_TILE>(a, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols), 0, pix, valid);
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + as);
+            if (++as == 2) { as = 0; pacc ^= 1; }
+        }
+    }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 2) tc::tmem_dealloc(tmem_base, (uint32_t)(2 * acc_cols));

@@ -126,6 +126,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t start, uint32_t sbo
     return d;
 }
 
+// Same for 32-byte swizzle: rows of 32 bytes (16 bf16 = one K = 16 step), 8-row groups of 256 bytes.
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t start, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((start >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                                   // SWIZZLE_32B
+    return d;
+}
+
 // Instruction descriptor of kind::f16: bf16 x bf16 -> fp32, both operands K-major, M = 128.
 __host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);

@@ -42,7 +42,7 @@ def main():
             return out
         setattr(ops, name, timed)
 
-    for name in ('pack_input', 'conv2d', 'avgpool2', 'freq_mean', 'gemm', 'gru_layer', 'head_finish'):
+    for name in ('pack_input', 'conv_first', 'conv2d', 'avgpool2', 'freq_mean', 'gemm', 'gru_layer', 'head_finish'):
         wrap(name)
     for rep in range(args.reps):
         records.clear()
@@ -53,7 +53,10 @@ def main():
         ms = s.elapsed_time(e)
         total += ms
         flops = 0.0
-        if name == 'conv2d':
+        if name == 'conv_first':
+            B, H, W, _ = shape
+            flops = 2.0 * B * H * W * 7 * 64 * 9
+        elif name == 'conv2d':
             B, H, W, Cin = shape
             taps, Cout, _ = wshape
             flops = 2.0 * B * H * W * Cin * Cout * taps

@@ -139,3 +139,20 @@ def test_gemm_pool_mean_gru_bf16x3(ops):
     assert rel_err(p, F.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)) < 1e-6
     m = ops.merge_planes(ops.freq_mean(ops.split_planes(x, 3).cuda(), planes=3).cpu(), 3)
     assert rel_err(m[:8], x.mean(dim=2).reshape(8, 64)) < 1e-6
+
+
+@pytest.mark.parametrize('B,H,W,planes', [(1, 16, 8, 1), (2, 37, 21, 1), (1, 40, 200, 1), (1, 20, 13, 3)])
+def test_conv_first(ops, B, H, W, planes):
+    g = torch.Generator().manual_seed(B + H + W)
+    x = torch.randn(B, 7, H, W, generator=g)
+    w = torch.randn(64, 7, 3, 3, generator=g) / 63 ** 0.5
+    bias = torch.randn(64, generator=g)
+    if planes == 1:
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    ref = torch.relu(F.conv2d(x.double(), w.double(), padding=1) + bias.double()[None, :, None, None]).permute(0, 2, 3, 1)
+    xp = ops.pack_input(x.cuda(), c_pad=16, planes=planes)
+    assert tuple(xp.shape) == (B, H, W, 16 * planes)
+    wp = torch.zeros(9, 64, 16)
+    wp[:, :, :7] = w.permute(2, 3, 0, 1).reshape(9, 64, 7)
+    out = ops.conv_first(xp, ops.split_planes(wp, planes).cuda(), bias.cuda(), relu=True, planes=planes).cpu()
+    assert rel_err(ops.merge_planes(out, planes), ref) < (1e-2 if planes == 1 else 1e-5)
