@@ -69,9 +69,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // Epilogue of one tile for one warp (32 output pixels): TMEM -> registers -> + bias (+ residual) -> ReLU ->
 // fp32 and / or bf16 (one or three planes) NHWC stores.  `taddr0` = accumulator stage address of this warp's
 // lane quarter; with planes == 3 the correction accumulator sits N_TILE columns further.
-// Epilogue of one tile for one warp (32 output pixels): TMEM -> registers -> + bias (+ residual) -> ReLU ->
-// fp32 and / or bf16 (one or three planes) NHWC stores.  `taddr0` = accumulator stage address of this warp's
-// lane quarter; with planes == 3 the correction accumulator sits N_TILE columns further.
 template <int N_TILE>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0, int n0, size_t pix, bool valid) {
 #pragma unroll 1
@@ -241,6 +238,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             int sa = 0, sb = 0, as = 0;
             uint32_t pa = 0, pb = 0, pacc = 0;
             if (a.resident_b) tc::mbar_wait(b_full, 0);
+            // One thread issues every MMA of the CTA, so its instruction count per MMA is on the critical path:
+            // descriptors are a constant (layout, SBO, version) plus the 16-byte-granular start address, and the
+            // tap / K-step offsets are compile-time constants added to the stage's base descriptor.
+            const uint64_t desc_fixed = tc::smem_desc_sw128(0, 1024);
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 tc::mbar_wait(acc_empty + as, pacc ^ 1);
                 tc::fence_after_sync();
@@ -250,36 +251,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 // epilogue adds the two.
                 const uint32_t tmem_main = tmem_base + (uint32_t)(as * acc_cols);
                 const uint32_t tmem_corr = tmem_main + (uint32_t)N_TILE;
-                uint32_t first_corr = 1;
-                uint32_t first = 1;
+                uint32_t acc_main = 0, acc_corr = 0;      // 0 until the first MMA into that accumulator
                 for (int c = 0; c < n_chunks; ++c) {
                     for (int ap = 0; ap < a.planes; ++ap) {
                         tc::mbar_wait(a_full + sa, pa);
-                        const uint32_t a_addr = tc::smem_u32(a_smem + sa * a_bytes);
+                        const uint64_t a_desc = desc_fixed + (uint64_t)(tc::smem_u32(a_smem + sa * a_bytes) >> 4);
                         for (int wp = 0; wp < a.planes - ap; ++wp) {
-                            for (int t = 0; t < a.taps; ++t) {
+                            const bool main_acc = ap == 0 && wp == 0;
+                            const uint32_t tmem_d = main_acc ? tmem_main : tmem_corr;
+                            uint32_t accumulate = main_acc ? acc_main : acc_corr;
+                            auto issue_tap = [&](int tap_off16) {     // tap_off16: A offset of the tap in 16-byte units
                                 if (!a.resident_b) tc::mbar_wait(b_full + sb, pb);
                                 tc::fence_after_sync();
-                                const int kh = a.taps == 9 ? t / 3 : 0, kw = a.taps == 9 ? t % 3 : 0;
-                                const uint32_t a_tap = a_addr + (uint32_t)(kw * kHaloBytes + kh * kTileW * 128);
-                                const uint32_t b_addr = tc::smem_u32(b_smem + (a.resident_b ? t : sb) * S::kBBytes);
+                                const uint64_t b_desc = desc_fixed + (uint64_t)(tc::smem_u32(b_smem + sb * S::kBBytes) >> 4);
 #pragma unroll
                                 for (int k = 0; k < kKC / 16; ++k) {
-                                    const uint64_t da = tc::smem_desc_sw128(a_tap + k * 32, 1024);
-                                    const uint64_t db = tc::smem_desc_sw128(b_addr + k * 32, 1024);
-                                    if (ap == 0 && wp == 0) {
-                                        tc::mma_bf16(tmem_main, da, db, idesc, first ? 0u : 1u);
-                                        first = 0;
-                                    } else {
-                                        tc::mma_bf16(tmem_corr, da, db, idesc, first_corr ? 0u : 1u);
-                                        first_corr = 0;
-                                    }
+                                    tc::mma_bf16(tmem_d, a_desc + (uint64_t)(tap_off16 + 2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+                                    accumulate = 1;
                                 }
                                 if (!a.resident_b) {
                                     tc::mma_commit(b_empty + sb);
                                     if (++sb == NB) { sb = 0; pb ^= 1; }
+                                } else {
+                                    ++sb;                             // resident: sb is just the tap index
                                 }
+                            };
+                            if (a.taps == 9) {
+                                if (a.resident_b) sb = 0;
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) issue_tap(((t % 3) * kHaloBytes + (t / 3) * kTileW * 128) >> 4);
+                            } else {
+                                issue_tap(0);
                             }
+                            if (main_acc) acc_main = 1; else acc_corr = 1;
                         }
                         tc::mma_commit(a_empty + sa);
                         if (++sa == kAStages) { sa = 0; pa ^= 1; }
@@ -406,31 +410,30 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
             int sa = 0, as = 0;
             uint32_t pa = 0, pacc = 0;
             tc::mbar_wait(w_full, 0);
-            const uint32_t w_addr = tc::smem_u32(w_smem);
+            const uint64_t desc_fixed = tc::smem_desc_sw32(0, 256);
+            const uint64_t w_desc = desc_fixed + (uint64_t)(tc::smem_u32(w_smem) >> 4);
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 tc::mbar_wait(acc_empty + as, pacc ^ 1);
                 tc::fence_after_sync();
                 const uint32_t tmem_main = tmem_base + (uint32_t)(as * acc_cols);
                 const uint32_t tmem_corr = tmem_main + (uint32_t)N_TILE;
-                uint32_t first = 1, first_corr = 1;
+                uint32_t acc_main = 0, acc_corr = 0;
                 for (int ap = 0; ap < a.planes; ++ap) {
                     tc::mbar_wait(a_full + sa, pa);
                     tc::fence_after_sync();
-                    const uint32_t a_addr = tc::smem_u32(a_smem + sa * a_bytes);
+                    const uint64_t a_desc = desc_fixed + (uint64_t)(tc::smem_u32(a_smem + sa * a_bytes) >> 4);
                     for (int wp = 0; wp < a.planes - ap; ++wp) {
+                        const bool main_acc = ap == 0 && wp == 0;
+                        const uint32_t tmem_d = main_acc ? tmem_main : tmem_corr;
+                        uint32_t accumulate = main_acc ? acc_main : acc_corr;
+                        const uint64_t wp_desc = w_desc + (uint64_t)((wp * 9 * kC1WBytes) >> 4);
 #pragma unroll
                         for (int t = 0; t < 9; ++t) {
-                            const int kh = t / 3, kw = t % 3;
-                            const uint64_t da = tc::smem_desc_sw32(a_addr + (uint32_t)(kw * kC1HaloBytes + kh * kTileW * kC1 * 2), 256);
-                            const uint64_t db = tc::smem_desc_sw32(w_addr + (uint32_t)((wp * 9 + t) * kC1WBytes), 256);
-                            if (ap == 0 && wp == 0) {
-                                tc::mma_bf16(tmem_main, da, db, idesc, first ? 0u : 1u);
-                                first = 0;
-                            } else {
-                                tc::mma_bf16(tmem_corr, da, db, idesc, first_corr ? 0u : 1u);
-                                first_corr = 0;
-                            }
+                            tc::mma_bf16(tmem_d, a_desc + (uint64_t)(((t % 3) * kC1HaloBytes + (t / 3) * kTileW * kC1 * 2) >> 4),
+                                         wp_desc + (uint64_t)((t * kC1WBytes) >> 4), idesc, accumulate);
+                            accumulate = 1;
                         }
+                        if (main_acc) acc_main = 1; else acc_corr = 1;
                     }
                     tc::mma_commit(a_empty + sa);
                     if (++sa == kC1AStages) { sa = 0; pa ^= 1; }

@@ -24,10 +24,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def disassemble(so_path, kernel_substr):
     tmp = tempfile.mkdtemp(prefix='cub_')
     subprocess.run(['cuobjdump', '-xelf', 'all', so_path], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if 'sm_100' in f][0]
-    txt = subprocess.run(['nvdisasm', '-gi', '-c', os.path.join(tmp, cubin)], check=True, stdout=subprocess.PIPE,
-                         stderr=subprocess.DEVNULL).stdout.decode()
-    lines = txt.split('\n')
+    lines = []
+    for cubin in sorted(f for f in os.listdir(tmp) if 'sm_100' in f):
+        txt = subprocess.run(['nvdisasm', '-gi', '-c', os.path.join(tmp, cubin)], check=True, stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL).stdout.decode()
+        lines += txt.split('\n')
     out = {}          # offset -> (inner (file, line), outer (file, line), sass)
     in_kernel = False
     pending = []
