@@ -128,6 +128,10 @@ int salsa_extract_host(const salsa_params_t *p, const float *audio_host, float *
 int salsa_lite_extract_host(const salsa_params_t *p, int32_t cutoff_bin, int32_t mode,
                             const float *audio_host, float *feature_host, int32_t clips_per_chunk);
 
+/* The host-buffer entry points keep their streams and device staging buffers between calls (per host thread);
+ * this frees them. */
+int salsa_host_release(void);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 uint64_t salsa_launch_count(int reset);

@@ -46,16 +46,25 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_
 
 // tuning knobs (crnn_set_option): -1 = automatic
 static int g_opt_resident = -1;
+static int g_opt_tma_store = -1;
+
+// output tensor map of the TMA-store epilogue: bf16 NHWC [B][H][W][Cout], box = one 16 x 8 tile x 64 channels
+static int make_out_tmap(CUtensorMap* m, const void* out, int B, int H, int W, int Cout) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+    return make_tmap(m, out, 4, dims, str, box);
+}
 
 template <int N_TILE>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tw, const ConvArgs& a, cudaStream_t st) {
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const ConvArgs& a, cudaStream_t st) {
     const size_t smem = ConvSmem<N_TILE>::total(a.taps, a.resident_b);
     SALSA_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(a.n_tiles, sms);
-    conv_tc_kernel<N_TILE><<<grid, kConvThreads, smem, st>>>(ta, tw, a);
+    conv_tc_kernel<N_TILE><<<grid, kConvThreads, smem, st>>>(ta, tw, to, a);
     count_launch();
     return check_cuda(cudaGetLastError(), "conv_tc_kernel");
 }
@@ -98,14 +107,20 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
     a.n_tiles = B * a.tiles_h * a.tiles_w * (Cout / n_tile);
     a.relu = relu;
     a.resident_b = resident;
+    a.tma_store = (planes == 1 && out && !out_f32) && (g_opt_tma_store < 0 ? 1 : g_opt_tma_store);
     a.pix_limit = pix_limit;
     a.bias = bias;
     a.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
     a.out_f32 = out_f32;
-    if (n_tile == 256) return launch_conv<256>(ta, tw, a, st);
-    if (n_tile == 128) return launch_conv<128>(ta, tw, a, st);
-    return launch_conv<64>(ta, tw, a, st);
+    CUtensorMap to = ta;
+    if (a.tma_store) {
+        int rc = make_out_tmap(&to, out, B, H, W, Cout);
+        if (rc) return rc;
+    }
+    if (n_tile == 256) return launch_conv<256>(ta, tw, to, a, st);
+    if (n_tile == 128) return launch_conv<128>(ta, tw, to, a, st);
+    return launch_conv<64>(ta, tw, to, a, st);
 }
 
 // first convolution: x NHWC bf16 [B][H][W][planes*16], w [9][64][planes*16]
@@ -138,6 +153,7 @@ static int conv_first(const void* x, const void* w, const float* bias, void* out
     a.n_tiles = B * a.tiles_h * a.tiles_w;
     a.relu = relu;
     a.resident_b = 1;
+    a.tma_store = planes == 1 && (g_opt_tma_store < 0 ? 1 : g_opt_tma_store);
     a.pix_limit = (long long)B * H * W;
     a.bias = bias;
     a.residual = nullptr;
@@ -148,7 +164,12 @@ static int conv_first(const void* x, const void* w, const float* bias, void* out
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    conv_first_kernel<<<std::min(a.n_tiles, sms), kConvThreads, smem, st>>>(ta, tw, a);
+    CUtensorMap to = ta;
+    if (a.tma_store) {
+        int rc = make_out_tmap(&to, out, B, H, W, 64);
+        if (rc) return rc;
+    }
+    conv_first_kernel<<<std::min(a.n_tiles, sms), kConvThreads, smem, st>>>(ta, tw, to, a);
     count_launch();
     return check_cuda(cudaGetLastError(), "conv_first_kernel");
 }
@@ -191,6 +212,7 @@ int crnn_gemm(const void* a, const void* w, const float* bias, void* out, float*
 int crnn_set_option(const char* name, int32_t value) {
     const std::string n = name ? name : "";
     if (n == "resident_b") g_opt_resident = value;
+    else if (n == "tma_store") g_opt_tma_store = value;
     else return fail(SALSA_EINVAL, "unknown option " + n);
     return SALSA_OK;
 }

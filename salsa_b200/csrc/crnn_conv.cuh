@@ -41,6 +41,7 @@ struct ConvArgs {
     int tiles_w, tiles_h;      // spatial tiles per image
     int n_tiles;               // B * tiles_h * tiles_w * (Cout / N_TILE)
     int relu;
+    int tma_store;             // bf16 output leaves through a swizzled staging tile and TMA stores (planes == 1)
     int resident_b;            // all weight tiles stay in shared memory for the whole kernel (Cin = Cout = 64)
     long long pix_limit;       // pixels (rows of a GEMM) beyond this index are not written
     const float* bias;                 // [Cout] or null
@@ -55,9 +56,12 @@ struct ConvSmem {
     static constexpr int kBBytes = N_TILE * 128;
     __host__ __device__ static constexpr int a_bytes(int taps) { return taps == 9 ? 3 * kHaloBytes : kPlainBytes; }
     __host__ __device__ static constexpr int b_tiles(int taps, int resident) { return resident ? taps : kBStages; }
+    static constexpr int kStgBufs = N_TILE >= 256 ? 1 : 2;          // output staging tiles (128 px x 64 ch bf16)
+    static constexpr int kStgBytes = 128 * 128;
+    static constexpr int kBiasBytes = 2048;                          // up to 512 output channels
     static constexpr size_t total(int taps, int resident) {
         return 1024 /* alignment slack */ + (size_t)kAStages * a_bytes(taps) + (size_t)b_tiles(taps, resident) * kBBytes +
-               256 /* barriers */;
+               (size_t)kStgBufs * kStgBytes + kBiasBytes + 256 /* barriers */;
     }
 };
 
@@ -134,9 +138,75 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0
     }
 }
 
+// Epilogue of one tile through shared memory and TMA (bf16 output, planes == 1): per 64-channel group the four
+// epilogue warps convert their accumulator rows (+ bias from shared memory, + residual, ReLU) to bf16 and write
+// them into a 128 x 64 staging tile in the 128-byte-swizzled layout of the output tensor map; one thread then
+// issues a TMA store, which writes whole 128-byte lines and clips the tile at the image border.  Two staging
+// tiles alternate (one for N_TILE = 256) so the store of group g overlaps the conversion of group g + 1.
+//   `row`      tile row = output pixel of this thread (0..127), `stg_count` running group counter (selects the tile)
+template <int N_TILE, int STG_BUFS>
+__device__ __forceinline__ void epilogue_tile_tma(const ConvArgs& a, const CUtensorMap* tm_out, unsigned char* stg, const float* bias_s,
+                                                  uint32_t taddr0, int n0, int b, int h0, int w0, size_t pix, bool valid, int row,
+                                                  uint32_t& stg_count) {
+    const bool issuer = threadIdx.x == 128;
+#pragma unroll 1
+    for (int g = 0; g < N_TILE / 64; ++g) {
+        unsigned char* tile = stg + (stg_count % STG_BUFS) * (128 * 128);
+        tc::named_barrier(1, 128);                      // the issuer has waited for the store that last read `tile`
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tc::tmem_ld32(taddr0 + (uint32_t)(g * 64 + half * 32), r);
+            const int n = n0 + g * 64 + half * 32;
+            uint4 res[4];
+            if (a.residual && valid) {
+                const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.Cout + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
+            }
+            tc::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (bias_s ? bias_s[n + i] : (a.bias ? __ldg(a.bias + n + i) : 0.0f));
+            if (a.residual && valid) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t w4[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                        v[i * 8 + e * 2] += __low2float(h2);
+                        v[i * 8 + e * 2 + 1] += __high2float(h2);
+                    }
+                }
+            }
+            if (a.relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 q4 = make_uint4(pack_bf16(v[i * 8], v[i * 8 + 1]), pack_bf16(v[i * 8 + 2], v[i * 8 + 3]),
+                                            pack_bf16(v[i * 8 + 4], v[i * 8 + 5]), pack_bf16(v[i * 8 + 6], v[i * 8 + 7]));
+                const int chunk = (half * 4 + i) ^ (row & 7);                 // 128-byte swizzle: 16-byte chunk ^ (row mod 8)
+                *reinterpret_cast<uint4*>(tile + row * 128 + chunk * 16) = q4;
+            }
+        }
+        tc::fence_proxy_async();                        // generic-proxy writes -> visible to the TMA engine
+        tc::named_barrier(2, 128);
+        if (issuer) {
+            tc::tma_store_4d(tm_out, tile, n0 + g * 64, w0, h0, b);
+            tc::tma_store_commit();
+            tc::tma_store_wait_read<STG_BUFS - 1>();
+        }
+        ++stg_count;
+    }
+}
+
 template <int N_TILE>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wgt,
+               const __grid_constant__ CUtensorMap tm_out, ConvArgs a) {
     using S = ConvSmem<N_TILE>;
     constexpr int NB = S::kBStages;
     extern __shared__ unsigned char smem_raw[];
@@ -144,7 +214,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int a_bytes = S::a_bytes(a.taps);
     unsigned char* a_smem = smem;
     unsigned char* b_smem = smem + kAStages * a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + S::b_tiles(a.taps, a.resident_b) * S::kBBytes);
+    unsigned char* stg_smem = b_smem + S::b_tiles(a.taps, a.resident_b) * S::kBBytes;      // [kStgBufs][128][128 B]
+    float* bias_s = reinterpret_cast<float*>(stg_smem + S::kStgBufs * S::kStgBytes);        // [Cout]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_smem + S::kStgBufs * S::kStgBytes + S::kBiasBytes);
     uint64_t* a_full = bars;                  // [kAStages]
     uint64_t* a_empty = a_full + kAStages;    // [kAStages]
     uint64_t* b_full = a_empty + kAStages;    // [NB]
@@ -154,9 +226,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a.Cout * (int)sizeof(float) > S::kBiasBytes) bias_s = nullptr;      // wide GEMMs read the bias from global memory
+    if (a.tma_store && bias_s)
+        for (int i = threadIdx.x; i < a.Cout; i += kConvThreads) bias_s[i] = a.bias ? a.bias[i] : 0.0f;
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tm_act);
         tc::prefetch_tmap(&tm_wgt);
+        if (a.tma_store) tc::prefetch_tmap(&tm_out);
         for (int i = 0; i < kAStages; ++i) {
             tc::mbar_init(a_full + i, 1);
             tc::mbar_init(a_empty + i, 1);
@@ -299,7 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         const int row = q * 32 + lane;           // tile row = output pixel
         const int hl = row / kTileW, wl = row % kTileW;
         int as = 0;
-        uint32_t pacc = 0;
+        uint32_t pacc = 0, stg_count = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             int n0, b, h0, w0;
             decode(tile, n0, b, h0, w0);
@@ -308,12 +384,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const bool valid = h < a.H && w < a.W && (long long)pix < a.pix_limit;
             tc::mbar_wait(acc_full + as, pacc);
             tc::fence_after_sync();
-            epilogue_tile<N_TILE>(a, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols), n0, pix, valid);
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
+            if (a.tma_store)
+                epilogue_tile_tma<N_TILE, S::kStgBufs>(a, &tm_out, stg_smem, bias_s, taddr0, n0, b, h0, w0, pix, valid, row, stg_count);
+            else
+                epilogue_tile<N_TILE>(a, taddr0, n0, pix, valid);
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + as);
             if (++as == 2) { as = 0; pacc ^= 1; }
         }
+        if (a.tma_store && threadIdx.x == 128) tc::tma_store_wait_read<0>();     // staging tiles must outlive their stores
     }
     // teardown
     tc::fence_before_sync();
@@ -334,18 +415,23 @@ constexpr int kC1WBytes = 64 * kC1 * 2;                        // 2048: weight t
 constexpr int kC1AStages = 4;
 
 __host__ __device__ constexpr size_t conv_first_smem(int planes) {
-    return 1024 + (size_t)planes * 9 * kC1WBytes + (size_t)kC1AStages * 3 * kC1HaloBytes + 256;
+    return 1024 + (size_t)planes * 9 * kC1WBytes + (size_t)kC1AStages * 3 * kC1HaloBytes + 1024 + 2 * 128 * 128 /* staging */ +
+           256 /* bias */ + 256;
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wgt, ConvArgs a) {
+conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wgt,
+                  const __grid_constant__ CUtensorMap tm_out, ConvArgs a) {
     constexpr int N_TILE = 64;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* w_smem = smem;                                         // [planes][9][64][16]
     unsigned char* a_smem = w_smem + a.planes * 9 * kC1WBytes;            // [stages][3][18][8][16]
     constexpr int a_bytes = 3 * kC1HaloBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + kC1AStages * a_bytes);
+    // the A ring ends at a multiple of 512 bytes; the staging tiles need 1024-byte alignment for the 128-byte swizzle
+    unsigned char* stg_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(a_smem + kC1AStages * a_bytes) + 1023) & ~(uintptr_t)1023);
+    float* bias_s = reinterpret_cast<float*>(stg_smem + 2 * 128 * 128);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bias_s) + 256);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + kC1AStages;
     uint64_t* w_full = a_empty + kC1AStages;
@@ -354,9 +440,11 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) bias_s[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tm_act);
         tc::prefetch_tmap(&tm_wgt);
+        if (a.tma_store) tc::prefetch_tmap(&tm_out);
         for (int i = 0; i < kC1AStages; ++i) {
             tc::mbar_init(a_full + i, 1);
             tc::mbar_init(a_empty + i, 1);
@@ -447,7 +535,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
         const int row = q * 32 + lane;
         const int hl = row / kTileW, wl = row % kTileW;
         int as = 0;
-        uint32_t pacc = 0;
+        uint32_t pacc = 0, stg_count = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             int b, h0, w0;
             decode(tile, b, h0, w0);
@@ -456,12 +544,17 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
             const bool valid = h < a.H && w < a.W;
             tc::mbar_wait(acc_full + as, pacc);
             tc::fence_after_sync();
-            epilogue_tile<N_TILE>(a, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols), 0, pix, valid);
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
+            if (a.tma_store)
+                epilogue_tile_tma<N_TILE, 2>(a, &tm_out, stg_smem, bias_s, taddr0, 0, b, h0, w0, pix, valid, row, stg_count);
+            else
+                epilogue_tile<N_TILE>(a, taddr0, 0, pix, valid);
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + as);
             if (++as == 2) { as = 0; pacc ^= 1; }
         }
+        if (a.tma_store && threadIdx.x == 128) tc::tma_store_wait_read<0>();
     }
     tc::fence_before_sync();
     __syncthreads();

@@ -518,26 +518,79 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
 // host-buffer variants: 3-stage pipeline over chunks of clips (H2D | kernels | D2H)
 // ---------------------------------------------------------------------------------------------
 namespace {
+constexpr int kPipeBufs = 3;
+
+// Streams, events and device staging buffers of the host-buffer entry points.  Cached per host thread
+// and grown on demand: allocating them per call cost about 10 % of a 120-clip call.
 struct HostPipeline {
+    int device = -1;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
-    cudaEvent_t in_done[2] = {nullptr, nullptr}, run_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
-    float* d_audio[2] = {nullptr, nullptr};
-    float* d_feat[2] = {nullptr, nullptr};
+    cudaEvent_t in_done[kPipeBufs] = {}, run_done[kPipeBufs] = {}, out_done[kPipeBufs] = {};
+    float* d_audio[kPipeBufs] = {};
+    float* d_feat[kPipeBufs] = {};
     void* d_work = nullptr;
-    ~HostPipeline() {
-        for (int i = 0; i < 2; ++i) {
+    size_t audio_bytes = 0, feat_bytes = 0, work_bytes = 0;
+
+    void release() {
+        for (int i = 0; i < kPipeBufs; ++i) {
             if (d_audio[i]) cudaFree(d_audio[i]);
             if (d_feat[i]) cudaFree(d_feat[i]);
             if (in_done[i]) cudaEventDestroy(in_done[i]);
             if (run_done[i]) cudaEventDestroy(run_done[i]);
             if (out_done[i]) cudaEventDestroy(out_done[i]);
+            d_audio[i] = d_feat[i] = nullptr;
+            in_done[i] = run_done[i] = out_done[i] = nullptr;
         }
         if (d_work) cudaFree(d_work);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_run) cudaStreamDestroy(s_run);
         if (s_out) cudaStreamDestroy(s_out);
+        d_work = nullptr;
+        s_in = s_run = s_out = nullptr;
+        audio_bytes = feat_bytes = work_bytes = 0;
+        device = -1;
+    }
+    int ensure(size_t ab, size_t fb, size_t wb) {
+        int dev = 0;
+        SALSA_CUDA(cudaGetDevice(&dev));
+        if (dev != device) {
+            release();
+            device = dev;
+            SALSA_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+            SALSA_CUDA(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+            SALSA_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+            for (int i = 0; i < kPipeBufs; ++i) {
+                SALSA_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+                SALSA_CUDA(cudaEventCreateWithFlags(&run_done[i], cudaEventDisableTiming));
+                SALSA_CUDA(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+            }
+        }
+        if (ab > audio_bytes) {
+            for (int i = 0; i < kPipeBufs; ++i) {
+                if (d_audio[i]) cudaFree(d_audio[i]);
+                d_audio[i] = nullptr;
+                SALSA_CUDA(cudaMalloc((void**)&d_audio[i], ab));
+            }
+            audio_bytes = ab;
+        }
+        if (fb > feat_bytes) {
+            for (int i = 0; i < kPipeBufs; ++i) {
+                if (d_feat[i]) cudaFree(d_feat[i]);
+                d_feat[i] = nullptr;
+                SALSA_CUDA(cudaMalloc((void**)&d_feat[i], fb));
+            }
+            feat_bytes = fb;
+        }
+        if (wb > work_bytes) {
+            if (d_work) cudaFree(d_work);
+            d_work = nullptr;
+            SALSA_CUDA(cudaMalloc(&d_work, wb));
+            work_bytes = wb;
+        }
+        return SALSA_OK;
     }
 };
+thread_local HostPipeline t_pipeline;
 
 template <typename Run>
 int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_t work_bytes, const float* audio_host,
@@ -546,26 +599,17 @@ int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_
     if (clips_per_chunk <= 0) clips_per_chunk = 16;
     clips_per_chunk = std::min(clips_per_chunk, p->n_clips);
     const size_t audio_elems = (size_t)p->n_chans * p->n_samples;
-    HostPipeline hp;
-    SALSA_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
-    SALSA_CUDA(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
-    SALSA_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        SALSA_CUDA(cudaEventCreateWithFlags(&hp.in_done[i], cudaEventDisableTiming));
-        SALSA_CUDA(cudaEventCreateWithFlags(&hp.run_done[i], cudaEventDisableTiming));
-        SALSA_CUDA(cudaEventCreateWithFlags(&hp.out_done[i], cudaEventDisableTiming));
-        SALSA_CUDA(cudaMalloc((void**)&hp.d_audio[i], clips_per_chunk * audio_elems * sizeof(float)));
-        SALSA_CUDA(cudaMalloc((void**)&hp.d_feat[i], clips_per_chunk * feat_elems_per_clip * sizeof(float)));
-    }
-    if (work_bytes) SALSA_CUDA(cudaMalloc(&hp.d_work, work_bytes));
+    HostPipeline& hp = t_pipeline;
+    int rc0 = hp.ensure(clips_per_chunk * audio_elems * sizeof(float), clips_per_chunk * feat_elems_per_clip * sizeof(float), work_bytes);
+    if (rc0) return rc0;
     const int n_chunks = (p->n_clips + clips_per_chunk - 1) / clips_per_chunk;
     for (int c = 0; c < n_chunks; ++c) {
-        const int buf = c & 1;
+        const int buf = c % kPipeBufs;
         const int first = c * clips_per_chunk;
         const int n = std::min(clips_per_chunk, p->n_clips - first);
-        // the audio buffer is free once the kernels of chunk c-2 are done, the feature buffer once its
-        // copy-out is done
-        if (c >= 2) {
+        // the audio buffer is free once the kernels of chunk c - kPipeBufs are done, the feature buffer once
+        // its copy-out is done (events of a previous call have completed: every call ends synchronised)
+        if (c >= kPipeBufs) {
             SALSA_CUDA(cudaStreamWaitEvent(hp.s_in, hp.run_done[buf], 0));
             SALSA_CUDA(cudaStreamWaitEvent(hp.s_run, hp.out_done[buf], 0));
         }
@@ -575,7 +619,7 @@ int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_
         SALSA_CUDA(cudaStreamWaitEvent(hp.s_run, hp.in_done[buf], 0));
         salsa_params_t pc = *p;
         pc.n_clips = n;
-        int rc = run(&pc, hp.d_audio[buf], hp.d_feat[buf], hp.d_work, work_bytes, hp.s_run);
+        int rc = run(&pc, hp.d_audio[buf], hp.d_feat[buf], hp.d_work, hp.work_bytes, hp.s_run);
         if (rc) return rc;
         SALSA_CUDA(cudaEventRecord(hp.run_done[buf], hp.s_run));
         SALSA_CUDA(cudaStreamWaitEvent(hp.s_out, hp.run_done[buf], 0));
@@ -585,6 +629,7 @@ int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_
     }
     SALSA_CUDA(cudaStreamSynchronize(hp.s_out));
     SALSA_CUDA(cudaStreamSynchronize(hp.s_run));
+    SALSA_CUDA(cudaStreamSynchronize(hp.s_in));
     return SALSA_OK;
 }
 }  // namespace
@@ -605,6 +650,11 @@ int salsa_extract_host(const salsa_params_t* p, const float* audio_host, float* 
                              [](const salsa_params_t* q, const float* a, float* f, void* w, size_t wb, cudaStream_t s) {
                                  return salsa_extract(q, a, f, w, wb, (void*)s);
                              });
+}
+
+int salsa_host_release(void) {
+    t_pipeline.release();
+    return SALSA_OK;
 }
 
 int salsa_lite_extract_host(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode, const float* audio_host,
