@@ -232,8 +232,10 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world, valid_frac):
     cfg = {
-        'workload': 'SALSA {} batch: {} synthetic 4-ch 24 kHz 60 s clips per GPU, n_fft=512 hop=300 '
-                    '(BASELINE.json configs[1])'.format(args.format.upper(), args.clips),
+        'workload': '{} {} batch: {} synthetic 4-ch 24 kHz 60 s clips per GPU, n_fft=512 hop=300 '
+                    '(BASELINE.json configs[{}])'.format('SALSA-Lite' if getattr(args, 'feature', 'salsa') == 'salsa_lite' else 'SALSA',
+                                                         args.format.upper(), args.clips,
+                                                         2 if getattr(args, 'feature', 'salsa') == 'salsa_lite' else 1),
         'clips_per_gpu': args.clips, 'clips_total': args.clips * world, 'audio_format': args.format,
         'stft_precision': args.stft_precision,
         'l2_policy': 'inputs larger than L2 ({:.1f} GB audio per GPU per step)'.format(
@@ -293,22 +295,41 @@ def bench_crnn(args, torch, dist, feat, rank, world, dev, peaks):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
     value = B * world / (ms / 1e3)
-    # end to end: pinned host features in, host logits out
-    nb = min(B, 8)
+    # end to end: pinned host features in, host logits out; the copy of step i+1 runs on a second stream while
+    # step i computes (two device input buffers)
+    nb = min(B, 16)
     h_x = torch.empty((nb,) + tuple(x.shape[1:]), dtype=torch.float32, pin_memory=True)
     h_x.copy_(x[:nb])
-    d_x = torch.empty_like(x[:nb])
+    d_x = [torch.empty_like(x[:nb]) for _ in range(2)]
     h_out = {k: torch.empty(v[:nb].shape, dtype=torch.float32, pin_memory=True) for k, v in out.items()}
-    d_x.copy_(h_x, non_blocking=True)
-    model.forward(d_x, n_frames=T)
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])
+            d_x[i & 1].copy_(h_x, non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    for e in consumed:
+        e.record()
+    upload(0)
+    torch.cuda.current_stream().wait_event(ready[0])
+    model.forward(d_x[0], n_frames=T)
+    consumed[0].record()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        d_x.copy_(h_x, non_blocking=True)
-        o = model.forward(d_x, n_frames=T)
+    upload(0)
+    for i in range(args.e2e_steps):
+        if i + 1 < args.e2e_steps:
+            upload(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        o = model.forward(d_x[i & 1], n_frames=T)
+        consumed[i & 1].record()
         for k in o:
             h_out[k].copy_(o[k], non_blocking=True)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -362,6 +383,8 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--clips', type=int, default=600, help='clips per GPU per step')
     ap.add_argument('--format', default='foa', choices=['foa', 'mic'])
+    ap.add_argument('--feature', default='salsa', choices=['salsa', 'salsa_lite'],
+                    help='salsa = BASELINE configs[1] (default); salsa_lite = configs[2] (SALSA-Lite MIC, no CRNN / CPU legs)')
     ap.add_argument('--stft-precision', type=int, default=64, choices=[32, 64])
     ap.add_argument('--e2e-clips', type=int, default=120, help='clips per GPU per end-to-end step (host buffers)')
     ap.add_argument('--e2e-steps', type=int, default=3)
@@ -369,6 +392,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-crnn', action='store_true')
+    ap.add_argument('--no-fast-mode', action='store_true', help='skip the float32-FFT comparison run')
     ap.add_argument('--crnn-batch', type=int, default=32, help='clips per CRNN forward per GPU')
     args = ap.parse_args()
 
@@ -389,7 +413,13 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     fmax = 9000 if args.format == 'foa' else 4000
-    ex = salsa_b200.SalsaExtractor(args.format, fmax_doa=fmax, stft_precision=args.stft_precision)
+    if args.feature == 'salsa_lite':
+        args.format, args.no_crnn, args.no_cpu_baseline = 'mic', True, True
+        ex_kwargs = dict(feature_type='salsa_lite', stft_precision=args.stft_precision)
+        ex = salsa_b200.SalsaLiteExtractor(**ex_kwargs)
+    else:
+        ex_kwargs = dict(audio_format=args.format, fmax_doa=fmax, stft_precision=args.stft_precision)
+        ex = salsa_b200.SalsaExtractor(**ex_kwargs)
     n_clips = args.clips
     audio = make_clips(torch, n_clips, args.format, dev, seed=1000 * rank)
     feat = torch.empty((n_clips, 7, N_FRAMES, ex.freq_dim), dtype=torch.float32, device=dev)
@@ -429,6 +459,32 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = n_clips * world / (ms_per_step / 1e3)
     valid_frac = float((feat[: min(n_clips, 8), 4:, :, :ex.upper_bin - ex.lower_bin] != 0).float().mean().item())
+    feat_bytes = feature_bytes_per_clip(ex.freq_dim)
+
+    # ---- the float32-FFT variant, for the record: speed and how far it is from the float64-FFT features ----
+    fast = None
+    if args.stft_precision == 64 and not args.no_fast_mode:
+        ex32 = type(ex)(**{**ex_kwargs, 'stft_precision': 32})
+        feat32 = torch.empty_like(feat)
+        ex32.extract(audio, out=feat32)
+        barrier()
+        start.record()
+        for _ in range(2):
+            ex32.extract(audio, out=feat32)
+        stop.record()
+        barrier()
+        t32 = torch.tensor([start.elapsed_time(stop) / 2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+        n_sp = 4
+        mism = int(((feat32[:, n_sp:] != 0) != (feat[:, n_sp:] != 0)).sum().item())
+        both = (feat32[:, n_sp:] != 0) & (feat[:, n_sp:] != 0)
+        fast = {'stft_precision': 32, 'value': n_clips * world / (float(t32.item()) / 1e3), 'unit': UNIT,
+                'ms_per_step': float(t32.item()),
+                'valid_bin_mask_mismatches_vs_fp64_fft': mism, 'bins_compared': int(feat[:, n_sp:].numel()),
+                'max_abs_diff_spectrogram_db': float((feat32[:, :n_sp] - feat[:, :n_sp]).abs().max().item()),
+                'max_abs_diff_spatial_on_common_bins': float(((feat32[:, n_sp:] - feat[:, n_sp:]).abs() * both).max().item())}
+        del feat32
 
     # ---- end to end through the host-buffer entry point ---------------------------------------
     e2e = None
@@ -524,7 +580,7 @@ def main():
         'dtype': 'f32 (covariance/eigenvector) + f64 (STFT, tracker)' if args.stft_precision == 64 else 'f32 (+ f64 tracker)',
         'data': 'synthetic', 'config': workload_config(args, world, valid_frac),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-        'crnn': crnn,
+        'fp32_fft_mode': fast, 'crnn': crnn,
     }
     print(json.dumps(line))
     if world > 1:

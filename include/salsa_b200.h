@@ -128,6 +128,14 @@ int salsa_extract_host(const salsa_params_t *p, const float *audio_host, float *
 int salsa_lite_extract_host(const salsa_params_t *p, int32_t cutoff_bin, int32_t mode,
                             const float *audio_host, float *feature_host, int32_t clips_per_chunk);
 
+/* Statistics of compute_scaler() (dataset/salsa_feature_extraction.py:204-262): adds, for spectrogram channels 0..3
+ * and every frequency, the sum and the sum of squares over all frames of all clips of `feature`
+ * ([n_clips][n_feat_chans][n_frames][feat_dim]) to sums (float64 [4][feat_dim][2], zeroed by the caller before the
+ * first batch).  mean = s1 / n, std = sqrt(s2 / n - mean^2) with n = frames seen (StandardScaler's population
+ * variance); across GPUs the sums are all-reduced first. */
+int salsa_scaler_accumulate(const float *feature, int32_t n_clips, int32_t n_feat_chans, int32_t n_frames,
+                            int32_t feat_dim, double *sums, void *stream);
+
 /* The host-buffer entry points keep their streams and device staging buffers between calls (per host thread);
  * this frees them. */
 int salsa_host_release(void);

@@ -52,9 +52,10 @@ int crnn_gemm(const void *a, const void *w, const float *bias, void *out, float 
 
 /* (B, C, T, F) fp32 NCHW feature batch (the tensor SeldModel.forward receives, models/seld_models.py:39-43)
  * -> bf16 NHWC [B][T_use][F][Cpad], channels C..Cpad-1 zero; frames >= T_use are dropped
- * (database.py:205-207 trims 4801 -> 4800). */
+ * (database.py:205-207 trims 4801 -> 4800).  With n_scaled > 0 the first n_scaled channels are normalised on the
+ * way, (x - mean[c][f]) / std[c][f] with mean / std float32 [n_scaled][F] (the scaler h5, database.py:196-202). */
 int crnn_pack_input(const float *x, void *y, int32_t B, int32_t C, int32_t T, int32_t F, int32_t T_use, int32_t Cpad,
-                    int32_t planes, void *stream);
+                    int32_t planes, const float *mean, const float *std, int32_t n_scaled, void *stream);
 
 /* F.avg_pool2d(x, kernel_size=(2, 2)) (models/model_utils.py:220, :349; nn.AvgPool2d :476), floor mode. */
 int crnn_avgpool2(const void *x, void *y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t planes, void *stream);

@@ -51,6 +51,7 @@ SIGNATURES = {
     'salsa_lite_extract': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _vp]),
     'salsa_extract_host': (ctypes.c_int, [_P, _vp, _vp, _i32]),
     'salsa_lite_extract_host': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _i32]),
+    'salsa_scaler_accumulate': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'salsa_host_release': (ctypes.c_int, []),
     'salsa_launch_count': (_u64, [ctypes.c_int]),
     'salsa_profile_enable': (ctypes.c_int, [ctypes.c_int]),
@@ -60,7 +61,7 @@ SIGNATURES = {
     'crnn_conv_first': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_set_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),
     'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    'crnn_pack_input': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_pack_input': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
     'crnn_avgpool2': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_freq_mean': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'crnn_gru_layer': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -112,6 +112,7 @@ class SeldModel:
         self.device = torch.device(device)
         self.training = False
         self._w = None
+        self._scaler = None
 
     # ---- nn.Module-like surface -----------------------------------------------------------------
     def eval(self):
@@ -174,6 +175,16 @@ class SeldModel:
         return self
 
     # ---- forward ----------------------------------------------------------------------------------
+    def set_scaler(self, mean, std):
+        """Fuse the data layer's normalisation into the input packing: channels 0..n-1 become (x - mean) / std with
+        mean, std (n, 1, F) as stored in `<fmt>_feature_scaler.h5` (database.py:87-96, :196-202).  None switches it off."""
+        if mean is None:
+            self._scaler = None
+        else:
+            self._scaler = (torch.as_tensor(np.asarray(mean), dtype=torch.float32).to(self.device),
+                            torch.as_tensor(np.asarray(std), dtype=torch.float32).to(self.device))
+        return self
+
     def encode(self, x, n_frames=None):
         """PannResNet22.forward: (B,7,T,F) fp32 CUDA -> (B, T/16, F/16, planes*512) bf16 NHWC.
         `n_frames` keeps only the first frames of x (the reference trims 4801 -> 4800 before the model,
@@ -185,7 +196,7 @@ class SeldModel:
         W, P = self._w, self.planes
         if self.encoder.n_input_channels > 16:
             raise NotImplementedError('at most 16 input channels')
-        h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames, c_pad=16, planes=P)
+        h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames, c_pad=16, planes=P, scaler=self._scaler)
         h = ops.conv_first(h, *W['cb1'], relu=True, planes=P)
         h = ops.conv2d(h, *W['cb2'], relu=True, planes=P)
         h = ops.avgpool2(h, planes=P)

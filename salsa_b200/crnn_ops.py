@@ -99,15 +99,24 @@ def gemm(a, w, bias=None, relu=False, M=None, out_f32=False, out=None, planes=1)
     return out
 
 
-def pack_input(x, t_use=None, c_pad=64, planes=1):
-    """(B,C,T,F) fp32 NCHW -> (B,t_use,F,planes*c_pad) bf16 NHWC."""
+def pack_input(x, t_use=None, c_pad=64, planes=1, scaler=None):
+    """(B,C,T,F) fp32 NCHW -> (B,t_use,F,planes*c_pad) bf16 NHWC.  scaler = (mean, std) CUDA float32 tensors
+    (n_scaled, 1, F) or (n_scaled, F): the first n_scaled channels become (x - mean) / std."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
         raise ValueError('x must be a CUDA float32 tensor (B, C, T, F)')
     x = x.contiguous()
     B, C, T, F = x.shape
     t_use = T if t_use is None else t_use
     y = torch.empty((B, t_use, F, planes * c_pad), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().crnn_pack_input(_p(x), _p(y), B, C, T, F, t_use, c_pad, planes, _st()))
+    mean = std = None
+    n_scaled = 0
+    if scaler is not None:
+        mean = scaler[0].to(x.device, torch.float32).reshape(-1, F).contiguous()
+        std = scaler[1].to(x.device, torch.float32).reshape(-1, F).contiguous()
+        n_scaled = mean.shape[0]
+        if std.shape != mean.shape or n_scaled > C:
+            raise ValueError('scaler mean / std must be (n_scaled <= C, 1, F)')
+    _native.check(_native.lib().crnn_pack_input(_p(x), _p(y), B, C, T, F, t_use, c_pad, planes, _p(mean), _p(std), n_scaled, _st()))
     return y
 
 

@@ -218,11 +218,12 @@ int crnn_set_option(const char* name, int32_t value) {
 }
 
 int crnn_pack_input(const float* x, void* y, int32_t B, int32_t C, int32_t T, int32_t F, int32_t T_use, int32_t Cpad,
-                    int32_t planes, void* stream) {
+                    int32_t planes, const float* mean, const float* std, int32_t n_scaled, void* stream) {
+    if (n_scaled < 0 || n_scaled > C || (n_scaled > 0 && (!mean || !std))) return fail(SALSA_EINVAL, "pack_input: bad scaler");
     if (!x || !y) return fail(SALSA_EINVAL, "pack_input: null pointer");
     if (Cpad % 8 != 0 || C > Cpad || T_use > T || B <= 0) return fail(SALSA_EINVAL, "pack_input: bad dimensions");
     const long long n = (long long)B * T_use * F;
-    pack_input_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, C, T, F, T_use, Cpad, planes);
+    pack_input_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, C, T, F, T_use, Cpad, planes, mean, std, n_scaled);
     count_launch();
     return check_cuda(cudaGetLastError(), "pack_input_kernel");
 }

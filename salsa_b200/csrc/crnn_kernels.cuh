@@ -36,7 +36,8 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], __nv_bfloat16*
 
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C, int T, int F,
-                                  int T_use, int Cpad, int planes) {
+                                  int T_use, int Cpad, int planes, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                  int n_scaled) {
     // one thread per output pixel; reads are coalesced along F, each thread writes Cpad bf16
     const long long n_pix = (long long)B * T_use * F;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
@@ -48,7 +49,13 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
         for (int c0 = 0; c0 < Cpad; c0 += 8) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (c0 + i < C) ? __ldg(src + (long long)(c0 + i) * T * F) : 0.0f;
+            for (int i = 0; i < 8; ++i) {
+                const int c = c0 + i;
+                v[i] = (c < C) ? __ldg(src + (long long)c * T * F) : 0.0f;
+                // scaler normalisation of the data layer, fused: (x - mean) / std on the spectrogram channels
+                // (database.py:196-202); a true float32 division, like the reference
+                if (c < n_scaled) v[i] = (v[i] - __ldg(mean + c * F + f)) / __ldg(stdv + c * F + f);
+            }
             split_store8(v, dst + c0, planes, Cpad);
         }
     }

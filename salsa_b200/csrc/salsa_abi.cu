@@ -652,6 +652,18 @@ int salsa_extract_host(const salsa_params_t* p, const float* audio_host, float* 
                              });
 }
 
+int salsa_scaler_accumulate(const float* feature, int32_t n_clips, int32_t n_feat_chans, int32_t n_frames, int32_t feat_dim,
+                            double* sums, void* stream) {
+    if (!feature || !sums) return fail(SALSA_EINVAL, "scaler: null pointer");
+    if (n_clips < 0 || n_feat_chans < 4 || n_frames <= 0 || feat_dim <= 0 || feat_dim > 256)
+        return fail(SALSA_EINVAL, "scaler: bad dimensions");
+    if (n_clips == 0) return SALSA_OK;
+    const int frames_per_block = 512;
+    dim3 grid((n_frames + frames_per_block - 1) / frames_per_block, 4, n_clips);
+    scaler_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feature, n_frames, feat_dim, n_feat_chans, frames_per_block, sums);
+    return check_launch("scaler_accumulate_kernel");
+}
+
 int salsa_host_release(void) {
     t_pipeline.release();
     return SALSA_OK;

@@ -614,4 +614,26 @@ __global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T>
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// scaler_accumulate_kernel: per-channel (0..3), per-frequency sum and sum of squares over all frames of
+// all clips, float64 -- the statistics compute_scaler() gathers with StandardScaler.partial_fit
+// (salsa_feature_extraction.py:204-262).  grid (frame chunks, 4 channels, clips), thread = frequency.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scaler_accumulate_kernel(const float* __restrict__ feature, int n_frames, int feat_dim,
+                                                                int n_feat_chans, int frames_per_block, double* __restrict__ sums) {
+    const int f = threadIdx.x;
+    if (f >= feat_dim) return;
+    const int ch = blockIdx.y, clip = blockIdx.z;
+    const int t0 = blockIdx.x * frames_per_block, t1 = min(n_frames, t0 + frames_per_block);
+    const float* p = feature + (((long long)clip * n_feat_chans + ch) * n_frames + t0) * feat_dim + f;
+    double s1 = 0.0, s2 = 0.0;
+    for (int t = t0; t < t1; ++t, p += feat_dim) {
+        const double v = (double)__ldg(p);
+        s1 += v;
+        s2 = fma(v, v, s2);
+    }
+    atomicAdd(sums + ((long long)ch * feat_dim + f) * 2, s1);
+    atomicAdd(sums + ((long long)ch * feat_dim + f) * 2 + 1, s2);
+}
+
 }  // namespace salsa

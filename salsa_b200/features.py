@@ -17,7 +17,7 @@ from . import _native
 from ._native import SalsaParams
 
 __all__ = ['doa_bins', 'MagStftExtractor', 'extract_normalized_eigenvector', 'SalsaExtractor',
-           'SalsaLiteExtractor', 'stft']
+           'SalsaLiteExtractor', 'stft', 'FeatureScaler', 'compute_scaler']
 
 
 def doa_bins(fs, n_fft, fmin_doa, fmax_doa):
@@ -302,3 +302,60 @@ class SalsaLiteExtractor:
             ctypes.byref(p), self.cutoff_bin, self.mode, ctypes.c_void_p(a.ctypes.data),
             ctypes.c_void_p(o.ctypes.data), int(clips_per_chunk)))
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# scaler (compute_scaler, salsa_feature_extraction.py:204-262)
+# ------------------------------------------------------------------------------------------------
+class FeatureScaler:
+    """Streaming counterpart of `compute_scaler`: per-channel (0..3), per-frequency mean and standard deviation
+    of the spectrogram channels over all frames of all clips (StandardScaler statistics, population variance).
+    `partial_fit` takes (B, 7, T, F) CUDA feature batches as the extractors produce them; `finalize` returns what
+    the reference stores in `<fmt>_feature_scaler.h5`: mean, std as float32 (4, 1, F).  With a process group the
+    sums are all-reduced first (one collective of 4*F*2 + 1 float64 values)."""
+
+    n_feature_channels = 4      # "hard coded number" (:224)
+
+    def __init__(self):
+        self._sums = None
+        self._frames = 0
+
+    def partial_fit(self, features: torch.Tensor):
+        _require_cuda()
+        if features.dim() != 4 or features.shape[1] < self.n_feature_channels or features.dtype != torch.float32 or not features.is_cuda:
+            raise ValueError('features must be a CUDA float32 tensor (B, >=4, T, F)')
+        features = features.contiguous()
+        B, C, T, F = features.shape
+        if self._sums is None:
+            self._sums = torch.zeros((self.n_feature_channels, F, 2), dtype=torch.float64, device=features.device)
+        elif self._sums.shape[1] != F:
+            raise ValueError('feature dimension changed from {} to {}'.format(self._sums.shape[1], F))
+        _native.check(_native.lib().salsa_scaler_accumulate(_ptr(features), B, C, T, F, _ptr(self._sums), _stream()))
+        self._frames += B * T
+        return self
+
+    @staticmethod
+    def reduce_statistics(sums: torch.Tensor, frames: float, group=None):
+        """(sums float64 (4, F, 2), frames seen) of this process -> mean, std float32 (4, 1, F) over ALL processes."""
+        import torch.distributed as dist
+        sums = sums.clone()
+        n = torch.tensor([float(frames)], dtype=torch.float64, device=sums.device)
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(sums, group=group)
+            dist.all_reduce(n, group=group)
+        mean = sums[:, :, 0] / n
+        var = torch.clamp(sums[:, :, 1] / n - mean * mean, min=0.0)
+        return (mean[:, None, :].to(torch.float32).cpu().numpy(), torch.sqrt(var)[:, None, :].to(torch.float32).cpu().numpy())
+
+    def finalize(self, group=None):
+        if self._sums is None:
+            raise RuntimeError('no features seen')
+        return self.reduce_statistics(self._sums, self._frames, group)
+
+
+def compute_scaler(feature_batches):
+    """(mean, std), each float32 (4, 1, F), over an iterable of (B, 7, T, F) CUDA feature batches."""
+    sc = FeatureScaler()
+    for fb in feature_batches:
+        sc.partial_fit(fb)
+    return sc.finalize()

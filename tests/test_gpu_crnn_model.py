@@ -115,3 +115,23 @@ def test_interface_errors():
         m(torch.zeros(1, 7, 32, 200).cuda())
     with pytest.raises(NotImplementedError):
         m.train()
+
+
+def test_fused_scaler_normalisation(model):
+    """(x - mean) / std of channels 0..3 fused into the input packing == normalising on the host first (database.py:196-202)."""
+    from oracle import crnn as ocrnn
+    g = torch.Generator().manual_seed(9)
+    x = ocrnn.model_input(6, (1, 7, 64, 200))
+    x[:, :4] = x[:, :4] * 12.0 - 55.0                      # dB-like spectrogram channels
+    mean = torch.empty(4, 1, 200).uniform_(-60, -50, generator=g)
+    std = torch.empty(4, 1, 200).uniform_(8, 15, generator=g)
+    xn = x.clone()
+    xn[:, :4] = (xn[:, :4] - mean) / std
+    ref = model(xn.cuda())
+    model.set_scaler(mean.numpy(), std.numpy())
+    try:
+        out = model(x.cuda())
+    finally:
+        model.set_scaler(None, None)
+    for k in ref:
+        assert torch.equal(out[k], ref[k])

@@ -229,3 +229,28 @@ def test_silence_and_ragged_lengths(sb):
         got = ex.extract(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
         assert got.shape == ref.shape == (7, 1 + n // 300, 200)
         check_feature(got, ref, what='ragged n={}'.format(n))
+
+
+def test_scaler_matches_oracle_and_sklearn(sb):
+    """compute_scaler (salsa_feature_extraction.py:204-262): StandardScaler statistics of channels 0..3."""
+    from oracle import salsa as osalsa, synth
+    from sklearn import preprocessing
+    clips = np.stack([synth.make_clip(40 + i, 'foa', seconds=1.0) for i in range(3)])
+    feats = sb.SalsaExtractor('foa').extract(torch.from_numpy(clips).cuda())
+    sc = sb.FeatureScaler()
+    sc.partial_fit(feats[:2])
+    sc.partial_fit(feats[2:])
+    mean, std = sc.finalize()
+    assert mean.shape == std.shape == (4, 1, 200) and mean.dtype == np.float32
+    f = feats.cpu().numpy()
+    for ch in range(4):
+        ref = preprocessing.StandardScaler()
+        for i in range(3):
+            ref.partial_fit(f[i, ch])
+        np.testing.assert_allclose(mean[ch, 0], ref.mean_, rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(std[ch, 0], np.sqrt(ref.var_), rtol=1e-5, atol=1e-5)
+    omean, ostd = osalsa.compute_scaler([f[i] for i in range(3)])
+    np.testing.assert_allclose(mean, omean, rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(std, ostd, rtol=1e-5, atol=1e-5)
+    m2, s2 = sb.compute_scaler([feats])
+    assert np.array_equal(m2, mean) and np.array_equal(s2, std)

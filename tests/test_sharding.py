@@ -41,6 +41,17 @@ def _worker(rank, world, port, n_clips, q):
         local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None].expand(hi - lo, 3, 4).contiguous()
         full = sharding.gather_clip_outputs(local, n_clips)
         ok = full.shape == (n_clips, 3, 4) and torch.equal(full[:, 0, 0], torch.arange(n_clips, dtype=torch.float32))
+        # scaler statistics: every rank holds the sums of its own clips; the reduction must equal the global result
+        from salsa_b200.features import FeatureScaler
+        g = torch.Generator().manual_seed(0)
+        data = torch.randn(n_clips, 4, 7, 5, generator=g, dtype=torch.float64) * 10 - 50        # (clips, ch, frames, F)
+        mine = data[lo:hi]
+        sums = torch.stack([mine.sum(dim=(0, 2)), (mine ** 2).sum(dim=(0, 2))], dim=-1)             # (4, F, 2)
+        mean, std = FeatureScaler.reduce_statistics(sums, (hi - lo) * 7)
+        ref_mean = data.permute(1, 0, 2, 3).reshape(4, -1, 5).mean(dim=1)
+        ref_std = data.permute(1, 0, 2, 3).reshape(4, -1, 5).std(dim=1, unbiased=False)
+        ok = ok and mean.shape == (4, 1, 5) and bool(torch.allclose(torch.from_numpy(mean[:, 0]).double(), ref_mean, atol=1e-5))
+        ok = ok and bool(torch.allclose(torch.from_numpy(std[:, 0]).double(), ref_std, atol=1e-5))
         # max-over-ranks timing reduction used by bench.py
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
