@@ -48,6 +48,31 @@ template <typename T> __device__ __forceinline__ Cx<T> cmulc(Cx<T> a, Cx<T> b) {
     return {a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im};
 }
 
+// Fused accumulations: every complex multiply-add is four FMAs (the compiler may not reassociate
+// "acc += a * b" into them on its own).
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+// acc += a * b
+template <typename T> __device__ __forceinline__ void cmac(Cx<T>& acc, Cx<T> a, Cx<T> b) {
+    acc.re = fma_t<T>(a.re, b.re, acc.re);
+    acc.re = fma_t<T>(-a.im, b.im, acc.re);
+    acc.im = fma_t<T>(a.re, b.im, acc.im);
+    acc.im = fma_t<T>(a.im, b.re, acc.im);
+}
+// acc += a * conj(b)
+template <typename T> __device__ __forceinline__ void cmacc(Cx<T>& acc, Cx<T> a, Cx<T> b) {
+    acc.re = fma_t<T>(a.re, b.re, acc.re);
+    acc.re = fma_t<T>(a.im, b.im, acc.re);
+    acc.im = fma_t<T>(a.im, b.re, acc.im);
+    acc.im = fma_t<T>(-a.re, b.im, acc.im);
+}
+// acc += |a|^2
+template <typename T> __device__ __forceinline__ void abs2_acc(T& acc, Cx<T> a) {
+    acc = fma_t<T>(a.re, a.re, acc);
+    acc = fma_t<T>(a.im, a.im, acc);
+}
+
 template <typename T>
 __device__ __forceinline__ void herm_zero(Herm4<T>& A) {
 #pragma unroll
@@ -61,14 +86,9 @@ template <typename T>
 __device__ __forceinline__ void herm_rank1(Herm4<T>& A, const Cx<T> (&x)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        A.d[i] += cabs2(x[i]);
+        abs2_acc(A.d[i], x[i]);
 #pragma unroll
-        for (int j = i + 1; j < 4; ++j) {
-            const Cx<T> p = cmulc(x[i], x[j]);
-            Cx<T>& o = A.o[herm_idx(i, j)];
-            o.re += p.re;
-            o.im += p.im;
-        }
+        for (int j = i + 1; j < 4; ++j) cmacc(A.o[herm_idx(i, j)], x[i], x[j]);
     }
 }
 
@@ -94,7 +114,7 @@ __device__ __forceinline__ Herm4<T> herm_square(const Herm4<T>& A) {
         T s = A.d[i] * A.d[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (k != i) s += cabs2(herm_at(A, i, k));
+            if (k != i) abs2_acc(s, herm_at(A, i, k));
         B.d[i] = s;
 #pragma unroll
         for (int j = i + 1; j < 4; ++j) {
@@ -104,9 +124,7 @@ __device__ __forceinline__ Herm4<T> herm_square(const Herm4<T>& A) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (k == i || k == j) continue;
-                const Cx<T> p = cmul(herm_at(A, i, k), herm_at(A, k, j));
-                acc.re += p.re;
-                acc.im += p.im;
+                cmac(acc, herm_at(A, i, k), herm_at(A, k, j));
             }
             B.o[herm_idx(i, j)] = acc;
         }
@@ -123,9 +141,7 @@ __device__ __forceinline__ void herm_matvec(const Herm4<T>& A, const Cx<T> (&x)[
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (k == i) continue;
-            const Cx<T> p = cmul(herm_at(A, i, k), x[k]);
-            acc.re += p.re;
-            acc.im += p.im;
+            cmac(acc, herm_at(A, i, k), x[k]);
         }
         y[i] = acc;
     }

@@ -6,8 +6,9 @@
 //
 // The 512 real samples are packed as 256 complex points z[n] = x[2n] + i x[2n+1] and transformed
 // with a 8 x 8 x 4 decimation: every lane owns 8 complex values, the two exchanges between the
-// three butterfly passes go through a per-warp shared-memory scratch, and a final split turns
-// Z[k] into the 257 bins of the real transform.  `T` is the arithmetic type: double reproduces the
+// three butterfly passes go through a per-warp shared-memory scratch, and a final split (in
+// registers, the mirrored partner comes by warp shuffle) turns Z[k] into the 257 bins of the real
+// transform.  `T` is the arithmetic type: double reproduces the
 // reference's float64 transform (results rounded to float32 afterwards, as librosa stores complex64),
 // float is the fast variant.
 #pragma once
@@ -103,13 +104,32 @@ __device__ __forceinline__ void load_frame(const float* __restrict__ x, int n, i
     }
 }
 
-// One warp: 256-point complex FFT of the windowed frame in `raw` (see load_frame).  Result Z[0..255]
-// is left in `scratch` in natural order (scratch must hold kScratchElems complex values).  `win`
-// points to the window in shared memory.
-// `w1` = W256^lane (lane_twiddle()), `tw_r` = the real-split table W512^k in shared memory.
+// Per-lane twiddle constants, loaded once per kernel and kept in registers.  Every other twiddle of
+// the transform is a product of one of these with itself or with a compile-time constant: shared
+// memory carries only the data exchanges (it is the pipe this transform is bound by).
 template <typename T>
-__device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __restrict__ win, const Cx<T> w1,
-                                            const Cx<T>* __restrict__ tw_r, Cx<T>* scratch, int lane) {
+struct LaneTwiddles {
+    Cx<T> w256;   // W256^lane          pass 1 -> 2
+    Cx<T> w32;    // W32^(lane & 3)     pass 2 -> 3
+    Cx<T> w512;   // W512^lane          real split
+};
+
+template <typename T>
+__device__ __forceinline__ LaneTwiddles<T> lane_twiddles(const FftTables<T>& tb, int lane) {
+    return {tb.tw_a[32 + lane], tb.tw_b[32 + lane], tb.tw_r[lane]};
+}
+
+template <typename T> __device__ __forceinline__ Cx<T> shfl_cx(Cx<T> v, int src) {
+    return {__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)};
+}
+
+// One warp: the 512-point real transform of the windowed frame in `raw` (see load_frame).
+// X[j] = bin lane + 32 j (j = 0..7) of this lane; `nyq` = bin 256 (valid in lane 0 only).
+// `win` points to the window in shared memory, `scratch` to kScratchElems complex values of per-warp
+// shared memory used by the two exchanges between the three butterfly passes.
+template <typename T>
+__device__ __forceinline__ void warp_rfft512(const float2 (&raw)[8], const T* __restrict__ win, const LaneTwiddles<T>& tw,
+                                             Cx<T>* scratch, int lane, Cx<T> (&X)[8], T& nyq) {
     Cx<T> v[8];
     // ---- window: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1],  m = lane + 32 n1
 #pragma unroll
@@ -117,12 +137,10 @@ __device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __r
         const int m = lane + 32 * n1;
         v[n1] = {(T)raw[n1].x * win[2 * m], (T)raw[n1].y * win[2 * m + 1]};
     }
-    // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1) = w1^k1.  Only w1 comes
-    //      from memory (a per-lane constant the caller keeps in registers); the powers cost six
-    //      complex products and are good to a few ulp of T.
+    // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1) = w256^k1
     dft8(v);
     {
-        const Cx<T> w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+        const Cx<T> w1 = tw.w256, w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
         v[1] = cmul(v[1], w1);
         v[2] = cmul(v[2], w2);
         v[3] = cmul(v[3], w3);
@@ -134,68 +152,68 @@ __device__ __forceinline__ void warp_fft256(const float2 (&raw)[8], const T* __r
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) scratch[k1 * kScratchPad + lane] = v[k1];
     __syncwarp();
-    // ---- pass 2: lane = (k1, m2); 8-point DFT over m1 of y[k1][4 m1 + m2], twiddle W32^(m2*j1)
+    // ---- pass 2: lane = (k1, m2); 8-point DFT over m1 of y[k1][4 m1 + m2], twiddle W32^(m2*j1) = w32^j1
     const int k1 = lane >> 2, m2 = lane & 3;
 #pragma unroll
     for (int m1 = 0; m1 < 8; ++m1) v[m1] = scratch[k1 * kScratchPad + 4 * m1 + m2];
     __syncwarp();
     dft8(v);
-    // twiddle W32^(m2*j1) = W512^(16 m2 j1) from the real-split table in shared memory (four distinct
-    // addresses per warp, all broadcasts); W512^(256 + x) = -W512^x
-#pragma unroll
-    for (int j1 = 1; j1 < 8; ++j1) {
-        const int x = 16 * m2 * j1;
-        Cx<T> w = tw_r[x & (kHalf - 1)];
-        if (x & kHalf) w = {-w.re, -w.im};
-        v[j1] = cmul(v[j1], w);
+    {
+        const Cx<T> u1 = tw.w32, u2 = cmul(u1, u1), u3 = cmul(u2, u1), u4 = cmul(u2, u2);
+        v[1] = cmul(v[1], u1);
+        v[2] = cmul(v[2], u2);
+        v[3] = cmul(v[3], u3);
+        v[4] = cmul(v[4], u4);
+        v[5] = cmul(v[5], cmul(u4, u1));
+        v[6] = cmul(v[6], cmul(u4, u2));
+        v[7] = cmul(v[7], cmul(u4, u3));
     }
     // u[k1][m2][j1] at k1*kUStrideK + m2*kUStrideM + j1  (strides chosen bank-conflict free)
 #pragma unroll
     for (int j1 = 0; j1 < 8; ++j1) scratch[k1 * kUStrideK + m2 * kUStrideM + j1] = v[j1];
     __syncwarp();
     // ---- pass 3: lane owns (k1 = lane&7, j1 = (lane>>3) + 4p), p = 0,1; 4-point DFT over m2
-    //      -> Z[k1 + 8 j1 + 64 j2] = Z[lane + 32 p + 64 j2]
-    Cx<T> w[2][4];
+    //      -> z[p + 2 j2] = Z[k1 + 8 j1 + 64 j2] = Z[lane + 32 (p + 2 j2)]
+    Cx<T> z[8];
     const int pk1 = lane & 7;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int pj1 = (lane >> 3) + 4 * p;
+        Cx<T> w[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[p][q] = scratch[pk1 * kUStrideK + q * kUStrideM + pj1];
-        dft4(w[p]);
+        for (int q = 0; q < 4; ++q) w[q] = scratch[pk1 * kUStrideK + q * kUStrideM + pj1];
+        dft4(w);
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) z[p + 2 * j2] = w[j2];
     }
-    __syncwarp();
+    __syncwarp();      // scratch may be reused by the caller / the next transform
+    // ---- real split, in registers: X[k] = E + W512^k O with E = (Z[k] + conj Z[256-k]) / 2,
+    //      O = -i (Z[k] - conj Z[256-k]) / 2.  For k = lane + 32 j the partner Z[256 - k] is z[7 - j] of lane
+    //      32 - lane (lane 0: its own z[(8 - j) & 7]); W512^k = w512 * W16^j with W16^j a constant.
+    nyq = z[0].re - z[0].im;
+    const int partner_lane = (32 - lane) & 31;
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+    const Cx<T> w16[8] = {{(T)1, (T)0}, {c1, -s1}, {h, -h}, {s1, -c1}, {(T)0, (T)-1}, {-s1, -c1}, {-h, -h}, {-c1, -s1}};
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) scratch[lane + 32 * p + 64 * j2] = w[p][j2];
-    __syncwarp();
+    for (int j = 0; j < 8; ++j) {
+        const Cx<T> other = shfl_cx(z[7 - j], partner_lane);
+        const Cx<T> own = z[(8 - j) & 7];
+        const Cx<T> a = z[j];
+        const Cx<T> b = lane == 0 ? own : other;
+        const Cx<T> e = {(T)0.5 * (a.re + b.re), (T)0.5 * (a.im - b.im)};
+        const Cx<T> o = {(T)0.5 * (a.im + b.im), (T)0.5 * (b.re - a.re)};
+        const Cx<T> t = cmul(o, j == 0 ? tw.w512 : cmul(tw.w512, w16[j]));
+        X[j] = {e.re + t.re, e.im + t.im};
+    }
 }
-
-// W256^lane, the per-lane constant of pass 1
-template <typename T>
-__device__ __forceinline__ Cx<T> lane_twiddle(const FftTables<T>& tb, int lane) { return tb.tw_a[32 + lane]; }
 
 // load + transform in one call
 template <typename T>
-__device__ __forceinline__ void warp_fft256_frame(const float* __restrict__ x, int n, int start,
-                                                  const T* __restrict__ win, const Cx<T> w1,
-                                                  const Cx<T>* __restrict__ tw_r, Cx<T>* scratch, int lane) {
+__device__ __forceinline__ void warp_rfft512_frame(const float* __restrict__ x, int n, int start, const T* __restrict__ win,
+                                                   const LaneTwiddles<T>& tw, Cx<T>* scratch, int lane, Cx<T> (&X)[8], T& nyq) {
     float2 raw[8];
     load_frame(x, n, start, lane, raw);
-    warp_fft256<T>(raw, win, w1, tw_r, scratch, lane);
-}
-
-// Bin k (0..256) of the 512-point real transform from the packed spectrum Z (natural order).
-template <typename T>
-__device__ __forceinline__ Cx<T> real_bin(const Cx<T>* Z, const Cx<T>* tw_r, int k) {
-    if (k == kHalf) return {Z[0].re - Z[0].im, (T)0};
-    const Cx<T> a = Z[k];
-    const Cx<T> b = Z[(kHalf - k) & (kHalf - 1)];
-    const Cx<T> e = {(T)0.5 * (a.re + b.re), (T)0.5 * (a.im - b.im)};     // (Z[k] + conj Z[N-k]) / 2
-    const Cx<T> o = {(T)0.5 * (a.im + b.im), (T)0.5 * (b.re - a.re)};     // -i (Z[k] - conj Z[N-k]) / 2
-    const Cx<T> t = cmul(o, tw_r[k]);
-    return {e.re + t.re, e.im + t.im};
+    warp_rfft512<T>(raw, win, tw, scratch, lane, X, nyq);
 }
 
 }  // namespace salsa

@@ -49,14 +49,12 @@ struct StftArgs {
 template <typename T>
 struct FftSmem {
     T win[kNfft];
-    Cx<T> tw_r[kHalf];
     Cx<T> scratch[kWarps][kScratchElems];
 };
 
 template <typename T>
 __device__ __forceinline__ void load_fft_smem(FftSmem<T>& s, const FftTables<T>& tb) {
     for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s.win[i] = tb.window[i];
-    for (int i = threadIdx.x; i < kHalf; i += blockDim.x) s.tw_r[i] = tb.tw_r[i];
 }
 
 // power_to_db(ref=1, amin=1e-10, top_db=None): 10 log10(max(amin, p)) (:195).  The argument is never
@@ -116,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
     load_fft_smem(s, tb);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Cx<T> w1 = lane_twiddle(tb, lane);
+    const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
     const int clip = blockIdx.y;
     const int f0 = blockIdx.x * a.frames_per_block;
     const int f1 = min(a.n_frames, f0 + a.frames_per_block);
@@ -126,14 +124,15 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
     for (int item = warp; item < (f1 - f0) * a.ch_count; item += kWarps) {
         const int t = f0 + item / a.ch_count;
         const int ch = item % a.ch_count;
-        warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, w1,
-                             s.tw_r, scratch, lane);
+        Cx<T> X[8];
+        T nyq;
+        warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, tw, scratch, lane,
+                              X, nyq);
         float p[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = lane + 32 * j;
-            const Cx<T> x = real_bin(scratch, s.tw_r, k);
-            const float re = (float)x.re, im = (float)x.im;     // librosa stores complex64
+            const float re = (float)X[j].re, im = (float)X[j].im;     // librosa stores complex64
             p[j] = power_f32(re, im);
             if (k >= a.lower && k < a.upper) {
                 const long long o = ((long long)clip * a.n_frames + t);
@@ -142,11 +141,8 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
                 if (a.power0 && ch == 0) a.power0[o * nb + (k - a.lower)] = fma((double)re, (double)re, (double)im * (double)im);
             }
         }
-        __syncwarp();
         if (a.spec) {
-            const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
-            const float p_nyq = power_f32((float)xn.re, 0.0f);
-            __syncwarp();
+            const float p_nyq = power_f32((float)nyq, 0.0f);
             float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
             write_logspec_row(p, p_nyq, row, a.bands, lane);
         }
@@ -412,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Cx<T> w1 = lane_twiddle(tb, lane);
+    const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
     const int clip = blockIdx.y;
     const int s0 = blockIdx.x * a.seg_len;
     const int s1 = min(a.n_frames, s0 + a.seg_len);
@@ -465,24 +461,20 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
             const int nxt = item + kWarps;
             if (nxt < n_items) load_frame(clip_audio + (long long)(nxt & 3) * a.n_samples, a.n_samples,
                                           frame_start(fa + (nxt >> 2)), lane, raw);
-            warp_fft256<T>(cur, s.win, w1, s.tw_r, scratch, lane);
+            Cx<T> X[8];
+            T nyq;
+            warp_rfft512<T>(cur, s.win, tw, scratch, lane, X, nyq);
             const int slot = (f - (s0 - kHop)) % R;
             float2* dst = ring + slot * row + ch * a.nbp;
             float p[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = lane + 32 * j;
-                const Cx<T> x = real_bin(scratch, s.tw_r, k);
-                const float re = (float)x.re, im = (float)x.im;
+                const float re = (float)X[j].re, im = (float)X[j].im;
                 p[j] = power_f32(re, im);
                 if (k >= a.lower && k < a.upper) dst[k - a.lower] = make_float2(re, im);
             }
-            float p_nyq = 0.0f;
-            if (a.bands.n_out == a.bands.n_lin) {
-                const Cx<T> xn = real_bin(scratch, s.tw_r, kHalf);
-                p_nyq = power_f32((float)xn.re, 0.0f);
-            }
-            __syncwarp();
+            const float p_nyq = power_f32((float)nyq, 0.0f);
             if (f >= s0 && f < s1) write_logspec_row(p, p_nyq, clip_feat + ch * chan_stride + (long long)f * feat_dim, a.bands, lane);
         }
     };
@@ -568,7 +560,7 @@ __global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T>
     load_fft_smem(s, tb);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Cx<T> w1 = lane_twiddle(tb, lane);
+    const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
     const int clip = blockIdx.y;
     const int f0 = blockIdx.x * a.frames_per_block;
     const int f1 = min(a.n_frames, f0 + a.frames_per_block);
@@ -582,15 +574,16 @@ __global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T>
         float2 x0[8];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            warp_fft256_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win,
-                                 w1, s.tw_r, scratch, lane);
+            Cx<T> X[8];
+            T nyq;
+            warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, tw, scratch,
+                                  lane, X, nyq);
             float* srow = clip_feat + ch * chan_stride + (long long)t * width;
             float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width;   // used for ch >= 1
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = lane + 32 * j;
-                const Cx<T> x = real_bin(scratch, s.tw_r, k);
-                const float re = (float)x.re, im = (float)x.im;
+                const float re = (float)X[j].re, im = (float)X[j].im;
                 if (ch == 0) x0[j] = make_float2(re, im);
                 const int c = k - a.lower;            // cropped index
                 if (c >= 0 && c < width) {
