@@ -125,17 +125,33 @@ template <typename T> __device__ __forceinline__ Cx<T> shfl_cx(Cx<T> v, int src)
 
 // One warp: the 512-point real transform of the windowed frame in `raw` (see load_frame).
 // X[j] = bin lane + 32 j (j = 0..7) of this lane; `nyq` = bin 256 (valid in lane 0 only).
-// `win` points to the window in shared memory, `scratch` to kScratchElems complex values of per-warp
+// `win` points to the window in shared memory (null: the periodic Hann window of length 512, computed from the
+// lane constants), `scratch` to kScratchElems complex values of per-warp
 // shared memory used by the two exchanges between the three butterfly passes.
 template <typename T>
 __device__ __forceinline__ void warp_rfft512(const float2 (&raw)[8], const T* __restrict__ win, const LaneTwiddles<T>& tw,
                                              Cx<T>* scratch, int lane, Cx<T> (&X)[8], T& nyq) {
     Cx<T> v[8];
     // ---- window: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1],  m = lane + 32 n1
+    if (win) {
 #pragma unroll
-    for (int n1 = 0; n1 < 8; ++n1) {
-        const int m = lane + 32 * n1;
-        v[n1] = {(T)raw[n1].x * win[2 * m], (T)raw[n1].y * win[2 * m + 1]};
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int m = lane + 32 * n1;
+            v[n1] = {(T)raw[n1].x * win[2 * m], (T)raw[n1].y * win[2 * m + 1]};
+        }
+    } else {
+        // periodic Hann of length 512 without a table: w[n] = 1/2 - 1/2 cos(2 pi n / 512) = 1/2 - 1/2 Re W512^n, and
+        // W512^(2m) = W256^m = w256 * W8^n1, W512^(2m+1) = W256^m * W512 (W8^n1 and W512 are constants)
+        const T h = (T)0.70710678118654752440;
+        const T c512 = (T)0.99992470183914454092, s512 = (T)0.01227153828571992608;    // cos, sin of 2 pi / 512
+        const Cx<T> w8[8] = {{(T)1, (T)0}, {h, -h}, {(T)0, (T)-1}, {-h, -h}, {(T)-1, (T)0}, {-h, h}, {(T)0, (T)1}, {h, h}};
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const Cx<T> pw = n1 == 0 ? tw.w256 : cmul(tw.w256, w8[n1]);
+            const T we = (T)0.5 - (T)0.5 * pw.re;
+            const T wo = (T)0.5 - (T)0.5 * (pw.re * c512 + pw.im * s512);
+            v[n1] = {(T)raw[n1].x * we, (T)raw[n1].y * wo};
+        }
     }
     // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1) = w256^k1
     dft8(v);

@@ -115,6 +115,11 @@ int get_tables(const double* window_host, DeviceTables* out) {
             return rc;
         st.ready = true;
     }
+    if (!window_host) {       // built-in periodic Hann of full length: computed in the kernels, no table
+        out->d = {st.tw_a_d, st.tw_b_d, st.tw_r_d, nullptr};
+        out->f = {st.tw_a_f, st.tw_b_f, st.tw_r_f, nullptr};
+        return SALSA_OK;
+    }
     const WindowEntry* hit = nullptr;
     for (const WindowEntry& w : st.windows)
         if (memcmp(w.values.data(), window_host, kNfft * sizeof(double)) == 0) hit = &w;
@@ -394,9 +399,10 @@ int salsa_stft(const salsa_params_t* p, const float* audio, float* X, float* log
     if (p->n_clips == 0) return SALSA_OK;
     if (!audio) return fail(SALSA_EINVAL, "audio is NULL");
     double win[kNfft];
-    host_window(p, win);
+    const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
+    if (!builtin_hann) host_window(p, win);
     DeviceTables tb;
-    if ((rc = get_tables(win, &tb))) return rc;
+    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     const long long clip_stride = (long long)p->n_chans * n_frames * band_layout(p).n_out;
     const int ch_count = (X || logspec) ? p->n_chans : 1;
@@ -453,9 +459,10 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     if (p->is_tracking && (!workspace || workspace_bytes < w.bytes))
         return fail(SALSA_ENOMEM, "workspace smaller than salsa_workspace_bytes()");
     double win[kNfft];
-    host_window(p, win);
+    const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
+    if (!builtin_hann) host_window(p, win);
     DeviceTables tb;
-    if ((rc = get_tables(win, &tb))) return rc;
+    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t* mask = nullptr;
     if (p->is_tracking) {
@@ -482,9 +489,10 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
     if (p->n_clips == 0) return SALSA_OK;
     if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
     double win[kNfft];
-    host_window(p, win);
+    const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
+    if (!builtin_hann) host_window(p, win);
     DeviceTables tb;
-    if ((rc = get_tables(win, &tb))) return rc;
+    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
     LiteArgs a;
     a.audio = audio;
     a.feature = feature;

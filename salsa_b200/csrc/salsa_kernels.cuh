@@ -54,7 +54,8 @@ struct FftSmem {
 
 template <typename T>
 __device__ __forceinline__ void load_fft_smem(FftSmem<T>& s, const FftTables<T>& tb) {
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s.win[i] = tb.window[i];
+    if (tb.window)
+        for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s.win[i] = tb.window[i];
 }
 
 // power_to_db(ref=1, amin=1e-10, top_db=None): 10 log10(max(amin, p)) (:195).  The argument is never
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
         const int ch = item % a.ch_count;
         Cx<T> X[8];
         T nyq;
-        warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, tw, scratch, lane,
-                              X, nyq);
+        warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, tb.window ? s.win : nullptr, tw, scratch,
+                              lane, X, nyq);
         float p[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
                                           frame_start(fa + (nxt >> 2)), lane, raw);
             Cx<T> X[8];
             T nyq;
-            warp_rfft512<T>(cur, s.win, tw, scratch, lane, X, nyq);
+            warp_rfft512<T>(cur, tb.window ? s.win : nullptr, tw, scratch, lane, X, nyq);
             const int slot = (f - (s0 - kHop)) % R;
             float2* dst = ring + slot * row + ch * a.nbp;
             float p[8];
@@ -554,7 +555,7 @@ struct LiteArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T> tb) {
+__global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables<T> tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
     load_fft_smem(s, tb);
@@ -576,8 +577,8 @@ __global__ void __launch_bounds__(kThreads) lite_kernel(LiteArgs a, FftTables<T>
         for (int ch = 0; ch < 4; ++ch) {
             Cx<T> X[8];
             T nyq;
-            warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, s.win, tw, scratch,
-                                  lane, X, nyq);
+            warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, tb.window ? s.win : nullptr, tw,
+                                  scratch, lane, X, nyq);
             float* srow = clip_feat + ch * chan_stride + (long long)t * width;
             float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width;   // used for ch >= 1
 #pragma unroll
