@@ -30,10 +30,11 @@ extern "C" {
 /* nn.Conv2d(k=3, pad=1 | k=1, stride 1, bias=False) + eval-mode BatchNorm2d (+ residual add) (+ ReLU):
  * ConvBlock.forward (models/model_utils.py:213-216), _ResnetBasicBlock.forward (:352-365), the
  * downsample branch (:474-481).  tcgen05 implicit GEMM, fp32 accumulation.
- * out (bf16) and/or out_f32 receive relu?(conv(x, w) + bias + residual). */
+ * out (bf16) and/or out_f32 receive relu?(conv(x, w) + bias + residual).  pool = 1 (planes = 1, bf16 output only)
+ * applies the following F.avg_pool2d(2x2) (:220, :349) in the epilogue: out is then [B][H/2][W/2][Cout]. */
 int crnn_conv2d(const void *x, const void *w, const float *bias, const void *residual, void *out, float *out_f32,
                 int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, int32_t planes,
-                void *stream);
+                int32_t pool, void *stream);
 
 /* The first convolution of the encoder (conv_block1.conv1 + bn1 + ReLU, models/model_utils.py:213-215) on an input
  * padded to 16 channels: x bf16 NHWC [B][H][W][planes*16], w bf16 [9][64][planes*16] -> out bf16 [B][H][W][planes*64]. */

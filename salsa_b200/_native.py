@@ -57,7 +57,7 @@ SIGNATURES = {
     'salsa_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'salsa_profile_read': (ctypes.c_int, [_i32, _vp, _vp, _vp]),
     # include/salsa_crnn.h
-    'crnn_conv2d': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_conv2d': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_conv_first': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_set_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),
     'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -198,18 +198,19 @@ class SeldModel:
             raise NotImplementedError('at most 16 input channels')
         h = ops.pack_input(x.to(self.device, torch.float32), t_use=n_frames, c_pad=16, planes=P, scaler=self._scaler)
         h = ops.conv_first(h, *W['cb1'], relu=True, planes=P)
-        h = ops.conv2d(h, *W['cb2'], relu=True, planes=P)
-        h = ops.avgpool2(h, planes=P)
+        h = ops.conv2d(h, *W['cb2'], relu=True, planes=P, pool=True)          # + F.avg_pool2d (model_utils.py:220)
         for li in range(1, 5):
             for bi in range(2):
                 if li > 1 and bi == 0:
-                    pooled = ops.avgpool2(h, planes=P)
-                    identity = ops.conv2d(pooled, *W[(li, bi, 'ds')], planes=P)
-                    out = ops.conv2d(pooled, *W[(li, bi, 1)], relu=True, planes=P)
+                    # `h` arrives already pooled: the producer of a stride-2 block's input applies the block's
+                    # avg_pool2d (model_utils.py:349, :476) in its epilogue
+                    identity = ops.conv2d(h, *W[(li, bi, 'ds')], planes=P)
+                    out = ops.conv2d(h, *W[(li, bi, 1)], relu=True, planes=P)
                 else:
                     identity = h
                     out = ops.conv2d(h, *W[(li, bi, 1)], relu=True, planes=P)
-                h = ops.conv2d(out, *W[(li, bi, 2)], residual=identity, relu=True, planes=P)
+                feeds_stride2 = bi == 1 and li < 4
+                h = ops.conv2d(out, *W[(li, bi, 2)], residual=identity, relu=True, planes=P, pool=feeds_stride2)
         return h
 
     def decode(self, enc):

@@ -43,9 +43,10 @@ def merge_planes(t, planes):
     return sum(t[..., i * c:(i + 1) * c].float() for i in range(planes))
 
 
-def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, planes=1):
+def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, planes=1, pool=False):
     """x (B,H,W,planes*Cin) bf16 NHWC, w (k*k,Cout,planes*Cin) bf16, bias (Cout,) fp32
-    -> (B,H,W,planes*Cout) bf16, or (B,H,W,Cout) fp32 with out_f32."""
+    -> (B,H,W,planes*Cout) bf16, or (B,H,W,Cout) fp32 with out_f32.  pool=True also applies the 2x2 average
+    pooling that follows (fused into the epilogue when planes == 1): -> (B,H//2,W//2,planes*Cout)."""
     _check_act(x)
     B, H, W, CinP = x.shape
     taps, Cout, Cin2 = w.shape
@@ -55,12 +56,19 @@ def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, 
         _check_act(residual)
         if tuple(residual.shape) != (B, H, W, planes * Cout):
             raise ValueError('residual shape mismatch')
+    fuse_pool = bool(pool) and planes == 1 and not out_f32 and H >= 2 and W >= 2
     if out is None:
-        out = (torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device) if out_f32 else
-               torch.empty((B, H, W, planes * Cout), dtype=torch.bfloat16, device=x.device))
+        if out_f32:
+            out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+        elif fuse_pool:
+            out = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device)
+        else:
+            out = torch.empty((B, H, W, planes * Cout), dtype=torch.bfloat16, device=x.device)
     o16, o32 = (None, out) if out.dtype == torch.float32 else (out, None)
     _native.check(_native.lib().crnn_conv2d(_p(x), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), B, H, W, CinP // planes, Cout,
-                                            3 if taps == 9 else 1, int(bool(relu)), planes, _st()))
+                                            3 if taps == 9 else 1, int(bool(relu)), planes, int(fuse_pool), _st()))
+    if pool and not fuse_pool:
+        out = avgpool2(out, planes=planes)
     return out
 
 

@@ -49,10 +49,14 @@ static int g_opt_resident = -1;
 static int g_opt_tma_store = -1;
 
 // output tensor map of the TMA-store epilogue: bf16 NHWC [B][H][W][Cout], box = one 16 x 8 tile x 64 channels
-static int make_out_tmap(CUtensorMap* m, const void* out, int B, int H, int W, int Cout) {
+static int make_out_tmap(CUtensorMap* m, const void* out, int B, int H, int W, int Cout, int pool) {
+    if (pool) {       // the pooled tensor [B][H/2][W/2][Cout], box = one pooled tile of 8 x 4 pixels
+        H /= 2;
+        W /= 2;
+    }
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)(pool ? kTileW / 2 : kTileW), (cuuint32_t)(pool ? kTileH / 2 : kTileH), 1};
     return make_tmap(m, out, 4, dims, str, box);
 }
 
@@ -71,7 +75,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
 
 // x: NHWC bf16 [B][H][W][Cin]; for a GEMM: B = 1, W = 8, H = ceil(M / 8), pix_limit = M
 static int conv_generic(const void* x, const void* w, const float* bias, const void* residual, void* out, float* out_f32, int B,
-                        int H, int W, int Cin, int Cout, int taps, int relu, int planes, long long pix_limit, cudaStream_t st) {
+                        int H, int W, int Cin, int Cout, int taps, int relu, int planes, int pool, long long pix_limit,
+                        cudaStream_t st) {
     if (planes != 1 && planes != 3) return fail(SALSA_EINVAL, "conv: planes must be 1 (bf16) or 3 (bf16x3)");
     if (!x || !w || (!out && !out_f32)) return fail(SALSA_EINVAL, "conv: null pointer");
     if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv: bad dimensions");
@@ -108,6 +113,8 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
     a.relu = relu;
     a.resident_b = resident;
     a.tma_store = (planes == 1 && out && !out_f32) && (g_opt_tma_store < 0 ? 1 : g_opt_tma_store);
+    a.pool = pool;
+    if (pool && (!a.tma_store || H < 2 || W < 2)) return fail(SALSA_EINVAL, "conv: fused pooling needs the bf16 single-plane output path");
     a.pix_limit = pix_limit;
     a.bias = bias;
     a.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
@@ -115,7 +122,7 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
     a.out_f32 = out_f32;
     CUtensorMap to = ta;
     if (a.tma_store) {
-        int rc = make_out_tmap(&to, out, B, H, W, Cout);
+        int rc = make_out_tmap(&to, out, B, H, W, Cout, pool);
         if (rc) return rc;
     }
     if (n_tile == 256) return launch_conv<256>(ta, tw, to, a, st);
@@ -154,6 +161,7 @@ static int conv_first(const void* x, const void* w, const float* bias, void* out
     a.relu = relu;
     a.resident_b = 1;
     a.tma_store = planes == 1 && (g_opt_tma_store < 0 ? 1 : g_opt_tma_store);
+    a.pool = 0;
     a.pix_limit = (long long)B * H * W;
     a.bias = bias;
     a.residual = nullptr;
@@ -166,7 +174,7 @@ static int conv_first(const void* x, const void* w, const float* bias, void* out
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     CUtensorMap to = ta;
     if (a.tma_store) {
-        int rc = make_out_tmap(&to, out, B, H, W, 64);
+        int rc = make_out_tmap(&to, out, B, H, W, 64, 0);
         if (rc) return rc;
     }
     conv_first_kernel<<<std::min(a.n_tiles, sms), kConvThreads, smem, st>>>(ta, tw, to, a);
@@ -191,10 +199,11 @@ using namespace salsa::crnn;
 extern "C" {
 
 int crnn_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* out, float* out_f32, int32_t B,
-                int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, int32_t planes, void* stream) {
+                int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, int32_t planes, int32_t pool,
+                void* stream) {
     if (ksize != 1 && ksize != 3) return fail(SALSA_EINVAL, "conv: kernel size must be 1 or 3");
-    return conv_generic(x, w, bias, residual, out, out_f32, B, H, W, Cin, Cout, ksize * ksize, relu, planes, (long long)B * H * W,
-                        (cudaStream_t)stream);
+    return conv_generic(x, w, bias, residual, out, out_f32, B, H, W, Cin, Cout, ksize * ksize, relu, planes, pool,
+                        (long long)B * H * W, (cudaStream_t)stream);
 }
 
 int crnn_conv_first(const void* x, const void* w, const float* bias, void* out, int32_t B, int32_t H, int32_t W, int32_t relu,
@@ -206,7 +215,7 @@ int crnn_conv_first(const void* x, const void* w, const float* bias, void* out, 
 int crnn_gemm(const void* a, const void* w, const float* bias, void* out, float* out_f32, int32_t M, int32_t N, int32_t K,
               int32_t relu, int32_t planes, void* stream) {
     if (M <= 0) return fail(SALSA_EINVAL, "gemm: M must be positive");
-    return conv_generic(a, w, bias, nullptr, out, out_f32, 1, (M + 7) / 8, 8, K, N, 1, relu, planes, M, (cudaStream_t)stream);
+    return conv_generic(a, w, bias, nullptr, out, out_f32, 1, (M + 7) / 8, 8, K, N, 1, relu, planes, 0, M, (cudaStream_t)stream);
 }
 
 int crnn_set_option(const char* name, int32_t value) {

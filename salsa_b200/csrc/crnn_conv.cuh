@@ -41,6 +41,7 @@ struct ConvArgs {
     int tiles_w, tiles_h;      // spatial tiles per image
     int n_tiles;               // B * tiles_h * tiles_w * (Cout / N_TILE)
     int relu;
+    int pool;                  // 2x2 average pooling fused into the TMA-store epilogue: the output is [B][H/2][W/2][Cout]
     int tma_store;             // bf16 output leaves through a swizzled staging tile and TMA stores (planes == 1)
     int resident_b;            // all weight tiles stay in shared memory for the whole kernel (Cin = Cout = 64)
     long long pix_limit;       // pixels (rows of a GEMM) beyond this index are not written
@@ -192,10 +193,45 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvArgs& a, const CUten
                 *reinterpret_cast<uint4*>(tile + row * 128 + chunk * 16) = q4;
             }
         }
+        if (a.pool) {
+            // F.avg_pool2d(kernel 2x2) of the finished tile, in place: 32 pooled pixels x 8 chunks = 256 tasks for the
+            // 128 epilogue threads.  Averages the bf16-rounded activations in fp32, exactly like avgpool2_kernel.
+            tc::named_barrier(2, 128);
+            uint4 pooled[2];
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int task = (int)threadIdx.x - 128 + 128 * s2;
+                const int pp = task >> 3, c = task & 7;
+                const int r00 = (pp >> 2) * 16 + (pp & 3) * 2;
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int r = r00 + (d & 1) + (d >> 1) * 8;
+                    const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) * 16));
+                    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                        acc[2 * e] += __low2float(h2);
+                        acc[2 * e + 1] += __high2float(h2);
+                    }
+                }
+                pooled[s2] = make_uint4(pack_bf16(0.25f * acc[0], 0.25f * acc[1]), pack_bf16(0.25f * acc[2], 0.25f * acc[3]),
+                                        pack_bf16(0.25f * acc[4], 0.25f * acc[5]), pack_bf16(0.25f * acc[6], 0.25f * acc[7]));
+            }
+            tc::named_barrier(3, 128);                  // every read of the full-resolution tile is done
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int task = (int)threadIdx.x - 128 + 128 * s2;
+                const int pp = task >> 3, c = task & 7;
+                *reinterpret_cast<uint4*>(tile + pp * 128 + ((c ^ (pp & 7)) * 16)) = pooled[s2];
+            }
+        }
         tc::fence_proxy_async();                        // generic-proxy writes -> visible to the TMA engine
-        tc::named_barrier(2, 128);
+        tc::named_barrier(a.pool ? 4 : 2, 128);
         if (issuer) {
-            tc::tma_store_4d(tm_out, tile, n0 + g * 64, w0, h0, b);
+            if (a.pool) tc::tma_store_4d(tm_out, tile, n0 + g * 64, w0 >> 1, h0 >> 1, b);
+            else tc::tma_store_4d(tm_out, tile, n0 + g * 64, w0, h0, b);
             tc::tma_store_commit();
             tc::tma_store_wait_read<STG_BUFS - 1>();
         }

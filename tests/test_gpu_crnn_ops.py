@@ -156,3 +156,17 @@ def test_conv_first(ops, B, H, W, planes):
     wp[:, :, :7] = w.permute(2, 3, 0, 1).reshape(9, 64, 7)
     out = ops.conv_first(xp, ops.split_planes(wp, planes).cuda(), bias.cuda(), relu=True, planes=planes).cpu()
     assert rel_err(ops.merge_planes(out, planes), ref) < (1e-2 if planes == 1 else 1e-5)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(1, 32, 16, 64, 64), (2, 37, 25, 64, 64), (1, 33, 12, 128, 256), (1, 50, 100, 64, 128)])
+def test_conv2d_fused_pool_equals_separate_pool(ops, B, H, W, Cin, Cout):
+    """pool=True (epilogue-fused F.avg_pool2d) must be bit-identical to conv2d followed by avgpool2, odd sizes included."""
+    g = torch.Generator().manual_seed(H + W + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g).bfloat16().cuda()
+    w = (torch.randn(9, Cout, Cin, generator=g) / (Cin * 9) ** 0.5).bfloat16().cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(B, H, W, Cout, generator=g).bfloat16().cuda()
+    sep = ops.avgpool2(ops.conv2d(x, w, bias, residual=res, relu=True))
+    fused = ops.conv2d(x, w, bias, residual=res, relu=True, pool=True)
+    assert tuple(fused.shape) == (B, H // 2, W // 2, Cout)
+    assert torch.equal(fused.view(torch.int16), sep.view(torch.int16))
