@@ -43,7 +43,8 @@ int crnn_conv_first(const void *x, const void *w, const float *bias, void *out, 
 
 /* Tuning knobs of the convolution kernels (not part of the reference surface): "resident_b" (0 / 1: weights resident
  * in shared memory for 64 -> 64 convolutions), "tma_store" (0 / 1: bf16 outputs leave through a swizzled staging
- * tile and TMA stores instead of per-thread stores); value -1 restores the built-in choice. */
+ * tile and TMA stores instead of per-thread stores), "gru_mma" (0 / 1: tensor-core recurrent step for planes = 1);
+ * value -1 restores the built-in choice. */
 int crnn_set_option(const char *name, int32_t value);
 
 /* nn.Linear / GRU input projection (models/decoders.py:44-46, :75-92): out[M][N] = relu?(a[M][K] w[N][K]^T + bias).

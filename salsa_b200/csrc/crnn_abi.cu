@@ -47,6 +47,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_
 // tuning knobs (crnn_set_option): -1 = automatic
 static int g_opt_resident = -1;
 static int g_opt_tma_store = -1;
+static int g_opt_gru_mma = -1;
 
 // output tensor map of the TMA-store epilogue: bf16 NHWC [B][H][W][Cout], box = one 16 x 8 tile x 64 channels
 static int make_out_tmap(CUtensorMap* m, const void* out, int B, int H, int W, int Cout, int pool) {
@@ -222,6 +223,7 @@ int crnn_set_option(const char* name, int32_t value) {
     const std::string n = name ? name : "";
     if (n == "resident_b") g_opt_resident = value;
     else if (n == "tma_store") g_opt_tma_store = value;
+    else if (n == "gru_mma") g_opt_gru_mma = value;
     else return fail(SALSA_EINVAL, "unknown option " + n);
     return SALSA_OK;
 }
@@ -271,6 +273,12 @@ int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, voi
     a.T = T;
     a.planes = planes;
     const int groups = (B + kGruClips - 1) / kGruClips;
+    if (planes == 1 && (g_opt_gru_mma < 0 ? 1 : g_opt_gru_mma)) {
+        SALSA_CUDA(cudaFuncSetAttribute(gru_layer_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruMmaSmemBytes));
+        gru_layer_mma_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruMmaSmemBytes, (cudaStream_t)stream>>>(a);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "gru_layer_mma_kernel");
+    }
     gru_layer_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruSmemBytes, (cudaStream_t)stream>>>(a);
     count_launch();
     return check_cuda(cudaGetLastError(), "gru_layer_kernel");

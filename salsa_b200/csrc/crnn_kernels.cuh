@@ -245,6 +245,111 @@ __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThread
 }
 
 // ------------------------------------------------------------------------------------------------
+// gru_layer_mma_kernel: the same recurrence with the per-step matrix product on the tensor cores
+// (mma.sync m16n8k16, bf16 operands, fp32 accumulation) -- the fast ('bf16') mode.  Same cluster layout as
+// gru_layer_kernel.  A CTA's 96 x 256 slice of W_hh lives in REGISTERS for the whole sequence as the A
+// fragments of six warps (one 16-row tile each, 64 registers per lane); the hidden state of the 8 clips
+// is the 256 x 8 B operand, kept in shared memory as bf16 [clip][k] and re-published through DSMEM every
+// step; the fp32 hidden state of a (unit, clip) pair stays in the register of the thread that updates it.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGruHPitch = kGruHidden + 8;      // bf16 elements per clip row of the B operand (bank-conflict-free)
+constexpr size_t kGruMmaSmemBytes = (size_t)2 * kGruClips * kGruHPitch * sizeof(__nv_bfloat16) + (size_t)3 * kGruUnits * kGruClips * sizeof(float);
+
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1) gru_layer_mma_kernel(GruArgs a) {
+    extern __shared__ __align__(16) unsigned char gsm_raw[];
+    __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(gsm_raw);                       // [2][8 clips][kGruHPitch]
+    float* gates = reinterpret_cast<float*>(hb + 2 * kGruClips * kGruHPitch);             // [96 rows][8 clips]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / kGruCluster;
+    const int dir = cid & 1, grp = cid >> 1;
+    const int b0c = grp * kGruClips;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+
+    // A fragments of this warp's 16-row tile (warps 0..5): local rows 16*warp + {g, g+8}
+    uint32_t afrag[kGruHidden / 16][4];
+    if (warp < 6) {
+        const float* w = a.w_hh + (size_t)dir * 3 * kGruHidden * kGruHidden;
+        auto grow = [&](int lr) { return (size_t)((lr / kGruUnits) * kGruHidden + rank * kGruUnits + (lr % kGruUnits)) * kGruHidden; };
+        const float* r0 = w + grow(16 * warp + g);
+        const float* r1 = w + grow(16 * warp + g + 8);
+#pragma unroll
+        for (int ks = 0; ks < kGruHidden / 16; ++ks) {
+            const int k = 16 * ks + 2 * t4;
+            __nv_bfloat162 v;
+            v = __floats2bfloat162_rn(r0[k], r0[k + 1]);     afrag[ks][0] = *reinterpret_cast<uint32_t*>(&v);
+            v = __floats2bfloat162_rn(r1[k], r1[k + 1]);     afrag[ks][1] = *reinterpret_cast<uint32_t*>(&v);
+            v = __floats2bfloat162_rn(r0[k + 8], r0[k + 9]); afrag[ks][2] = *reinterpret_cast<uint32_t*>(&v);
+            v = __floats2bfloat162_rn(r1[k + 8], r1[k + 9]); afrag[ks][3] = *reinterpret_cast<uint32_t*>(&v);
+        }
+    }
+    for (int i = tid; i < 2 * kGruClips * kGruHPitch; i += kGruThreads) hb[i] = __float2bfloat16(0.0f);
+    cluster.sync();
+
+    const int jl = tid & 31, bl = tid >> 5;               // gate mapping: (unit, clip)
+    const int j = rank * kGruUnits + jl;
+    const float* bh = a.b_hh + (size_t)dir * 3 * kGruHidden;
+    const float b_hr = bh[j], b_hz = bh[kGruHidden + j], b_hn = bh[2 * kGruHidden + j];
+    const int b = b0c + bl;
+    const bool live = b < a.B;
+    float h_prev = 0.0f;
+
+    for (int s = 0; s < a.T; ++s) {
+        const int t = dir ? a.T - 1 - s : s;
+        const __nv_bfloat16* hc = hb + (s & 1) * kGruClips * kGruHPitch;
+        __nv_bfloat16* hn = hb + ((s + 1) & 1) * kGruClips * kGruHPitch;
+        float xr = 0.0f, xz = 0.0f, xn = 0.0f;
+        if (live) {
+            const float* xp = a.xproj + ((size_t)b * a.T + t) * (2 * 3 * kGruHidden) + dir * 3 * kGruHidden + j;
+            xr = __ldg(xp);
+            xz = __ldg(xp + kGruHidden);
+            xn = __ldg(xp + 2 * kGruHidden);
+        }
+        if (warp < 6) {
+            // two independent accumulators (even / odd k steps) halve the dependent MMA chain
+            float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t* hrow = reinterpret_cast<const uint32_t*>(hc + g * kGruHPitch) + t4;       // clip g, k = 2*t4
+#pragma unroll
+            for (int ks = 0; ks < kGruHidden / 16; ks += 2) {
+                mma_bf16_16x8x16(d0, afrag[ks], hrow[8 * ks], hrow[8 * ks + 4]);
+                mma_bf16_16x8x16(d1, afrag[ks + 1], hrow[8 * ks + 8], hrow[8 * ks + 12]);
+            }
+            // C fragment: rows g / g+8 of the tile, clips 2*t4, 2*t4+1
+            float* g0 = gates + (16 * warp + g) * kGruClips + 2 * t4;
+            *reinterpret_cast<float2*>(g0) = make_float2(d0[0] + d1[0], d0[1] + d1[1]);
+            *reinterpret_cast<float2*>(g0 + 8 * kGruClips) = make_float2(d0[2] + d1[2], d0[3] + d1[3]);
+        }
+        __syncthreads();
+        {
+            const float ar = gates[jl * kGruClips + bl];
+            const float az = gates[(kGruUnits + jl) * kGruClips + bl];
+            const float an = gates[(2 * kGruUnits + jl) * kGruClips + bl];
+            const float r = 1.0f / (1.0f + __expf(-(xr + ar + b_hr)));
+            const float z = 1.0f / (1.0f + __expf(-(xz + az + b_hz)));
+            const float n = tanhf(xn + r * (an + b_hn));
+            const float h_new = (1.0f - z) * n + z * h_prev;
+            h_prev = h_new;
+            const __nv_bfloat16 hb16 = __float2bfloat16(h_new);
+#pragma unroll
+            for (int c = 0; c < kGruCluster; ++c) {
+                __nv_bfloat16* remote = cluster.map_shared_rank(hn, c);
+                remote[bl * kGruHPitch + j] = hb16;
+            }
+            if (live) a.y[((size_t)b * a.T + t) * (2 * kGruHidden) + dir * kGruHidden + j] = hb16;
+        }
+        cluster.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // head GEMM output (rows, 64) fp32: cols 0..11 SED logits, 12..47 x|y|z before tanh
 __global__ void head_finish_kernel(const float* __restrict__ z, float* __restrict__ logits, float* __restrict__ doa, int rows,
                                    int n_classes) {
