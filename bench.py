@@ -589,5 +589,32 @@ def main():
     return 0
 
 
+def _main_with_clean_stdout():
+    """Libraries (NCCL's version banner, for one) write to file descriptor 1; the contract is ONE JSON line on stdout.
+    Everything is sent to stderr while the benchmark runs and only the result line goes to the real stdout."""
+    import io
+    real_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    py_stdout, sys.stdout = sys.stdout, buf
+    try:
+        rc = main()
+    finally:
+        sys.stdout = py_stdout
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    out = buf.getvalue()
+    json_lines = [ln for ln in out.splitlines() if ln.startswith('{')]
+    for ln in out.splitlines():
+        if not ln.startswith('{'):
+            print(ln, file=sys.stderr)
+    if json_lines:
+        print(json_lines[-1])
+        sys.stdout.flush()
+    return rc
+
+
 if __name__ == '__main__':
-    sys.exit(main())
+    sys.exit(_main_with_clean_stdout())
