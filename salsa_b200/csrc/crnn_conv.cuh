@@ -17,7 +17,8 @@
 //   warp 1     MMA issuer: 4 x tcgen05.mma (K = 16) per (chunk, tap); tcgen05.commit releases the
 //              shared-memory stages and finally publishes the accumulator.
 //   warp 2     TMEM allocation.
-//   warps 4-7  epilogue: tcgen05.ld -> + bias (+ residual) -> ReLU -> bf16 / fp32 NHWC stores.
+//   warps 4-11 epilogue (two per TMEM lane quarter): tcgen05.ld -> + bias (+ residual) -> ReLU -> bf16 staging
+//              tile -> TMA store (or direct fp32 / three-plane stores).
 // Persistent: grid = min(tiles, SMs), static round-robin over tiles.
 #pragma once
 #include <cuda_bf16.h>
@@ -29,7 +30,9 @@ namespace crnn {
 
 constexpr int kTileH = 16, kTileW = 8;       // 128 output pixels per tile
 constexpr int kKC = 64;                       // channels per K chunk = one 128-byte swizzle row
-constexpr int kConvThreads = 256;
+constexpr int kEpiWarps = 8;                  // two warps per TMEM lane quarter: each takes one 32-column half of a 64-channel group
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = 128 + kEpiThreads;
 constexpr int kAStages = 2;
 constexpr int kHaloBytes = (kTileH + 2) * kTileW * 128;    // one column-shifted halo tile (3x3)
 constexpr int kPlainBytes = kTileH * kTileW * 128;         // A tile of a 1x1 convolution / GEMM
@@ -77,7 +80,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int N_TILE>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0, int n0, size_t pix, bool valid) {
 #pragma unroll 1
-    for (int j = 0; j < N_TILE / 32; ++j) {
+    for (int j = ((int)threadIdx.x - 128) >> 7; j < N_TILE / 32; j += 2) {      // the two warps of a lane quarter alternate
         uint32_t r[32];
         const uint32_t taddr = taddr0 + (uint32_t)(j * 32);
         tc::tmem_ld32(taddr, r);
@@ -139,8 +142,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0
     }
 }
 
-// Epilogue of one tile through shared memory and TMA (bf16 output, planes == 1): per 64-channel group the four
-// epilogue warps convert their accumulator rows (+ bias from shared memory, + residual, ReLU) to bf16 and write
+// Epilogue of one tile through shared memory and TMA (bf16 output, planes == 1): per 64-channel group the eight
+// epilogue warps (two per TMEM lane quarter, one 32-column half each) convert their accumulator rows (+ bias from shared memory, + residual, ReLU) to bf16 and write
 // them into a 128 x 64 staging tile in the 128-byte-swizzled layout of the output tensor map; one thread then
 // issues a TMA store, which writes whole 128-byte lines and clips the tile at the image border.  Two staging
 // tiles alternate (one for N_TILE = 256) so the store of group g overlaps the conversion of group g + 1.
@@ -148,28 +151,40 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0
 template <int N_TILE, int STG_BUFS>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvArgs& a, const CUtensorMap* tm_out, unsigned char* stg, const float* bias_s,
                                                   uint32_t taddr0, int n0, int b, int h0, int w0, size_t pix, bool valid, int row,
-                                                  uint32_t& stg_count) {
+                                                  uint32_t& stg_count, uint64_t* acc_full_bar, uint32_t acc_parity) {
     const bool issuer = threadIdx.x == 128;
+    const int half = ((int)threadIdx.x - 128) >> 7;       // which 32-column half of every 64-channel group this warp converts
+    const bool has_res = a.residual != nullptr && valid;
+    // Residual values of the next 32-channel piece are requested one piece ahead -- the first one before the
+    // accumulator is even complete -- so that their global-memory latency hides behind the MMAs / the previous piece.
+    const uint4* res_base = reinterpret_cast<const uint4*>(a.residual + pix * a.Cout + n0 + half * 32);
+    uint4 res_next[4];
+    if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res_next[i] = __ldg(res_base + i);
+    }
+    tc::mbar_wait(acc_full_bar, acc_parity);
+    tc::fence_after_sync();
 #pragma unroll 1
     for (int g = 0; g < N_TILE / 64; ++g) {
         unsigned char* tile = stg + (stg_count % STG_BUFS) * (128 * 128);
-        tc::named_barrier(1, 128);                      // the issuer has waited for the store that last read `tile`
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        tc::named_barrier(1, kEpiThreads);              // the issuer has waited for the store that last read `tile`
+        {
             uint32_t r[32];
             tc::tmem_ld32(taddr0 + (uint32_t)(g * 64 + half * 32), r);
             const int n = n0 + g * 64 + half * 32;
             uint4 res[4];
-            if (a.residual && valid) {
-                const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.Cout + n);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
+            for (int i = 0; i < 4; ++i) res[i] = res_next[i];
+            if (has_res && g + 1 < N_TILE / 64) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) res_next[i] = __ldg(res_base + (g + 1) * 8 + i);
             }
             tc::tmem_ld_wait();
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (bias_s ? bias_s[n + i] : (a.bias ? __ldg(a.bias + n + i) : 0.0f));
-            if (a.residual && valid) {
+            if (has_res) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t w4[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
@@ -194,13 +209,13 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvArgs& a, const CUten
             }
         }
         if (a.pool) {
-            // F.avg_pool2d(kernel 2x2) of the finished tile, in place: 32 pooled pixels x 8 chunks = 256 tasks for the
-            // 128 epilogue threads.  Averages the bf16-rounded activations in fp32, exactly like avgpool2_kernel.
-            tc::named_barrier(2, 128);
-            uint4 pooled[2];
+            // F.avg_pool2d(kernel 2x2) of the finished tile, in place: 32 pooled pixels x 8 chunks = 256 tasks, one per
+            // epilogue thread.  Averages the bf16-rounded activations in fp32, exactly like avgpool2_kernel.
+            tc::named_barrier(2, kEpiThreads);
+            uint4 pooled[1];
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int task = (int)threadIdx.x - 128 + 128 * s2;
+            for (int s2 = 0; s2 < 1; ++s2) {
+                const int task = (int)threadIdx.x - 128;
                 const int pp = task >> 3, c = task & 7;
                 const int r00 = (pp >> 2) * 16 + (pp & 3) * 2;
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -219,16 +234,16 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvArgs& a, const CUten
                 pooled[s2] = make_uint4(pack_bf16(0.25f * acc[0], 0.25f * acc[1]), pack_bf16(0.25f * acc[2], 0.25f * acc[3]),
                                         pack_bf16(0.25f * acc[4], 0.25f * acc[5]), pack_bf16(0.25f * acc[6], 0.25f * acc[7]));
             }
-            tc::named_barrier(3, 128);                  // every read of the full-resolution tile is done
+            tc::named_barrier(3, kEpiThreads);          // every read of the full-resolution tile is done
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int task = (int)threadIdx.x - 128 + 128 * s2;
+            for (int s2 = 0; s2 < 1; ++s2) {
+                const int task = (int)threadIdx.x - 128;
                 const int pp = task >> 3, c = task & 7;
                 *reinterpret_cast<uint4*>(tile + pp * 128 + ((c ^ (pp & 7)) * 16)) = pooled[s2];
             }
         }
         tc::fence_proxy_async();                        // generic-proxy writes -> visible to the TMA engine
-        tc::named_barrier(a.pool ? 4 : 2, 128);
+        tc::named_barrier(a.pool ? 4 : 2, kEpiThreads);
         if (issuer) {
             if (a.pool) tc::tma_store_4d(tm_out, tile, n0 + g * 64, w0 >> 1, h0 >> 1, b);
             else tc::tma_store_4d(tm_out, tile, n0 + g * 64, w0, h0, b);
@@ -279,7 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(acc_full + i, 1);
-            tc::mbar_init(acc_empty + i, 4);
+            tc::mbar_init(acc_empty + i, kEpiWarps);
         }
         tc::fence_barrier_init();
     }
@@ -418,13 +433,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const int h = h0 + hl, w = w0 + wl;
             const size_t pix = ((size_t)b * a.H + h) * a.W + w;
             const bool valid = h < a.H && w < a.W && (long long)pix < a.pix_limit;
-            tc::mbar_wait(acc_full + as, pacc);
-            tc::fence_after_sync();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
-            if (a.tma_store)
-                epilogue_tile_tma<N_TILE, S::kStgBufs>(a, &tm_out, stg_smem, bias_s, taddr0, n0, b, h0, w0, pix, valid, row, stg_count);
-            else
+            if (a.tma_store) {
+                epilogue_tile_tma<N_TILE, S::kStgBufs>(a, &tm_out, stg_smem, bias_s, taddr0, n0, b, h0, w0, pix, valid, row, stg_count,
+                                                       acc_full + as, pacc);
+            } else {
+                tc::mbar_wait(acc_full + as, pacc);
+                tc::fence_after_sync();
                 epilogue_tile<N_TILE>(a, taddr0, n0, pix, valid);
+            }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + as);
@@ -488,7 +505,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
         tc::mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(acc_full + i, 1);
-            tc::mbar_init(acc_empty + i, 4);
+            tc::mbar_init(acc_empty + i, kEpiWarps);
         }
         tc::fence_barrier_init();
     }
@@ -578,13 +595,15 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
             const int h = h0 + hl, w = w0 + wl;
             const size_t pix = ((size_t)b * a.H + h) * a.W + w;
             const bool valid = h < a.H && w < a.W;
-            tc::mbar_wait(acc_full + as, pacc);
-            tc::fence_after_sync();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
-            if (a.tma_store)
-                epilogue_tile_tma<N_TILE, 2>(a, &tm_out, stg_smem, bias_s, taddr0, 0, b, h0, w0, pix, valid, row, stg_count);
-            else
+            if (a.tma_store) {
+                epilogue_tile_tma<N_TILE, 2>(a, &tm_out, stg_smem, bias_s, taddr0, 0, b, h0, w0, pix, valid, row, stg_count, acc_full + as,
+                                             pacc);
+            } else {
+                tc::mbar_wait(acc_full + as, pacc);
+                tc::fence_after_sync();
                 epilogue_tile<N_TILE>(a, taddr0, 0, pix, valid);
+            }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + as);
