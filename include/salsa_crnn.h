@@ -76,6 +76,12 @@ int crnn_gru_layer(const float *xproj, const float *w_hh, const float *b_hh, voi
  * event|x|y|z second-layer outputs in columns 0..4*n_classes-1; logits = z[:, :n], doa = tanh(z[:, n:4n]). */
 int crnn_head_finish(const float *z, float *logits, float *doa, int32_t rows, int32_t n_classes, void *stream);
 
+/* Output decoding of BaseModel.write_classwise_output_to_file (models/interfaces.py:224-246), reg_xyz format, on
+ * label-rate outputs: logits fp32 [rows][n_classes], doa fp32 [rows][3*n_classes] (x | y | z) ->
+ * active[rows][n_classes] = sigmoid(logit) >= threshold, azi / ele int16 whole degrees (np.around, 180 -> -180). */
+int crnn_decode_events(const float *logits, const float *doa, int32_t rows, int32_t n_classes, float threshold,
+                       uint8_t *active, int16_t *azi, int16_t *ele, void *stream);
+
 /* interpolate_tensor (models/model_utils.py:57-75): out[b][i][:] = in[b][idx[i]][:], idx computed by the
  * host exactly as the reference does (floor(arange(n_out) / ratio) in float32). */
 int crnn_gather_time(const float *in, const int32_t *idx, float *out, int32_t B, int32_t n_in, int32_t n_out,

@@ -159,6 +159,35 @@ def interpolate_tensor(tensor, ratio: float = 1.0):
     return tensor[:, input_idx]
 
 
+def decode_events(event_frame_logit, doa_frame_output, sed_threshold: float = 0.3, max_nframes_per_file: int = None,
+                  eval_version: str = '2021'):
+    """write_classwise_output_to_file (models/interfaces.py:210-258) for ONE file given as a single chunk
+    (batch dimension 1): the rows of the submission csv."""
+    n_classes = event_frame_logit.shape[-1]
+    doa = doa_frame_output.detach().cpu().numpy()
+    event = torch.sigmoid(event_frame_logit).detach().cpu().numpy()
+    assert event.shape[0] == 1
+    event, doa = event[0], doa[0]
+    event = (event >= sed_threshold)
+    n_frames = event.shape[0] if max_nframes_per_file is None else max_nframes_per_file
+    assert event.shape[0] >= n_frames, 'n_output_frames of sed < max_nframes_per_file'
+    x, y, z = doa[:, :n_classes], doa[:, n_classes:2 * n_classes], doa[:, 2 * n_classes:]
+    azi_out = np.around(np.arctan2(y, x) * 180.0 / np.pi)
+    ele_out = np.around(np.arctan2(z, np.sqrt(x ** 2 + y ** 2)) * 180.0 / np.pi)
+    outputs = []
+    for iframe in np.arange(n_frames):
+        for class_idx in np.where(event[iframe] == 1)[0]:
+            azi = int(azi_out[iframe, class_idx])
+            if azi == 180:
+                azi = -180
+            ele = int(ele_out[iframe, class_idx])
+            if eval_version == '2021':
+                outputs.append([int(iframe), int(class_idx), 0, azi, ele])
+            else:
+                outputs.append([int(iframe), int(class_idx), azi, ele])
+    return outputs
+
+
 def model_input(seed: int = 2, shape=(2, 7, 128, 200)) -> torch.Tensor:
     """Deterministic feature-like input: log-spectrogram-scale first four channels, [-1, 1] spatial ones."""
     g = torch.Generator().manual_seed(seed)

@@ -239,3 +239,24 @@ class SeldModel:
         ratio = self.time_downsample_ratio * self.label_rate / self.feature_rate
         idx = ops.interpolate_index(out['event_frame_logit'].shape[1], ratio)
         return {k: ops.gather_time(v, idx) for k, v in out.items()}
+
+    def events(self, x, sed_threshold: float = 0.3, max_nframes_per_file: int = None, eval_version: str = '2021'):
+        """predict + the decoding of `write_classwise_output_to_file` (models/interfaces.py:210-258) for whole-clip inputs
+        (one chunk per file, as the reference's test configuration): per clip the list of rows the reference writes to the
+        submission csv, [frame, class, 0, azimuth, elevation] (2021) or [frame, class, azimuth, elevation]."""
+        pred = self.predict(x)
+        logit, doa = pred['event_frame_logit'], pred['doa_frame_output']
+        B, T, n = logit.shape
+        active, azi, ele = ops.decode_events(logit.reshape(B * T, n), doa.reshape(B * T, 3 * n), sed_threshold)
+        active = active.reshape(B, T, n).cpu().numpy()
+        azi, ele = azi.reshape(B, T, n).cpu().numpy(), ele.reshape(B, T, n).cpu().numpy()
+        n_frames = T if max_nframes_per_file is None else max_nframes_per_file
+        assert T >= n_frames, 'n_output_frames of sed < max_nframes_per_file'
+        rows = []
+        for b in range(B):
+            fr, cl = np.nonzero(active[b, :n_frames])
+            if eval_version == '2021':
+                rows.append([[int(f), int(c), 0, int(azi[b, f, c]), int(ele[b, f, c])] for f, c in zip(fr, cl)])
+            else:
+                rows.append([[int(f), int(c), int(azi[b, f, c]), int(ele[b, f, c])] for f, c in zip(fr, cl)])
+        return rows

@@ -180,3 +180,18 @@ def gather_time(x, idx):
     out = torch.empty((B, len(idx), width), dtype=torch.float32, device=x.device)
     _native.check(_native.lib().crnn_gather_time(_p(x), _p(d_idx), _p(out), B, n_in, len(idx), width, _st()))
     return out
+
+
+def decode_events(logits, doa, threshold=0.3):
+    """logits (rows, n) fp32 CUDA, doa (rows, 3n) fp32 CUDA -> active (rows, n) bool, azi, ele (rows, n) int16
+    (write_classwise_output_to_file, models/interfaces.py:224-246)."""
+    logits, doa = logits.contiguous(), doa.contiguous()
+    rows, n = logits.shape
+    if tuple(doa.shape) != (rows, 3 * n):
+        raise ValueError('doa must be (rows, 3 * n_classes)')
+    active = torch.empty((rows, n), dtype=torch.uint8, device=logits.device)
+    azi = torch.empty((rows, n), dtype=torch.int16, device=logits.device)
+    ele = torch.empty((rows, n), dtype=torch.int16, device=logits.device)
+    _native.check(_native.lib().crnn_decode_events(_p(logits), _p(doa), rows, n, ctypes.c_float(threshold), _p(active), _p(azi),
+                                                   _p(ele), _st()))
+    return active.bool(), azi, ele

@@ -292,6 +292,16 @@ int crnn_head_finish(const float* z, float* logits, float* doa, int32_t rows, in
     return check_cuda(cudaGetLastError(), "head_finish_kernel");
 }
 
+int crnn_decode_events(const float* logits, const float* doa, int32_t rows, int32_t n_classes, float threshold, uint8_t* active,
+                       int16_t* azi, int16_t* ele, void* stream) {
+    if (!logits || !doa || !active || !azi || !ele) return fail(SALSA_EINVAL, "decode_events: null pointer");
+    if (rows <= 0 || n_classes <= 0) return SALSA_OK;
+    decode_events_kernel<<<grid_for((long long)rows * n_classes, 256), 256, 0, (cudaStream_t)stream>>>(logits, doa, rows, n_classes,
+                                                                                                      threshold, active, azi, ele);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "decode_events_kernel");
+}
+
 int crnn_gather_time(const float* in, const int32_t* idx, float* out, int32_t B, int32_t n_in, int32_t n_out, int32_t width,
                      void* stream) {
     if (!in || !idx || !out) return fail(SALSA_EINVAL, "gather_time: null pointer");

@@ -362,6 +362,36 @@ __global__ void head_finish_kernel(const float* __restrict__ z, float* __restric
     }
 }
 
+// Output decoding of BaseModel.write_classwise_output_to_file (models/interfaces.py:224-246), reg_xyz format:
+// active = sigmoid(logit) >= threshold; azimuth / elevation in whole degrees from the (x, y, z) regression,
+// np.around (half to even) of the float32 degree value, azimuth 180 -> -180.
+// One thread per (row, class); rows = clips x frames.
+__global__ void decode_events_kernel(const float* __restrict__ logits, const float* __restrict__ doa, int rows, int n_classes,
+                                     float threshold, uint8_t* __restrict__ active, int16_t* __restrict__ azi,
+                                     int16_t* __restrict__ ele) {
+    const int total = rows * n_classes;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / n_classes, c = i - r * n_classes;
+        // torch.sigmoid in float32, then the comparison against a Python float (promoted to float64 by NumPy)
+        const float prob = 1.0f / (1.0f + expf(-logits[i]));
+        active[i] = (double)prob >= (double)threshold ? 1 : 0;
+        const float x = doa[(size_t)r * 3 * n_classes + c];
+        const float y = doa[(size_t)r * 3 * n_classes + n_classes + c];
+        const float z = doa[(size_t)r * 3 * n_classes + 2 * n_classes + c];
+        // float32 arithmetic like NumPy on float32 arrays; the transcendental itself is evaluated in float64 and rounded,
+        // i.e. the correctly rounded float32 value
+        const float a_rad = (float)atan2((double)y, (double)x);
+        const float hyp = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));      // no FMA contraction: NumPy rounds each step
+        const float e_rad = (float)atan2((double)z, (double)hyp);
+        const float k180 = 180.0f, kpi = 3.14159265358979323846f;
+        int a_deg = (int)rintf(__fdiv_rn(__fmul_rn(a_rad, k180), kpi));
+        const int e_deg = (int)rintf(__fdiv_rn(__fmul_rn(e_rad, k180), kpi));
+        if (a_deg == 180) a_deg = -180;
+        azi[i] = (int16_t)a_deg;
+        ele[i] = (int16_t)e_deg;
+    }
+}
+
 // out[b][i][:] = in[b][idx[i]][:]
 __global__ void gather_time_kernel(const float* __restrict__ in, const int* __restrict__ idx, float* __restrict__ out, int B,
                                    int n_in, int n_out, int width) {

@@ -135,3 +135,31 @@ def test_fused_scaler_normalisation(model):
         model.set_scaler(None, None)
     for k in ref:
         assert torch.equal(out[k], ref[k])
+
+
+def test_event_decoding_matches_oracle(model):
+    """sigmoid threshold, arctan2 -> whole degrees, csv rows (interfaces.py:210-258): integer outputs must be identical."""
+    from oracle import crnn as ocrnn
+    x = ocrnn.model_input(8, (2, 7, 160, 200))
+    pred = model.predict(x.cuda())
+    rows = model.events(x.cuda(), sed_threshold=0.3)
+    assert len(rows) == 2
+    for b in range(2):
+        ref = ocrnn.decode_events(pred['event_frame_logit'][b:b + 1].cpu(), pred['doa_frame_output'][b:b + 1].cpu(), 0.3)
+        assert rows[b] == ref
+        assert len(ref) > 10
+    # the decoding kernel alone on a dense grid of directions, including the +-180 and +-90 degree edges
+    import salsa_b200
+    g = torch.Generator().manual_seed(3)
+    doa = torch.randn(4000, 36, generator=g)
+    doa[:50, 12:24] = 0.0                      # y = 0: azimuth 0 or 180 -> -180
+    doa[:25, :12] = -doa[:25, :12].abs()
+    logits = torch.randn(4000, 12, generator=g) * 3
+    active, azi, ele = salsa_b200.crnn_ops.decode_events(logits.cuda(), doa.cuda(), 0.3)
+    xs, ys, zs = doa[:, :12].numpy(), doa[:, 12:24].numpy(), doa[:, 24:].numpy()
+    ref_azi = np.around(np.arctan2(ys, xs) * 180.0 / np.pi).astype(int)
+    ref_azi[ref_azi == 180] = -180
+    ref_ele = np.around(np.arctan2(zs, np.sqrt(xs ** 2 + ys ** 2)) * 180.0 / np.pi).astype(int)
+    assert np.array_equal(azi.cpu().numpy().astype(int), ref_azi)
+    assert np.array_equal(ele.cpu().numpy().astype(int), ref_ele)
+    assert np.array_equal(active.cpu().numpy(), (torch.sigmoid(logits).numpy() >= 0.3))
