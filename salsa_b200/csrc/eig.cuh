@@ -289,14 +289,4 @@ __device__ __forceinline__ void normalise_foa(const Cx<T> (&v)[4], float (&out)[
     for (int i = 0; i < 3; ++i) out[i] = (float)(n[i] * s);
 }
 
-// MIC: angle(u[1:] conj(u[0])) / (delta * absolute_bin)  (reference :121-123).
-template <typename T>
-__device__ __forceinline__ void normalise_mic(const Cx<T> (&v)[4], double inv_delta_bin, float (&out)[3]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const Cx<T> p = cmulc(v[i + 1], v[0]);
-        out[i] = (float)(atan2((double)p.im, (double)p.re) * inv_delta_bin);
-    }
-}
-
 }  // namespace salsa

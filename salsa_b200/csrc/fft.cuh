@@ -66,10 +66,11 @@ __device__ __forceinline__ void dft4(Cx<T> (&v)[4]) {
     v[1] = cadd(a1, a3); v[3] = csub(a1, a3);
 }
 
-// Per-lane twiddle tables, built once by the host in long double and rounded (salsa_abi.cu).
-//   tw_a[k1][lane] = exp(-2 pi i * lane*k1 / 256)          k1 = 0..7   (pass 1 -> pass 2)
-//   tw_b[j1][lane] = exp(-2 pi i * (lane&3)*j1 / 32)       j1 = 0..7   (pass 2 -> pass 3)
-//   tw_r[k]        = exp(-2 pi i * k / 512)                k = 0..255  (real split)
+// Twiddle tables, built once by the host in long double and rounded (salsa_abi.cu).  The kernels read
+// three values per lane from them (lane_twiddles) and derive everything else in registers.
+//   tw_a[k1][lane] = exp(-2 pi i * lane*k1 / 256)          k1 = 0..7   (row 1 is used)
+//   tw_b[j1][lane] = exp(-2 pi i * (lane&3)*j1 / 32)       j1 = 0..7   (row 1 is used)
+//   tw_r[k]        = exp(-2 pi i * k / 512)                k = 0..255  (k = lane is used)
 template <typename T>
 struct FftTables {
     const Cx<T>* tw_a;
