@@ -136,10 +136,6 @@ int salsa_lite_extract_host(const salsa_params_t *p, int32_t cutoff_bin, int32_t
 int salsa_scaler_accumulate(const float *feature, int32_t n_clips, int32_t n_feat_chans, int32_t n_frames,
                             int32_t feat_dim, double *sums, void *stream);
 
-/* Tuning knob (not part of the reference surface): "fused_variant" = 0 (phase-alternating fused kernel, two CTAs per SM),
- * 1 (warp-specialised fused kernel, one 16-warp CTA per SM), -1 (built-in choice). */
-int salsa_set_option(const char *name, int32_t value);
-
 /* The host-buffer entry points keep their streams and device staging buffers between calls (per host thread);
  * this frees them. */
 int salsa_host_release(void);

@@ -52,7 +52,6 @@ SIGNATURES = {
     'salsa_extract_host': (ctypes.c_int, [_P, _vp, _vp, _i32]),
     'salsa_lite_extract_host': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _i32]),
     'salsa_scaler_accumulate': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
-    'salsa_set_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),
     'salsa_host_release': (ctypes.c_int, []),
     'salsa_launch_count': (_u64, [ctypes.c_int]),
     'salsa_profile_enable': (ctypes.c_int, [ctypes.c_int]),

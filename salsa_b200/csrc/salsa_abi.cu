@@ -274,8 +274,6 @@ static int launch_tracker(const double* power0, uint32_t* mask, int n_clips, int
 }
 
 constexpr int kFusedFT = 4;   // new frames per step of salsa_fused_kernel
-constexpr bool kDefaultWarpSpecialised = false;
-static int g_fused_variant = -1;    // salsa_set_option("fused_variant"): 0 = phase-alternating kernel, 1 = warp-specialised, -1 = default
 
 static int choose_seg_len(int n_clips, int n_frames) {
     // aim for >= 4 CTAs per SM slot (2 resident CTAs x 148 SMs) while keeping the 6-frame halo small
@@ -309,21 +307,6 @@ static int launch_fused(const salsa_params_t* p, const DeviceTables& tb, const f
     dim3 grid((a.n_frames + a.seg_len - 1) / a.seg_len, p->n_clips);
     if (a.nbp > 256) return fail(SALSA_EINVAL, "more than 256 spatial bins");
     ProfScope prof("salsa_fused_kernel", st);
-    const bool ws = g_fused_variant < 0 ? kDefaultWarpSpecialised : g_fused_variant == 1;
-    if (ws) {         // warp-specialised variant: one CTA of 16 warps per SM
-        if (p->stft_precision == 64) {
-            const size_t smem = fused_ws_smem_bytes<double>(a.nbp);
-            int rc = set_smem(salsa_fused_ws_kernel<double>, smem);
-            if (rc) return rc;
-            salsa_fused_ws_kernel<double><<<grid, kWsThreads, smem, st>>>(a, tb.d);
-        } else {
-            const size_t smem = fused_ws_smem_bytes<float>(a.nbp);
-            int rc = set_smem(salsa_fused_ws_kernel<float>, smem);
-            if (rc) return rc;
-            salsa_fused_ws_kernel<float><<<grid, kWsThreads, smem, st>>>(a, tb.f);
-        }
-        return check_launch("salsa_fused_ws_kernel");
-    }
     if (p->stft_precision == 64) {
         const size_t smem = fused_smem_bytes<double, kFusedFT>(a.nbp);
         int rc = set_smem(salsa_fused_kernel<double, kFusedFT>, smem);
@@ -687,13 +670,6 @@ int salsa_scaler_accumulate(const float* feature, int32_t n_clips, int32_t n_fea
     dim3 grid((n_frames + frames_per_block - 1) / frames_per_block, 4, n_clips);
     scaler_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feature, n_frames, feat_dim, n_feat_chans, frames_per_block, sums);
     return check_launch("scaler_accumulate_kernel");
-}
-
-int salsa_set_option(const char* name, int32_t value) {
-    const std::string n = name ? name : "";
-    if (n == "fused_variant") g_fused_variant = value;
-    else return fail(SALSA_EINVAL, "unknown option " + n);
-    return SALSA_OK;
 }
 
 int salsa_host_release(void) {

@@ -11,7 +11,6 @@
 #pragma once
 #include "eig.cuh"
 #include "fft.cuh"
-#include "tc_ptx.cuh"
 
 namespace salsa {
 
@@ -535,199 +534,6 @@ __global__ void __launch_bounds__(kThreads, 2) salsa_fused_kernel(FusedArgs a, F
             }
         }
         __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// salsa_fused_ws_kernel: the same clip path, warp-specialised.  One CTA of 16 warps per SM:
-//   warps 0-7   FFT producers: transform groups of 4 frames (16 (frame, channel) items per group, two per warp)
-//               into a shared-memory ring of 6 groups, write the log-spectrogram rows, arrive on full[group];
-//   warps 8-15  eigen consumers: per step of 4 frames compact the tracker mask, wait for the three groups the
-//               7-frame windows touch, run the eigenvector step, arrive on done[step], write the spatial rows.
-// The two halves only meet at mbarriers (full / done), so the float64 + shared-memory-heavy transform and the
-// float32-heavy eigen step overlap continuously instead of alternating behind CTA-wide barriers.
-// Group j holds frames [s0 - 4 + 4j, s0 + 4j); consumer step s = frames of group s + 1 and needs groups s..s+2.
-// ------------------------------------------------------------------------------------------------
-constexpr int kWsFT = 4;                      // frames per group / step
-constexpr int kWsGroups = 6;                  // ring depth in groups
-constexpr int kWsSlots = kWsFT * kWsGroups;   // ring depth in frames
-constexpr int kWsFWarps = 8, kWsEWarps = 8;
-constexpr int kWsThreads = 32 * (kWsFWarps + kWsEWarps);
-
-template <typename T>
-__host__ __device__ inline size_t fused_ws_smem_bytes(int nbp) {
-    return sizeof(FftSmem<T>) + (size_t)kWsSlots * 4 * nbp * sizeof(float2) + (size_t)2 * 3 * kWsFT * nbp * sizeof(float) +
-           (size_t)2 * kWsFT * nbp * sizeof(uint16_t) + 2 * kWsFT * 8 * sizeof(uint32_t) + 2 * kWsGroups * sizeof(uint64_t) + 16;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kWsThreads, 1) salsa_fused_ws_kernel(FusedArgs a, FftTables<T> tb) {
-    static_assert(kWsFWarps == kWarps, "FftSmem has one scratch area per producer warp");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
-    float2* ring = reinterpret_cast<float2*>(smem_raw + sizeof(FftSmem<T>));                   // [kWsSlots][4][nbp]
-    float* stage = reinterpret_cast<float*>(ring + (size_t)kWsSlots * 4 * a.nbp);               // [2][3][FT][nbp]
-    uint16_t* list = reinterpret_cast<uint16_t*>(stage + (size_t)2 * 3 * kWsFT * a.nbp);        // [2][FT * nbp]
-    uint32_t* smask = reinterpret_cast<uint32_t*>(list + (size_t)2 * kWsFT * a.nbp);            // [2][FT][8]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smask + 2 * kWsFT * 8);                        // [kWsGroups]
-    uint64_t* done = full + kWsGroups;                                                          // [kWsGroups]
-    int* n_items = reinterpret_cast<int*>(done + kWsGroups);                                    // [2]
-
-    load_fft_smem(s, tb);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kWsGroups; ++i) {
-            tc::mbar_init(full + i, kWsFWarps);
-            tc::mbar_init(done + i, kWsEWarps);
-        }
-        n_items[0] = n_items[1] = 0;
-        tc::fence_barrier_init();
-    }
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int clip = blockIdx.y;
-    const int s0 = blockIdx.x * a.seg_len;
-    const int s1 = min(a.n_frames, s0 + a.seg_len);
-    const int n_bins = a.upper - a.lower;
-    const int n_words = (n_bins + 31) >> 5;
-    const int feat_dim = a.bands.n_out;
-    const long long chan_stride = (long long)a.n_frames * feat_dim;
-    const float* clip_audio = a.audio + (long long)clip * 4 * a.n_samples;
-    float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
-    const int row = 4 * a.nbp;                                       // float2 per ring slot
-    const int n_steps = (s1 - s0 + kWsFT - 1) / kWsFT;
-    const int n_groups = n_steps + 2;                                // groups 0 .. n_steps + 1 cover frames s0 - 4 .. s1 + 3 or more
-
-    if (warp < kWsFWarps) {
-        // ======================= producers =======================
-        const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
-        Cx<T>* scratch = s.scratch[warp];
-        auto frame_start = [&](int f) {
-            f %= a.n_frames;                                         // wrap padding of the frame axis (:43)
-            if (f < 0) f += a.n_frames;
-            return f * a.hop - kNfft / 2;
-        };
-        float2 raw[8];
-        // item i of group j: frame s0 - 4 + 4 j + (i >> 2), channel i & 3; this warp owns items warp and warp + 8
-        load_frame(clip_audio + (long long)(warp & 3) * a.n_samples, a.n_samples, frame_start(s0 - kWsFT + (warp >> 2)), lane, raw);
-        for (int j = 0; j < n_groups; ++j) {
-            if (j >= kWsGroups) tc::mbar_wait(done + j % kWsGroups, (uint32_t)((j / kWsGroups - 1) & 1));
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int item = warp + 8 * half;
-                const int fl = item >> 2, ch = item & 3;
-                const int f = s0 - kWsFT + kWsFT * j + fl;
-                float2 cur[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cur[i] = raw[i];
-                {   // request the samples of this warp's next item before transforming the current one
-                    const int nj = half == 0 ? j : j + 1;
-                    const int nitem = half == 0 ? warp + 8 : warp;
-                    if (nj < n_groups)
-                        load_frame(clip_audio + (long long)(nitem & 3) * a.n_samples, a.n_samples,
-                                   frame_start(s0 - kWsFT + kWsFT * nj + (nitem >> 2)), lane, raw);
-                }
-                Cx<T> X[8];
-                T nyq;
-                warp_rfft512<T>(cur, tb.window ? s.win : nullptr, tw, scratch, lane, X, nyq);
-                float2* dst = ring + ((kWsFT * j + fl) % kWsSlots) * row + ch * a.nbp;
-                float p[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int k = lane + 32 * jj;
-                    const float re = (float)X[jj].re, im = (float)X[jj].im;
-                    p[jj] = power_f32(re, im);
-                    if (k >= a.lower && k < a.upper) dst[k - a.lower] = make_float2(re, im);
-                }
-                const float p_nyq = power_f32((float)nyq, 0.0f);
-                if (f >= s0 && f < s1) write_logspec_row(p, p_nyq, clip_feat + ch * chan_stride + (long long)f * feat_dim, a.bands, lane);
-            }
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(full + j % kWsGroups);
-        }
-    } else {
-        // ======================= consumers =======================
-        const int ew = warp - kWsFWarps;                             // 0..7
-        const int etid = (int)threadIdx.x - 32 * kWsFWarps;          // 0..255
-        constexpr int kEThreads = 32 * kWsEWarps;
-        const uint32_t tail_bits = (n_bins & 31) ? ((1u << (n_bins & 31)) - 1u) : 0xffffffffu;
-        const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
-        const uint32_t ch_bytes = (uint32_t)(a.nbp * sizeof(float2));
-        for (int st = 0; st < n_steps; ++st) {
-            const int buf = st & 1;
-            const int t0 = s0 + kWsFT * st;
-            const int nt = min(kWsFT, s1 - t0);
-            uint16_t* lst = list + buf * kWsFT * a.nbp;
-            uint32_t* msk = smask + buf * kWsFT * 8;
-            float* stg = stage + (size_t)buf * 3 * kWsFT * a.nbp;
-            // ---- compaction of the selected (frame, bin) items (does not need the ring)
-            for (int w = ew; w < nt * n_words; w += kWsEWarps) {
-                const int tl = w / n_words, wi = w - tl * n_words;
-                uint32_t bits = a.mask ? a.mask[((long long)clip * a.n_frames + t0 + tl) * n_words + wi] : 0xffffffffu;
-                if (wi == n_words - 1) bits &= tail_bits;
-                int base = 0;
-                if (lane == 0) {
-                    msk[tl * 8 + wi] = bits;
-                    base = atomicAdd(n_items + buf, __popc(bits));
-                }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if ((bits >> lane) & 1u) lst[base + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((tl << 8) | (wi * 32 + lane));
-            }
-            tc::named_barrier(1, kEThreads);
-            if (etid == 0) n_items[buf ^ 1] = 0;                     // for the next step; its last reader passed barrier 2 of step st - 1
-            // ---- the windows of this step touch groups st .. st + 2
-            if (st == 0) {
-                tc::mbar_wait(full + 0, 0);
-                tc::mbar_wait(full + 1, 0);
-            }
-            tc::mbar_wait(full + (st + 2) % kWsGroups, (uint32_t)(((st + 2) / kWsGroups) & 1));
-            const int count = n_items[buf];
-            for (int item = etid; item < count; item += kEThreads) {
-                const int code = lst[item];
-                const int tl = code >> 8, b = code & 255;
-                // frame t = t0 + tl sits at ring position 4 (st + 1) + tl; its window starts three frames earlier
-                int slot = (kWsFT * (st + 1) + tl - kHop) % kWsSlots;
-                uint32_t fa[kWin];
-#pragma unroll
-                for (int k = 0; k < kWin; ++k) {
-                    fa[k] = ring_addr + (uint32_t)((slot * row + b) * sizeof(float2));
-                    slot = slot + 1 == kWsSlots ? 0 : slot + 1;
-                }
-                float o[3];
-                auto load = [&](int k, int ch) -> float2 { return lds_f2(fa[k] + ch * ch_bytes); };
-                eig_bin(load, a.eig, b, o);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) stg[(i * kWsFT + tl) * a.nbp + b] = o[i];
-            }
-            tc::named_barrier(2, kEThreads);
-            if (lane == 0) tc::mbar_arrive(done + st % kWsGroups);   // ring groups <= st may be overwritten
-            // ---- the three spatial rows of every frame, whole rows
-            if ((feat_dim & 3) == 0) {
-                const int groups = feat_dim >> 2;
-                for (int g = etid; g < 3 * nt * groups; g += kEThreads) {
-                    const int r = g / groups, k = (g - r * groups) * 4;
-                    const int i = r / nt, tl = r - i * nt;
-                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (k < n_bins) {
-                        const uint32_t bits = msk[tl * 8 + (k >> 5)] >> (k & 31);
-                        const float* sp = stg + (i * kWsFT + tl) * a.nbp + k;
-                        if (bits & 1u) v.x = sp[0];
-                        if (bits & 2u) v.y = sp[1];
-                        if (bits & 4u) v.z = sp[2];
-                        if (bits & 8u) v.w = sp[3];
-                    }
-                    *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * feat_dim + k) = v;
-                }
-            } else {
-                for (int g = etid; g < 3 * nt * feat_dim; g += kEThreads) {
-                    const int r = g / feat_dim, k = g - r * feat_dim;
-                    const int i = r / nt, tl = r - i * nt;
-                    float v = 0.0f;
-                    if (k < n_bins && ((msk[tl * 8 + (k >> 5)] >> (k & 31)) & 1u)) v = stg[(i * kWsFT + tl) * a.nbp + k];
-                    clip_feat[(4 + i) * chan_stride + (long long)(t0 + tl) * feat_dim + k] = v;
-                }
-            }
-        }
     }
 }
 
