@@ -29,13 +29,13 @@ struct alignas(2 * sizeof(T)) Cx {
     T re, im;
 };
 
-template <typename T> __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return {a.re + b.re, a.im + b.im}; }
-template <typename T> __device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) { return {a.re - b.re, a.im - b.im}; }
-template <typename T> __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return {a.re + b.re, a.im + b.im}; }
+template <typename T> __host__ __device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) { return {a.re - b.re, a.im - b.im}; }
+template <typename T> __host__ __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
     return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
 }
 // multiply by -i (forward-transform quarter turn)
-template <typename T> __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.im, -a.re}; }
+template <typename T> __host__ __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.im, -a.re}; }
 
 // In-place forward 8-point DFT: out[k] = sum_n in[n] exp(-2 pi i n k / 8).
 template <typename T>

@@ -1,5 +1,6 @@
 // C ABI of libsalsa_b200.so: feature-extraction entry points (see include/salsa_b200.h).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -189,15 +190,22 @@ static EigArgs eig_args(const salsa_params_t* p) {
     e.test = p->is_tracking ? 1 : 0;
     e.cond = (float)p->cond_num;
     e.cond_d = p->cond_num;
-    // n squarings + one matrix-vector product give the exponent 2^(n+1); choose n so that
-    // cond^-(2^(n+1)) < 1e-7.  Without a usable gap (no test, cond <= 1) iterate longer.
-    int n_sq = 10;
+    // n squarings and m (1 or 2) products of the squared matrix with its dominant column give the exponent
+    // (1 + m) 2^n; a bin is only kept when lambda1 > cond * lambda2, so choose the cheapest (n, m) with
+    // cond^-exponent < 1e-7 (a product costs half a squaring): cond = 5 -> n = 2, m = 2, exponent 12, 4e-9.
+    // Without a usable gap (no test, cond <= 1) iterate longer.
+    int n_sq = 10, n_mv = 1;
     if (e.test && p->cond_num > 1.0) {
         const double need = log(1e7) / log(p->cond_num);
         n_sq = (int)ceil(log2(need)) - 1;
         n_sq = std::max(2, std::min(10, n_sq));
+        if (n_sq > 2 && 3.0 * ldexp(1.0, n_sq - 1) >= need) {
+            n_sq -= 1;
+            n_mv = 2;
+        }
     }
     e.n_sq = n_sq;
+    e.n_mv = n_mv;
     const double delta = 2.0 * M_PI * (double)p->fs / ((double)p->n_fft * 343.0);
     e.inv_delta = 1.0 / delta;
     e.lower = p->lower_bin;
@@ -226,8 +234,18 @@ static int set_smem(K kernel, size_t bytes) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float2* X, float* spec,
-                       long long spec_clip_stride, double* power0, int ch_count, cudaStream_t st) {
+template <typename T, int CH>
+static int launch_stft_t(const StftArgs& a, const FftTables<T>& tb, dim3 grid, cudaStream_t st) {
+    const size_t smem = sizeof(FftSmem<T>);
+    int rc = set_smem(stft_kernel<T, CH>, smem);
+    if (rc) return rc;
+    stft_kernel<T, CH><<<grid, kThreads, smem, st>>>(a, tb);
+    return SALSA_OK;
+}
+
+// X rows: x_origin = lower_bin and x_pitch = n_bins (the op-level layout), or x_origin = 0 and x_pitch = kXPitch (clip path)
+static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float2* X, int x_pitch, int x_origin,
+                       float* spec, long long spec_clip_stride, double* power0, int ch_count, cudaStream_t st) {
     if (p->n_clips == 0) return SALSA_OK;
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     StftArgs a;
@@ -242,35 +260,37 @@ static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const fl
     a.frames_per_block = 32;
     a.bands = band_layout(p);
     a.X = X;
+    a.x_pitch = x_pitch;
+    a.x_origin = x_origin;
     a.spec = spec;
     a.spec_clip_stride = spec_clip_stride;
     a.spec_chan_stride = (long long)n_frames * a.bands.n_out;
     a.power0 = power0;
     dim3 grid((n_frames + a.frames_per_block - 1) / a.frames_per_block, p->n_clips);
     ProfScope prof("stft_kernel", st);
-    if (p->stft_precision == 64) {
-        const size_t smem = sizeof(FftSmem<double>);
-        int rc = set_smem(stft_kernel<double>, smem);
-        if (rc) return rc;
-        stft_kernel<double><<<grid, kThreads, smem, st>>>(a, tb.d);
-    } else {
-        const size_t smem = sizeof(FftSmem<float>);
-        int rc = set_smem(stft_kernel<float>, smem);
-        if (rc) return rc;
-        stft_kernel<float><<<grid, kThreads, smem, st>>>(a, tb.f);
-    }
+    int rc;
+    if (ch_count != 1 && ch_count != 4) return fail(SALSA_EINVAL, "stft: 1 or 4 channels");
+    if (p->stft_precision == 64)
+        rc = ch_count == 4 ? launch_stft_t<double, 4>(a, tb.d, grid, st) : launch_stft_t<double, 1>(a, tb.d, grid, st);
+    else
+        rc = ch_count == 4 ? launch_stft_t<float, 4>(a, tb.f, grid, st) : launch_stft_t<float, 1>(a, tb.f, grid, st);
+    if (rc) return rc;
     return check_launch("stft_kernel");
 }
 
-static int launch_tracker(const double* power0, uint32_t* mask, int n_clips, int n_frames, int n_bins,
-                          cudaStream_t st) {
+template <typename Src>
+static int launch_tracker(Src src, uint32_t* mask, int n_clips, int n_frames, int n_bins, cudaStream_t st) {
     if (n_clips == 0) return SALSA_OK;
     const int n_words = (n_bins + 31) / 32;
     const int wpb = std::min(n_words, 8);                       // warps per block
     dim3 grid((n_words + wpb - 1) / wpb, n_clips);
     ProfScope prof("tracker_kernel", st);
-    tracker_kernel<<<grid, wpb * 32, 0, st>>>(power0, mask, n_frames, n_bins, tracker_consts());
+    tracker_kernel<Src><<<grid, wpb * 32, 0, st>>>(src, mask, n_frames, n_bins, tracker_consts());
     return check_launch("tracker_kernel");
+}
+
+static TrackerPower0 tracker_power0(const double* power0, int n_frames, int n_bins) {
+    return {power0, (long long)n_frames * n_bins, (long long)n_bins};
 }
 
 constexpr int kFusedFT = 4;   // new frames per step of salsa_fused_kernel
@@ -321,23 +341,101 @@ static int launch_fused(const salsa_params_t* p, const DeviceTables& tb, const f
     return check_launch("salsa_fused_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// The clip path exists in two arrangements of the same arithmetic (bit-identical results):
+//   split  stft_kernel (all channels: X -> HBM, log-spectrogram rows) | tracker_kernel (on channel 0 of X) |
+//          eig_rows_kernel (+ eig_redo_kernel for the few bins that need float64).  X costs 59 MB of
+//          HBM traffic per clip on top of the 50 MB of algorithmic bytes, but every kernel runs at its own register
+//          budget / occupancy and the channel-0 transform is not done twice.  Default.
+//   fused  stft_kernel (channel 0 only -> |X0|^2) | tracker_kernel | salsa_fused_kernel (X lives in a shared-memory
+//          ring).  Minimal HBM traffic; selected with SALSA_B200_PIPELINE=fused.
+// ---------------------------------------------------------------------------------------------
+enum Pipeline { kPipelineSplit = 0, kPipelineFused = 1 };
+
+static Pipeline pipeline_choice() {
+    const char* e = getenv("SALSA_B200_PIPELINE");
+    if (e && strcmp(e, "fused") == 0) return kPipelineFused;
+    return kPipelineSplit;
+}
+
+static int env_int(const char* name, int fallback) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : fallback;
+}
+
 struct Workspace {
-    double* power0;
+    double* power0;    // fused
+    float2* X;         // split
     uint32_t* mask;
+    uint32_t* redo;    // split
     size_t bytes;
 };
 
-static Workspace carve_workspace(const salsa_params_t* p, void* base) {
+static size_t round256(size_t v) { return (v + 255) / 256 * 256; }
+
+static Workspace carve_workspace(const salsa_params_t* p, void* base, Pipeline pl) {
     const size_t n_frames = (size_t)salsa_n_frames(p->n_samples, p->hop_len);
     const size_t n_bins = (size_t)(p->upper_bin - p->lower_bin);
-    const size_t pw = (size_t)p->n_clips * n_frames * n_bins * sizeof(double);
-    const size_t mk = (size_t)p->n_clips * n_frames * ((n_bins + 31) / 32) * sizeof(uint32_t);
-    Workspace w;
-    w.power0 = reinterpret_cast<double*>(base);
-    w.mask = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(base) + ((pw + 255) / 256) * 256);
-    w.bytes = ((pw + 255) / 256) * 256 + ((mk + 255) / 256) * 256;
-    if (!p->is_tracking) w.bytes = 256;
+    const size_t mk = round256((size_t)p->n_clips * n_frames * ((n_bins + 31) / 32) * sizeof(uint32_t));
+    char* at = reinterpret_cast<char*>(base);
+    Workspace w = {};
+    if (pl == kPipelineSplit) {
+        const size_t xb = round256((size_t)p->n_clips * n_frames * 4 * kXPitch * sizeof(float2));
+        w.X = reinterpret_cast<float2*>(at);
+        w.mask = reinterpret_cast<uint32_t*>(at + xb);
+        w.redo = reinterpret_cast<uint32_t*>(at + xb + mk);
+        w.bytes = xb + 2 * mk;
+    } else {
+        const size_t pw = round256((size_t)p->n_clips * n_frames * n_bins * sizeof(double));
+        w.power0 = reinterpret_cast<double*>(at);
+        w.mask = reinterpret_cast<uint32_t*>(at + pw);
+        w.bytes = pw + mk;
+        if (!p->is_tracking) w.bytes = 256;
+    }
     return w;
+}
+
+constexpr int kEigFT = 8;     // frames per CTA of eig_rows_kernel
+
+template <int MINB, int NSQ>
+static int launch_eig_rows_t(const EigRowsArgs& a, dim3 grid, cudaStream_t st) {
+    const size_t smem = eig_rows_smem_bytes<kEigFT>(a.pitch);
+    int rc = set_smem(eig_rows_kernel<kEigFT, MINB, NSQ>, smem);
+    if (rc) return rc;
+    eig_rows_kernel<kEigFT, MINB, NSQ><<<grid, 256, smem, st>>>(a);
+    return SALSA_OK;
+}
+
+static int launch_eig_rows(const salsa_params_t* p, const Workspace& w, const uint32_t* mask, float* feature, cudaStream_t st) {
+    if (p->n_clips == 0) return SALSA_OK;
+    EigRowsArgs a;
+    a.X = w.X + p->lower_bin;          // rows of X are indexed by the absolute bin; the kernels index spatial bins
+    a.mask = mask;
+    a.redo = w.redo;
+    a.feature = feature;
+    a.n_frames = salsa_n_frames(p->n_samples, p->hop_len);
+    a.n_bins = p->upper_bin - p->lower_bin;
+    a.pitch = (a.n_bins + 31) / 32 * 32;
+    a.feat_dim = band_layout(p).n_out;
+    a.eig = eig_args(p);
+    if (a.pitch > kXPitch) return fail(SALSA_EINVAL, "more than 256 spatial bins");
+    dim3 grid((a.n_frames + kEigFT - 1) / kEigFT, p->n_clips);
+    int rc;
+    {
+        ProfScope prof("eig_rows_kernel", st);
+        const int minb = env_int("SALSA_B200_EIG_MINB", 3);
+        if (a.eig.n_sq == 2)       // the default (cond_num = 5): squarings unrolled at compile time
+            rc = minb == 2 ? launch_eig_rows_t<2, 2>(a, grid, st) : (minb == 4 ? launch_eig_rows_t<4, 2>(a, grid, st) : launch_eig_rows_t<3, 2>(a, grid, st));
+        else
+            rc = launch_eig_rows_t<3, 0>(a, grid, st);
+        if (rc) return rc;
+        if ((rc = check_launch("eig_rows_kernel"))) return rc;
+    }
+    if (!a.eig.test) return SALSA_OK;      // without the coherence test no verdict is ever ambiguous
+    const long long n_words_total = (long long)p->n_clips * a.n_frames * ((a.n_bins + 31) / 32);
+    ProfScope prof("eig_redo_kernel", st);
+    eig_redo_kernel<<<(unsigned)((n_words_total + 127) / 128), 128, 0, st>>>(a, n_words_total);
+    return check_launch("eig_redo_kernel");
 }
 
 }  // namespace salsa
@@ -406,15 +504,15 @@ int salsa_stft(const salsa_params_t* p, const float* audio, float* X, float* log
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     const long long clip_stride = (long long)p->n_chans * n_frames * band_layout(p).n_out;
     const int ch_count = (X || logspec) ? p->n_chans : 1;
-    return launch_stft(p, tb, audio, reinterpret_cast<float2*>(X), logspec, clip_stride, power0, ch_count,
-                       (cudaStream_t)stream);
+    return launch_stft(p, tb, audio, reinterpret_cast<float2*>(X), p->upper_bin - p->lower_bin, p->lower_bin, logspec, clip_stride,
+                       power0, ch_count, (cudaStream_t)stream);
 }
 
 int salsa_tracker(const double* power0, uint32_t* mask, int32_t n_clips, int32_t n_frames, int32_t n_bins,
                   void* stream) {
     if (!power0 || !mask) return fail(SALSA_EINVAL, "power0 / mask is NULL");
     if (n_clips < 0 || n_frames <= 0 || n_bins <= 0) return fail(SALSA_EINVAL, "bad tracker dimensions");
-    return launch_tracker(power0, mask, n_clips, n_frames, n_bins, (cudaStream_t)stream);
+    return launch_tracker(tracker_power0(power0, n_frames, n_bins), mask, n_clips, n_frames, n_bins, (cudaStream_t)stream);
 }
 
 int salsa_spectrum_from_reference(const double* X_ref, float* X, double* power0, int32_t n_bins, int32_t n_frames,
@@ -446,7 +544,7 @@ int salsa_eigenvector(const salsa_params_t* p, const float* X, const uint32_t* m
 
 size_t salsa_workspace_bytes(const salsa_params_t* p) {
     if (validate_params(p)) return 0;
-    return carve_workspace(p, nullptr).bytes;
+    return carve_workspace(p, nullptr, pipeline_choice()).bytes;
 }
 
 int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, void* workspace, size_t workspace_bytes,
@@ -455,8 +553,9 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     if (rc) return rc;
     if (p->n_clips == 0) return SALSA_OK;
     if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
-    const Workspace w = carve_workspace(p, workspace);
-    if (p->is_tracking && (!workspace || workspace_bytes < w.bytes))
+    const Pipeline pl = pipeline_choice();
+    const Workspace w = carve_workspace(p, workspace, pl);
+    if ((p->is_tracking || pl == kPipelineSplit) && (!workspace || workspace_bytes < w.bytes))
         return fail(SALSA_ENOMEM, "workspace smaller than salsa_workspace_bytes()");
     double win[kNfft];
     const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
@@ -464,16 +563,30 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     DeviceTables tb;
     if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
+    const int n_bins = p->upper_bin - p->lower_bin;
     const uint32_t* mask = nullptr;
+    if (pl == kPipelineSplit) {
+        const long long clip_stride = 7LL * n_frames * band_layout(p).n_out;
+        if ((rc = launch_stft(p, tb, audio, w.X, kXPitch, 0, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
+        if (p->is_tracking) {
+            // The tracker is a sequential recurrence over the whole clip in float64 on |X0|^2 of the complex64
+            // spectrum (what the reference computes, :53-55); with stft_precision = 32 the selection follows that
+            // spectrum, as the reference's would.
+            const TrackerSpectrum src = {w.X + p->lower_bin, (long long)n_frames * 4 * kXPitch, 4LL * kXPitch};
+            if ((rc = launch_tracker(src, w.mask, p->n_clips, n_frames, n_bins, st))) return rc;
+            mask = w.mask;
+        }
+        return launch_eig_rows(p, w, mask, feature, st);
+    }
     if (p->is_tracking) {
         // pass A: channel-0 spectrum in float64 -> tracker (a sequential recurrence over the whole clip,
         // so it has to finish before any bin can be selected).  Always float64: one flipped
         // comparison would shift the floor of that bin for the rest of the clip.
         salsa_params_t pa = *p;
         pa.stft_precision = 64;
-        if ((rc = launch_stft(&pa, tb, audio, nullptr, nullptr, 0, w.power0, 1, st))) return rc;
-        const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
-        if ((rc = launch_tracker(w.power0, w.mask, p->n_clips, n_frames, p->upper_bin - p->lower_bin, st))) return rc;
+        if ((rc = launch_stft(&pa, tb, audio, nullptr, 0, 0, nullptr, 0, w.power0, 1, st))) return rc;
+        if ((rc = launch_tracker(tracker_power0(w.power0, n_frames, n_bins), w.mask, p->n_clips, n_frames, n_bins, st))) return rc;
         mask = w.mask;
     }
     return launch_fused(p, tb, audio, feature, mask, st);

@@ -16,8 +16,6 @@ namespace salsa {
 
 constexpr int kWarps = 8;                // warps per CTA in the STFT-bearing kernels
 constexpr int kThreads = kWarps * 32;
-constexpr int kHop = 3;                  // n_hopframes of the reference ("do not change")
-constexpr int kWin = 2 * kHop + 1;       // 7 frames per covariance
 constexpr float kAmin = 1e-10f;          // power_to_db amin (salsa_feature_extraction.py:195)
 
 // Layout of the log-linear bands (MagStftExtractor.__init__, :153-175):
@@ -39,7 +37,10 @@ struct StftArgs {
     int ch_count;         // channels 0..ch_count-1 are transformed
     int frames_per_block;
     BandLayout bands;
-    float2* X;            // [clip][frame][n_chans][upper-lower] or null
+    float2* X;            // [clip][frame][n_chans][x_pitch] or null (bins lower..upper-1 of each row are written)
+    int x_pitch;          // row length of X in complex values
+    int x_origin;         // bin stored at element 0 of a row: `lower` (op-level layout, x_pitch = upper - lower), or 0 (clip path:
+                          // rows indexed by the absolute bin, x_pitch = kXPitch; bins below `lower` are stored but never read)
     float* spec;          // log-linear spectrogram or null
     long long spec_clip_stride;
     long long spec_chan_stride;   // row (frame) stride is bands.n_out
@@ -81,16 +82,21 @@ __device__ __forceinline__ float power_f32(float re, float im) { return fmaf(re,
 __device__ __forceinline__ void write_logspec_row(const float (&p)[8], float p_nyq, float* row, BandLayout bands,
                                                   int lane) {
     const bool compress = bands.n_out > bands.n_lin;
-    // linear part: band = bin - 1
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int band = lane + 32 * j - 1;
-        if (band >= 0 && band < bands.n_lin) row[band] = power_db(p[j]);
-    }
     if (!compress) {
+        // linear layout: band = bin - 1 for bins 1..n_fft/2
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int band = lane + 32 * j - 1;
+            if (band >= 0 && band < bands.n_lin) row[band] = power_db(p[j]);
+        }
         if (lane == 0) row[kHalf - 1] = power_db(p_nyq);
         return;
     }
+    // compressed layout (n_lin = 192): bands 0..191 = bins 1..192, i.e. p[0..5] of every lane but bin 0, and bin 192
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+        if (j > 0 || lane > 0) row[lane + 32 * j - 1] = power_db(p[j]);
+    if (lane == 0) row[191] = power_db(p[6]);
     // r6 / r7[lane] = power of bin 193 + lane / 225 + lane (bin 256 is not part of the last band)
     const float up6 = __shfl_down_sync(0xffffffffu, p[6], 1), up7 = __shfl_down_sync(0xffffffffu, p[7], 1);
     const float first7 = __shfl_sync(0xffffffffu, p[7], 0);
@@ -108,8 +114,8 @@ __device__ __forceinline__ void write_logspec_row(const float (&p)[8], float p_n
 // ------------------------------------------------------------------------------------------------
 // stft_kernel: grid (frame blocks, clips); one warp per (frame, channel) item.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T> tb) {
+template <typename T, int CH>
+__global__ void __launch_bounds__(kThreads, 2) stft_kernel(StftArgs a, FftTables<T> tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
     load_fft_smem(s, tb);
@@ -122,24 +128,44 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
     const int nb = a.upper - a.lower;
     const float* clip_audio = a.audio + (long long)clip * a.n_chans * a.n_samples;
     Cx<T>* scratch = s.scratch[warp];
-    for (int item = warp; item < (f1 - f0) * a.ch_count; item += kWarps) {
-        const int t = f0 + item / a.ch_count;
-        const int ch = item % a.ch_count;
+    const int n_items = (f1 - f0) * CH;             // CH = channels transformed (a.ch_count)
+    // the samples of a warp's next (frame, channel) item are requested before the current one is transformed
+    float2 raw[8];
+    int t = f0 + warp / CH, ch = warp % CH;
+    if (warp < n_items) load_frame(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, lane, raw);
+    for (int item = warp; item < n_items; item += kWarps) {
+        float2 cur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = raw[i];
+        const int nxt = item + kWarps;
+        const int tn = f0 + nxt / CH, chn = nxt % CH;
+        if (nxt < n_items) load_frame(clip_audio + (long long)chn * a.n_samples, a.n_samples, tn * a.hop - kNfft / 2, lane, raw);
         Cx<T> X[8];
         T nyq;
-        warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, tb.window ? s.win : nullptr, tw, scratch,
-                              lane, X, nyq);
+        warp_rfft512<T>(cur, tb.window ? s.win : nullptr, tw, scratch, lane, X, nyq);
+        const long long o = ((long long)clip * a.n_frames + t);
+        float2* xrow = a.X ? a.X + (o * a.n_chans + ch) * a.x_pitch - a.x_origin : nullptr;
+        double* prow = (a.power0 && ch == 0) ? a.power0 + o * nb - a.lower : nullptr;
         float p[8];
+        float2 xc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = lane + 32 * j;
-            const float re = (float)X[j].re, im = (float)X[j].im;     // librosa stores complex64
-            p[j] = power_f32(re, im);
-            if (k >= a.lower && k < a.upper) {
-                const long long o = ((long long)clip * a.n_frames + t);
-                if (a.X) a.X[(o * a.n_chans + ch) * nb + (k - a.lower)] = make_float2(re, im);
-                // np.abs(complex128) ** 2 (:53-55) up to one float64 ulp
-                if (a.power0 && ch == 0) a.power0[o * nb + (k - a.lower)] = fma((double)re, (double)re, (double)im * (double)im);
+            xc[j] = make_float2((float)X[j].re, (float)X[j].im);     // librosa stores complex64
+            p[j] = power_f32(xc[j].x, xc[j].y);
+        }
+        if (xrow && a.x_origin == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (32 * j < a.upper) xrow[lane + 32 * j] = xc[j];    // warp-uniform predicate, whole 256-byte segments
+        } else if (xrow || prow) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = lane + 32 * j;
+                if (k >= a.lower && k < a.upper) {
+                    if (xrow) xrow[k] = xc[j];
+                    // np.abs(complex128) ** 2 (:53-55) up to one float64 ulp
+                    if (prow) prow[k] = fma((double)xc[j].x, (double)xc[j].x, (double)xc[j].y * (double)xc[j].y);
+                }
             }
         }
         if (a.spec) {
@@ -147,6 +173,8 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(StftArgs a, FftTables<T>
             float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
             write_logspec_row(p, p_nyq, row, a.bands, lane);
         }
+        t = tn;
+        ch = chn;
     }
 }
 
@@ -159,18 +187,36 @@ struct TrackerConsts {
     int n_sig_frames, n_init_frames;
 };
 
-__global__ void __launch_bounds__(256) tracker_kernel(const double* __restrict__ power0, uint32_t* __restrict__ mask,
-                                                      int n_frames, int n_bins, TrackerConsts c) {
+// Input of the tracker: |X0|^2 in float64, either precomputed (power0, [clip][frame][n_bins]) or taken from channel 0
+// of the complex64 spectrum X ([clip][frame][4][pitch]) -- the same fma as stft_kernel's power0, so both give
+// identical bits.
+struct TrackerPower0 {
+    const double* p;
+    long long clip_stride, frame_stride;
+    __device__ __forceinline__ double operator()(int clip, int t, int b) const { return p[clip * clip_stride + t * frame_stride + b]; }
+};
+struct TrackerSpectrum {
+    const float2* x;
+    long long clip_stride, frame_stride;
+    __device__ __forceinline__ double operator()(int clip, int t, int b) const {
+        const float2 v = __ldg(x + clip * clip_stride + t * frame_stride + b);
+        return fma((double)v.x, (double)v.x, (double)v.y * (double)v.y);
+    }
+};
+
+template <typename Src>
+__global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restrict__ mask, int n_frames, int n_bins,
+                                                      TrackerConsts c) {
     const int clip = blockIdx.y;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int word = b >> 5, n_words = (n_bins + 31) >> 5;
     const bool live = b < n_bins;
-    const double* a = power0 + (long long)clip * n_frames * n_bins + (live ? b : 0);
+    const int bb = live ? b : 0;
     uint32_t* mrow = mask + (long long)clip * n_frames * n_words + word;
     auto at = [&](int t) -> double {   // wrapped frame access (np.pad 'wrap', :43)
         t %= n_frames;
         if (t < 0) t += n_frames;
-        return live ? a[(long long)t * n_bins] : 0.0;
+        return live ? src(clip, t, bb) : 0.0;
     };
     // initial floor: 0.5 * mean(sig[0:5]), sig = sqrt(mean of three powers)   (:53-58)
     const int n_init = min(c.n_init_frames, n_frames);
@@ -187,7 +233,7 @@ __global__ void __launch_bounds__(256) tracker_kernel(const double* __restrict__
     constexpr int kChunk = 8;
     double nxt[kChunk];
 #pragma unroll
-    for (int i = 0; i < kChunk; ++i) nxt[i] = (i < n_frames && live) ? a[(long long)i * n_bins] : 0.0;
+    for (int i = 0; i < kChunk; ++i) nxt[i] = (i < n_frames && live) ? src(clip, i, bb) : 0.0;
     for (int t0 = 0; t0 < n_frames; t0 += kChunk) {
         double buf[kChunk];
 #pragma unroll
@@ -195,7 +241,7 @@ __global__ void __launch_bounds__(256) tracker_kernel(const double* __restrict__
 #pragma unroll
         for (int i = 0; i < kChunk; ++i) {   // prefetch of the next chunk overlaps the recurrence below
             const int t = t0 + kChunk + i;
-            nxt[i] = (t < n_frames && live) ? a[(long long)t * n_bins] : 0.0;
+            nxt[i] = (t < n_frames && live) ? src(clip, t, bb) : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < kChunk; ++i) {
@@ -219,89 +265,6 @@ __global__ void __launch_bounds__(256) tracker_kernel(const double* __restrict__
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The eigenvector step for one TF bin.  `load(k, ch)` returns X[frame t - 3 + k][ch], k = 0..6.
-// ------------------------------------------------------------------------------------------------
-struct EigArgs {
-    int format;          // SALSA_FORMAT_*
-    int test;            // apply the coherence test (is_tracking)
-    int n_sq;            // squarings, float32 path
-    float cond;
-    double cond_d;
-    double inv_delta;    // 1 / delta, delta = 2 pi fs / (n_fft c)   (:38-40)
-    int lower;           // absolute index of spatial bin 0
-};
-
-template <typename T, typename Load>
-__device__ __forceinline__ void accumulate_cov(Herm4<T>& R, Load load) {
-    herm_zero(R);
-#pragma unroll
-    for (int f = 0; f < kWin; ++f) {
-        Cx<T> x[4];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            const float2 v = load(f, ch);
-            x[ch] = {(T)v.x, (T)v.y};
-        }
-        herm_rank1(R, x);
-    }
-}
-
-// float64 re-evaluation of a bin whose float32 verdict could not be certified
-template <typename Load>
-__device__ __forceinline__ int eig_bin_f64(Load load, const EigArgs& e, float (&out)[3], int b) {
-    Herm4<double> R;
-    accumulate_cov<double>(R, load);
-    Cx<double> v[4];
-    int verdict = principal_eigenvector<double>(R, e.n_sq + 2, e.test != 0, e.cond_d, 0.0, v);
-    if (verdict == kEigAmbiguous) verdict = kEigFail;
-    if (verdict == kEigPass) {
-        if (e.format == SALSA_FORMAT_FOA) {
-            normalise_foa(v, out);
-        } else {
-            const double s = e.inv_delta / (double)(b + e.lower);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const Cx<double> p = cmulc(v[i + 1], v[0]);
-                out[i] = (float)(atan2(p.im, p.re) * s);
-            }
-        }
-    }
-    return verdict;
-}
-
-// Returns true when the bin is valid; out[] holds the three spatial features (zeros otherwise).
-template <typename Load>
-__device__ __forceinline__ bool eig_bin(Load load, const EigArgs& e, int b, float (&out)[3]) {
-    out[0] = out[1] = out[2] = 0.0f;
-    Herm4<float> R;
-    accumulate_cov<float>(R, load);
-    Cx<float> v[4];
-    int verdict = principal_eigenvector<float>(R, e.n_sq, e.test != 0, e.cond, 1e-4f, v);
-    if (verdict == kEigAmbiguous) {
-        verdict = eig_bin_f64(load, e, out, b);
-        return verdict == kEigPass;
-    }
-    if (!e.test && !(herm_trace(R) > 0.0f)) {
-        // is_tracking=False on an all-zero bin: svd gives u = I, so FOA divides 0 by 0 (NaN) and
-        // MIC yields angle(0) = 0, exactly as the reference does.
-        if (e.format == SALSA_FORMAT_FOA) out[0] = out[1] = out[2] = __int_as_float(0x7fc00000);
-        return true;
-    }
-    if (verdict != kEigPass) return false;
-    if (e.format == SALSA_FORMAT_FOA) {
-        normalise_foa(v, out);
-    } else {
-        const float s = (float)(e.inv_delta / (double)(b + e.lower));
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const Cx<float> p = cmulc(v[i + 1], v[0]);
-            out[i] = atan2f(p.im, p.re) * s;
-        }
-    }
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,6 +317,173 @@ __global__ void __launch_bounds__(256) eig_kernel(const float2* __restrict__ X, 
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) out[(((long long)clip * 3 + i) * n_frames + t) * n_bins + b] = o[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// eig_rows_kernel: the eigenvector step of the clip path when the spectrum X is resident in HBM
+// ([clip][frame][4][pitch] complex64, written by stft_kernel).  grid (frame tiles of FT, clips).
+//   1  the tracker mask words of the tile are compacted into a dense list of selected (frame, bin) items, so that
+//      the eigenvector step runs with full warps whatever the selection looks like;
+//   2  one thread per list item: covariance over 7 (wrapped) frames read through the read-only path (a frame of X is
+//      used by 7 neighbouring frames and by the neighbouring tiles: L1 / L2 serve the re-reads), float32
+//      eigenvector, certified coherence test, normalisation -> staging tile in shared memory.  Bins whose float32
+//      verdict cannot be certified are marked in `redo` (same layout as the mask) for eig_redo_kernel;
+//   3  the 3 x FT spatial rows are written to HBM as whole rows (float4), zeros where the bin was not selected /
+//      not valid / above the last spatial bin (:373-374).
+// No float64 code in this kernel: it stays small enough for 3 CTAs of 256 threads per SM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kXPitch = 256;   // row length (complex values) of the clip path's X in HBM: compile-time, so that the 28 loads
+                               // of a covariance are immediate offsets from 7 frame pointers; only bins < n_bins are touched
+
+struct EigRowsArgs {
+    const float2* X;         // [clip][n_frames][4][kXPitch]
+    const uint32_t* mask;    // tracker selection or null (is_tracking = false)
+    uint32_t* redo;          // [clip][n_frames][n_words], every word is written
+    float* feature;          // [clip][7][n_frames][feat_dim]; channels 4..6 are written
+    int n_frames, n_bins, pitch, feat_dim;   // pitch: row length of the shared-memory tiles (n_bins rounded up to 32)
+    EigArgs eig;
+};
+
+template <int FT>
+__host__ __device__ inline size_t eig_rows_smem_bytes(int pitch) {
+    return (size_t)3 * FT * pitch * sizeof(float) + (size_t)FT * pitch * sizeof(uint16_t) + 2 * FT * 8 * sizeof(uint32_t) + 16;
+}
+
+template <int FT, int MINB, int NSQ>
+__global__ void __launch_bounds__(256, MINB) eig_rows_kernel(EigRowsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);                                   // [3][FT][pitch]
+    uint16_t* list = reinterpret_cast<uint16_t*>(stage + (size_t)3 * FT * a.pitch);       // [FT * pitch]
+    uint32_t* smask = reinterpret_cast<uint32_t*>(list + (size_t)FT * a.pitch);           // [FT][8]
+    uint32_t* sredo = smask + FT * 8;                                                      // [FT][8]
+    int* n_items = reinterpret_cast<int*>(sredo + FT * 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int clip = blockIdx.y;
+    const int t0 = blockIdx.x * FT;
+    const int nt = min(FT, a.n_frames - t0);
+    const int n_words = (a.n_bins + 31) >> 5;
+    const uint32_t tail_bits = (a.n_bins & 31) ? ((1u << (a.n_bins & 31)) - 1u) : 0xffffffffu;
+    if (threadIdx.x == 0) *n_items = 0;
+    if (threadIdx.x < FT * 8) sredo[threadIdx.x] = 0u;
+    __syncthreads();
+    // ---- 1
+    for (int w = warp; w < nt * n_words; w += 8) {
+        const int tl = w / n_words, wi = w - tl * n_words;
+        uint32_t bits = a.mask ? __ldg(a.mask + ((long long)clip * a.n_frames + t0 + tl) * n_words + wi) : 0xffffffffu;
+        if (wi == n_words - 1) bits &= tail_bits;
+        int base = 0;
+        if (lane == 0) {
+            smask[tl * 8 + wi] = bits;
+            base = atomicAdd(n_items, __popc(bits));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((bits >> lane) & 1u) list[base + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((tl << 8) | (wi * 32 + lane));
+    }
+    __syncthreads();
+    // ---- 2
+    const int count = *n_items;
+    const float2* clip_x = a.X + (long long)clip * a.n_frames * 4 * kXPitch;
+    constexpr int frame_stride = 4 * kXPitch;
+    auto finish = [&](int verdict, int tl, int b, const float (&o)[3]) {
+        if (verdict == kEigAmbiguous) atomicOr(&sredo[tl * 8 + (b >> 5)], 1u << (b & 31));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) stage[(i * FT + tl) * a.pitch + b] = o[i];
+    };
+    if (t0 >= kHop && t0 + FT + kHop <= a.n_frames) {
+        // no frame of this tile's windows wraps (all tiles but the first and the last of a clip): the 28 loads of a
+        // covariance are immediate offsets from one pointer
+        for (int item = threadIdx.x; item < count; item += 256) {
+            const int code = list[item];
+            const int tl = code >> 8, b = code & 255;
+            const float2* base = clip_x + (t0 + tl - kHop) * frame_stride + b;
+            float o[3];
+            auto load = [&](int k, int ch) -> float2 { return __ldg(base + k * frame_stride + ch * kXPitch); };
+            finish(eig_bin_f32<NSQ>(load, a.eig, b, o), tl, b, o);
+        }
+    } else {
+        for (int item = threadIdx.x; item < count; item += 256) {
+            const int code = list[item];
+            const int tl = code >> 8, b = code & 255;
+            const float2* fp[kWin];
+            int tt = t0 + tl - kHop;                              // wrap padding of the frame axis (:43)
+            tt %= a.n_frames;
+            if (tt < 0) tt += a.n_frames;
+#pragma unroll
+            for (int k = 0; k < kWin; ++k) {
+                fp[k] = clip_x + tt * frame_stride + b;
+                tt = tt + 1 == a.n_frames ? 0 : tt + 1;
+            }
+            float o[3];
+            auto load = [&](int k, int ch) -> float2 { return __ldg(fp[k] + ch * kXPitch); };
+            finish(eig_bin_f32<NSQ>(load, a.eig, b, o), tl, b, o);
+        }
+    }
+    __syncthreads();
+    // ---- 3
+    if (threadIdx.x < nt * n_words) {
+        const int tl = threadIdx.x / n_words, wi = threadIdx.x - tl * n_words;
+        a.redo[((long long)clip * a.n_frames + t0 + tl) * n_words + wi] = sredo[tl * 8 + wi];
+    }
+    const long long chan_stride = (long long)a.n_frames * a.feat_dim;
+    float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
+    if ((a.feat_dim & 3) == 0) {
+        const int groups = a.feat_dim >> 2;
+        for (int g = threadIdx.x; g < 3 * nt * groups; g += 256) {
+            const int r = g / groups, k = (g - r * groups) * 4;      // r = channel * nt + frame
+            const int i = r / nt, tl = r - i * nt;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (k < a.n_bins) {
+                const uint32_t bits = smask[tl * 8 + (k >> 5)] >> (k & 31);
+                const float* sp = stage + (i * FT + tl) * a.pitch + k;
+                if (bits & 1u) v.x = sp[0];
+                if (bits & 2u) v.y = sp[1];
+                if (bits & 4u) v.z = sp[2];
+                if (bits & 8u) v.w = sp[3];
+            }
+            *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + k) = v;
+        }
+    } else {
+        for (int g = threadIdx.x; g < 3 * nt * a.feat_dim; g += 256) {
+            const int r = g / a.feat_dim, k = g - r * a.feat_dim;
+            const int i = r / nt, tl = r - i * nt;
+            float v = 0.0f;
+            if (k < a.n_bins && ((smask[tl * 8 + (k >> 5)] >> (k & 31)) & 1u)) v = stage[(i * FT + tl) * a.pitch + k];
+            clip_feat[(4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + k] = v;
+        }
+    }
+}
+
+// eig_redo_kernel: float64 re-evaluation of the bins eig_rows_kernel marked (a few per million); one thread per
+// mask word, valid results overwrite the zeros eig_rows_kernel left in the feature rows.
+__global__ void __launch_bounds__(128) eig_redo_kernel(EigRowsArgs a, long long n_words_total) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words_total) return;
+    uint32_t bits = __ldg(a.redo + w);
+    if (!bits) return;
+    const int n_words = (a.n_bins + 31) >> 5;
+    const int wi = (int)(w % n_words);
+    const long long ft = w / n_words;
+    const int t = (int)(ft % a.n_frames), clip = (int)(ft / a.n_frames);
+    const float2* clip_x = a.X + (long long)clip * a.n_frames * 4 * kXPitch;
+    const long long chan_stride = (long long)a.n_frames * a.feat_dim;
+    float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
+    while (bits) {
+        const int b = wi * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const float2* fp[kWin];
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            int tt = (t - kHop + k) % a.n_frames;
+            if (tt < 0) tt += a.n_frames;
+            fp[k] = clip_x + (long long)tt * 4 * kXPitch + b;
+        }
+        auto load = [&](int k, int ch) -> float2 { return __ldg(fp[k] + ch * kXPitch); };
+        float o[3] = {0.0f, 0.0f, 0.0f};
+        if (eig_bin_f64(load, a.eig, o, b) == kEigPass) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) clip_feat[(4 + i) * chan_stride + (long long)t * a.feat_dim + b] = o[i];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
