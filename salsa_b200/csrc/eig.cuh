@@ -87,6 +87,11 @@ template <typename T> SALSA_HD void abs2_pair_acc(Cx<T>& acc, Cx<T> a) {
     acc.re = fma_t<T>(a.re, a.re, acc.re);
     acc.im = fma_t<T>(a.im, a.im, acc.im);
 }
+// acc.re += a.re b.re ; acc.im += a.im b.im   (Re(conj(a) b) accumulated as a pair)
+template <typename T> SALSA_HD void dot_pair_acc(Cx<T>& acc, Cx<T> a, Cx<T> b) {
+    acc.re = fma_t<T>(a.re, b.re, acc.re);
+    acc.im = fma_t<T>(a.im, b.im, acc.im);
+}
 // a * s (s real)
 template <typename T> SALSA_HD Cx<T> cscale(Cx<T> a, T s) { return {a.re * s, a.im * s}; }
 
@@ -137,6 +142,9 @@ template <> SALSA_HD void cmacc<float>(Cx<float>& acc, Cx<float> a, Cx<float> b)
 template <> SALSA_HD void abs2_pair_acc<float>(Cx<float>& acc, Cx<float> a) {
     const uint64_t p = pk2(a.re, a.im);
     acc = unpk2(fma2(p, p, pk2(acc.re, acc.im)));
+}
+template <> SALSA_HD void dot_pair_acc<float>(Cx<float>& acc, Cx<float> a, Cx<float> b) {
+    acc = unpk2(fma2(pk2(a.re, a.im), pk2(b.re, b.im), pk2(acc.re, acc.im)));
 }
 template <> SALSA_HD Cx<float> cscale<float>(Cx<float> a, float s) { return unpk2(mul2(pk2(a.re, a.im), pk2(s, s))); }
 #endif
@@ -252,6 +260,17 @@ template <> SALSA_HD float rcp_scale<float>(float x) {
 #endif
 }
 template <> SALSA_HD double rcp_scale<double>(double x) { return 1.0 / x; }
+// fourth root of a positive number to a few ulp (two MUFU.RSQ on the device)
+template <typename T> SALSA_HD T root4(T x);
+template <> SALSA_HD float root4<float>(float x) {
+#ifdef __CUDA_ARCH__
+    const float s = x * rsqrtf(x);
+    return s * rsqrtf(s);
+#else
+    return sqrtf(sqrtf(x));
+#endif
+}
+template <> SALSA_HD double root4<double>(double x) { return sqrt(sqrt(x)); }
 template <> SALSA_HD double rsqrt_t<double>(double x) { return 1.0 / sqrt(x); }
 
 // Principal eigenvector of the (un-normalised) covariance R, coherence verdict.
@@ -289,6 +308,7 @@ SALSA_HD int principal_eigenvector(const Herm4<T>& Rin, int n_sq_rt, bool second
     }
     // column with the largest diagonal entry of B ~ lambda^m v v^H, multiplied by B once (or twice) more:
     // v ~ R^(2 * 2^n_sq) e_p   (R^(3 * 2^n_sq) e_p)
+    T lam1_pow4 = (T)-1;
     int p = 0;
     T best = B.d[0];
 #pragma unroll
@@ -312,6 +332,18 @@ SALSA_HD int principal_eigenvector(const Herm4<T>& Rin, int n_sq_rt, bool second
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[i] = v[i];
             herm_matvec(B, c, v);
+            if (NSQ == 2) {
+                // B = R^4 exactly here (no rescaling between two squarings), so the Rayleigh quotient of B at
+                // c = R^8 e_p is a lower bound of lambda1^4, exact to O((lambda2/lambda1)^16): lambda1 without the
+                // product R v that the Rayleigh quotient of R would cost
+                Cx<T> num = {(T)0, (T)0}, den = {(T)0, (T)0};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dot_pair_acc(num, c[i], v[i]);
+                    abs2_pair_acc(den, c[i]);
+                }
+                lam1_pow4 = (num.re + num.im) * rcp_scale<T>(den.re + den.im);
+            }
         }
     }
     T nv = (cabs2(v[0]) + cabs2(v[1])) + (cabs2(v[2]) + cabs2(v[3]));
@@ -320,12 +352,18 @@ SALSA_HD int principal_eigenvector(const Herm4<T>& Rin, int n_sq_rt, bool second
     for (int i = 0; i < 4; ++i) v[i] = cscale(v[i], inv);
     if (!test) return kEigPass;
 
-    // lambda1 (of the trace-normalised R) and the deflated 3x3 block
+    // lambda1 (of the trace-normalised R)
     Cx<T> rv[4];
-    herm_matvec(R, v, rv);
-    T lam1 = (T)0;
+    T lam1;
+    const bool have_rv = !(lam1_pow4 > (T)0);
+    if (have_rv) {
+        herm_matvec(R, v, rv);
+        lam1 = (T)0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) lam1 += v[i].re * rv[i].re + v[i].im * rv[i].im;   // Re(v^H R v), |v| = 1
+        for (int i = 0; i < 4; ++i) lam1 += v[i].re * rv[i].re + v[i].im * rv[i].im;   // Re(v^H R v), |v| = 1
+    } else {
+        lam1 = root4<T>(lam1_pow4);
+    }
     if (cond < (T)1) return lam1 > (T)0 ? kEigPass : kEigFail;                      // s1*cond < s0 always
     const T mu = lam1 / cond;
     // Shortcuts from the Frobenius norm.  rest = lambda2^2 + lambda3^2 + lambda4^2 = ||R||_F^2 - lambda1^2, and the
@@ -341,7 +379,8 @@ SALSA_HD int principal_eigenvector(const Herm4<T>& Rin, int n_sq_rt, bool second
     if (rest + slack <= ((T)1 - (T)4 * tau) * mu2) return kEigPass;
     if (rest - slack >= (T)3 * ((T)1 + (T)4 * tau) * mu2) return kEigFail;
 
-    // Householder w = v - alpha e0, alpha = -exp(i arg v0) |v| = -exp(i arg v0)
+    // the deflated 3x3 block.  Householder w = v - alpha e0, alpha = -exp(i arg v0) |v| = -exp(i arg v0)
+    if (!have_rv) herm_matvec(R, v, rv);
     const T a0 = sqrt(cabs2(v[0]));
     Cx<T> ph = a0 > (T)0 ? Cx<T>{v[0].re / a0, v[0].im / a0} : Cx<T>{(T)1, (T)0};
     const Cx<T> alpha = {-ph.re, -ph.im};

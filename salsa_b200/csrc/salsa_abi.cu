@@ -243,8 +243,7 @@ static int launch_stft_t(const StftArgs& a, const FftTables<T>& tb, dim3 grid, c
     return SALSA_OK;
 }
 
-// X rows: x_origin = lower_bin and x_pitch = n_bins (the op-level layout), or x_origin = 0 and x_pitch = kXPitch (clip path)
-static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float2* X, int x_pitch, int x_origin,
+static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float2* X, int x_pitch,
                        float* spec, long long spec_clip_stride, double* power0, int ch_count, cudaStream_t st) {
     if (p->n_clips == 0) return SALSA_OK;
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
@@ -261,7 +260,6 @@ static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const fl
     a.bands = band_layout(p);
     a.X = X;
     a.x_pitch = x_pitch;
-    a.x_origin = x_origin;
     a.spec = spec;
     a.spec_clip_stride = spec_clip_stride;
     a.spec_chan_stride = (long long)n_frames * a.bands.n_out;
@@ -395,41 +393,41 @@ static Workspace carve_workspace(const salsa_params_t* p, void* base, Pipeline p
     return w;
 }
 
-constexpr int kEigFT = 8;     // frames per CTA of eig_rows_kernel
+constexpr int kEigFT = 32;     // frames per CTA of eig_tile_kernel
 
 template <int MINB, int NSQ>
-static int launch_eig_rows_t(const EigRowsArgs& a, dim3 grid, cudaStream_t st) {
-    const size_t smem = eig_rows_smem_bytes<kEigFT>(a.pitch);
-    int rc = set_smem(eig_rows_kernel<kEigFT, MINB, NSQ>, smem);
+static int launch_eig_tile_t(const EigRowsArgs& a, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = eig_tile_smem_bytes<kEigFT>();
+    int rc = set_smem(eig_tile_kernel<kEigFT, MINB, NSQ>, smem);
     if (rc) return rc;
-    eig_rows_kernel<kEigFT, MINB, NSQ><<<grid, 256, smem, st>>>(a);
+    eig_tile_kernel<kEigFT, MINB, NSQ><<<grid, 256, smem, st>>>(a);
     return SALSA_OK;
 }
 
 static int launch_eig_rows(const salsa_params_t* p, const Workspace& w, const uint32_t* mask, float* feature, cudaStream_t st) {
     if (p->n_clips == 0) return SALSA_OK;
     EigRowsArgs a;
-    a.X = w.X + p->lower_bin;          // rows of X are indexed by the absolute bin; the kernels index spatial bins
+    a.X = w.X;
     a.mask = mask;
     a.redo = w.redo;
     a.feature = feature;
     a.n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     a.n_bins = p->upper_bin - p->lower_bin;
-    a.pitch = (a.n_bins + 31) / 32 * 32;
     a.feat_dim = band_layout(p).n_out;
     a.eig = eig_args(p);
-    if (a.pitch > kXPitch) return fail(SALSA_EINVAL, "more than 256 spatial bins");
-    dim3 grid((a.n_frames + kEigFT - 1) / kEigFT, p->n_clips);
+    if (a.n_bins > kXPitch) return fail(SALSA_EINVAL, "more than 256 spatial bins");
+    if (a.feat_dim & 3) return fail(SALSA_EINVAL, "feature width must be a multiple of 4");
+    dim3 grid((a.n_frames + kEigFT - 1) / kEigFT, (a.n_bins + kTileBins - 1) / kTileBins, p->n_clips);
     int rc;
     {
-        ProfScope prof("eig_rows_kernel", st);
-        const int minb = env_int("SALSA_B200_EIG_MINB", 3);
+        ProfScope prof("eig_tile_kernel", st);
+        const int minb = env_int("SALSA_B200_EIG_MINB", 4);
         if (a.eig.n_sq == 2)       // the default (cond_num = 5): squarings unrolled at compile time
-            rc = minb == 2 ? launch_eig_rows_t<2, 2>(a, grid, st) : (minb == 4 ? launch_eig_rows_t<4, 2>(a, grid, st) : launch_eig_rows_t<3, 2>(a, grid, st));
+            rc = minb == 2 ? launch_eig_tile_t<2, 2>(a, grid, st) : (minb == 3 ? launch_eig_tile_t<3, 2>(a, grid, st) : launch_eig_tile_t<4, 2>(a, grid, st));
         else
-            rc = launch_eig_rows_t<3, 0>(a, grid, st);
+            rc = launch_eig_tile_t<3, 0>(a, grid, st);
         if (rc) return rc;
-        if ((rc = check_launch("eig_rows_kernel"))) return rc;
+        if ((rc = check_launch("eig_tile_kernel"))) return rc;
     }
     if (!a.eig.test) return SALSA_OK;      // without the coherence test no verdict is ever ambiguous
     const long long n_words_total = (long long)p->n_clips * a.n_frames * ((a.n_bins + 31) / 32);
@@ -504,7 +502,7 @@ int salsa_stft(const salsa_params_t* p, const float* audio, float* X, float* log
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     const long long clip_stride = (long long)p->n_chans * n_frames * band_layout(p).n_out;
     const int ch_count = (X || logspec) ? p->n_chans : 1;
-    return launch_stft(p, tb, audio, reinterpret_cast<float2*>(X), p->upper_bin - p->lower_bin, p->lower_bin, logspec, clip_stride,
+    return launch_stft(p, tb, audio, reinterpret_cast<float2*>(X), p->upper_bin - p->lower_bin, logspec, clip_stride,
                        power0, ch_count, (cudaStream_t)stream);
 }
 
@@ -568,12 +566,12 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     const uint32_t* mask = nullptr;
     if (pl == kPipelineSplit) {
         const long long clip_stride = 7LL * n_frames * band_layout(p).n_out;
-        if ((rc = launch_stft(p, tb, audio, w.X, kXPitch, 0, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
+        if ((rc = launch_stft(p, tb, audio, w.X, kXPitch, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
         if (p->is_tracking) {
             // The tracker is a sequential recurrence over the whole clip in float64 on |X0|^2 of the complex64
             // spectrum (what the reference computes, :53-55); with stft_precision = 32 the selection follows that
             // spectrum, as the reference's would.
-            const TrackerSpectrum src = {w.X + p->lower_bin, (long long)n_frames * 4 * kXPitch, 4LL * kXPitch};
+            const TrackerSpectrum src = {w.X, (long long)n_frames * 4 * kXPitch, 4LL * kXPitch};
             if ((rc = launch_tracker(src, w.mask, p->n_clips, n_frames, n_bins, st))) return rc;
             mask = w.mask;
         }
@@ -585,7 +583,7 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
         // comparison would shift the floor of that bin for the rest of the clip.
         salsa_params_t pa = *p;
         pa.stft_precision = 64;
-        if ((rc = launch_stft(&pa, tb, audio, nullptr, 0, 0, nullptr, 0, w.power0, 1, st))) return rc;
+        if ((rc = launch_stft(&pa, tb, audio, nullptr, 0, nullptr, 0, w.power0, 1, st))) return rc;
         if ((rc = launch_tracker(tracker_power0(w.power0, n_frames, n_bins), w.mask, p->n_clips, n_frames, n_bins, st))) return rc;
         mask = w.mask;
     }

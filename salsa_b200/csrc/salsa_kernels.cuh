@@ -11,6 +11,7 @@
 #pragma once
 #include "eig.cuh"
 #include "fft.cuh"
+#include "tc_ptx.cuh"
 
 namespace salsa {
 
@@ -38,9 +39,8 @@ struct StftArgs {
     int frames_per_block;
     BandLayout bands;
     float2* X;            // [clip][frame][n_chans][x_pitch] or null (bins lower..upper-1 of each row are written)
-    int x_pitch;          // row length of X in complex values
-    int x_origin;         // bin stored at element 0 of a row: `lower` (op-level layout, x_pitch = upper - lower), or 0 (clip path:
-                          // rows indexed by the absolute bin, x_pitch = kXPitch; bins below `lower` are stored but never read)
+    int x_pitch;          // row length of X in complex values (element b of a row = bin lower + b): upper - lower for the
+                          // op-level layout, kXPitch on the clip path
     float* spec;          // log-linear spectrogram or null
     long long spec_clip_stride;
     long long spec_chan_stride;   // row (frame) stride is bands.n_out
@@ -144,28 +144,18 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(StftArgs a, FftTables
         T nyq;
         warp_rfft512<T>(cur, tb.window ? s.win : nullptr, tw, scratch, lane, X, nyq);
         const long long o = ((long long)clip * a.n_frames + t);
-        float2* xrow = a.X ? a.X + (o * a.n_chans + ch) * a.x_pitch - a.x_origin : nullptr;
+        float2* xrow = a.X ? a.X + (o * a.n_chans + ch) * a.x_pitch - a.lower : nullptr;
         double* prow = (a.power0 && ch == 0) ? a.power0 + o * nb - a.lower : nullptr;
         float p[8];
-        float2 xc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            xc[j] = make_float2((float)X[j].re, (float)X[j].im);     // librosa stores complex64
-            p[j] = power_f32(xc[j].x, xc[j].y);
-        }
-        if (xrow && a.x_origin == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (32 * j < a.upper) xrow[lane + 32 * j] = xc[j];    // warp-uniform predicate, whole 256-byte segments
-        } else if (xrow || prow) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = lane + 32 * j;
-                if (k >= a.lower && k < a.upper) {
-                    if (xrow) xrow[k] = xc[j];
-                    // np.abs(complex128) ** 2 (:53-55) up to one float64 ulp
-                    if (prow) prow[k] = fma((double)xc[j].x, (double)xc[j].x, (double)xc[j].y * (double)xc[j].y);
-                }
+            const int k = lane + 32 * j;
+            const float re = (float)X[j].re, im = (float)X[j].im;     // librosa stores complex64
+            p[j] = power_f32(re, im);
+            if ((unsigned)(k - a.lower) < (unsigned)nb) {
+                if (xrow) xrow[k] = make_float2(re, im);
+                // np.abs(complex128) ** 2 (:53-55) up to one float64 ulp
+                if (prow) prow[k] = fma((double)re, (double)re, (double)im * (double)im);
             }
         }
         if (a.spec) {
@@ -320,135 +310,144 @@ __global__ void __launch_bounds__(256) eig_kernel(const float2* __restrict__ X, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// eig_rows_kernel: the eigenvector step of the clip path when the spectrum X is resident in HBM
-// ([clip][frame][4][pitch] complex64, written by stft_kernel).  grid (frame tiles of FT, clips).
-//   1  the tracker mask words of the tile are compacted into a dense list of selected (frame, bin) items, so that
-//      the eigenvector step runs with full warps whatever the selection looks like;
-//   2  one thread per list item: covariance over 7 (wrapped) frames read through the read-only path (a frame of X is
-//      used by 7 neighbouring frames and by the neighbouring tiles: L1 / L2 serve the re-reads), float32
-//      eigenvector, certified coherence test, normalisation -> staging tile in shared memory.  Bins whose float32
-//      verdict cannot be certified are marked in `redo` (same layout as the mask) for eig_redo_kernel;
-//   3  the 3 x FT spatial rows are written to HBM as whole rows (float4), zeros where the bin was not selected /
-//      not valid / above the last spatial bin (:373-374).
-// No float64 code in this kernel: it stays small enough for 3 CTAs of 256 threads per SM.
+// eig_tile_kernel: the eigenvector step of the clip path when the spectrum X is resident in HBM
+// ([clip][frame][4][kXPitch] complex64 indexed by spatial bin, written by stft_kernel).
+// grid (frame tiles of FT, bin tiles of 32, clips); 256 threads.
+//   1  the (FT + 6) x 4 rows of 32 bins the tile's covariances touch are brought into shared memory by TMA bulk
+//      copies (one 256-byte row per issuing thread, completion on one mbarrier; the wrap padding of the frame axis,
+//      :43, is just the row address).  Every X element is then read 7 times from shared memory instead of L2.
+//      Meanwhile the tracker mask words of the tile are compacted into a dense list of selected (frame, bin) items,
+//      so that the eigenvector step runs with full warps whatever the selection looks like;
+//   2  one thread per list item: covariance over 7 frames (28 LDS.64 at immediate offsets), float32 eigenvector,
+//      certified coherence test, normalisation -> staging tile.  Bins whose float32 verdict cannot be certified are
+//      marked in `redo` (same layout as the mask) for eig_redo_kernel;
+//   3  the 3 x FT row segments are written to HBM as float4, zeros where the bin was not selected / not valid; the
+//      last bin tile also zero-fills the columns above the last spatial bin (:373-374).
+// No float64 code in this kernel: 64 registers, 4 CTAs (32 warps) per SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kXPitch = 256;   // row length (complex values) of the clip path's X in HBM: compile-time, so that the 28 loads
-                               // of a covariance are immediate offsets from 7 frame pointers; only bins < n_bins are touched
+constexpr int kXPitch = 256;   // row length (complex values) of the clip path's X in HBM; only bins < n_bins are written
+constexpr int kTileBins = 32;
 
 struct EigRowsArgs {
-    const float2* X;         // [clip][n_frames][4][kXPitch]
+    const float2* X;         // [clip][n_frames][4][kXPitch], element b of a row = spatial bin b
     const uint32_t* mask;    // tracker selection or null (is_tracking = false)
     uint32_t* redo;          // [clip][n_frames][n_words], every word is written
-    float* feature;          // [clip][7][n_frames][feat_dim]; channels 4..6 are written
-    int n_frames, n_bins, pitch, feat_dim;   // pitch: row length of the shared-memory tiles (n_bins rounded up to 32)
+    float* feature;          // [clip][7][n_frames][feat_dim] (feat_dim a multiple of 4); channels 4..6 are written
+    int n_frames, n_bins, feat_dim;
     EigArgs eig;
 };
 
 template <int FT>
-__host__ __device__ inline size_t eig_rows_smem_bytes(int pitch) {
-    return (size_t)3 * FT * pitch * sizeof(float) + (size_t)FT * pitch * sizeof(uint16_t) + 2 * FT * 8 * sizeof(uint32_t) + 16;
+__host__ __device__ constexpr size_t eig_tile_smem_bytes() {
+    return (size_t)(FT + 2 * kHop) * 4 * kTileBins * sizeof(float2) + (size_t)3 * FT * kTileBins * sizeof(float) +
+           (size_t)FT * kTileBins * sizeof(uint16_t) + 2 * FT * sizeof(uint32_t) + 16;
 }
 
 template <int FT, int MINB, int NSQ>
-__global__ void __launch_bounds__(256, MINB) eig_rows_kernel(EigRowsArgs a) {
+__global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
+    constexpr int BB = kTileBins, R = FT + 2 * kHop;
+    static_assert((FT & (FT - 1)) == 0 && (FT * BB * 2) % 8 == 0, "FT a power of two; the mbarrier must stay 8-byte aligned");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* stage = reinterpret_cast<float*>(smem_raw);                                   // [3][FT][pitch]
-    uint16_t* list = reinterpret_cast<uint16_t*>(stage + (size_t)3 * FT * a.pitch);       // [FT * pitch]
-    uint32_t* smask = reinterpret_cast<uint32_t*>(list + (size_t)FT * a.pitch);           // [FT][8]
-    uint32_t* sredo = smask + FT * 8;                                                      // [FT][8]
-    int* n_items = reinterpret_cast<int*>(sredo + FT * 8);
+    float2* xs = reinterpret_cast<float2*>(smem_raw);                                     // [R][4][BB]
+    float* stage = reinterpret_cast<float*>(xs + R * 4 * BB);                             // [3][FT][BB]
+    uint16_t* list = reinterpret_cast<uint16_t*>(stage + 3 * FT * BB);                    // [FT * BB]
+    uint32_t* smask = reinterpret_cast<uint32_t*>(list + FT * BB);                        // [FT]
+    uint32_t* sredo = smask + FT;                                                          // [FT]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sredo + FT);
+    int* n_items = reinterpret_cast<int*>(bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int clip = blockIdx.y;
+    const int clip = blockIdx.z, bt = blockIdx.y;
     const int t0 = blockIdx.x * FT;
     const int nt = min(FT, a.n_frames - t0);
     const int n_words = (a.n_bins + 31) >> 5;
     const uint32_t tail_bits = (a.n_bins & 31) ? ((1u << (a.n_bins & 31)) - 1u) : 0xffffffffu;
-    if (threadIdx.x == 0) *n_items = 0;
-    if (threadIdx.x < FT * 8) sredo[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (threadIdx.x < FT) sredo[threadIdx.x] = 0u;
     __syncthreads();
     // ---- 1
-    for (int w = warp; w < nt * n_words; w += 8) {
-        const int tl = w / n_words, wi = w - tl * n_words;
-        uint32_t bits = a.mask ? __ldg(a.mask + ((long long)clip * a.n_frames + t0 + tl) * n_words + wi) : 0xffffffffu;
-        if (wi == n_words - 1) bits &= tail_bits;
-        int base = 0;
-        if (lane == 0) {
-            smask[tl * 8 + wi] = bits;
-            base = atomicAdd(n_items, __popc(bits));
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if ((bits >> lane) & 1u) list[base + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((tl << 8) | (wi * 32 + lane));
+    const int n_rows = (nt + 2 * kHop) * 4;
+    if (threadIdx.x == 0) tc::mbar_expect_tx(bar, (uint32_t)(n_rows * BB * sizeof(float2)));
+    if (threadIdx.x < n_rows) {
+        int f = (t0 - kHop + (int)(threadIdx.x >> 2)) % a.n_frames;      // wrap padding of the frame axis (:43)
+        if (f < 0) f += a.n_frames;
+        const float2* src = a.X + (((long long)clip * a.n_frames + f) * 4 + (threadIdx.x & 3)) * kXPitch + bt * BB;
+        tc::bulk_load_1d(xs + threadIdx.x * BB, src, BB * sizeof(float2), bar);
     }
+    {
+        // every warp scans the popcounts of the tile's FT <= 32 mask words (lane = frame) and expands its own frames
+        // at the offsets the scan gives: no atomics, and the list is sorted by (frame, bin)
+        static_assert(FT <= 32, "one mask word per lane");
+        uint32_t bits = 0u;
+        if (lane < nt) {
+            bits = a.mask ? __ldg(a.mask + ((long long)clip * a.n_frames + t0 + lane) * n_words + bt) : 0xffffffffu;
+            if (bt == n_words - 1) bits &= tail_bits;
+        }
+        int incl = __popc(bits);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (warp == 0) {
+            if (lane < FT) smask[lane] = bits;
+            if (lane == 31) *n_items = incl;
+        }
+        const int excl = incl - __popc(bits);
+#pragma unroll
+        for (int q = 0; q < (FT + 7) / 8; ++q) {
+            const int tl = warp + 8 * q;                     // frames of this warp
+            const uint32_t w = __shfl_sync(0xffffffffu, bits, tl & 31);
+            const int base = __shfl_sync(0xffffffffu, excl, tl & 31);
+            if (tl < FT && ((w >> lane) & 1u)) list[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((tl << 5) | lane);
+        }
+    }
+    if (warp == 0) tc::mbar_wait(bar, 0);      // one warp polls the mbarrier, the others sleep at the barrier below
     __syncthreads();
     // ---- 2
     const int count = *n_items;
-    const float2* clip_x = a.X + (long long)clip * a.n_frames * 4 * kXPitch;
-    constexpr int frame_stride = 4 * kXPitch;
-    auto finish = [&](int verdict, int tl, int b, const float (&o)[3]) {
-        if (verdict == kEigAmbiguous) atomicOr(&sredo[tl * 8 + (b >> 5)], 1u << (b & 31));
+    const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
+    for (int item = threadIdx.x; item < count; item += 256) {
+        const int code = list[item];
+        const int tl = code >> 5, bl = code & 31;
+        const uint32_t base = xs_addr + (uint32_t)((tl * 4 * BB + bl) * sizeof(float2));   // X[t - 3][ch 0][bin]
+        float o[3];
+        auto load = [&](int k, int ch) -> float2 { return lds_f2(base + (uint32_t)((k * 4 + ch) * BB * sizeof(float2))); };
+        const int verdict = eig_bin_f32<NSQ>(load, a.eig, bt * BB + bl, o);
+        if (verdict == kEigAmbiguous) atomicOr(&sredo[tl], 1u << bl);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) stage[(i * FT + tl) * a.pitch + b] = o[i];
-    };
-    if (t0 >= kHop && t0 + FT + kHop <= a.n_frames) {
-        // no frame of this tile's windows wraps (all tiles but the first and the last of a clip): the 28 loads of a
-        // covariance are immediate offsets from one pointer
-        for (int item = threadIdx.x; item < count; item += 256) {
-            const int code = list[item];
-            const int tl = code >> 8, b = code & 255;
-            const float2* base = clip_x + (t0 + tl - kHop) * frame_stride + b;
-            float o[3];
-            auto load = [&](int k, int ch) -> float2 { return __ldg(base + k * frame_stride + ch * kXPitch); };
-            finish(eig_bin_f32<NSQ>(load, a.eig, b, o), tl, b, o);
-        }
-    } else {
-        for (int item = threadIdx.x; item < count; item += 256) {
-            const int code = list[item];
-            const int tl = code >> 8, b = code & 255;
-            const float2* fp[kWin];
-            int tt = t0 + tl - kHop;                              // wrap padding of the frame axis (:43)
-            tt %= a.n_frames;
-            if (tt < 0) tt += a.n_frames;
-#pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                fp[k] = clip_x + tt * frame_stride + b;
-                tt = tt + 1 == a.n_frames ? 0 : tt + 1;
-            }
-            float o[3];
-            auto load = [&](int k, int ch) -> float2 { return __ldg(fp[k] + ch * kXPitch); };
-            finish(eig_bin_f32<NSQ>(load, a.eig, b, o), tl, b, o);
-        }
+        for (int i = 0; i < 3; ++i) stage[(i * FT + tl) * BB + bl] = o[i];
     }
     __syncthreads();
     // ---- 3
-    if (threadIdx.x < nt * n_words) {
-        const int tl = threadIdx.x / n_words, wi = threadIdx.x - tl * n_words;
-        a.redo[((long long)clip * a.n_frames + t0 + tl) * n_words + wi] = sredo[tl * 8 + wi];
-    }
+    if (threadIdx.x < nt) a.redo[((long long)clip * a.n_frames + t0 + threadIdx.x) * n_words + bt] = sredo[threadIdx.x];
     const long long chan_stride = (long long)a.n_frames * a.feat_dim;
     float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
-    if ((a.feat_dim & 3) == 0) {
-        const int groups = a.feat_dim >> 2;
-        for (int g = threadIdx.x; g < 3 * nt * groups; g += 256) {
-            const int r = g / groups, k = (g - r * groups) * 4;      // r = channel * nt + frame
+    const int c0 = bt * BB;
+    // row segment s = channel * FT + frame; a warp writes four 128-byte segments per step (8 lanes x float4 each)
+    for (int s = (threadIdx.x >> 3); s < 3 * FT; s += 32) {
+        const int i = s / FT, tl = s % FT;                           // FT is a compile-time power of two
+        if (tl >= nt) continue;
+        const int k = (threadIdx.x & 7) * 4;
+        const uint32_t bits = smask[tl] >> k;
+        const float4 sv = *reinterpret_cast<const float4*>(stage + s * BB + k);
+        float4 v;
+        v.x = (bits & 1u) ? sv.x : 0.0f;
+        v.y = (bits & 2u) ? sv.y : 0.0f;
+        v.z = (bits & 4u) ? sv.z : 0.0f;
+        v.w = (bits & 8u) ? sv.w : 0.0f;
+        *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + c0 + k) = v;
+    }
+    if (bt == n_words - 1) {
+        // the last bin tile zero-fills the columns above the last spatial bin (:373-374)
+        const int extra = (a.feat_dim - c0 - BB) >> 2;               // float4 per row
+        for (int g = threadIdx.x; g < 3 * nt * extra; g += 256) {
+            const int r = g / extra, q = g - r * extra;
             const int i = r / nt, tl = r - i * nt;
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (k < a.n_bins) {
-                const uint32_t bits = smask[tl * 8 + (k >> 5)] >> (k & 31);
-                const float* sp = stage + (i * FT + tl) * a.pitch + k;
-                if (bits & 1u) v.x = sp[0];
-                if (bits & 2u) v.y = sp[1];
-                if (bits & 4u) v.z = sp[2];
-                if (bits & 8u) v.w = sp[3];
-            }
-            *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + k) = v;
-        }
-    } else {
-        for (int g = threadIdx.x; g < 3 * nt * a.feat_dim; g += 256) {
-            const int r = g / a.feat_dim, k = g - r * a.feat_dim;
-            const int i = r / nt, tl = r - i * nt;
-            float v = 0.0f;
-            if (k < a.n_bins && ((smask[tl * 8 + (k >> 5)] >> (k & 31)) & 1u)) v = stage[(i * FT + tl) * a.pitch + k];
-            clip_feat[(4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + k] = v;
+            *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + c0 + BB + 4 * q) =
+                make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
     }
 }

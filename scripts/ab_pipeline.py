@@ -39,7 +39,7 @@ def main():
     torch.cuda.set_device(0)
     audio = bench.make_clips(torch, n, 'foa', torch.device('cuda:0'), 0)
     base = None
-    variants = [{'SALSA_B200_PIPELINE': 'fused'}, {}, {'SALSA_B200_EIG_MINB': '2'}, {'SALSA_B200_EIG_MINB': '4'}]
+    variants = [{'SALSA_B200_PIPELINE': 'fused'}, {}, {'SALSA_B200_EIG_MINB': '2'}, {'SALSA_B200_EIG_MINB': '3'}]
     variants += [{'SALSA_B200_STFT_VARIANT': v} for v in os.environ.get('AB_STFT_VARIANTS', '').split(',') if v]
     for env in variants:
         feat, rec = run(audio, dict(env))
@@ -48,6 +48,9 @@ def main():
         else:
             same_bits = bool(torch.equal(feat.view(torch.int32), base.view(torch.int32)))
             rec['spec_bits_equal_to_fused'] = bool(torch.equal(feat[:, :4].view(torch.int32), base[:, :4].view(torch.int32)))
+            d = (feat[:, :4] - base[:, :4]).abs()
+            rec['spec_values_differing'] = int((d != 0).sum().item())
+            rec['spec_max_abs_diff_db'] = float(d.max().item())
             rec['mask_mismatches_vs_fused'] = int(((feat[:, 4:] != 0) != (base[:, 4:] != 0)).sum().item())
             rec['max_abs_diff_spatial'] = float((feat[:, 4:] - base[:, 4:]).abs().max().item())
             rec['all_bits_equal_to_fused'] = same_bits
