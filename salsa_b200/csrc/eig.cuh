@@ -271,6 +271,16 @@ template <> SALSA_HD float root4<float>(float x) {
 #endif
 }
 template <> SALSA_HD double root4<double>(double x) { return sqrt(sqrt(x)); }
+// square root of a positive number to a few ulp
+template <typename T> SALSA_HD T sqrt_fast(T x);
+template <> SALSA_HD float sqrt_fast<float>(float x) {
+#ifdef __CUDA_ARCH__
+    return x * rsqrtf(x);
+#else
+    return sqrtf(x);
+#endif
+}
+template <> SALSA_HD double sqrt_fast<double>(double x) { return sqrt(x); }
 template <> SALSA_HD double rsqrt_t<double>(double x) { return 1.0 / sqrt(x); }
 
 // Principal eigenvector of the (un-normalised) covariance R, coherence verdict.

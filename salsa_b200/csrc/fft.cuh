@@ -112,28 +112,25 @@ template <typename T>
 struct LaneTwiddles {
     Cx<T> w256;   // W256^lane          pass 1 -> 2
     Cx<T> w32;    // W32^(lane & 3)     pass 2 -> 3
-    Cx<T> w512;   // W512^lane          real split
+    Cx<T> w512h;  // W512^lane / 2      real split (the 1/2 of the odd part folded in)
 };
 
 template <typename T>
 __device__ __forceinline__ LaneTwiddles<T> lane_twiddles(const FftTables<T>& tb, int lane) {
-    return {tb.tw_a[32 + lane], tb.tw_b[32 + lane], tb.tw_r[lane]};
+    const Cx<T> r = tb.tw_r[lane];
+    return {tb.tw_a[32 + lane], tb.tw_b[32 + lane], {(T)0.5 * r.re, (T)0.5 * r.im}};
 }
 
 template <typename T> __device__ __forceinline__ Cx<T> shfl_cx(Cx<T> v, int src) {
     return {__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)};
 }
 
-// One warp: the 512-point real transform of the windowed frame in `raw` (see load_frame).
-// X[j] = bin lane + 32 j (j = 0..7) of this lane; `nyq` = bin 256 (valid in lane 0 only).
-// `win` points to the window in shared memory (null: the periodic Hann window of length 512, computed from the
-// lane constants), `scratch` to kScratchElems complex values of per-warp
-// shared memory used by the two exchanges between the three butterfly passes.
+// One warp: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1], m = lane + 32 n1, from the samples in `raw` (see load_frame).
+// `win` points to the window in shared memory (null: the periodic Hann window of length 512, computed from the lane
+// constants).  Split from the passes so that callers can refill `raw` with the next frame as soon as it is consumed.
 template <typename T>
-__device__ __forceinline__ void warp_rfft512(const float2 (&raw)[8], const T* __restrict__ win, const LaneTwiddles<T>& tw,
-                                             Cx<T>* scratch, int lane, Cx<T> (&X)[8], T& nyq) {
-    Cx<T> v[8];
-    // ---- window: z[m] = x[2m] w[2m] + i x[2m+1] w[2m+1],  m = lane + 32 n1
+__device__ __forceinline__ void window_frame(const float2 (&raw)[8], const T* __restrict__ win, const LaneTwiddles<T>& tw, int lane,
+                                             Cx<T> (&v)[8]) {
     if (win) {
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
@@ -154,6 +151,15 @@ __device__ __forceinline__ void warp_rfft512(const float2 (&raw)[8], const T* __
             v[n1] = {(T)raw[n1].x * we, (T)raw[n1].y * wo};
         }
     }
+}
+
+// One warp: the 512-point real transform of the windowed, packed frame in v (see window_frame).
+// X[j] = bin lane + 32 j (j = 0..7) of this lane; `nyq` = bin 256 (valid in lane 0 only).
+// `scratch` points to kScratchElems complex values of per-warp shared memory used by the two exchanges between the
+// three butterfly passes.
+template <typename T>
+__device__ __forceinline__ void warp_fft_passes(Cx<T> (&v)[8], const LaneTwiddles<T>& tw, Cx<T>* scratch, int lane, Cx<T> (&X)[8],
+                                                T& nyq) {
     // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1) = w256^k1
     dft8(v);
     {
@@ -206,7 +212,9 @@ __device__ __forceinline__ void warp_rfft512(const float2 (&raw)[8], const T* __
     __syncwarp();      // scratch may be reused by the caller / the next transform
     // ---- real split, in registers: X[k] = E + W512^k O with E = (Z[k] + conj Z[256-k]) / 2,
     //      O = -i (Z[k] - conj Z[256-k]) / 2.  For k = lane + 32 j the partner Z[256 - k] is z[7 - j] of lane
-    //      32 - lane (lane 0: its own z[(8 - j) & 7]); W512^k = w512 * W16^j with W16^j a constant.
+    //      32 - lane (lane 0: its own z[(8 - j) & 7]); W512^k = w512 * W16^j with W16^j a constant.  The factor 1/2
+    //      of O lives in the twiddle (tw.w512h = W512^lane / 2), the one of E in the final multiply-add:
+    //      10 instead of 14 operations per bin.
     nyq = z[0].re - z[0].im;
     const int partner_lane = (32 - lane) & 31;
     const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
@@ -217,11 +225,21 @@ __device__ __forceinline__ void warp_rfft512(const float2 (&raw)[8], const T* __
         const Cx<T> own = z[(8 - j) & 7];
         const Cx<T> a = z[j];
         const Cx<T> b = lane == 0 ? own : other;
-        const Cx<T> e = {(T)0.5 * (a.re + b.re), (T)0.5 * (a.im - b.im)};
-        const Cx<T> o = {(T)0.5 * (a.im + b.im), (T)0.5 * (b.re - a.re)};
-        const Cx<T> t = cmul(o, j == 0 ? tw.w512 : cmul(tw.w512, w16[j]));
-        X[j] = {e.re + t.re, e.im + t.im};
+        const T sr = a.re + b.re, si = a.im - b.im;          // 2 E
+        const T dr = a.im + b.im, di = b.re - a.re;          // 2 O
+        const Cx<T> wh = j == 0 ? tw.w512h : cmul(tw.w512h, w16[j]);
+        const T tr = dr * wh.re - di * wh.im, ti = dr * wh.im + di * wh.re;
+        X[j] = {(T)0.5 * sr + tr, (T)0.5 * si + ti};
     }
+}
+
+// window + passes in one call
+template <typename T>
+__device__ __forceinline__ void warp_rfft512(const float2 (&raw)[8], const T* __restrict__ win, const LaneTwiddles<T>& tw,
+                                             Cx<T>* scratch, int lane, Cx<T> (&X)[8], T& nyq) {
+    Cx<T> v[8];
+    window_frame<T>(raw, win, tw, lane, v);
+    warp_fft_passes<T>(v, tw, scratch, lane, X, nyq);
 }
 
 // load + transform in one call

@@ -234,16 +234,16 @@ static int set_smem(K kernel, size_t bytes) {
 // ---------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------
-template <typename T, int CH>
+template <typename T, int CH, int OUT>
 static int launch_stft_t(const StftArgs& a, const FftTables<T>& tb, dim3 grid, cudaStream_t st) {
     const size_t smem = sizeof(FftSmem<T>);
-    int rc = set_smem(stft_kernel<T, CH>, smem);
+    int rc = set_smem(stft_kernel<T, CH, OUT>, smem);
     if (rc) return rc;
-    stft_kernel<T, CH><<<grid, kThreads, smem, st>>>(a, tb);
+    stft_kernel<T, CH, OUT><<<grid, kThreads, smem, st>>>(a, tb);
     return SALSA_OK;
 }
 
-static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float2* X, int x_pitch,
+static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const float* audio, float2* X, int x_pitch, int x_tiles,
                        float* spec, long long spec_clip_stride, double* power0, int ch_count, cudaStream_t st) {
     if (p->n_clips == 0) return SALSA_OK;
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
@@ -260,6 +260,7 @@ static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const fl
     a.bands = band_layout(p);
     a.X = X;
     a.x_pitch = x_pitch;
+    a.x_tiles = x_tiles;
     a.spec = spec;
     a.spec_clip_stride = spec_clip_stride;
     a.spec_chan_stride = (long long)n_frames * a.bands.n_out;
@@ -268,22 +269,32 @@ static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const fl
     ProfScope prof("stft_kernel", st);
     int rc;
     if (ch_count != 1 && ch_count != 4) return fail(SALSA_EINVAL, "stft: 1 or 4 channels");
-    if (p->stft_precision == 64)
-        rc = ch_count == 4 ? launch_stft_t<double, 4>(a, tb.d, grid, st) : launch_stft_t<double, 1>(a, tb.d, grid, st);
+    const bool d = p->stft_precision == 64;
+    if (x_tiles > 0 && (ch_count != 4 || !X || !spec || power0)) return fail(SALSA_EINVAL, "stft: tiled X is the clip path's layout");
+    if (x_tiles > 0 && p->lower_bin < kTileBins)            // clip path, split arrangement
+        rc = d ? launch_stft_t<double, 4, kStftX | kStftSpec | kStftTiled>(a, tb.d, grid, st)
+               : launch_stft_t<float, 4, kStftX | kStftSpec | kStftTiled>(a, tb.f, grid, st);
+    else if (x_tiles > 0)
+        rc = d ? launch_stft_t<double, 4, kStftX | kStftSpec | kStftTiledAny>(a, tb.d, grid, st)
+               : launch_stft_t<float, 4, kStftX | kStftSpec | kStftTiledAny>(a, tb.f, grid, st);
+    else if (ch_count == 1 && !X && !spec && power0)        // clip path, fused arrangement (pass A)
+        rc = d ? launch_stft_t<double, 1, kStftPower0>(a, tb.d, grid, st) : launch_stft_t<float, 1, kStftPower0>(a, tb.f, grid, st);
+    else if (ch_count == 4)
+        rc = d ? launch_stft_t<double, 4, kStftAny>(a, tb.d, grid, st) : launch_stft_t<float, 4, kStftAny>(a, tb.f, grid, st);
     else
-        rc = ch_count == 4 ? launch_stft_t<float, 4>(a, tb.f, grid, st) : launch_stft_t<float, 1>(a, tb.f, grid, st);
+        rc = d ? launch_stft_t<double, 1, kStftAny>(a, tb.d, grid, st) : launch_stft_t<float, 1, kStftAny>(a, tb.f, grid, st);
     if (rc) return rc;
     return check_launch("stft_kernel");
 }
 
 template <typename Src>
-static int launch_tracker(Src src, uint32_t* mask, int n_clips, int n_frames, int n_bins, cudaStream_t st) {
+static int launch_tracker(Src src, uint32_t* mask, int n_clips, int n_frames, int first_bin, int n_bins, cudaStream_t st) {
     if (n_clips == 0) return SALSA_OK;
     const int n_words = (n_bins + 31) / 32;
     const int wpb = std::min(n_words, 8);                       // warps per block
     dim3 grid((n_words + wpb - 1) / wpb, n_clips);
     ProfScope prof("tracker_kernel", st);
-    tracker_kernel<Src><<<grid, wpb * 32, 0, st>>>(src, mask, n_frames, n_bins, tracker_consts());
+    tracker_kernel<Src><<<grid, wpb * 32, 0, st>>>(src, mask, n_frames, first_bin, n_bins, tracker_consts());
     return check_launch("tracker_kernel");
 }
 
@@ -356,16 +367,12 @@ static Pipeline pipeline_choice() {
     return kPipelineSplit;
 }
 
-static int env_int(const char* name, int fallback) {
-    const char* e = getenv(name);
-    return e && *e ? atoi(e) : fallback;
-}
-
 struct Workspace {
     double* power0;    // fused
-    float2* X;         // split
-    uint32_t* mask;
+    float2* X;         // split: tiled spectrum
+    uint32_t* mask;    // [clip][frame][words of 32 spatial bins]
     uint32_t* redo;    // split
+    int n_tiles;       // split
     size_t bytes;
 };
 
@@ -374,17 +381,19 @@ static size_t round256(size_t v) { return (v + 255) / 256 * 256; }
 static Workspace carve_workspace(const salsa_params_t* p, void* base, Pipeline pl) {
     const size_t n_frames = (size_t)salsa_n_frames(p->n_samples, p->hop_len);
     const size_t n_bins = (size_t)(p->upper_bin - p->lower_bin);
-    const size_t mk = round256((size_t)p->n_clips * n_frames * ((n_bins + 31) / 32) * sizeof(uint32_t));
     char* at = reinterpret_cast<char*>(base);
     Workspace w = {};
     if (pl == kPipelineSplit) {
-        const size_t xb = round256((size_t)p->n_clips * n_frames * 4 * kXPitch * sizeof(float2));
+        w.n_tiles = (int)((n_bins + kTileBins - 1) / kTileBins);
+        const size_t xb = round256((size_t)p->n_clips * w.n_tiles * n_frames * kTileFrameElems * sizeof(float2));
+        const size_t mk = round256((size_t)p->n_clips * n_frames * w.n_tiles * sizeof(uint32_t));
         w.X = reinterpret_cast<float2*>(at);
         w.mask = reinterpret_cast<uint32_t*>(at + xb);
         w.redo = reinterpret_cast<uint32_t*>(at + xb + mk);
         w.bytes = xb + 2 * mk;
     } else {
         const size_t pw = round256((size_t)p->n_clips * n_frames * n_bins * sizeof(double));
+        const size_t mk = round256((size_t)p->n_clips * n_frames * ((n_bins + 31) / 32) * sizeof(uint32_t));
         w.power0 = reinterpret_cast<double*>(at);
         w.mask = reinterpret_cast<uint32_t*>(at + pw);
         w.bytes = pw + mk;
@@ -396,41 +405,40 @@ static Workspace carve_workspace(const salsa_params_t* p, void* base, Pipeline p
 constexpr int kEigFT = 32;     // frames per CTA of eig_tile_kernel
 
 template <int MINB, int NSQ>
-static int launch_eig_tile_t(const EigRowsArgs& a, dim3 grid, cudaStream_t st) {
+static int launch_eig_tile_t(const EigTileArgs& a, cudaStream_t st, int n_clips) {
     constexpr size_t smem = eig_tile_smem_bytes<kEigFT>();
     int rc = set_smem(eig_tile_kernel<kEigFT, MINB, NSQ>, smem);
     if (rc) return rc;
+    dim3 grid((a.n_frames + kEigFT - 1) / kEigFT, a.n_tiles, n_clips);
     eig_tile_kernel<kEigFT, MINB, NSQ><<<grid, 256, smem, st>>>(a);
     return SALSA_OK;
 }
 
 static int launch_eig_rows(const salsa_params_t* p, const Workspace& w, const uint32_t* mask, float* feature, cudaStream_t st) {
     if (p->n_clips == 0) return SALSA_OK;
-    EigRowsArgs a;
+    EigTileArgs a;
     a.X = w.X;
     a.mask = mask;
     a.redo = w.redo;
     a.feature = feature;
     a.n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     a.n_bins = p->upper_bin - p->lower_bin;
+    a.n_tiles = w.n_tiles;
     a.feat_dim = band_layout(p).n_out;
     a.eig = eig_args(p);
-    if (a.n_bins > kXPitch) return fail(SALSA_EINVAL, "more than 256 spatial bins");
     if (a.feat_dim & 3) return fail(SALSA_EINVAL, "feature width must be a multiple of 4");
-    dim3 grid((a.n_frames + kEigFT - 1) / kEigFT, (a.n_bins + kTileBins - 1) / kTileBins, p->n_clips);
     int rc;
     {
         ProfScope prof("eig_tile_kernel", st);
-        const int minb = env_int("SALSA_B200_EIG_MINB", 4);
         if (a.eig.n_sq == 2)       // the default (cond_num = 5): squarings unrolled at compile time
-            rc = minb == 2 ? launch_eig_tile_t<2, 2>(a, grid, st) : (minb == 3 ? launch_eig_tile_t<3, 2>(a, grid, st) : launch_eig_tile_t<4, 2>(a, grid, st));
+            rc = launch_eig_tile_t<4, 2>(a, st, p->n_clips);
         else
-            rc = launch_eig_tile_t<3, 0>(a, grid, st);
+            rc = launch_eig_tile_t<3, 0>(a, st, p->n_clips);
         if (rc) return rc;
         if ((rc = check_launch("eig_tile_kernel"))) return rc;
     }
     if (!a.eig.test) return SALSA_OK;      // without the coherence test no verdict is ever ambiguous
-    const long long n_words_total = (long long)p->n_clips * a.n_frames * ((a.n_bins + 31) / 32);
+    const long long n_words_total = (long long)p->n_clips * a.n_frames * a.n_tiles;
     ProfScope prof("eig_redo_kernel", st);
     eig_redo_kernel<<<(unsigned)((n_words_total + 127) / 128), 128, 0, st>>>(a, n_words_total);
     return check_launch("eig_redo_kernel");
@@ -502,7 +510,7 @@ int salsa_stft(const salsa_params_t* p, const float* audio, float* X, float* log
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     const long long clip_stride = (long long)p->n_chans * n_frames * band_layout(p).n_out;
     const int ch_count = (X || logspec) ? p->n_chans : 1;
-    return launch_stft(p, tb, audio, reinterpret_cast<float2*>(X), p->upper_bin - p->lower_bin, logspec, clip_stride,
+    return launch_stft(p, tb, audio, reinterpret_cast<float2*>(X), p->upper_bin - p->lower_bin, 0, logspec, clip_stride,
                        power0, ch_count, (cudaStream_t)stream);
 }
 
@@ -510,7 +518,7 @@ int salsa_tracker(const double* power0, uint32_t* mask, int32_t n_clips, int32_t
                   void* stream) {
     if (!power0 || !mask) return fail(SALSA_EINVAL, "power0 / mask is NULL");
     if (n_clips < 0 || n_frames <= 0 || n_bins <= 0) return fail(SALSA_EINVAL, "bad tracker dimensions");
-    return launch_tracker(tracker_power0(power0, n_frames, n_bins), mask, n_clips, n_frames, n_bins, (cudaStream_t)stream);
+    return launch_tracker(tracker_power0(power0, n_frames, n_bins), mask, n_clips, n_frames, 0, n_bins, (cudaStream_t)stream);
 }
 
 int salsa_spectrum_from_reference(const double* X_ref, float* X, double* power0, int32_t n_bins, int32_t n_frames,
@@ -566,13 +574,13 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     const uint32_t* mask = nullptr;
     if (pl == kPipelineSplit) {
         const long long clip_stride = 7LL * n_frames * band_layout(p).n_out;
-        if ((rc = launch_stft(p, tb, audio, w.X, kXPitch, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
+        if ((rc = launch_stft(p, tb, audio, w.X, 0, w.n_tiles, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
         if (p->is_tracking) {
             // The tracker is a sequential recurrence over the whole clip in float64 on |X0|^2 of the complex64
             // spectrum (what the reference computes, :53-55); with stft_precision = 32 the selection follows that
             // spectrum, as the reference's would.
-            const TrackerSpectrum src = {w.X, (long long)n_frames * 4 * kXPitch, 4LL * kXPitch};
-            if ((rc = launch_tracker(src, w.mask, p->n_clips, n_frames, n_bins, st))) return rc;
+            const TrackerTiles src = {w.X, w.n_tiles, n_frames};
+            if ((rc = launch_tracker(src, w.mask, p->n_clips, n_frames, 0, n_bins, st))) return rc;
             mask = w.mask;
         }
         return launch_eig_rows(p, w, mask, feature, st);
@@ -583,8 +591,8 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
         // comparison would shift the floor of that bin for the rest of the clip.
         salsa_params_t pa = *p;
         pa.stft_precision = 64;
-        if ((rc = launch_stft(&pa, tb, audio, nullptr, 0, nullptr, 0, w.power0, 1, st))) return rc;
-        if ((rc = launch_tracker(tracker_power0(w.power0, n_frames, n_bins), w.mask, p->n_clips, n_frames, n_bins, st))) return rc;
+        if ((rc = launch_stft(&pa, tb, audio, nullptr, 0, 0, nullptr, 0, w.power0, 1, st))) return rc;
+        if ((rc = launch_tracker(tracker_power0(w.power0, n_frames, n_bins), w.mask, p->n_clips, n_frames, 0, n_bins, st))) return rc;
         mask = w.mask;
     }
     return launch_fused(p, tb, audio, feature, mask, st);

@@ -18,6 +18,8 @@ namespace salsa {
 constexpr int kWarps = 8;                // warps per CTA in the STFT-bearing kernels
 constexpr int kThreads = kWarps * 32;
 constexpr float kAmin = 1e-10f;          // power_to_db amin (salsa_feature_extraction.py:195)
+constexpr int kTileBins = 32;            // clip path: X lives in HBM in tiles of 32 bins (see eig_tile_kernel)
+constexpr int kTileFrameElems = 4 * kTileBins;       // complex values per (tile, frame)
 
 // Layout of the log-linear bands (MagStftExtractor.__init__, :153-175):
 // band < n_lin -> bin band+1 (weight 1); n_lin <= band < n_out -> 8 bins (the last one fewer,
@@ -39,8 +41,8 @@ struct StftArgs {
     int frames_per_block;
     BandLayout bands;
     float2* X;            // [clip][frame][n_chans][x_pitch] or null (bins lower..upper-1 of each row are written)
-    int x_pitch;          // row length of X in complex values (element b of a row = bin lower + b): upper - lower for the
-                          // op-level layout, kXPitch on the clip path
+    int x_pitch;          // row layout: row length of X in complex values (element b of a row = bin lower + b)
+    int x_tiles;          // > 0: tiled layout X[clip][frame][tile][channel][32] of the clip path with this many tiles
     float* spec;          // log-linear spectrogram or null
     long long spec_clip_stride;
     long long spec_chan_stride;   // row (frame) stride is bands.n_out
@@ -114,7 +116,13 @@ __device__ __forceinline__ void write_logspec_row(const float (&p)[8], float p_n
 // ------------------------------------------------------------------------------------------------
 // stft_kernel: grid (frame blocks, clips); one warp per (frame, channel) item.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int CH>
+// OUT: which outputs exist, known at compile time on the clip path so that no pointer is tested per bin
+// (kStftAny: test the pointers of StftArgs at run time -- the op-level entry point).
+constexpr int kStftX = 1, kStftPower0 = 2, kStftSpec = 4, kStftAny = -1;
+// kStftTiled: X goes to the tiled layout of the clip path (lower_bin < 32); kStftTiledAny: same for any lower_bin
+constexpr int kStftTiled = 8, kStftTiledAny = 16;
+
+template <typename T, int CH, int OUT>
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(StftArgs a, FftTables<T> tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
@@ -126,39 +134,51 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(StftArgs a, FftTables
     const int f0 = blockIdx.x * a.frames_per_block;
     const int f1 = min(a.n_frames, f0 + a.frames_per_block);
     const int nb = a.upper - a.lower;
+    const bool has_x = OUT == kStftAny ? a.X != nullptr : (OUT & kStftX) != 0;
+    const bool has_p0 = OUT == kStftAny ? a.power0 != nullptr : (OUT & kStftPower0) != 0;
+    const bool has_spec = OUT == kStftAny ? a.spec != nullptr : (OUT & kStftSpec) != 0;
+    constexpr bool tiled = OUT != kStftAny && (OUT & (kStftTiled | kStftTiledAny)) != 0;
     const float* clip_audio = a.audio + (long long)clip * a.n_chans * a.n_samples;
     Cx<T>* scratch = s.scratch[warp];
+    const T* win = tb.window ? s.win : nullptr;
     const int n_items = (f1 - f0) * CH;             // CH = channels transformed (a.ch_count)
-    // the samples of a warp's next (frame, channel) item are requested before the current one is transformed
+    const int lane_off = lane - a.lower + (lane < a.lower ? kTileBins - kTileFrameElems : 0);
     float2 raw[8];
     int t = f0 + warp / CH, ch = warp % CH;
     if (warp < n_items) load_frame(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, lane, raw);
     for (int item = warp; item < n_items; item += kWarps) {
-        float2 cur[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = raw[i];
+        Cx<T> v[8];
+        window_frame<T>(raw, win, tw, lane, v);
+        // `raw` is consumed: the samples of this warp's next (frame, channel) item are requested before the passes
         const int nxt = item + kWarps;
         const int tn = f0 + nxt / CH, chn = nxt % CH;
         if (nxt < n_items) load_frame(clip_audio + (long long)chn * a.n_samples, a.n_samples, tn * a.hop - kNfft / 2, lane, raw);
         Cx<T> X[8];
         T nyq;
-        warp_rfft512<T>(cur, tb.window ? s.win : nullptr, tw, scratch, lane, X, nyq);
+        warp_fft_passes<T>(v, tw, scratch, lane, X, nyq);
         const long long o = ((long long)clip * a.n_frames + t);
-        float2* xrow = a.X ? a.X + (o * a.n_chans + ch) * a.x_pitch - a.lower : nullptr;
-        double* prow = (a.power0 && ch == 0) ? a.power0 + o * nb - a.lower : nullptr;
+        float2* xrow = a.X + (o * a.n_chans + ch) * a.x_pitch - a.lower;
+        double* prow = a.power0 + o * nb - a.lower;
+        float2* xtile = a.X + o * a.x_tiles * kTileFrameElems + ch * kTileBins;
         float p[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = lane + 32 * j;
             const float re = (float)X[j].re, im = (float)X[j].im;     // librosa stores complex64
             p[j] = power_f32(re, im);
-            if ((unsigned)(k - a.lower) < (unsigned)nb) {
-                if (xrow) xrow[k] = make_float2(re, im);
+            if (tiled && (unsigned)(k - a.lower) < (unsigned)nb) {
+                // tiled layout: spatial bin b = k - lower -> tile b / 32, position b % 32.  With lower < 32 that is tile j
+                // (j - 1 for the first `lower` lanes) at a per-lane offset that does not depend on j
+                if (OUT & kStftTiled) xtile[j * kTileFrameElems + lane_off] = make_float2(re, im);
+                else xtile[((k - a.lower) >> 5) * kTileFrameElems + ((k - a.lower) & 31)] = make_float2(re, im);
+            }
+            if (!tiled && (has_x || has_p0) && (unsigned)(k - a.lower) < (unsigned)nb) {
+                if (has_x) xrow[k] = make_float2(re, im);
                 // np.abs(complex128) ** 2 (:53-55) up to one float64 ulp
-                if (prow) prow[k] = fma((double)re, (double)re, (double)im * (double)im);
+                if (has_p0 && ch == 0) prow[k] = fma((double)re, (double)re, (double)im * (double)im);
             }
         }
-        if (a.spec) {
+        if (has_spec) {
             const float p_nyq = power_f32((float)nyq, 0.0f);
             float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
             write_logspec_row(p, p_nyq, row, a.bands, lane);
@@ -194,14 +214,25 @@ struct TrackerSpectrum {
     }
 };
 
+// clip path: channel 0 of the tiled spectrum
+struct TrackerTiles {
+    const float2* x;
+    int n_tiles, n_frames;
+    __device__ __forceinline__ double operator()(int clip, int t, int b) const {
+        const float2 v = __ldg(x + (((long long)clip * n_frames + t) * n_tiles + (b >> 5)) * kTileFrameElems + (b & 31));
+        return fma((double)v.x, (double)v.x, (double)v.y * (double)v.y);
+    }
+};
+
+// bins first_bin .. n_bins - 1 are tracked (bits of the bins below first_bin stay clear)
 template <typename Src>
-__global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restrict__ mask, int n_frames, int n_bins,
+__global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restrict__ mask, int n_frames, int first_bin, int n_bins,
                                                       TrackerConsts c) {
     const int clip = blockIdx.y;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int word = b >> 5, n_words = (n_bins + 31) >> 5;
-    const bool live = b < n_bins;
-    const int bb = live ? b : 0;
+    const bool live = b >= first_bin && b < n_bins;
+    const int bb = live ? b : first_bin;
     uint32_t* mrow = mask + (long long)clip * n_frames * n_words + word;
     auto at = [&](int t) -> double {   // wrapped frame access (np.pad 'wrap', :43)
         t %= n_frames;
@@ -310,46 +341,47 @@ __global__ void __launch_bounds__(256) eig_kernel(const float2* __restrict__ X, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// eig_tile_kernel: the eigenvector step of the clip path when the spectrum X is resident in HBM
-// ([clip][frame][4][kXPitch] complex64 indexed by spatial bin, written by stft_kernel).
-// grid (frame tiles of FT, bin tiles of 32, clips); 256 threads.
-//   1  the (FT + 6) x 4 rows of 32 bins the tile's covariances touch are brought into shared memory by TMA bulk
-//      copies (one 256-byte row per issuing thread, completion on one mbarrier; the wrap padding of the frame axis,
-//      :43, is just the row address).  Every X element is then read 7 times from shared memory instead of L2.
-//      Meanwhile the tracker mask words of the tile are compacted into a dense list of selected (frame, bin) items,
-//      so that the eigenvector step runs with full warps whatever the selection looks like;
-//   2  one thread per list item: covariance over 7 frames (28 LDS.64 at immediate offsets), float32 eigenvector,
-//      certified coherence test, normalisation -> staging tile.  Bins whose float32 verdict cannot be certified are
-//      marked in `redo` (same layout as the mask) for eig_redo_kernel;
-//   3  the 3 x FT row segments are written to HBM as float4, zeros where the bin was not selected / not valid; the
-//      last bin tile also zero-fills the columns above the last spatial bin (:373-374).
+// Clip path, split arrangement: the spectrum X lives in HBM in TILES of 32 spatial bins (b = bin - lower_bin),
+//     X[clip][frame][tile = b / 32][channel][b % 32]   (complex64; tiles 0 .. (n_bins - 1) / 32)
+// so that the 4 channels x 32 bins of one (frame, tile) are 1 KB contiguous -- one TMA bulk copy per frame of an
+// eig_tile_kernel CTA -- while stft_kernel still writes all rows of a frame inside one 6 KB block.  A tile is also one
+// word of the tracker mask and one aligned 128-byte segment of a feature row.
+// ------------------------------------------------------------------------------------------------
+// eig_tile_kernel: the eigenvector step.  grid (frame tiles of FT = 32, bin tiles, clips); 256 threads.
+//   1  the FT + 6 frames of this bin tile are brought into shared memory by TMA bulk copies (1 KB per frame, one
+//      issuing thread per frame, completion on one mbarrier; the wrap padding of the frame axis, :43, is just the
+//      source address).  Every X element is then read 7 times from shared memory.  Meanwhile the tracker mask words of
+//      the tile are compacted into a dense list of selected (frame, bin) items, so that the eigenvector step runs with
+//      full warps whatever the selection looks like;
+//   2  one thread per list item: covariance over 7 frames (28 LDS.64 at immediate offsets), float32 eigenvector
+//      (FFMA2 complex arithmetic), certified coherence test, normalisation -> staging tile.  Bins whose float32 verdict
+//      cannot be certified are marked in `redo` for eig_redo_kernel;
+//   3  the 3 x FT row segments go to HBM, zeros where the bin was not selected / not valid; the last bin tile also
+//      zero-fills the columns above the last spatial bin (:373-374).
 // No float64 code in this kernel: 64 registers, 4 CTAs (32 warps) per SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kXPitch = 256;   // row length (complex values) of the clip path's X in HBM; only bins < n_bins are written
-constexpr int kTileBins = 32;
-
-struct EigRowsArgs {
-    const float2* X;         // [clip][n_frames][4][kXPitch], element b of a row = spatial bin b
-    const uint32_t* mask;    // tracker selection or null (is_tracking = false)
-    uint32_t* redo;          // [clip][n_frames][n_words], every word is written
+struct EigTileArgs {
+    const float2* X;         // tiled spectrum (see above)
+    const uint32_t* mask;    // [clip][n_frames][n_tiles] tracker selection, or null (is_tracking = false)
+    uint32_t* redo;          // [clip][n_frames][n_tiles], every word is written
     float* feature;          // [clip][7][n_frames][feat_dim] (feat_dim a multiple of 4); channels 4..6 are written
-    int n_frames, n_bins, feat_dim;
+    int n_frames, n_bins, n_tiles, feat_dim;
     EigArgs eig;
 };
 
 template <int FT>
 __host__ __device__ constexpr size_t eig_tile_smem_bytes() {
-    return (size_t)(FT + 2 * kHop) * 4 * kTileBins * sizeof(float2) + (size_t)3 * FT * kTileBins * sizeof(float) +
+    return (size_t)(FT + 2 * kHop) * kTileFrameElems * sizeof(float2) + (size_t)3 * FT * kTileBins * sizeof(float) +
            (size_t)FT * kTileBins * sizeof(uint16_t) + 2 * FT * sizeof(uint32_t) + 16;
 }
 
 template <int FT, int MINB, int NSQ>
-__global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
+__global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigTileArgs a) {
     constexpr int BB = kTileBins, R = FT + 2 * kHop;
-    static_assert((FT & (FT - 1)) == 0 && (FT * BB * 2) % 8 == 0, "FT a power of two; the mbarrier must stay 8-byte aligned");
+    static_assert(FT == 32, "one mask word per lane in the compaction scan");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);                                     // [R][4][BB]
-    float* stage = reinterpret_cast<float*>(xs + R * 4 * BB);                             // [3][FT][BB]
+    float* stage = reinterpret_cast<float*>(xs + R * kTileFrameElems);                    // [3][FT][BB]
     uint16_t* list = reinterpret_cast<uint16_t*>(stage + 3 * FT * BB);                    // [FT * BB]
     uint32_t* smask = reinterpret_cast<uint32_t*>(list + FT * BB);                        // [FT]
     uint32_t* sredo = smask + FT;                                                          // [FT]
@@ -359,8 +391,6 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
     const int clip = blockIdx.z, bt = blockIdx.y;
     const int t0 = blockIdx.x * FT;
     const int nt = min(FT, a.n_frames - t0);
-    const int n_words = (a.n_bins + 31) >> 5;
-    const uint32_t tail_bits = (a.n_bins & 31) ? ((1u << (a.n_bins & 31)) - 1u) : 0xffffffffu;
     if (threadIdx.x == 0) {
         tc::mbar_init(bar, 1);
         tc::fence_barrier_init();
@@ -368,22 +398,21 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
     if (threadIdx.x < FT) sredo[threadIdx.x] = 0u;
     __syncthreads();
     // ---- 1
-    const int n_rows = (nt + 2 * kHop) * 4;
-    if (threadIdx.x == 0) tc::mbar_expect_tx(bar, (uint32_t)(n_rows * BB * sizeof(float2)));
+    const int n_rows = nt + 2 * kHop;
+    if (threadIdx.x == 0) tc::mbar_expect_tx(bar, (uint32_t)(n_rows * kTileFrameElems * sizeof(float2)));
     if (threadIdx.x < n_rows) {
-        int f = (t0 - kHop + (int)(threadIdx.x >> 2)) % a.n_frames;      // wrap padding of the frame axis (:43)
+        int f = (t0 - kHop + (int)threadIdx.x) % a.n_frames;             // wrap padding of the frame axis (:43)
         if (f < 0) f += a.n_frames;
-        const float2* src = a.X + (((long long)clip * a.n_frames + f) * 4 + (threadIdx.x & 3)) * kXPitch + bt * BB;
-        tc::bulk_load_1d(xs + threadIdx.x * BB, src, BB * sizeof(float2), bar);
+        const float2* src = a.X + (((long long)clip * a.n_frames + f) * a.n_tiles + bt) * kTileFrameElems;
+        tc::bulk_load_1d(xs + threadIdx.x * kTileFrameElems, src, kTileFrameElems * sizeof(float2), bar);
     }
     {
-        // every warp scans the popcounts of the tile's FT <= 32 mask words (lane = frame) and expands its own frames
-        // at the offsets the scan gives: no atomics, and the list is sorted by (frame, bin)
-        static_assert(FT <= 32, "one mask word per lane");
+        // every warp scans the popcounts of the tile's 32 mask words (lane = frame) and expands its own frames at the
+        // offsets the scan gives: no atomics, and the list is sorted by (frame, bin)
         uint32_t bits = 0u;
         if (lane < nt) {
-            bits = a.mask ? __ldg(a.mask + ((long long)clip * a.n_frames + t0 + lane) * n_words + bt) : 0xffffffffu;
-            if (bt == n_words - 1) bits &= tail_bits;
+            bits = a.mask ? __ldg(a.mask + ((long long)clip * a.n_frames + t0 + lane) * a.n_tiles + bt) : 0xffffffffu;
+            if (bt == a.n_tiles - 1 && (a.n_bins & 31)) bits &= (1u << (a.n_bins & 31)) - 1u;
         }
         int incl = __popc(bits);
 #pragma unroll
@@ -392,16 +421,16 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
             if (lane >= d) incl += up;
         }
         if (warp == 0) {
-            if (lane < FT) smask[lane] = bits;
+            smask[lane] = bits;
             if (lane == 31) *n_items = incl;
         }
         const int excl = incl - __popc(bits);
 #pragma unroll
-        for (int q = 0; q < (FT + 7) / 8; ++q) {
+        for (int q = 0; q < FT / 8; ++q) {
             const int tl = warp + 8 * q;                     // frames of this warp
-            const uint32_t w = __shfl_sync(0xffffffffu, bits, tl & 31);
-            const int base = __shfl_sync(0xffffffffu, excl, tl & 31);
-            if (tl < FT && ((w >> lane) & 1u)) list[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((tl << 5) | lane);
+            const uint32_t w = __shfl_sync(0xffffffffu, bits, tl);
+            const int base = __shfl_sync(0xffffffffu, excl, tl);
+            if ((w >> lane) & 1u) list[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((tl << 5) | lane);
         }
     }
     if (warp == 0) tc::mbar_wait(bar, 0);      // one warp polls the mbarrier, the others sleep at the barrier below
@@ -412,7 +441,7 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
     for (int item = threadIdx.x; item < count; item += 256) {
         const int code = list[item];
         const int tl = code >> 5, bl = code & 31;
-        const uint32_t base = xs_addr + (uint32_t)((tl * 4 * BB + bl) * sizeof(float2));   // X[t - 3][ch 0][bin]
+        const uint32_t base = xs_addr + (uint32_t)((tl * kTileFrameElems + bl) * sizeof(float2));   // X[t - 3][ch 0][bin]
         float o[3];
         auto load = [&](int k, int ch) -> float2 { return lds_f2(base + (uint32_t)((k * 4 + ch) * BB * sizeof(float2))); };
         const int verdict = eig_bin_f32<NSQ>(load, a.eig, bt * BB + bl, o);
@@ -422,13 +451,13 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
     }
     __syncthreads();
     // ---- 3
-    if (threadIdx.x < nt) a.redo[((long long)clip * a.n_frames + t0 + threadIdx.x) * n_words + bt] = sredo[threadIdx.x];
+    if (threadIdx.x < nt) a.redo[((long long)clip * a.n_frames + t0 + threadIdx.x) * a.n_tiles + bt] = sredo[threadIdx.x];
     const long long chan_stride = (long long)a.n_frames * a.feat_dim;
     float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
     const int c0 = bt * BB;
     // row segment s = channel * FT + frame; a warp writes four 128-byte segments per step (8 lanes x float4 each)
     for (int s = (threadIdx.x >> 3); s < 3 * FT; s += 32) {
-        const int i = s / FT, tl = s % FT;                           // FT is a compile-time power of two
+        const int i = s / FT, tl = s % FT;
         if (tl >= nt) continue;
         const int k = (threadIdx.x & 7) * 4;
         const uint32_t bits = smask[tl] >> k;
@@ -440,7 +469,7 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
         v.w = (bits & 8u) ? sv.w : 0.0f;
         *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + c0 + k) = v;
     }
-    if (bt == n_words - 1) {
+    if (bt == a.n_tiles - 1) {
         // the last bin tile zero-fills the columns above the last spatial bin (:373-374)
         const int extra = (a.feat_dim - c0 - BB) >> 2;               // float4 per row
         for (int g = threadIdx.x; g < 3 * nt * extra; g += 256) {
@@ -452,31 +481,31 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigRowsArgs a) {
     }
 }
 
-// eig_redo_kernel: float64 re-evaluation of the bins eig_rows_kernel marked (a few per million); one thread per
-// mask word, valid results overwrite the zeros eig_rows_kernel left in the feature rows.
-__global__ void __launch_bounds__(128) eig_redo_kernel(EigRowsArgs a, long long n_words_total) {
+// eig_redo_kernel: float64 re-evaluation of the bins eig_tile_kernel marked (a few per 100 000); one thread per
+// mask word, valid results overwrite the zeros eig_tile_kernel left in the feature rows.
+__global__ void __launch_bounds__(128) eig_redo_kernel(EigTileArgs a, long long n_words_total) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words_total) return;
     uint32_t bits = __ldg(a.redo + w);
     if (!bits) return;
-    const int n_words = (a.n_bins + 31) >> 5;
-    const int wi = (int)(w % n_words);
-    const long long ft = w / n_words;
+    const int bt = (int)(w % a.n_tiles);
+    const long long ft = w / a.n_tiles;
     const int t = (int)(ft % a.n_frames), clip = (int)(ft / a.n_frames);
-    const float2* clip_x = a.X + (long long)clip * a.n_frames * 4 * kXPitch;
+    const float2* tile_x = a.X + ((long long)clip * a.n_frames * a.n_tiles + bt) * kTileFrameElems;
     const long long chan_stride = (long long)a.n_frames * a.feat_dim;
     float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
     while (bits) {
-        const int b = wi * 32 + __ffs(bits) - 1;
+        const int bl = __ffs(bits) - 1;
         bits &= bits - 1;
         const float2* fp[kWin];
 #pragma unroll
         for (int k = 0; k < kWin; ++k) {
             int tt = (t - kHop + k) % a.n_frames;
             if (tt < 0) tt += a.n_frames;
-            fp[k] = clip_x + (long long)tt * 4 * kXPitch + b;
+            fp[k] = tile_x + (long long)tt * a.n_tiles * kTileFrameElems + bl;
         }
-        auto load = [&](int k, int ch) -> float2 { return __ldg(fp[k] + ch * kXPitch); };
+        auto load = [&](int k, int ch) -> float2 { return __ldg(fp[k] + ch * kTileBins); };
+        const int b = bt * kTileBins + bl;                    // spatial bin = feature column
         float o[3] = {0.0f, 0.0f, 0.0f};
         if (eig_bin_f64(load, a.eig, o, b) == kEigPass) {
 #pragma unroll

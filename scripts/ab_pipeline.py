@@ -13,7 +13,7 @@ from salsa_b200 import _native
 
 
 def run(audio, env, steps=3):
-    for k in ('SALSA_B200_PIPELINE', 'SALSA_B200_EIG_MINB', 'SALSA_B200_STFT_VARIANT'):
+    for k in ('SALSA_B200_PIPELINE', 'SALSA_B200_EIG_SHAPE', 'SALSA_B200_STFT_VARIANT'):
         os.environ.pop(k, None)
     os.environ.update(env)
     ex = salsa_b200.SalsaExtractor('foa')
@@ -39,7 +39,7 @@ def main():
     torch.cuda.set_device(0)
     audio = bench.make_clips(torch, n, 'foa', torch.device('cuda:0'), 0)
     base = None
-    variants = [{'SALSA_B200_PIPELINE': 'fused'}, {}, {'SALSA_B200_EIG_MINB': '2'}, {'SALSA_B200_EIG_MINB': '3'}]
+    variants = [{'SALSA_B200_PIPELINE': 'fused'}, {}]
     variants += [{'SALSA_B200_STFT_VARIANT': v} for v in os.environ.get('AB_STFT_VARIANTS', '').split(',') if v]
     for env in variants:
         feat, rec = run(audio, dict(env))
