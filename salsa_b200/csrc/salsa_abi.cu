@@ -402,15 +402,13 @@ static Workspace carve_workspace(const salsa_params_t* p, void* base, Pipeline p
     return w;
 }
 
-constexpr int kEigFT = 32;     // frames per CTA of eig_tile_kernel
-
-template <int MINB, int NSQ>
+template <int FT, int MINB, int NSQ>
 static int launch_eig_tile_t(const EigTileArgs& a, cudaStream_t st, int n_clips) {
-    constexpr size_t smem = eig_tile_smem_bytes<kEigFT>();
-    int rc = set_smem(eig_tile_kernel<kEigFT, MINB, NSQ>, smem);
+    constexpr size_t smem = eig_tile_smem_bytes<FT>();
+    int rc = set_smem(eig_tile_kernel<FT, MINB, NSQ>, smem);
     if (rc) return rc;
-    dim3 grid((a.n_frames + kEigFT - 1) / kEigFT, a.n_tiles, n_clips);
-    eig_tile_kernel<kEigFT, MINB, NSQ><<<grid, 256, smem, st>>>(a);
+    dim3 grid((a.n_frames + FT - 1) / FT, a.n_tiles, n_clips);
+    eig_tile_kernel<FT, MINB, NSQ><<<grid, 256, smem, st>>>(a);
     return SALSA_OK;
 }
 
@@ -431,9 +429,9 @@ static int launch_eig_rows(const salsa_params_t* p, const Workspace& w, const ui
     {
         ProfScope prof("eig_tile_kernel", st);
         if (a.eig.n_sq == 2)       // the default (cond_num = 5): squarings unrolled at compile time
-            rc = launch_eig_tile_t<4, 2>(a, st, p->n_clips);
+            rc = launch_eig_tile_t<32, 4, 2>(a, st, p->n_clips);
         else
-            rc = launch_eig_tile_t<3, 0>(a, st, p->n_clips);
+            rc = launch_eig_tile_t<32, 3, 0>(a, st, p->n_clips);
         if (rc) return rc;
         if ((rc = check_launch("eig_tile_kernel"))) return rc;
     }

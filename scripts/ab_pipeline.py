@@ -13,7 +13,7 @@ from salsa_b200 import _native
 
 
 def run(audio, env, steps=3):
-    for k in ('SALSA_B200_PIPELINE', 'SALSA_B200_EIG_SHAPE', 'SALSA_B200_STFT_VARIANT'):
+    for k in ('SALSA_B200_PIPELINE',):
         os.environ.pop(k, None)
     os.environ.update(env)
     ex = salsa_b200.SalsaExtractor('foa')

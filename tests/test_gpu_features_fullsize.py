@@ -96,3 +96,37 @@ def test_value_ranges_and_padding(sb, clips):
     assert torch.all(mic[4:, :, :84].abs() <= bound * (1 + 1e-6))
     lite = sb.SalsaLiteExtractor().extract(mic_audio)[0]
     assert lite.shape == (7, 4801, 191) and torch.all(lite[4:, :, 42:] == 0) and torch.isfinite(lite).all()
+
+
+@pytest.mark.parametrize('fmt,fmax', [('foa', 9000), ('mic', 4000)])
+def test_split_and_fused_arrangements_agree(sb, clips, fmt, fmax, monkeypatch):
+    """The clip path exists in two arrangements of the same arithmetic (salsa_abi.cu: split = STFT -> X in HBM ->
+    tracker -> eig_tile_kernel, fused = X in a shared-memory ring): same selection bit for bit, values to float32
+    rounding (the FFT is compiled into two kernels; a handful of spectrogram values differ in the last bit)."""
+    audio = clips[:3]
+    monkeypatch.delenv('SALSA_B200_PIPELINE', raising=False)
+    split = sb.SalsaExtractor(fmt, fmax_doa=fmax).extract(audio)
+    monkeypatch.setenv('SALSA_B200_PIPELINE', 'fused')
+    fused = sb.SalsaExtractor(fmt, fmax_doa=fmax).extract(audio)
+    monkeypatch.delenv('SALSA_B200_PIPELINE', raising=False)
+    assert torch.equal(split[:, 4:] != 0, fused[:, 4:] != 0)
+    assert (split[:, :4] - fused[:, :4]).abs().max().item() <= 1e-5
+    assert ((split[:, :4] != fused[:, :4]).float().mean().item()) < 1e-6
+    assert (split[:, 4:] - fused[:, 4:]).abs().max().item() <= 2e-6
+
+
+def test_full_clip_mic_matches_oracle(sb):
+    from oracle import salsa as osalsa, synth
+    audio = synth.make_clip(5, 'mic', seconds=60.0)
+    ref = osalsa.salsa_clip(audio, 'mic', fmax_doa=4000)
+    out = sb.SalsaExtractor('mic', fmax_doa=4000).extract(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
+    assert out.shape == ref.shape == (7, 4801, 200)
+    assert np.abs(out[:4] - ref[:4]).max() <= 1e-4 * 100
+    sup_a, sup_b = out[4:] != 0, ref[4:] != 0
+    assert int(np.count_nonzero(sup_a != sup_b)) == 0
+    # a phase within rounding of +-pi may come out with the other sign: compare away from the cut
+    delta = 2 * np.pi * 24000 / (512 * 343.0)
+    phase = np.abs(ref[4:, :, :84] * delta * np.arange(1, 85))
+    keep = np.abs(phase - np.pi) > 1e-3
+    assert np.abs(out[4:, :, :84] - ref[4:, :, :84])[keep].max() <= 1e-4
+    assert np.all(out[4:, :, 84:] == 0)
