@@ -625,14 +625,26 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
     dim3 grid((a.n_frames + a.frames_per_block - 1) / a.frames_per_block, p->n_clips);
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof("lite_kernel", st);
+    // bins below 32 * NJ can carry a phase difference: cropped index < upper_cropped <=> bin < upper_bin + lower_bin
+    const bool narrow = p->upper_bin + p->lower_bin <= 64;
     if (p->stft_precision == 64) {
         const size_t smem = sizeof(FftSmem<double>);
-        if ((rc = set_smem(lite_kernel<double>, smem))) return rc;
-        lite_kernel<double><<<grid, kThreads, smem, st>>>(a, tb.d);
+        if (narrow) {
+            if ((rc = set_smem(lite_kernel<double, 2>, smem))) return rc;
+            lite_kernel<double, 2><<<grid, kThreads, smem, st>>>(a, tb.d);
+        } else {
+            if ((rc = set_smem(lite_kernel<double, 8>, smem))) return rc;
+            lite_kernel<double, 8><<<grid, kThreads, smem, st>>>(a, tb.d);
+        }
     } else {
         const size_t smem = sizeof(FftSmem<float>);
-        if ((rc = set_smem(lite_kernel<float>, smem))) return rc;
-        lite_kernel<float><<<grid, kThreads, smem, st>>>(a, tb.f);
+        if (narrow) {
+            if ((rc = set_smem(lite_kernel<float, 2>, smem))) return rc;
+            lite_kernel<float, 2><<<grid, kThreads, smem, st>>>(a, tb.f);
+        } else {
+            if ((rc = set_smem(lite_kernel<float, 8>, smem))) return rc;
+            lite_kernel<float, 8><<<grid, kThreads, smem, st>>>(a, tb.f);
+        }
     }
     return check_launch("lite_kernel");
 }

@@ -702,7 +702,9 @@ struct LiteArgs {
     int frames_per_block;
 };
 
-template <typename T>
+// NJ: number of 32-bin register groups of channel 0 that are kept for the phase differences (bins < 32 NJ reach the
+// spatial channels): 2 covers the reference's fmax_doa = 2000 Hz (upper_bin 42), 8 is the general case.
+template <typename T, int NJ>
 __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables<T> tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
@@ -718,28 +720,34 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
     const float* clip_audio = a.audio + (long long)clip * 4 * a.n_samples;
     float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
     Cx<T>* scratch = s.scratch[warp];
+    const T* win = tb.window ? s.win : nullptr;
     const float inv_pi = 0.318309886183790671538f;
+    float2 raw[8];
+    if (f0 + warp < f1) load_frame(clip_audio, a.n_samples, (f0 + warp) * a.hop - kNfft / 2, lane, raw);
     for (int t = f0 + warp; t < f1; t += kWarps) {
-        float2 x0[8];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        float2 x0[NJ];
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {      // one copy of the transform: unrolling the channels spills
+            Cx<T> v[8];
+            window_frame<T>(raw, win, tw, lane, v);
+            // `raw` is consumed: request the next channel of this frame (or channel 0 of this warp's next frame)
+            if (ch < 3) load_frame(clip_audio + (long long)(ch + 1) * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, lane, raw);
+            else if (t + kWarps < f1) load_frame(clip_audio, a.n_samples, (t + kWarps) * a.hop - kNfft / 2, lane, raw);
             Cx<T> X[8];
             T nyq;
-            warp_rfft512_frame<T>(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, tb.window ? s.win : nullptr, tw,
-                                  scratch, lane, X, nyq);
-            float* srow = clip_feat + ch * chan_stride + (long long)t * width;
-            float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width;   // used for ch >= 1
+            warp_fft_passes<T>(v, tw, scratch, lane, X, nyq);
+            float* srow = clip_feat + ch * chan_stride + (long long)t * width - a.lower;         // indexed by the bin
+            float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width - a.lower;   // used for ch >= 1
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = lane + 32 * j;
                 const float re = (float)X[j].re, im = (float)X[j].im;
-                if (ch == 0) x0[j] = make_float2(re, im);
-                const int c = k - a.lower;            // cropped index
-                if (c >= 0 && c < width) {
-                    srow[c] = power_db(power_f32(re, im));     // (np.abs(stft) ** 2).T -> power_to_db (:104-105)
+                if (ch == 0 && j < NJ) x0[j] = make_float2(re, im);
+                if ((unsigned)(k - a.lower) < (unsigned)width) {
+                    srow[k] = power_db(power_f32(re, im));     // (np.abs(stft) ** 2).T -> power_to_db (:104-105)
                     if (ch > 0) {
                         float ph = 0.0f;
-                        if (c < a.upper_cropped) {
+                        if (j < NJ && k - a.lower < a.upper_cropped) {
                             // X_ch conj(X_0) with exact float64 products (:111), angle in float32
                             const double pr = (double)re * x0[j].x + (double)im * x0[j].y;
                             const double pi = (double)im * x0[j].x - (double)re * x0[j].y;
@@ -747,11 +755,10 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
                             ph = a.mode == SALSA_LITE_IPD ? ang * inv_pi
                                                           : ang * (float)(a.inv_delta / (double)max(k, 1));
                         }
-                        prow[c] = ph;
+                        prow[k] = ph;
                     }
                 }
             }
-            __syncwarp();
         }
     }
 }
