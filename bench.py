@@ -11,8 +11,9 @@ that batch.  1 clip = 1 audio-minute, so clips/s == audio-minutes/s.
 * `value`      : device-resident (audio and features stay in HBM), CUDA events, max over ranks.
 * `e2e`        : the same metric through the host-buffer C-ABI entry point `salsa_extract_host`
                  (pinned host audio in, pinned host features out, H2D / kernels / D2H pipelined).
-* `roofline`   : dominant kernel (salsa_fused_kernel) against the measured HBM copy bandwidth in
-                 MEASURED_PEAKS.json, algorithmic bytes = audio read once + features written once.
+* `roofline`   : dominant kernel (stft_kernel on the default split arrangement) against the measured HBM copy
+                 bandwidth in MEASURED_PEAKS.json; algorithmic bytes = the part of "audio read once + features written
+                 once" that kernel moves; `roofline.path` gives the same for the whole step.
 * `cpu_baseline`: the oracle (a line-by-line port of the reference's per-bin LAPACK loop) on all
                  host cores over a bounded sample of the same clips.
 
@@ -366,6 +367,30 @@ def bench_crnn(args, torch, dist, feat, rank, world, dev, peaks):
                                  'note': 'logits within 1e-4 of the float32 reference (tests/test_gpu_crnn_model.py), 6x the MMA work'}
     del m3
     if rank == 0 and not args.no_cpu_baseline:
+        # stock PyTorch / cuDNN under bf16 autocast on the same GPU, for the convolution stack only (the
+        # encoder holds 99.5 % of the FLOPs; the oracle's step-by-step GRU is a Python loop and would be unfair).
+        # A baseline beside the number, like the CPU leg: it executes the oracle's functional encoder, not the product.
+        try:
+            from oracle import crnn as ocrnn
+            sd = {k: v.to(dev) for k, v in salsa_b200.crnn.random_state_dict(0).items() if k.startswith('encoder.')}
+            bc = min(B, 8)
+            xc = x[:bc, :, :T].contiguous()
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                ocrnn.encoder_forward(sd, xc)
+                torch.cuda.synchronize()
+                start.record()
+                for _ in range(3):
+                    ocrnn.encoder_forward(sd, xc)
+                stop.record()
+                torch.cuda.synchronize()
+            res['cudnn_bf16_encoder_baseline'] = {
+                'value': bc * 3 / (start.elapsed_time(stop) / 1e3), 'unit': 'clips/s', 'batch': bc,
+                'note': 'torch {} eager F.conv2d / batch_norm / avg_pool2d under bf16 autocast, encoder only (no GRU, no heads)'.format(
+                    torch.__version__)}
+            del sd, xc
+            torch.cuda.empty_cache()
+        except Exception as exc:          # the baseline must never take the product line down
+            res['cudnn_bf16_encoder_baseline'] = {'unavailable': repr(exc)[:200]}
         import torch as _t
         tc = _crnn_cpu_chunk(None)
         tc = min(tc, _crnn_cpu_chunk(None))
@@ -541,16 +566,25 @@ def main():
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     dom = max(kernels.items(), key=lambda kv: kv[1][0]) if kernels else (None, (0.0, 0))
     total_kernel_ms = sum(v[0] for v in kernels.values())
-    algo_bytes = n_clips * (AUDIO_BYTES_PER_CLIP + feat_bytes)
+    # algorithmic bytes (audio read once + features written once, 49 925 600 B per SALSA clip) split over the
+    # kernels that move them: stft_kernel reads the audio and writes the 4 spectrogram channels, eig_tile_kernel writes
+    # the 3 spatial channels; the fused kernels move everything.  X and the masks between the kernels are NOT counted.
+    path_bytes = n_clips * (AUDIO_BYTES_PER_CLIP + feat_bytes)
+    share = {'stft_kernel': (AUDIO_BYTES_PER_CLIP + feat_bytes * 4 // 7) if 'eig_tile_kernel' in kernels else 0,
+             'eig_tile_kernel': feat_bytes * 3 // 7}
     roofline = None
     if dom[0]:
         avg_ms = dom[1][0] / dom[1][1]
+        algo_bytes = n_clips * share.get(dom[0], AUDIO_BYTES_PER_CLIP + feat_bytes)
         achieved = algo_bytes / (avg_ms / 1e3) / 1e9
+        path_achieved = path_bytes / (ms_per_step / 1e3) / 1e9
         roofline = {'bound': 'hbm', 'kernel': dom[0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': avg_ms,
                     'share_of_step': dom[1][0] / total_kernel_ms,
-                    'kernels_ms_per_step': {k: v[0] / args.steps for k, v in kernels.items()}}
+                    'kernels_ms_per_step': {k: v[0] / args.steps for k, v in kernels.items()},
+                    'path': {'algorithmic_bytes_per_step': path_bytes, 'achieved': path_achieved, 'frac': path_achieved / peak,
+                             'note': 'all kernels of the step: audio read once + features written once over ms_per_step'}}
         traffic_path = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.isfile(traffic_path):
             try:
