@@ -200,26 +200,34 @@ struct TrackerConsts {
 // Input of the tracker: |X0|^2 in float64, either precomputed (power0, [clip][frame][n_bins]) or taken from channel 0
 // of the clip path's tiled complex64 spectrum -- the same fma as stft_kernel's power0, so both give identical bits.
 struct TrackerPower0 {
+    using Raw = double;
     const double* p;
     long long clip_stride, frame_stride;
-    __device__ __forceinline__ double operator()(int clip, int t, int b) const { return p[clip * clip_stride + t * frame_stride + b]; }
-};
-// clip path: channel 0 of the tiled spectrum
-struct TrackerTiles {
-    const float2* x;
-    int n_tiles, n_frames;
-    __device__ __forceinline__ double operator()(int clip, int t, int b) const {
-        const float2 v = __ldg(x + (((long long)clip * n_frames + t) * n_tiles + (b >> 5)) * kTileFrameElems + (b & 31));
-        return fma((double)v.x, (double)v.x, (double)v.y * (double)v.y);
-    }
+    __device__ __forceinline__ Raw load(int clip, int t, int b) const { return p[clip * clip_stride + t * frame_stride + b]; }
+    static __device__ __forceinline__ double power(Raw r) { return r; }
 };
 
-// bins first_bin .. n_bins - 1 are tracked (bits of the bins below first_bin stay clear)
+// clip path: channel 0 of the tiled spectrum
+struct TrackerTiles {
+    using Raw = float2;
+    const float2* x;
+    int n_tiles, n_frames;
+    __device__ __forceinline__ Raw load(int clip, int t, int b) const {
+        return __ldg(x + (((long long)clip * n_frames + t) * n_tiles + (b >> 5)) * kTileFrameElems + (b & 31));
+    }
+    static __device__ __forceinline__ double power(Raw v) { return fma((double)v.x, (double)v.x, (double)v.y * (double)v.y); }
+};
+
+// bins first_bin .. n_bins - 1 are tracked (bits of the bins below first_bin stay clear).
+// The kernel is one dependent chain of 4801 steps per warp, so its duration hardly depends on the batch (1.6 ms for 32
+// clips, 2.1 ms for 600 with the loads one chunk ahead): the loads run THREE chunks of 8 frames ahead of the recurrence
+// and stay raw (complex64) until their chunk is processed, so that nothing in program order waits for them.
 // Running the tracker on a side stream beside the transform of channels 1..3 was tried and gains nothing: stft_kernel
 // holds the whole register file, the tracker's CTAs only get in as it drains.
 template <typename Src>
 __global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restrict__ mask, int n_frames, int first_bin, int n_bins,
                                                       TrackerConsts c) {
+    using Raw = typename Src::Raw;
     const int clip = blockIdx.y;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int word = b >> 5, n_words = (n_bins + 31) >> 5;
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restr
     auto at = [&](int t) -> double {   // wrapped frame access (np.pad 'wrap', :43)
         t %= n_frames;
         if (t < 0) t += n_frames;
-        return live ? src(clip, t, bb) : 0.0;
+        return live ? Src::power(src.load(clip, t, bb)) : 0.0;
     };
     // initial floor: 0.5 * mean(sig[0:5]), sig = sqrt(mean of three powers)   (:53-58)
     const int n_init = min(c.n_init_frames, n_frames);
@@ -243,23 +251,19 @@ __global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restr
     // comparisons by a few 1e-16 relative, far inside what hypot()'s last bit already leaves open.
     const double third = 1.0 / 3.0;
     const double snr2 = c.snr_ratio * c.snr_ratio;
-    constexpr int kChunk = 8;         // frames in flight per thread; measured per 600 clips: 4 -> 2.6 ms, 8 -> 2.1, 16 -> 4.8, 32 -> 7.2
-    double nxt[kChunk];
+    constexpr int kChunk = 8;
+    auto fetch = [&](Raw (&r)[kChunk], int t0) {
 #pragma unroll
-    for (int i = 0; i < kChunk; ++i) nxt[i] = (i < n_frames && live) ? src(clip, i, bb) : 0.0;
-    for (int t0 = 0; t0 < n_frames; t0 += kChunk) {
-        double buf[kChunk];
+        for (int i = 0; i < kChunk; ++i) r[i] = src.load(clip, min(t0 + i, n_frames - 1), bb);     // clamped: always a valid address
+    };
+    auto process = [&](const Raw (&r)[kChunk], int t0) {
+        double pw[kChunk];
 #pragma unroll
-        for (int i = 0; i < kChunk; ++i) buf[i] = nxt[i];
-#pragma unroll
-        for (int i = 0; i < kChunk; ++i) {   // prefetch of the next chunk overlaps the recurrence below
-            const int t = t0 + kChunk + i;
-            nxt[i] = (t < n_frames && live) ? src(clip, t, bb) : 0.0;
-        }
+        for (int i = 0; i < kChunk; ++i) pw[i] = live ? Src::power(r[i]) : 0.0;
 #pragma unroll
         for (int i = 0; i < kChunk; ++i) {
             if (t0 + i < n_frames) {
-                const double a0 = buf[i];
+                const double a0 = pw[i];
                 const double q = ((a0 + a1) + a2) * third;
                 a2 = a1;
                 a1 = a0;
@@ -277,6 +281,18 @@ __global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restr
                 if ((threadIdx.x & 31) == 0) mrow[(long long)(t0 + i) * n_words] = bits;
             }
         }
+    };
+    Raw r0[kChunk], r1[kChunk], r2[kChunk];
+    fetch(r0, 0);
+    fetch(r1, kChunk);
+    fetch(r2, 2 * kChunk);
+    for (int t0 = 0; t0 < n_frames; t0 += 3 * kChunk) {
+        process(r0, t0);
+        fetch(r0, t0 + 3 * kChunk);
+        process(r1, t0 + kChunk);
+        fetch(r1, t0 + 4 * kChunk);
+        process(r2, t0 + 2 * kChunk);
+        fetch(r2, t0 + 5 * kChunk);
     }
 }
 
