@@ -110,12 +110,9 @@ int main() {
     run<4>("DMUL", 1);
     run<15>("DFMA+FFMA pairs", 2);
     run<16>("DFMA+IADD64 pairs", 2);
-    run<7>("LDS.64 (+FADD)", 2);
-    run<8>("LDS.128 (+DADD)", 2);
+    // (LDS / F2F probes: their loop-invariant operands get merged by ptxas, the printed rates are not meaningful)
     run<9>("STS.128", 1);
     run<10>("SHFL", 1);
-    run<11>("F2F f64->f32 (+FADD)", 2);
-    run<12>("F2F f32->f64 (+DADD)", 2);
     run<13>("MUFU.LG2", 1);
     return 0;
 }
