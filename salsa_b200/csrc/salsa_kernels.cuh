@@ -366,7 +366,9 @@ __global__ void __launch_bounds__(256) eig_kernel(const float2* __restrict__ X, 
 //      cannot be certified are marked in `redo` for eig_redo_kernel;
 //   3  the 3 x FT row segments go to HBM, zeros where the bin was not selected / not valid; the last bin tile also
 //      zero-fills the columns above the last spatial bin (:373-374).
-// No float64 code in this kernel: 64 registers, 4 CTAs (32 warps) per SM.
+// No float64 code in this kernel: 64 registers, 4 CTAs (32 warps) per SM.  (Walking several frame tiles per CTA with the
+// next tile's copy issued behind the row output was measured: no gain, 10.3 vs 10.0 ms -- with 4 CTAs per SM the copy
+// latency is already covered by the other CTAs.)
 // ------------------------------------------------------------------------------------------------
 struct EigTileArgs {
     const float2* X;         // tiled spectrum (see above)
