@@ -87,6 +87,18 @@ int crnn_decode_events(const float *logits, const float *doa, int32_t rows, int3
 int crnn_gather_time(const float *in, const int32_t *idx, float *out, int32_t B, int32_t n_in, int32_t n_out,
                      int32_t width, void *stream);
 
+/* Training-time augmentations that commute with the SALSA feature layout, on a device batch:
+ * TfmapRandomSwapChannelFoa.apply (utilities/transforms.py:394-437), TfmapRandomSwapChannelMic.apply (:470-523) and
+ * RandomShiftUpDownNp.apply (:298-320, mode='reflect', all channels), composed as dataset/datamodule.py:45-83 composes
+ * them (joint swap, then the shift).  The random draws stay with the host (the reference's NumPy draws):
+ *   ops int32 [B][4] = {format (0 foa / 1 mic), swap flags (bit i = m[i], 0 = transform skipped),
+ *                       shift_len (0 = skipped), direction (0 up / 1 down)}       -- a DEVICE array
+ *   x, out    fp32 [B][7][T][F]  (out != x)
+ *   y_doa, y_out fp32 [B][Ty][3*n_classes] (x | y | z per class), both NULL to leave the labels alone.
+ * Permutations, sign flips and single float32 subtractions in the reference's order: bit-identical results. */
+int crnn_augment(const float *x, float *out, const float *y_doa, float *y_out, const int32_t *ops, int32_t B,
+                 int32_t T, int32_t F, int32_t Ty, int32_t n_classes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

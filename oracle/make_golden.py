@@ -103,6 +103,30 @@ def model_cases():
     return out
 
 
+def augment_cases():
+    """Outputs of the unmodified reference augmentation classes (utilities/transforms.py) under np.random.seed:
+    the joint FOA / MIC channel swaps and the frequency shift, composed as dataset/datamodule.py:45-83 composes them for
+    the SALSA features.  Inputs are regenerated from `seed`; draws are replayed by oracle/augment.py's draw_* functions."""
+    T = ref_import.transforms_module()
+    out = {}
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((7, 24, 40)).astype(np.float32)
+    y_sed = (rng.random((6, 12)) > 0.5).astype(np.float32)
+    y_doa = rng.standard_normal((6, 36)).astype(np.float32)
+    out['x'], out['y_sed'], out['y_doa'] = x, y_sed, y_doa
+    for fmt, cls in (('foa', T.TfmapRandomSwapChannelFoa), ('mic', T.TfmapRandomSwapChannelMic)):
+        joint = T.ComposeMapTransform([cls(n_classes=12)])
+        single = T.ComposeTransformNp([T.RandomShiftUpDownNp(freq_shift_range=10)])
+        for seed in range(24):
+            np.random.seed(seed)
+            xa, ya_sed, ya_doa = joint(x, y_sed, y_doa)            # datamodule order: joint transform, then the shift
+            xa = single(xa)
+            out['{}_{}_x'.format(fmt, seed)] = np.ascontiguousarray(xa)
+            out['{}_{}_y_doa'.format(fmt, seed)] = np.ascontiguousarray(ya_doa)
+            assert np.array_equal(ya_sed, y_sed)
+    return out
+
+
 def main(argv=None):
     if not ref_import.available():
         print('reference checkout not found; golden vectors can only be generated in the build container')
@@ -114,6 +138,8 @@ def main(argv=None):
     if argv and 'model' in argv:
         # inputs and weights are regenerated from their seeds (oracle/crnn.py); only outputs are stored
         np.savez_compressed(os.path.join(GOLDEN_DIR, 'model_cases.npz'), **model_cases())
+    if argv and 'augment' in argv:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'augment_cases.npz'), **augment_cases())
     for fn in sorted(os.listdir(GOLDEN_DIR)):
         print('{:32s} {:10d} B'.format(fn, os.path.getsize(os.path.join(GOLDEN_DIR, fn))))
     return 0

@@ -50,6 +50,13 @@ def features_module():
     return importlib.import_module('dataset.salsa_feature_extraction')
 
 
+def transforms_module():
+    """-> the reference module `utilities.transforms` (verbatim; NumPy only)."""
+    _ensure_path()
+    import importlib
+    return importlib.import_module('utilities.transforms')
+
+
 def models_module():
     """-> the reference package `models` (verbatim torch modules)."""
     import torch.nn as nn

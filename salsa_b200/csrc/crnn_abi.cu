@@ -311,4 +311,20 @@ int crnn_gather_time(const float* in, const int32_t* idx, float* out, int32_t B,
     return check_cuda(cudaGetLastError(), "gather_time_kernel");
 }
 
+int crnn_augment(const float* x, float* out, const float* y_doa, float* y_out, const int32_t* ops, int32_t B, int32_t T, int32_t F,
+                 int32_t Ty, int32_t n_classes, void* stream) {
+    if (!x || !out || !ops) return fail(SALSA_EINVAL, "augment: null pointer");
+    if (x == out || (y_doa && y_doa == y_out)) return fail(SALSA_EINVAL, "augment: in-place operation is not supported");
+    if ((y_doa == nullptr) != (y_out == nullptr)) return fail(SALSA_EINVAL, "augment: y_doa and y_out go together");
+    if (B <= 0 || T <= 0 || F <= 0) return SALSA_OK;
+    augment_kernel<<<grid_for((long long)B * T * F, 256), 256, 0, (cudaStream_t)stream>>>(x, out, reinterpret_cast<const int4*>(ops), B, T, F);
+    count_launch();
+    int rc = check_cuda(cudaGetLastError(), "augment_kernel");
+    if (rc || !y_doa || Ty <= 0 || n_classes <= 0) return rc;
+    augment_doa_kernel<<<grid_for((long long)B * Ty * n_classes, 256), 256, 0, (cudaStream_t)stream>>>(
+        y_doa, y_out, reinterpret_cast<const int4*>(ops), B, Ty, n_classes);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "augment_doa_kernel");
+}
+
 }  // extern "C"

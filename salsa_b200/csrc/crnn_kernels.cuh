@@ -6,6 +6,7 @@
 //   gru_layer_kernel      one bidirectional GRU layer, recurrent part (decoders.py:44-46, :126)
 //   head_finish_kernel    split of the fused head GEMM, tanh on the DOA part (decoders.py:137-147)
 //   gather_time_kernel    interpolate_tensor's index gather      (model_utils.py:57-75)
+//   augment_kernel        training-time channel swaps + frequency shift of a feature batch (utilities/transforms.py)
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
@@ -401,6 +402,99 @@ __global__ void gather_time_kernel(const float* __restrict__ in, const int* __re
         const long long r = i / width;
         const int o = (int)(r % n_out), b = (int)(r / n_out);
         out[i] = in[((long long)b * n_in + idx[o]) * width + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training-time augmentations that commute with the SALSA feature layout, one pass over the batch:
+//   TfmapRandomSwapChannelFoa.apply  (utilities/transforms.py:394-437)   x: W Y Z X | Y Z X
+//   TfmapRandomSwapChannelMic.apply  (:470-523)                          x: M1 M2 M3 M4 | p12 p13 p14
+//   RandomShiftUpDownNp.apply        (:298-320, mode = 'reflect', all channels)
+// The swaps act across the 7 channels of one (t, f) point, the shift is an index map along f, so out[:, t, f] is the
+// swap of x[:, t, src(f)].  The float32 operations are the reference's, in its order (one subtraction per value at
+// most per step): results are bit-identical.  ops[b] = {format, swap flags (bit i = m[i]), shift_len, direction}.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void swap_channels(float (&v)[7], int format, int m) {
+    if (format == 0) {                      // FOA
+        if (m & 1) {                        // swap x and y
+            float t = v[1]; v[1] = v[3]; v[3] = t;
+            t = v[4]; v[4] = v[6]; v[6] = t;
+        }
+        if (m & 2) v[6] = -v[6];
+        if (m & 4) v[4] = -v[4];
+        if (m & 8) v[5] = -v[5];
+    } else {                                // MIC
+        if (m & 1) {                        // swap M2 and M3
+            float t = v[1]; v[1] = v[2]; v[2] = t;
+            t = v[4]; v[4] = v[5]; v[5] = t;
+        }
+        if (m & 2) {                        // swap M1 and M4
+            const float c4 = v[4], c5 = v[5], c6 = v[6];
+            const float t = v[0]; v[0] = v[3]; v[3] = t;
+            v[6] = -c6;
+            v[5] = c5 - c6;
+            v[4] = c4 - c6;
+        }
+        if (m & 4) {                        // swap M1 and M2, M3 and M4
+            const float c4 = v[4], c5 = v[5], c6 = v[6];
+            float t = v[0]; v[0] = v[1]; v[1] = t;
+            t = v[2]; v[2] = v[3]; v[3] = t;
+            v[4] = -c4;
+            v[5] = c6 - c4;
+            v[6] = c5 - c4;
+        }
+    }
+}
+
+__global__ void augment_kernel(const float* __restrict__ x, float* __restrict__ out, const int4* __restrict__ ops, int B, int T, int F) {
+    const long long total = (long long)B * T * F;
+    const long long plane = (long long)T * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const long long r = i / F;
+        const int t = (int)(r % T), b = (int)(r / T);
+        const int4 op = ops[b];
+        int fs = f;
+        if (op.z > 0) {
+            // np.pad(..., mode='reflect') then crop: 'up' pads shift_len values in front, 'down' behind
+            if (op.w == 0) fs = f < op.z ? op.z - f : f - op.z;
+            else fs = f + op.z < F ? f + op.z : 2 * (F - 1) - (f + op.z);
+        }
+        const float* src = x + (long long)b * 7 * plane + (long long)t * F + fs;
+        float v[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) v[c] = src[c * plane];
+        swap_channels(v, op.x, op.y);
+        float* dst = out + (long long)b * 7 * plane + (long long)t * F + f;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) dst[c * plane] = v[c];
+    }
+}
+
+// y_doa [B][Ty][3 n] = x | y | z per class: the label side of the two channel swaps
+__global__ void augment_doa_kernel(const float* __restrict__ y, float* __restrict__ out, const int4* __restrict__ ops, int B, int Ty, int n) {
+    const long long total = (long long)B * Ty * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % n);
+        const long long r = i / n;                    // b * Ty + ty
+        const int b = (int)(r / Ty);
+        const int4 op = ops[b];
+        const float* row = y + r * 3 * n;
+        float vx = row[k], vy = row[n + k], vz = row[2 * n + k];
+        const int m = op.y;
+        if (m & 1) { const float t = vx; vx = vy; vy = t; }
+        if (op.x == 0) {
+            if (m & 2) vx = -vx;
+            if (m & 4) vy = -vy;
+            if (m & 8) vz = -vz;
+        } else {
+            if (m & 2) { const float t = -vx; vx = -vy; vy = t; }
+            if (m & 4) { vy = -vy; vz = -vz; }
+        }
+        float* orow = out + r * 3 * n;
+        orow[k] = vx;
+        orow[n + k] = vy;
+        orow[2 * n + k] = vz;
     }
 }
 

@@ -172,6 +172,34 @@ def test_salsa_clip_matches_oracle_5s(sb, fmt, fmax):
     check_feature(out.cpu().numpy()[0], ref, what='5 s {}'.format(fmt))
 
 
+@pytest.mark.parametrize('fmt,fmin,fmax,cond', [
+    ('foa', 200, 9000, 5.0),      # lower_bin 4: the first lanes of every 32-bin register group belong to the previous X tile
+    ('foa', 1600, 6000, 5.0),     # lower_bin 34 >= 32: the general tiled-store path of stft_kernel
+    ('mic', 50, 3000, 5.0),       # upper_bin 64: exactly two full tiles
+    ('foa', 50, 9000, 2.0),       # cond_num 2 / 20: other power-iteration schedules than the compiled-in one
+    ('foa', 50, 9000, 20.0),
+])
+def test_salsa_clip_other_ranges_and_thresholds(sb, fmt, fmin, fmax, cond):
+    from oracle import salsa as osalsa, synth
+    audio = synth.make_clip(17, fmt, seconds=2.0)
+    ref, aux = osalsa.salsa_clip(audio, fmt, fmin_doa=fmin, fmax_doa=fmax, cond_num=cond, return_aux=True)
+    ex = sb.SalsaExtractor(audio_format=fmt, fmin_doa=fmin, fmax_doa=fmax, cond_num=cond)
+    out = ex.extract(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
+    close(out[:4], ref[:4], 'spectrogram')
+    assert np.array_equal(out[4:] != 0, ref[4:] != 0), 'valid-bin mask'
+    # with cond < 4 the two leading eigenvalues of a kept bin may be close: LAPACK's vector is then only determined
+    # to what the gap allows, compare where the gap is at least 4
+    gap = (aux['s'][..., 0] >= 4.0 * aux['s'][..., 1]).T                      # (T, n_bins)
+    sel = np.zeros(ref[4:].shape, dtype=bool)
+    sel[:, :, :gap.shape[1]] = gap[None]
+    if fmt == 'mic':
+        delta = 2 * np.pi * 24000 / (512 * 343.0)
+        n_bins = gap.shape[1]
+        phase = np.abs(ref[4:, :, :n_bins] * delta * (np.arange(n_bins) + ex.lower_bin))
+        sel[:, :, :n_bins] &= np.abs(phase - np.pi) > 1e-3
+    close(out[4:][sel], ref[4:][sel], 'spatial')
+
+
 def test_salsa_no_tracking_matches_oracle(sb, golden):
     from oracle import salsa as osalsa
     g = golden('clip_cases')

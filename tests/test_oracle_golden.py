@@ -192,3 +192,25 @@ def test_crnn_oracle_matches_live_reference():
     out = ocrnn.forward(ocrnn.make_state_dict(1), x)
     for k in ref:
         np.testing.assert_allclose(out[k].numpy(), ref[k].numpy(), rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# augmentations: oracle/augment.py against the unmodified reference classes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fmt', ['foa', 'mic'])
+def test_augment_oracle_matches_reference_golden(golden, fmt):
+    from oracle import augment as oaug
+    g = golden('augment_cases')
+    x, y_doa = g['x'], g['y_doa']
+    seen = set()
+    for seed in range(24):
+        np.random.seed(seed)                         # replay the reference's draws in its order
+        m = oaug.draw_swap_foa() if fmt == 'foa' else oaug.draw_swap_mic()
+        xa, ya = (x, y_doa) if m is None else (oaug.swap_foa if fmt == 'foa' else oaug.swap_mic)(x, y_doa, m)
+        sh = oaug.draw_shift(x.shape[2])
+        if sh is not None:
+            xa = oaug.shift_updown(xa, *sh)
+        seen.add((None if m is None else tuple(int(v) for v in m), sh))
+        assert np.array_equal(xa, g['{}_{}_x'.format(fmt, seed)]), (fmt, seed)          # bit-exact: permutations, signs, one subtraction
+        assert np.array_equal(ya, g['{}_{}_y_doa'.format(fmt, seed)]), (fmt, seed)
+    assert len(seen) > 12                            # the seeds exercise many different draws
