@@ -351,11 +351,12 @@ static int launch_fused(const salsa_params_t* p, const DeviceTables& tb, const f
 }
 
 // ---------------------------------------------------------------------------------------------
-// The clip path exists in two arrangements of the same arithmetic (bit-identical results):
-//   split  stft_kernel (all channels: X -> HBM, log-spectrogram rows) | tracker_kernel (on channel 0 of X) |
-//          eig_rows_kernel (+ eig_redo_kernel for the few bins that need float64).  X costs 59 MB of
+// The clip path exists in two arrangements of the same arithmetic (same selection bit for bit, values to float32
+// rounding: tests/test_gpu_features_fullsize.py):
+//   split  stft_kernel (all channels: X -> HBM in tiles, log-spectrogram rows) | tracker_kernel (on channel 0 of X) |
+//          eig_tile_kernel (+ eig_redo_kernel for the few bins that need float64).  X costs 59 MB of
 //          HBM traffic per clip on top of the 50 MB of algorithmic bytes, but every kernel runs at its own register
-//          budget / occupancy and the channel-0 transform is not done twice.  Default.
+//          budget / occupancy and the channel-0 transform is not done twice: 25.8 against 40.7 ms per 600 clips.  Default.
 //   fused  stft_kernel (channel 0 only -> |X0|^2) | tracker_kernel | salsa_fused_kernel (X lives in a shared-memory
 //          ring).  Minimal HBM traffic; selected with SALSA_B200_PIPELINE=fused.
 // ---------------------------------------------------------------------------------------------
@@ -412,7 +413,7 @@ static int launch_eig_tile_t(const EigTileArgs& a, cudaStream_t st, int n_clips)
     return SALSA_OK;
 }
 
-static int launch_eig_rows(const salsa_params_t* p, const Workspace& w, const uint32_t* mask, float* feature, cudaStream_t st) {
+static int launch_eig_tile(const salsa_params_t* p, const Workspace& w, const uint32_t* mask, float* feature, cudaStream_t st) {
     if (p->n_clips == 0) return SALSA_OK;
     EigTileArgs a;
     a.X = w.X;
@@ -581,7 +582,7 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
             if ((rc = launch_tracker(src, w.mask, p->n_clips, n_frames, 0, n_bins, st))) return rc;
             mask = w.mask;
         }
-        return launch_eig_rows(p, w, mask, feature, st);
+        return launch_eig_tile(p, w, mask, feature, st);
     }
     if (p->is_tracking) {
         // pass A: channel-0 spectrum in float64 -> tracker (a sequential recurrence over the whole clip,

@@ -1,11 +1,14 @@
 // SALSA / SALSA-Lite feature kernels for sm_100a.
 //
-//   stft_kernel          a1 + a3  librosa.stft (+ MagStftExtractor.extract, + |X0|^2 for the tracker)
+//   stft_kernel          a1 + a3  librosa.stft (+ MagStftExtractor.extract; the spectrum goes to the tiled X of the clip path)
 //   tracker_kernel       a4 + a5  noise-floor tracker (float64 recurrence over frames)
-//   eig_kernel           a6 - a8  covariance / eigenvector / coherence / normalisation from X in HBM
-//   salsa_fused_kernel   a1, a3, a6 - a9 in one pass: STFT -> shared-memory ring of frames ->
+//   eig_tile_kernel      a6 - a9  clip path: covariance / eigenvector / coherence / normalisation from TMA-staged tiles of X,
+//                        (3, T, F) spatial rows of the feature tensor; eig_redo_kernel = its float64 second opinion
+//   eig_kernel           a6 - a8  the same step for the op-level seam extract_normalized_eigenvector(X, ...)
+//   salsa_fused_kernel   a1, a3, a6 - a9 in one pass (alternative arrangement): STFT -> shared-memory ring of frames ->
 //                        eigenvector step -> (7, T, F) feature rows; X never touches HBM
 //   lite_kernel          a10      SALSA-Lite / SALSA-IPD
+//   scaler_accumulate_kernel  a11 compute_scaler statistics
 //
 // (row numbers: SURVEY.md section 8a; reference lines are cited at each function.)
 #pragma once
