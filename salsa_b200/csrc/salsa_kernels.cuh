@@ -388,9 +388,10 @@ __host__ __device__ constexpr size_t eig_tile_smem_bytes() {
            (size_t)FT * kTileBins * sizeof(uint16_t) + 2 * FT * sizeof(uint32_t) + 16;
 }
 
-template <int FT, int MINB, int NSQ>
-__global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigTileArgs a) {
-    constexpr int BB = kTileBins, R = FT + 2 * kHop;
+template <int FT, int MINB, int NSQ, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, MINB) eig_tile_kernel(EigTileArgs a) {
+    constexpr int BB = kTileBins, R = FT + 2 * kHop, NT = WARPS * 32;
+    static_assert(FT % WARPS == 0 && NT >= R, "frames dealt to the warps; one copy-issuing thread per frame");
     static_assert(FT == 32, "one mask word per lane in the compaction scan (24 frames per tile measured 7 % slower)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);                                     // [R][4][BB]
@@ -439,8 +440,8 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigTileArgs a) {
         }
         const int excl = incl - __popc(bits);
 #pragma unroll
-        for (int q = 0; q < FT / 8; ++q) {
-            const int tl = warp + 8 * q;                     // frames of this warp
+        for (int q = 0; q < FT / WARPS; ++q) {
+            const int tl = warp + WARPS * q;                 // frames of this warp
             const uint32_t w = __shfl_sync(0xffffffffu, bits, tl);
             const int base = __shfl_sync(0xffffffffu, excl, tl);
             if ((w >> lane) & 1u) list[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((tl << 5) | lane);
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigTileArgs a) {
     // ---- 2
     const int count = *n_items;
     const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
-    for (int item = threadIdx.x; item < count; item += 256) {
+    for (int item = threadIdx.x; item < count; item += NT) {
         const int code = list[item];
         const int tl = code >> 5, bl = code & 31;
         const uint32_t base = xs_addr + (uint32_t)((tl * kTileFrameElems + bl) * sizeof(float2));   // X[t - 3][ch 0][bin]
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigTileArgs a) {
     float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
     const int c0 = bt * BB;
     // row segment s = channel * FT + frame; a warp writes four 128-byte segments per step (8 lanes x float4 each)
-    for (int s = (threadIdx.x >> 3); s < 3 * FT; s += 32) {
+    for (int s = (threadIdx.x >> 3); s < 3 * FT; s += NT / 8) {
         const int i = s / FT, tl = s % FT;
         if (tl >= nt) continue;
         const int k = (threadIdx.x & 7) * 4;
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(256, MINB) eig_tile_kernel(EigTileArgs a) {
     if (bt == a.n_tiles - 1) {
         // the last bin tile zero-fills the columns above the last spatial bin (:373-374)
         const int extra = (a.feat_dim - c0 - BB) >> 2;               // float4 per row
-        for (int g = threadIdx.x; g < 3 * nt * extra; g += 256) {
+        for (int g = threadIdx.x; g < 3 * nt * extra; g += NT) {
             const int r = g / extra, q = g - r * extra;
             const int i = r / nt, tl = r - i * nt;
             *reinterpret_cast<float4*>(clip_feat + (4 + i) * chan_stride + (long long)(t0 + tl) * a.feat_dim + c0 + BB + 4 * q) =
