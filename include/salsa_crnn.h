@@ -99,6 +99,17 @@ int crnn_gather_time(const float *in, const int32_t *idx, float *out, int32_t B,
 int crnn_augment(const float *x, float *out, const float *y_doa, float *y_out, const int32_t *ops, int32_t B,
                  int32_t T, int32_t F, int32_t Ty, int32_t n_classes, void *stream);
 
+/* BaseModel.compute_loss for output_format='reg_xyz' (models/interfaces.py:273-355; SURVEY.md 8 f1, loss row):
+ * sed_loss = mean BCE-with-logits over [rows][n_classes]; doa_loss = sum over x, y, z of sum(|pred - gt| * event_gt) /
+ * sum(event_gt); loss = w_sed * sed_loss + w_doa * doa_loss (seld.yml:53-55: 0.3 / 0.7).
+ *   logit, event_gt fp32 [rows][n_classes]; doa, doa_gt fp32 [rows][3*n_classes] (x | y | z), rows = batch * label frames,
+ *   time axes already aligned by the caller (compute_masked_reg_loss :337-341)
+ *   sums   float64 [5] device scratch (zeroed here); loss fp32 [3] device = {loss, sed_loss, doa_loss}
+ *   g_logit / g_doa: optional gradients of `loss` with respect to logit / doa (same shapes), NULL to skip. */
+int crnn_seld_loss(const float *logit, const float *doa, const float *event_gt, const float *doa_gt, int64_t rows,
+                   int32_t n_classes, float w_sed, float w_doa, double *sums, float *loss, float *g_logit,
+                   float *g_doa, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

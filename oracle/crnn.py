@@ -188,6 +188,33 @@ def decode_events(event_frame_logit, doa_frame_output, sed_threshold: float = 0.
     return outputs
 
 
+def seld_loss(event_logit, doa_output, event_gt, doa_gt, loss_weight=(0.3, 0.7), n_classes: int = 12):
+    """BaseModel.compute_loss for output_format='reg_xyz' (models/interfaces.py:273-355): binary cross-entropy with
+    logits on the event activity + masked MAE on the x, y, z regressions, each normalised by the number of active
+    (frame, class) cells.  -> (loss, sed_loss, doa_loss) as float32 tensors."""
+    sed_loss = F.binary_cross_entropy_with_logits(input=event_logit, target=event_gt)
+    n = n_classes
+    N = min(doa_output.shape[1], doa_gt.shape[1])
+    mask = event_gt[:, :N]
+    norm = torch.sum(mask)
+    doa_loss = 0.0
+    for i in range(3):
+        doa_loss = doa_loss + torch.sum(torch.abs(doa_output[:, :N, i * n:(i + 1) * n] - doa_gt[:, :N, i * n:(i + 1) * n]) * mask) / norm
+    return loss_weight[0] * sed_loss + loss_weight[1] * doa_loss, sed_loss, doa_loss
+
+
+def seld_loss_inputs(seed: int = 4, batch: int = 3, n_frames: int = 80, n_classes: int = 12):
+    """Deterministic (logit, doa, event_gt, doa_gt) of the label-rate shapes (B, 80, 12) / (B, 80, 36)."""
+    g = torch.Generator().manual_seed(seed)
+    logit = 3.0 * torch.randn((batch, n_frames, n_classes), generator=g)
+    doa = torch.tanh(torch.randn((batch, n_frames, 3 * n_classes), generator=g))
+    event_gt = (torch.rand((batch, n_frames, n_classes), generator=g) < 0.2).float()
+    v = torch.randn((batch, n_frames, 3, n_classes), generator=g)
+    v = v / v.norm(dim=2, keepdim=True)
+    doa_gt = (v * event_gt[:, :, None, :]).reshape(batch, n_frames, 3 * n_classes)
+    return logit, doa, event_gt, doa_gt
+
+
 def model_input(seed: int = 2, shape=(2, 7, 128, 200)) -> torch.Tensor:
     """Deterministic feature-like input: log-spectrogram-scale first four channels, [-1, 1] spatial ones."""
     g = torch.Generator().manual_seed(seed)

@@ -100,6 +100,11 @@ def model_cases():
         y2 = model(xin2)
     out['lite_event_frame_logit'] = y2['event_frame_logit'].numpy()
     out['lite_doa_frame_output'] = y2['doa_frame_output'].numpy()
+    # BaseModel.compute_loss (interfaces.py:273-355) on the deterministic inputs of oracle/crnn.py: seld_loss_inputs
+    logit, doa, event_gt, doa_gt = ocrnn.seld_loss_inputs()
+    loss = model.compute_loss(target_dict={'event_frame_gt': event_gt, 'doa_frame_gt': doa_gt},
+                              pred_dict={'event_frame_logit': logit, 'doa_frame_output': doa})
+    out['loss_values'] = np.array([float(v) for v in loss], dtype=np.float64)
     return out
 
 

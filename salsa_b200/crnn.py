@@ -240,6 +240,15 @@ class SeldModel:
         idx = ops.interpolate_index(out['event_frame_logit'].shape[1], ratio)
         return {k: ops.gather_time(v, idx) for k, v in out.items()}
 
+    def compute_loss(self, target_dict, pred_dict, loss_weight=(0.3, 0.7)):
+        """BaseModel.compute_loss (models/interfaces.py:273-286) for reg_xyz outputs at the label rate:
+        target_dict['event_frame_gt' / 'doa_frame_gt'], pred_dict['event_frame_logit' / 'doa_frame_output'] (CUDA tensors)
+        -> (loss, sed_loss, doa_loss) as 0-d float32 CUDA tensors (the reference logs them in common_step,
+        models/seld_models.py:51-66)."""
+        out = ops.seld_loss(pred_dict['event_frame_logit'], pred_dict['doa_frame_output'], target_dict['event_frame_gt'],
+                            target_dict['doa_frame_gt'], loss_weight=loss_weight)
+        return out[0], out[1], out[2]
+
     def events(self, x, sed_threshold: float = 0.3, max_nframes_per_file: int = None, eval_version: str = '2021'):
         """predict + the decoding of `write_classwise_output_to_file` (models/interfaces.py:210-258) for whole-clip inputs
         (one chunk per file, as the reference's test configuration): per clip the list of rows the reference writes to the

@@ -195,3 +195,26 @@ def decode_events(logits, doa, threshold=0.3):
     _native.check(_native.lib().crnn_decode_events(_p(logits), _p(doa), rows, n, ctypes.c_float(threshold), _p(active), _p(azi),
                                                    _p(ele), _st()))
     return active.bool(), azi, ele
+
+
+def seld_loss(event_logit, doa_output, event_gt, doa_gt, loss_weight=(0.3, 0.7), with_grad: bool = False):
+    """BaseModel.compute_loss for output_format='reg_xyz' (models/interfaces.py:273-355) on CUDA tensors:
+    event_logit / event_gt (B, T, n), doa_output / doa_gt (B, T', 3 n) -> float32 tensor (3,) = (loss, sed_loss, doa_loss)
+    and, with_grad, the gradients of `loss` with respect to event_logit and doa_output."""
+    if not (event_logit.is_cuda and doa_output.is_cuda and event_gt.is_cuda and doa_gt.is_cuda):
+        raise ValueError('seld_loss: CUDA tensors expected (there is no CPU fallback)')
+    B, T, n = event_logit.shape
+    if tuple(event_gt.shape) != (B, T, n) or doa_output.shape[2] != 3 * n or doa_gt.shape[2] != 3 * n:
+        raise ValueError('seld_loss: inconsistent shapes')
+    N = min(doa_output.shape[1], doa_gt.shape[1])          # compute_masked_reg_loss aligns the time axes (:337-341)
+    if N != T:
+        raise ValueError('seld_loss: the event and DOA outputs must share their time axis (label rate)')
+    f = lambda t: t[:, :N].contiguous().float()
+    logit, doa, egt, dgt = f(event_logit), f(doa_output), f(event_gt), f(doa_gt)
+    sums = torch.empty(5, dtype=torch.float64, device=logit.device)
+    loss = torch.empty(3, dtype=torch.float32, device=logit.device)
+    g_logit = torch.empty_like(logit) if with_grad else None
+    g_doa = torch.empty_like(doa) if with_grad else None
+    _native.check(_native.lib().crnn_seld_loss(_p(logit), _p(doa), _p(egt), _p(dgt), B * N, n, ctypes.c_float(loss_weight[0]),
+                                               ctypes.c_float(loss_weight[1]), _p(sums), _p(loss), _p(g_logit), _p(g_doa), _st()))
+    return (loss, g_logit, g_doa) if with_grad else loss

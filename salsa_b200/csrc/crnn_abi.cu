@@ -327,4 +327,22 @@ int crnn_augment(const float* x, float* out, const float* y_doa, float* y_out, c
     return check_cuda(cudaGetLastError(), "augment_doa_kernel");
 }
 
+int crnn_seld_loss(const float* logit, const float* doa, const float* event_gt, const float* doa_gt, int64_t rows, int32_t n_classes,
+                   float w_sed, float w_doa, double* sums, float* loss, float* g_logit, float* g_doa, void* stream) {
+    if (!logit || !doa || !event_gt || !doa_gt || !sums || !loss) return fail(SALSA_EINVAL, "seld_loss: null pointer");
+    if (rows <= 0 || n_classes <= 0) return fail(SALSA_EINVAL, "seld_loss: empty input");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_cuda(cudaMemsetAsync(sums, 0, 5 * sizeof(double), st), "cudaMemsetAsync");
+    if (rc) return rc;
+    const long long cells = (long long)rows * n_classes;
+    const int blocks = std::min(grid_for(cells, 256), 1024);
+    seld_loss_sum_kernel<<<blocks, 256, 0, st>>>(logit, doa, event_gt, doa_gt, rows, n_classes, sums);
+    count_launch();
+    if ((rc = check_cuda(cudaGetLastError(), "seld_loss_sum_kernel"))) return rc;
+    seld_loss_finish_kernel<<<(g_logit || g_doa) ? blocks : 1, 256, 0, st>>>(logit, doa, event_gt, doa_gt, rows, n_classes, w_sed, w_doa, sums,
+                                                                           loss, g_logit, g_doa);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "seld_loss_finish_kernel");
+}
+
 }  // extern "C"

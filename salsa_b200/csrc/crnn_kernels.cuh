@@ -7,6 +7,7 @@
 //   head_finish_kernel    split of the fused head GEMM, tanh on the DOA part (decoders.py:137-147)
 //   gather_time_kernel    interpolate_tensor's index gather      (model_utils.py:57-75)
 //   augment_kernel        training-time channel swaps + frequency shift of a feature batch (utilities/transforms.py)
+//   seld_loss_*_kernel    BaseModel.compute_loss, reg_xyz (models/interfaces.py:273-355), and its gradient
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
@@ -495,6 +496,80 @@ __global__ void augment_doa_kernel(const float* __restrict__ y, float* __restric
         orow[k] = vx;
         orow[n + k] = vy;
         orow[2 * n + k] = vz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BaseModel.compute_loss for output_format = 'reg_xyz' (models/interfaces.py:273-355):
+//   sed_loss = mean over (row, class) of BCE-with-logits;  doa_loss = sum over x, y, z of sum(|pred - gt| mask) / sum(mask)
+//   loss     = w_sed sed_loss + w_doa doa_loss
+// One cell = one (row, class): logit[cell], event_gt[cell] (the mask) and the three regressions at [row][c + k n].
+// seld_loss_sum_kernel accumulates {sum bce, sum |dx| m, sum |dy| m, sum |dz| m, sum m} in float64 (block tree, then one
+// atomicAdd per block and value); seld_loss_finish_kernel turns the sums into (loss, sed_loss, doa_loss) and, when asked,
+// d loss / d logit = w_sed (sigmoid(logit) - gt) / cells and d loss / d doa = w_doa sign(pred - gt) mask / sum(mask).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seld_loss_sum_kernel(const float* __restrict__ logit, const float* __restrict__ doa,
+                                                            const float* __restrict__ event_gt, const float* __restrict__ doa_gt,
+                                                            long long rows, int n, double* __restrict__ sums) {
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const long long cells = rows * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n;
+        const int c = (int)(i - r * n);
+        const float l = logit[i], y = event_gt[i];
+        // torch's stable form: max(l, 0) - l y + log1p(exp(-|l|))
+        acc[0] += (double)(fmaxf(l, 0.0f) - l * y + log1pf(expf(-fabsf(l))));
+        const float* p = doa + r * 3 * n + c;
+        const float* g = doa_gt + r * 3 * n + c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[1 + k] += (double)(fabsf(p[k * n] - g[k * n]) * y);
+        acc[4] += (double)y;
+    }
+    __shared__ double red[5][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) red[k][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+        atomicAdd(sums + threadIdx.x, v);
+    }
+}
+
+__global__ void seld_loss_finish_kernel(const float* __restrict__ logit, const float* __restrict__ doa, const float* __restrict__ event_gt,
+                                        const float* __restrict__ doa_gt, long long rows, int n, float w_sed, float w_doa,
+                                        const double* __restrict__ sums, float* __restrict__ loss, float* __restrict__ g_logit,
+                                        float* __restrict__ g_doa) {
+    const long long cells = rows * n;
+    const double norm = sums[4];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double sed = sums[0] / (double)cells;
+        const double dl = (sums[1] + sums[2] + sums[3]) / norm;      // 0 / 0 = NaN without any active cell, as the reference
+        loss[0] = (float)((double)w_sed * sed + (double)w_doa * dl);
+        loss[1] = (float)sed;
+        loss[2] = (float)dl;
+    }
+    if (!g_logit && !g_doa) return;
+    const float inv_cells = (float)(1.0 / (double)cells), inv_norm = (float)(1.0 / norm);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n;
+        const int c = (int)(i - r * n);
+        const float l = logit[i], y = event_gt[i];
+        if (g_logit) g_logit[i] = w_sed * (1.0f / (1.0f + expf(-l)) - y) * inv_cells;
+        if (g_doa) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const long long j = r * 3 * n + c + k * n;
+                const float d = doa[j] - doa_gt[j];
+                g_doa[j] = w_doa * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * y * inv_norm;
+            }
+        }
     }
 }
 

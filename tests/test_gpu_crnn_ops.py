@@ -170,3 +170,25 @@ def test_conv2d_fused_pool_equals_separate_pool(ops, B, H, W, Cin, Cout):
     fused = ops.conv2d(x, w, bias, residual=res, relu=True, pool=True)
     assert tuple(fused.shape) == (B, H // 2, W // 2, Cout)
     assert torch.equal(fused.view(torch.int16), sep.view(torch.int16))
+
+
+def test_seld_loss_matches_reference_golden_and_autograd(golden):
+    """crnn_seld_loss against (a) the value the unmodified reference BaseModel.compute_loss returned for the same inputs
+    (tests/golden/model_cases.npz: loss_values), (b) the oracle restatement and its autograd gradients."""
+    from oracle import crnn as ocrnn
+    from salsa_b200 import crnn_ops as ops
+    logit, doa, egt, dgt = ocrnn.seld_loss_inputs()
+    ref = golden('model_cases')['loss_values']
+    loss, g_logit, g_doa = ops.seld_loss(logit.cuda(), doa.cuda(), egt.cuda(), dgt.cuda(), with_grad=True)
+    np.testing.assert_allclose(loss.cpu().numpy().astype(np.float64), ref, rtol=2e-6, atol=0)
+    lt, dt = logit.clone().requires_grad_(True), doa.clone().requires_grad_(True)
+    ocrnn.seld_loss(lt, dt, egt, dgt)[0].backward()
+    np.testing.assert_allclose(g_logit.cpu().numpy(), lt.grad.numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(g_doa.cpu().numpy(), dt.grad.numpy(), rtol=1e-5, atol=1e-9)
+    # other weights, a larger batch, no active cell at all (0 / 0 = NaN like the reference)
+    big = ocrnn.seld_loss_inputs(seed=9, batch=32, n_frames=600)
+    got = ops.seld_loss(*[t.cuda() for t in big], loss_weight=(0.5, 0.5)).cpu().numpy()
+    want = np.array([float(v) for v in ocrnn.seld_loss(*big, loss_weight=(0.5, 0.5))])
+    np.testing.assert_allclose(got, want, rtol=5e-6)
+    none = ops.seld_loss(logit.cuda(), doa.cuda(), torch.zeros_like(egt).cuda(), torch.zeros_like(dgt).cuda()).cpu().numpy()
+    assert np.isfinite(none[1]) and np.isnan(none[2]) and np.isnan(none[0])
