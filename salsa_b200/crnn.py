@@ -233,9 +233,9 @@ class SeldModel:
         """x: (batch_size, n_channels, n_timesteps, n_features) -> the reference's output dict (seld_models.py:39-49)."""
         return self.decode(self.encode(x, n_frames))
 
-    def predict(self, x):
+    def predict(self, x, n_frames=None):
         """forward + interpolate_tensor to the label rate, as `common_step` does (seld_models.py:58-64)."""
-        out = self.forward(x)
+        out = self.forward(x, n_frames)
         ratio = self.time_downsample_ratio * self.label_rate / self.feature_rate
         idx = ops.interpolate_index(out['event_frame_logit'].shape[1], ratio)
         return {k: ops.gather_time(v, idx) for k, v in out.items()}
@@ -249,11 +249,11 @@ class SeldModel:
                             target_dict['doa_frame_gt'], loss_weight=loss_weight)
         return out[0], out[1], out[2]
 
-    def events(self, x, sed_threshold: float = 0.3, max_nframes_per_file: int = None, eval_version: str = '2021'):
+    def events(self, x, sed_threshold: float = 0.3, max_nframes_per_file: int = None, eval_version: str = '2021', n_frames=None):
         """predict + the decoding of `write_classwise_output_to_file` (models/interfaces.py:210-258) for whole-clip inputs
         (one chunk per file, as the reference's test configuration): per clip the list of rows the reference writes to the
         submission csv, [frame, class, 0, azimuth, elevation] (2021) or [frame, class, azimuth, elevation]."""
-        pred = self.predict(x)
+        pred = self.predict(x, n_frames)
         logit, doa = pred['event_frame_logit'], pred['doa_frame_output']
         B, T, n = logit.shape
         active, azi, ele = ops.decode_events(logit.reshape(B * T, n), doa.reshape(B * T, 3 * n), sed_threshold)

@@ -163,3 +163,30 @@ def test_event_decoding_matches_oracle(model):
     assert np.array_equal(azi.cpu().numpy().astype(int), ref_azi)
     assert np.array_equal(ele.cpu().numpy().astype(int), ref_ele)
     assert np.array_equal(active.cpu().numpy(), (torch.sigmoid(logits).numpy() >= 0.3))
+
+
+def test_pipeline_audio_to_outputs():
+    """SeldPipeline = SalsaExtractor -> (scaler fused into the input packing) -> SeldModel on device memory: identical to
+    running the three stages by hand, and the 4801st frame is dropped like Database does (database.py:205-207)."""
+    import salsa_b200
+    from oracle import crnn as ocrnn, synth
+    audio = torch.from_numpy(np.stack([synth.make_clip(40 + i, 'foa', seconds=3.2) for i in range(2)])).cuda()
+    ex = salsa_b200.SalsaExtractor('foa')
+    model = salsa_b200.SeldModel(salsa_b200.PannResNet22(n_input_channels=7),
+                                 salsa_b200.SeldDecoder(512, n_classes=12, output_format='reg_xyz', decoder_type='bigru',
+                                                        freq_pool='avg', decoder_size=256), label_rate=10, feature_rate=80.0)
+    model.load_state_dict(ocrnn.make_state_dict(0))
+    feat = ex.extract(audio)
+    mean, std = salsa_b200.compute_scaler([feat])
+    pipe = salsa_b200.SeldPipeline(ex, model, scaler=(mean, std))
+    T = feat.shape[2]
+    assert T == 257 and pipe._n_frames(T) == 256
+    out = pipe(audio)
+    want = model.forward(feat, n_frames=256)
+    for k in want:
+        assert tuple(out[k].shape) == (2, 16, 12 if k == 'event_frame_logit' else 36)
+        assert torch.equal(out[k], want[k])
+    pred = pipe.predict(audio)
+    assert tuple(pred['event_frame_logit'].shape) == (2, 32, 12)          # 16 * 10 / 80 -> ratio 2
+    rows = pipe.events(audio)
+    assert len(rows) == 2 and all(len(r) == 5 for clip in rows for r in clip)
