@@ -110,6 +110,12 @@ int crnn_seld_loss(const float *logit, const float *doa, const float *event_gt, 
                    int32_t n_classes, float w_sed, float w_doa, double *sums, float *loss, float *g_logit,
                    float *g_doa, void *stream);
 
+/* One torch.optim.Adam step (models/interfaces.py:85-95: no weight decay, no amsgrad) on a flat fp32 buffer of n values,
+ * with the lr / beta1 of this batch as LearningRateScheduler sets them (utilities/learning_utils.py:39-52); `step`
+ * counts from 1; the hyper-parameters are doubles like torch's Python scalars (1 - beta is formed before rounding).  param, exp_avg and exp_avg_sq are updated in place (optimiser row). */
+int crnn_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr, double beta1,
+                   double beta2, double eps, int32_t step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ from .features import (FeatureScaler, MagStftExtractor, SalsaExtractor, SalsaLit
 from .crnn import PannResNet22, SeldDecoder, SeldModel  # noqa: F401
 from . import crnn_ops  # noqa: F401
 from . import augment  # noqa: F401
+from . import optim  # noqa: F401
 from .pipeline import SeldPipeline  # noqa: F401
 
 __version__ = '0.1.0'

@@ -2,6 +2,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <math.h>
+
 #include <algorithm>
 #include <mutex>
 #include <string>
@@ -343,6 +345,20 @@ int crnn_seld_loss(const float* logit, const float* doa, const float* event_gt, 
                                                                            loss, g_logit, g_doa);
     count_launch();
     return check_cuda(cudaGetLastError(), "seld_loss_finish_kernel");
+}
+
+int crnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
+                   double eps, int32_t step, void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq) return fail(SALSA_EINVAL, "adam_step: null pointer");
+    if (step < 1) return fail(SALSA_EINVAL, "adam_step: step counts from 1");
+    if (n <= 0) return SALSA_OK;
+    // bias corrections in double like torch's Python scalars, then rounded once
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    const float step_size = (float)(lr / bc1), bias2_sqrt = (float)sqrt(bc2);
+    adam_step_kernel<<<std::min(grid_for(n, 256), 4096), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, step_size, bias2_sqrt);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "adam_step_kernel");
 }
 
 }  // extern "C"

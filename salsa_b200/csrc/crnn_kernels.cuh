@@ -573,5 +573,29 @@ __global__ void seld_loss_finish_kernel(const float* __restrict__ logit, const f
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One Adam step on a flat float32 parameter buffer: torch.optim.Adam as the reference configures it
+// (models/interfaces.py:85-95: default betas / eps, no weight decay, no amsgrad) with the learning rate and beta1 that
+// LearningRateScheduler sets before every batch (utilities/learning_utils.py:39-52).  The float32 operations are
+// torch's single-tensor path in its order (lerp, addcmul, sqrt / sqrt(bias_correction2) + eps, addcdiv).
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_step_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
+                                 float* __restrict__ exp_avg_sq, long long n, float w, float beta2, float one_minus_beta2, float eps,
+                                 float step_size, float bias2_sqrt) {
+    // w = 1 - beta1 and one_minus_beta2 are formed in double by the host, as torch forms them from its Python floats
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float g = grad[i];
+        float m = exp_avg[i];
+        const float diff = g - m;
+        m = w < 0.5f ? fmaf(w, diff, m) : g - diff * (1.0f - w);          // Tensor.lerp_
+        float v = exp_avg_sq[i] * beta2;
+        v = fmaf(one_minus_beta2 * g, g, v);                               // addcmul_(grad, grad, value = 1 - beta2)
+        exp_avg[i] = m;
+        exp_avg_sq[i] = v;
+        const float denom = sqrtf(v) / bias2_sqrt + eps;
+        param[i] = param[i] - step_size * (m / denom);                     // addcdiv_(exp_avg, denom, value = -step_size)
+    }
+}
+
 }  // namespace crnn
 }  // namespace salsa

@@ -192,3 +192,36 @@ def test_seld_loss_matches_reference_golden_and_autograd(golden):
     np.testing.assert_allclose(got, want, rtol=5e-6)
     none = ops.seld_loss(logit.cuda(), doa.cuda(), torch.zeros_like(egt).cuda(), torch.zeros_like(dgt).cuda()).cpu().numpy()
     assert np.isfinite(none[1]) and np.isnan(none[2]) and np.isnan(none[0])
+
+
+def test_adam_and_schedule_match_torch():
+    """salsa_b200.optim.Adam + LearningRateScheduler against torch.optim.Adam driven by the schedule arithmetic of
+    utilities/learning_utils.py:39-52 (np.interp over the step milestones), over steps that cross a milestone."""
+    from salsa_b200 import optim
+    g = torch.Generator().manual_seed(11)
+    p0 = torch.randn(100_003, generator=g)
+    sched = optim.LearningRateScheduler(steps_per_epoch=4, max_epochs=5)
+    assert sched.step_milestones == [0, 9, 18, 20]
+    ref_p = torch.nn.Parameter(p0.clone().cuda())
+    ref = torch.optim.Adam([ref_p], lr=1e-3)
+    mine_p = p0.clone().cuda()
+    mine = optim.Adam(mine_p, lr=1e-3)
+    for step in range(12):
+        epoch, batch_idx = divmod(step, 4)
+        grad = torch.randn(p0.shape, generator=g).cuda() * (1.0 + step)
+        lr, mom = sched.at(epoch, batch_idx)
+        assert lr == float(np.interp(step, [0, 9, 18, 20], (1e-4, 1e-2, 1e-3, 1e-4)))
+        for group in ref.param_groups:
+            group['lr'], group['betas'] = lr, (mom, 0.999)
+        ref_p.grad = grad.clone()
+        ref.step()
+        sched.apply(mine, epoch, batch_idx)
+        mine.step(grad)
+    err = (mine_p - ref_p.detach()).abs().max().item()
+    assert err <= 2e-7 * p0.abs().max().item(), err
+    print('adam: max |param diff|', err)
+    st = ref.state[ref_p]
+    # the moments agree to float32 rounding of their own scale (torch's fused lerp may round the last bit differently)
+    for mine_t, ref_t in ((mine.exp_avg, st['exp_avg']), (mine.exp_avg_sq, st['exp_avg_sq'])):
+        d = (mine_t - ref_t).abs().max().item()
+        assert d <= 1e-6 * ref_t.abs().max().item(), (d, ref_t.abs().max().item())
