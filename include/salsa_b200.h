@@ -107,7 +107,10 @@ int salsa_eigenvector(const salsa_params_t *p, const float *X, const uint32_t *m
 
 /* ---- clip level ------------------------------------------------------------------------------ */
 
-/* Bytes of device scratch needed by salsa_extract / salsa_lite_extract for these parameters. */
+/* Bytes of device scratch needed by salsa_extract for these parameters: the complex64 spectrum of the spatial bins in
+ * tiles of 32 bins ([clip][frame][tile][4][32], 29.5 MB per 60 s FOA clip) and two bit masks.  With the environment
+ * variable SALSA_B200_PIPELINE=fused (read at every call) the spectrum stays in shared memory and the scratch holds
+ * |X0|^2 instead (7.5 MB per clip); results are the same, the fused arrangement is 1.5x slower. */
 size_t salsa_workspace_bytes(const salsa_params_t *p);
 
 /* Per-clip body of extract_features() (dataset/salsa_feature_extraction.py:353-377) for a batch of
