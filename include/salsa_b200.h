@@ -131,6 +131,16 @@ int salsa_extract_host(const salsa_params_t *p, const float *audio_host, float *
 int salsa_lite_extract_host(const salsa_params_t *p, int32_t cutoff_bin, int32_t mode,
                             const float *audio_host, float *feature_host, int32_t clips_per_chunk);
 
+/* salsa_extract_host for 16-bit PCM input: audio_host int16 [n_clips][4][n_samples], the samples of the dataset's wav
+ * files before librosa.load / soundfile turn them into float32 = sample / 32768 (salsa_feature_extraction.py:353).  Half
+ * the host-to-device bytes; the conversion runs on the device and the features are bit-identical to feeding the float32
+ * audio. */
+int salsa_extract_host_pcm16(const salsa_params_t *p, const int16_t *audio_host, float *feature_host,
+                             int32_t clips_per_chunk);
+
+/* The conversion alone, on device buffers (both 16-byte aligned): audio[i] = pcm[i] / 32768. */
+int salsa_pcm16_to_float(const int16_t *pcm, float *audio, int64_t n, void *stream);
+
 /* Statistics of compute_scaler() (dataset/salsa_feature_extraction.py:204-262): adds, for spectrogram channels 0..3
  * and every frequency, the sum and the sum of squares over all frames of all clips of `feature`
  * ([n_clips][n_feat_chans][n_frames][feat_dim]) to sums (float64 [4][feat_dim][2], zeroed by the caller before the

@@ -3,6 +3,7 @@
 The library is the product; there is no Python / CPU fallback: loading fails loudly when the
 shared object has not been built (`python -c "import __graft_entry__ as g; g.build()"`).
 """
+import contextlib
 import ctypes
 import os
 
@@ -51,6 +52,8 @@ SIGNATURES = {
     'salsa_lite_extract': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _vp]),
     'salsa_extract_host': (ctypes.c_int, [_P, _vp, _vp, _i32]),
     'salsa_lite_extract_host': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _i32]),
+    'salsa_extract_host_pcm16': (ctypes.c_int, [_P, _vp, _vp, _i32]),
+    'salsa_pcm16_to_float': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     'salsa_scaler_accumulate': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'salsa_host_release': (ctypes.c_int, []),
     'salsa_launch_count': (_u64, [ctypes.c_int]),
@@ -96,6 +99,25 @@ def check(rc):
         if rc == SALSA_EINVAL:
             raise ValueError(msg)
         raise NativeError('salsa_b200 error {}: {}'.format(rc, msg))
+
+
+@contextlib.contextmanager
+def device_of(t):
+    """Makes the device of CUDA tensor `t` current for the duration of a native call and yields that device's current
+    stream as the `void *stream` argument: the library launches on the CURRENT device (its tables, kernel attributes and
+    staging buffers are per device), so a tensor on another GPU must switch the device first."""
+    import torch
+    if not t.is_cuda:
+        raise ValueError('a CUDA tensor is required (salsa_b200 has no CPU fallback)')
+    with torch.cuda.device(t.device):
+        yield ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def same_device(*tensors):
+    """Raises unless every given CUDA tensor (None entries are skipped) lives on one device."""
+    devs = {t.device for t in tensors if t is not None}
+    if len(devs) > 1:
+        raise ValueError('tensors live on different devices: {}'.format(sorted(str(d) for d in devs)))
 
 
 def profile_enable(on=True):

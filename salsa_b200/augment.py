@@ -122,6 +122,7 @@ class BatchAugment:
             Ty, n = y_doa.shape[1], y_doa.shape[2] // 3
             y_out = torch.empty_like(y_doa)
         vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
-        _native.check(_native.lib().crnn_augment(vp(x), vp(out), vp(y_doa), vp(y_out), vp(d_ops), B, T, F, Ty, n,
-                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        _native.same_device(x, y_doa)
+        with _native.device_of(x) as st:
+            _native.check(_native.lib().crnn_augment(vp(x), vp(out), vp(y_doa), vp(y_out), vp(d_ops), B, T, F, Ty, n, st))
         return out, y_sed, y_out

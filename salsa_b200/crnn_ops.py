@@ -15,8 +15,11 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _st():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _call(name, t, *args):
+    """One native call on the device (and that device's current stream) of CUDA tensor `t`; the stream is the entry
+    point's last argument."""
+    with _native.device_of(t) as st:
+        _native.check(getattr(_native.lib(), name)(*args, st))
 
 
 def _check_act(x):
@@ -65,8 +68,8 @@ def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, 
         else:
             out = torch.empty((B, H, W, planes * Cout), dtype=torch.bfloat16, device=x.device)
     o16, o32 = (None, out) if out.dtype == torch.float32 else (out, None)
-    _native.check(_native.lib().crnn_conv2d(_p(x), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), B, H, W, CinP // planes, Cout,
-                                            3 if taps == 9 else 1, int(bool(relu)), planes, int(fuse_pool), _st()))
+    _call('crnn_conv2d', x, _p(x), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), B, H, W, CinP // planes, Cout,
+                                            3 if taps == 9 else 1, int(bool(relu)), planes, int(fuse_pool))
     if pool and not fuse_pool:
         out = avgpool2(out, planes=planes)
     return out
@@ -79,7 +82,7 @@ def conv_first(x, w, bias=None, relu=True, planes=1):
     if C != 16 * planes or tuple(w.shape) != (9, 64, 16 * planes) or w.dtype != torch.bfloat16 or not w.is_contiguous():
         raise ValueError('conv_first expects 16 (padded) input channels and 64 output channels')
     out = torch.empty((B, H, W, planes * 64), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().crnn_conv_first(_p(x), _p(w), _p(bias), _p(out), B, H, W, int(bool(relu)), planes, _st()))
+    _call('crnn_conv_first', x, _p(x), _p(w), _p(bias), _p(out), B, H, W, int(bool(relu)), planes)
     return out
 
 
@@ -103,7 +106,7 @@ def gemm(a, w, bias=None, relu=False, M=None, out_f32=False, out=None, planes=1)
         out = (torch.zeros((Mpad, N), dtype=torch.float32, device=a.device) if out_f32 else
                torch.zeros((Mpad, planes * N), dtype=torch.bfloat16, device=a.device))
     o16, o32 = (None, out) if out.dtype == torch.float32 else (out, None)
-    _native.check(_native.lib().crnn_gemm(_p(a), _p(w), _p(bias), _p(o16), _p(o32), M, N, K // planes, int(bool(relu)), planes, _st()))
+    _call('crnn_gemm', a, _p(a), _p(w), _p(bias), _p(o16), _p(o32), M, N, K // planes, int(bool(relu)), planes)
     return out
 
 
@@ -124,7 +127,7 @@ def pack_input(x, t_use=None, c_pad=64, planes=1, scaler=None):
         n_scaled = mean.shape[0]
         if std.shape != mean.shape or n_scaled > C:
             raise ValueError('scaler mean / std must be (n_scaled <= C, 1, F)')
-    _native.check(_native.lib().crnn_pack_input(_p(x), _p(y), B, C, T, F, t_use, c_pad, planes, _p(mean), _p(std), n_scaled, _st()))
+    _call('crnn_pack_input', x, _p(x), _p(y), B, C, T, F, t_use, c_pad, planes, _p(mean), _p(std), n_scaled)
     return y
 
 
@@ -132,7 +135,7 @@ def avgpool2(x, planes=1):
     _check_act(x)
     B, H, W, C = x.shape
     y = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().crnn_avgpool2(_p(x), _p(y), B, H, W, C // planes, planes, _st()))
+    _call('crnn_avgpool2', x, _p(x), _p(y), B, H, W, C // planes, planes)
     return y
 
 
@@ -141,7 +144,7 @@ def freq_mean(x, planes=1):
     _check_act(x)
     B, H, W, C = x.shape
     y = torch.zeros((pad_rows(B * H), C), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().crnn_freq_mean(_p(x), _p(y), B * H, W, C // planes, planes, _st()))
+    _call('crnn_freq_mean', x, _p(x), _p(y), B * H, W, C // planes, planes)
     return y
 
 
@@ -150,14 +153,14 @@ def gru_layer(xproj, w_hh, b_hh, B, T, planes=1):
     if xproj.dtype != torch.float32 or xproj.shape[1] != 1536 or not xproj.is_contiguous():
         raise ValueError('xproj must be contiguous fp32 (rows, 1536)')
     y = torch.zeros((pad_rows(B * T), planes * 512), dtype=torch.bfloat16, device=xproj.device)
-    _native.check(_native.lib().crnn_gru_layer(_p(xproj), _p(w_hh), _p(b_hh), _p(y), B, T, planes, _st()))
+    _call('crnn_gru_layer', xproj, _p(xproj), _p(w_hh), _p(b_hh), _p(y), B, T, planes)
     return y
 
 
 def head_finish(z, rows, n_classes):
     logits = torch.empty((rows, n_classes), dtype=torch.float32, device=z.device)
     doa = torch.empty((rows, 3 * n_classes), dtype=torch.float32, device=z.device)
-    _native.check(_native.lib().crnn_head_finish(_p(z), _p(logits), _p(doa), rows, n_classes, _st()))
+    _call('crnn_head_finish', z, _p(z), _p(logits), _p(doa), rows, n_classes)
     return logits, doa
 
 
@@ -178,7 +181,7 @@ def gather_time(x, idx):
         raise IndexError('interpolation index out of range')
     d_idx = torch.from_numpy(np.asarray(idx, dtype=np.int32)).to(x.device)
     out = torch.empty((B, len(idx), width), dtype=torch.float32, device=x.device)
-    _native.check(_native.lib().crnn_gather_time(_p(x), _p(d_idx), _p(out), B, n_in, len(idx), width, _st()))
+    _call('crnn_gather_time', x, _p(x), _p(d_idx), _p(out), B, n_in, len(idx), width)
     return out
 
 
@@ -192,8 +195,8 @@ def decode_events(logits, doa, threshold=0.3):
     active = torch.empty((rows, n), dtype=torch.uint8, device=logits.device)
     azi = torch.empty((rows, n), dtype=torch.int16, device=logits.device)
     ele = torch.empty((rows, n), dtype=torch.int16, device=logits.device)
-    _native.check(_native.lib().crnn_decode_events(_p(logits), _p(doa), rows, n, ctypes.c_float(threshold), _p(active), _p(azi),
-                                                   _p(ele), _st()))
+    _call('crnn_decode_events', logits, _p(logits), _p(doa), rows, n, ctypes.c_float(threshold), _p(active), _p(azi),
+                                                   _p(ele))
     return active.bool(), azi, ele
 
 
@@ -215,6 +218,6 @@ def seld_loss(event_logit, doa_output, event_gt, doa_gt, loss_weight=(0.3, 0.7),
     loss = torch.empty(3, dtype=torch.float32, device=logit.device)
     g_logit = torch.empty_like(logit) if with_grad else None
     g_doa = torch.empty_like(doa) if with_grad else None
-    _native.check(_native.lib().crnn_seld_loss(_p(logit), _p(doa), _p(egt), _p(dgt), B * N, n, ctypes.c_float(loss_weight[0]),
-                                               ctypes.c_float(loss_weight[1]), _p(sums), _p(loss), _p(g_logit), _p(g_doa), _st()))
+    _call('crnn_seld_loss', logit, _p(logit), _p(doa), _p(egt), _p(dgt), B * N, n, ctypes.c_float(loss_weight[0]),
+                                               ctypes.c_float(loss_weight[1]), _p(sums), _p(loss), _p(g_logit), _p(g_doa))
     return (loss, g_logit, g_doa) if with_grad else loss

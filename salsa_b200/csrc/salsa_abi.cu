@@ -270,8 +270,14 @@ static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const fl
     int rc;
     if (ch_count != 1 && ch_count != 4) return fail(SALSA_EINVAL, "stft: 1 or 4 channels");
     const bool d = p->stft_precision == 64;
-    if (x_tiles > 0 && (ch_count != 4 || !X || !spec || power0)) return fail(SALSA_EINVAL, "stft: tiled X is the clip path's layout");
-    if (x_tiles > 0 && p->lower_bin < kTileBins)            // clip path, split arrangement
+    if (x_tiles > 0 && (ch_count != 4 || !X || power0)) return fail(SALSA_EINVAL, "stft: tiled X is the clip path's layout");
+    if (x_tiles > 0 && !spec)                               // clip path with a separate spectrogram window: X only
+        rc = p->lower_bin < kTileBins
+                 ? (d ? launch_stft_t<double, 4, kStftX | kStftTiled>(a, tb.d, grid, st)
+                      : launch_stft_t<float, 4, kStftX | kStftTiled>(a, tb.f, grid, st))
+                 : (d ? launch_stft_t<double, 4, kStftX | kStftTiledAny>(a, tb.d, grid, st)
+                      : launch_stft_t<float, 4, kStftX | kStftTiledAny>(a, tb.f, grid, st));
+    else if (x_tiles > 0 && p->lower_bin < kTileBins)       // clip path, split arrangement
         rc = d ? launch_stft_t<double, 4, kStftX | kStftSpec | kStftTiled>(a, tb.d, grid, st)
                : launch_stft_t<float, 4, kStftX | kStftSpec | kStftTiled>(a, tb.f, grid, st);
     else if (x_tiles > 0)
@@ -306,8 +312,9 @@ constexpr int kFusedFT = 4;   // new frames per step of salsa_fused_kernel
 
 static int choose_seg_len(int n_clips, int n_frames) {
     // aim for >= 4 CTAs per SM slot (2 resident CTAs x 148 SMs) while keeping the 6-frame halo small
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long want = 4LL * 2 * sms;
     long long segs_per_clip = (want + n_clips - 1) / std::max(1, n_clips);
     segs_per_clip = std::max(1LL, std::min<long long>(segs_per_clip, (n_frames + 31) / 32));
@@ -426,6 +433,9 @@ static int launch_eig_tile(const salsa_params_t* p, const Workspace& w, const ui
     a.feat_dim = band_layout(p).n_out;
     a.eig = eig_args(p);
     if (a.feat_dim & 3) return fail(SALSA_EINVAL, "feature width must be a multiple of 4");
+    // the reference places (upper_bin - lower_bin) columns into a (3, T, freq_dim) array (:373-374): more bins than
+    // columns is its broadcast error
+    if (a.n_bins > a.feat_dim) return fail(SALSA_EINVAL, "upper_bin - lower_bin exceeds the feature width");
     int rc;
     {
         ProfScope prof("eig_tile_kernel", st);
@@ -560,6 +570,9 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     if (rc) return rc;
     if (p->n_clips == 0) return SALSA_OK;
     if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    // the reference places (upper_bin - lower_bin) columns into a (3, T, freq_dim) array (:373-374): more bins than
+    // columns is its broadcast error
+    if (p->upper_bin - p->lower_bin > band_layout(p).n_out) return fail(SALSA_EINVAL, "upper_bin - lower_bin exceeds the feature width");
     const Pipeline pl = pipeline_choice();
     const Workspace w = carve_workspace(p, workspace, pl);
     if ((p->is_tracking || pl == kPipelineSplit) && (!workspace || workspace_bytes < w.bytes))
@@ -567,15 +580,24 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     double win[kNfft];
     const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
     if (!builtin_hann) host_window(p, win);
-    DeviceTables tb;
-    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
+    // win_len / window configure MagStftExtractor only (:324-325, :184-192); the spectrum that feeds the eigenvector step
+    // is librosa's default full-length Hann whatever they are (:359-361)
+    DeviceTables tb, tb_hann;
+    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb)) || (rc = get_tables(nullptr, &tb_hann))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     const int n_bins = p->upper_bin - p->lower_bin;
     const uint32_t* mask = nullptr;
+    if (pl == kPipelineFused && !builtin_hann)
+        return fail(SALSA_EINVAL, "SALSA_B200_PIPELINE=fused supports the full-length Hann window only");
     if (pl == kPipelineSplit) {
         const long long clip_stride = 7LL * n_frames * band_layout(p).n_out;
-        if ((rc = launch_stft(p, tb, audio, w.X, 0, w.n_tiles, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
+        if (builtin_hann) {
+            if ((rc = launch_stft(p, tb, audio, w.X, 0, w.n_tiles, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
+        } else {
+            if ((rc = launch_stft(p, tb, audio, nullptr, 0, 0, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
+            if ((rc = launch_stft(p, tb_hann, audio, w.X, 0, w.n_tiles, nullptr, 0, nullptr, p->n_chans, st))) return rc;
+        }
         if (p->is_tracking) {
             // The tracker is a sequential recurrence over the whole clip in float64 on |X0|^2 of the complex64
             // spectrum (what the reference computes, :53-55); with stft_precision = 32 the selection follows that
@@ -608,11 +630,10 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
         return fail(SALSA_EINVAL, "Upper bin for spatial feature is higher than cutoff bin for spectrogram!");
     if (p->n_clips == 0) return SALSA_OK;
     if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
-    double win[kNfft];
-    const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
-    if (!builtin_hann) host_window(p, win);
+    // the reference reads win_len from the config but never passes it on (salsa_lite_feature_extraction.py:44, :97-98):
+    // every SALSA-Lite transform uses librosa's default full-length Hann, so win_len / window are ignored here too
     DeviceTables tb;
-    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
+    if ((rc = get_tables(nullptr, &tb))) return rc;
     LiteArgs a;
     a.audio = audio;
     a.feature = feature;
@@ -652,6 +673,16 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
     return check_launch("lite_kernel");
 }
 
+int salsa_pcm16_to_float(const int16_t* pcm, float* audio, int64_t n, void* stream) {
+    if (!pcm || !audio) return fail(SALSA_EINVAL, "pcm16_to_float: null pointer");
+    if (n <= 0) return SALSA_OK;
+    if ((reinterpret_cast<uintptr_t>(pcm) | reinterpret_cast<uintptr_t>(audio)) & 15) return fail(SALSA_EINVAL, "pcm16_to_float: pointers must be 16-byte aligned");
+    const long long groups = (n + 7) / 8;
+    const int blocks = (int)std::min<long long>((groups + 255) / 256, 148LL * 16);
+    pcm16_to_float_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pcm, audio, n);
+    return check_launch("pcm16_to_float_kernel");
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
@@ -668,17 +699,20 @@ struct HostPipeline {
     cudaEvent_t in_done[kPipeBufs] = {}, run_done[kPipeBufs] = {}, out_done[kPipeBufs] = {};
     float* d_audio[kPipeBufs] = {};
     float* d_feat[kPipeBufs] = {};
+    int16_t* d_pcm[kPipeBufs] = {};     // 16-bit input staging (salsa_extract_host_pcm16)
     void* d_work = nullptr;
-    size_t audio_bytes = 0, feat_bytes = 0, work_bytes = 0;
+    size_t audio_bytes = 0, feat_bytes = 0, work_bytes = 0, pcm_bytes = 0;
 
     void release() {
         for (int i = 0; i < kPipeBufs; ++i) {
             if (d_audio[i]) cudaFree(d_audio[i]);
             if (d_feat[i]) cudaFree(d_feat[i]);
+            if (d_pcm[i]) cudaFree(d_pcm[i]);
             if (in_done[i]) cudaEventDestroy(in_done[i]);
             if (run_done[i]) cudaEventDestroy(run_done[i]);
             if (out_done[i]) cudaEventDestroy(out_done[i]);
             d_audio[i] = d_feat[i] = nullptr;
+            d_pcm[i] = nullptr;
             in_done[i] = run_done[i] = out_done[i] = nullptr;
         }
         if (d_work) cudaFree(d_work);
@@ -687,10 +721,10 @@ struct HostPipeline {
         if (s_out) cudaStreamDestroy(s_out);
         d_work = nullptr;
         s_in = s_run = s_out = nullptr;
-        audio_bytes = feat_bytes = work_bytes = 0;
+        audio_bytes = feat_bytes = work_bytes = pcm_bytes = 0;
         device = -1;
     }
-    int ensure(size_t ab, size_t fb, size_t wb) {
+    int ensure(size_t ab, size_t fb, size_t wb, size_t pb) {
         int dev = 0;
         SALSA_CUDA(cudaGetDevice(&dev));
         if (dev != device) {
@@ -721,6 +755,14 @@ struct HostPipeline {
             }
             feat_bytes = fb;
         }
+        if (pb > pcm_bytes) {
+            for (int i = 0; i < kPipeBufs; ++i) {
+                if (d_pcm[i]) cudaFree(d_pcm[i]);
+                d_pcm[i] = nullptr;
+                SALSA_CUDA(cudaMalloc((void**)&d_pcm[i], pb));
+            }
+            pcm_bytes = pb;
+        }
         if (wb > work_bytes) {
             if (d_work) cudaFree(d_work);
             d_work = nullptr;
@@ -732,15 +774,19 @@ struct HostPipeline {
 };
 thread_local HostPipeline t_pipeline;
 
-template <typename Run>
-int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_t work_bytes, const float* audio_host,
+// In: float (the audio as librosa.load returns it) or int16_t (the 16-bit PCM of the wav files themselves,
+// salsa_feature_extraction.py:353: half the host-to-device bytes; converted on the device, sample / 32768 as soundfile does)
+template <typename In, typename Run>
+int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_t work_bytes, const In* audio_host,
                       float* feature_host, int clips_per_chunk, Run run) {
+    constexpr bool pcm = sizeof(In) == 2;
     if (p->n_clips == 0) return SALSA_OK;
     if (clips_per_chunk <= 0) clips_per_chunk = 16;
     clips_per_chunk = std::min(clips_per_chunk, p->n_clips);
     const size_t audio_elems = (size_t)p->n_chans * p->n_samples;
     HostPipeline& hp = t_pipeline;
-    int rc0 = hp.ensure(clips_per_chunk * audio_elems * sizeof(float), clips_per_chunk * feat_elems_per_clip * sizeof(float), work_bytes);
+    int rc0 = hp.ensure(clips_per_chunk * audio_elems * sizeof(float), clips_per_chunk * feat_elems_per_clip * sizeof(float), work_bytes,
+                        pcm ? clips_per_chunk * audio_elems * sizeof(int16_t) : 0);
     if (rc0) return rc0;
     const int n_chunks = (p->n_clips + clips_per_chunk - 1) / clips_per_chunk;
     for (int c = 0; c < n_chunks; ++c) {
@@ -753,14 +799,25 @@ int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_
             SALSA_CUDA(cudaStreamWaitEvent(hp.s_in, hp.run_done[buf], 0));
             SALSA_CUDA(cudaStreamWaitEvent(hp.s_run, hp.out_done[buf], 0));
         }
-        SALSA_CUDA(cudaMemcpyAsync(hp.d_audio[buf], audio_host + (size_t)first * audio_elems,
-                                   (size_t)n * audio_elems * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
+        void* d_in = pcm ? (void*)hp.d_pcm[buf] : (void*)hp.d_audio[buf];
+        SALSA_CUDA(cudaMemcpyAsync(d_in, audio_host + (size_t)first * audio_elems, (size_t)n * audio_elems * sizeof(In),
+                                   cudaMemcpyHostToDevice, hp.s_in));
         SALSA_CUDA(cudaEventRecord(hp.in_done[buf], hp.s_in));
         SALSA_CUDA(cudaStreamWaitEvent(hp.s_run, hp.in_done[buf], 0));
+        if (pcm) {
+            int rcp = salsa_pcm16_to_float(hp.d_pcm[buf], hp.d_audio[buf], (int64_t)((size_t)n * audio_elems), (void*)hp.s_run);
+            if (rcp) return rcp;
+        }
         salsa_params_t pc = *p;
         pc.n_clips = n;
         int rc = run(&pc, hp.d_audio[buf], hp.d_feat[buf], hp.d_work, hp.work_bytes, hp.s_run);
-        if (rc) return rc;
+        if (rc) {
+            // copies of earlier chunks may still be in flight into the caller's buffers: every call ends synchronised
+            cudaStreamSynchronize(hp.s_in);
+            cudaStreamSynchronize(hp.s_run);
+            cudaStreamSynchronize(hp.s_out);
+            return rc;
+        }
         SALSA_CUDA(cudaEventRecord(hp.run_done[buf], hp.s_run));
         SALSA_CUDA(cudaStreamWaitEvent(hp.s_out, hp.run_done[buf], 0));
         SALSA_CUDA(cudaMemcpyAsync(feature_host + (size_t)first * feat_elems_per_clip, hp.d_feat[buf],
@@ -775,6 +832,21 @@ int run_host_pipeline(const salsa_params_t* p, size_t feat_elems_per_clip, size_
 }  // namespace
 
 extern "C" {
+
+int salsa_extract_host_pcm16(const salsa_params_t* p, const int16_t* audio_host, float* feature_host, int32_t clips_per_chunk) {
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (!audio_host || !feature_host) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    const size_t n_frames = (size_t)salsa_n_frames(p->n_samples, p->hop_len);
+    const size_t feat = 7 * n_frames * (size_t)band_layout(p).n_out;
+    salsa_params_t pc = *p;
+    pc.n_clips = std::min(p->n_clips, clips_per_chunk > 0 ? clips_per_chunk : 16);
+    const size_t work = salsa_workspace_bytes(&pc);
+    return run_host_pipeline(p, feat, work, audio_host, feature_host, clips_per_chunk,
+                             [](const salsa_params_t* q, const float* a, float* f, void* w, size_t wb, cudaStream_t s) {
+                                 return salsa_extract(q, a, f, w, wb, (void*)s);
+                             });
+}
 
 int salsa_extract_host(const salsa_params_t* p, const float* audio_host, float* feature_host,
                        int32_t clips_per_chunk) {

@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(256) tracker_kernel(Src src, uint32_t* __restr
                 if (nf < c.floor_min) nf = c.floor_min;
                 const bool sel = live && (q > snr2 * (nf * nf));
                 const uint32_t bits = __ballot_sync(0xffffffffu, sel);
-                if ((threadIdx.x & 31) == 0) mrow[(long long)(t0 + i) * n_words] = bits;
+                // `word < n_words`: a block's surplus warps (n_words not a multiple of the warps per block) take part in
+                // nothing but the ballot
+                if ((threadIdx.x & 31) == 0 && word < n_words) mrow[(long long)(t0 + i) * n_words] = bits;
             }
         }
     };
@@ -479,6 +481,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) eig_tile_kernel(EigTileArgs 
         const int i = s / FT, tl = s % FT;
         if (tl >= nt) continue;
         const int k = (threadIdx.x & 7) * 4;
+        if (c0 + k >= a.feat_dim) continue;        // the last bin tile may reach past the feature row (n_bins <= feat_dim < 32 n_tiles)
         const uint32_t bits = smask[tl] >> k;
         const float4 sv = *reinterpret_cast<const float4*>(stage + s * BB + k);
         float4 v;
@@ -789,6 +792,30 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pcm16_to_float_kernel: 16-bit PCM samples -> float32, sample / 32768 (exact), as soundfile / librosa.load hand the wav
+// files of the dataset to the reference (salsa_feature_extraction.py:353).  8 samples per thread and step.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __restrict__ pcm, float* __restrict__ audio, long long n) {
+    const long long groups = n >> 3;
+    const float s = 1.0f / 32768.0f;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(pcm) + g);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float4 lo, hi;
+        lo.x = (float)(short)(w[0] & 0xffff) * s; lo.y = (float)(w[0] >> 16) * s;
+        lo.z = (float)(short)(w[1] & 0xffff) * s; lo.w = (float)(w[1] >> 16) * s;
+        hi.x = (float)(short)(w[2] & 0xffff) * s; hi.y = (float)(w[2] >> 16) * s;
+        hi.z = (float)(short)(w[3] & 0xffff) * s; hi.w = (float)(w[3] >> 16) * s;
+        reinterpret_cast<float4*>(audio)[2 * g] = lo;
+        reinterpret_cast<float4*>(audio)[2 * g + 1] = hi;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+        const long long i = (groups << 3) + threadIdx.x;
+        audio[i] = (float)pcm[i] * s;
     }
 }
 

@@ -41,6 +41,12 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def _check_out(out, shape, device):
+    if not isinstance(out, torch.Tensor) or tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 \
+            or not out.is_contiguous() or out.device != device:
+        raise ValueError('out must be a contiguous float32 tensor of shape {} on {}'.format(tuple(shape), device))
+
+
 def _window_table(window, win_length, n_fft):
     """None for the built-in periodic Hann, else a float64 table like librosa builds
     (scipy.signal.get_window(..., fftbins=True), centre padded)."""
@@ -216,15 +222,16 @@ class SalsaExtractor:
         T = self.n_frames(N)
         if out is None:
             out = torch.empty((B, 7, T, self.freq_dim), dtype=torch.float32, device=audio.device)
-        elif tuple(out.shape) != (B, 7, T, self.freq_dim) or out.dtype != torch.float32 or not out.is_contiguous():
-            raise ValueError('out must be a contiguous float32 tensor of shape {}'.format((B, 7, T, self.freq_dim)))
+        else:
+            _check_out(out, (B, 7, T, self.freq_dim), audio.device)
         need = lib.salsa_workspace_bytes(ctypes.byref(p))
         if need == 0 and B > 0:
             _native.check(_native.SALSA_EINVAL)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != audio.device:
             self._workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=audio.device)
-        _native.check(lib.salsa_extract(ctypes.byref(p), _ptr(audio), _ptr(out), _ptr(self._workspace),
-                                        self._workspace.numel(), _stream()))
+        with _native.device_of(audio) as st:
+            _native.check(lib.salsa_extract(ctypes.byref(p), _ptr(audio), _ptr(out), _ptr(self._workspace),
+                                            self._workspace.numel(), st))
         return out
 
     def extract_host(self, audio: np.ndarray, out: np.ndarray = None, clips_per_chunk: int = 16) -> np.ndarray:
@@ -265,7 +272,9 @@ class SalsaLiteExtractor:
         self.mode = _native.LITE_NIPD if feature_type == 'salsa_lite' else _native.LITE_IPD
 
     def _make_params(self, n_clips, n_samples):
-        return _params(n_clips, n_samples, fs=self.fs, n_fft=self.n_fft, hop_len=self.hop_len, win_len=self.win_len,
+        # win_len is read from the config but never used by the reference (salsa_lite_feature_extraction.py:44, :97-98:
+        # librosa's default full-length Hann): accepted for the same signature, not forwarded
+        return _params(n_clips, n_samples, fs=self.fs, n_fft=self.n_fft, hop_len=self.hop_len, win_len=self.n_fft,
                        lower_bin=self.lower_bin, upper_bin=self.upper_bin, audio_format='mic',
                        stft_precision=self.stft_precision)
 
@@ -282,9 +291,12 @@ class SalsaLiteExtractor:
         T = self.n_frames(N)
         if out is None:
             out = torch.empty((B, 7, T, self.freq_dim), dtype=torch.float32, device=audio.device)
+        else:
+            _check_out(out, (B, 7, T, self.freq_dim), audio.device)
         p = self._make_params(B, N)
-        _native.check(_native.lib().salsa_lite_extract(ctypes.byref(p), self.cutoff_bin, self.mode, _ptr(audio),
-                                                       _ptr(out), _stream()))
+        with _native.device_of(audio) as st:
+            _native.check(_native.lib().salsa_lite_extract(ctypes.byref(p), self.cutoff_bin, self.mode, _ptr(audio),
+                                                           _ptr(out), st))
         return out
 
     def extract_host(self, audio: np.ndarray, out: np.ndarray = None, clips_per_chunk: int = 16) -> np.ndarray:
@@ -297,6 +309,8 @@ class SalsaLiteExtractor:
         if out is None:
             out = np.empty((B, 7, T, self.freq_dim), dtype=np.float32)
         o = out.numpy() if isinstance(out, torch.Tensor) else out
+        if o.shape != (B, 7, T, self.freq_dim) or o.dtype != np.float32 or not o.flags['C_CONTIGUOUS']:
+            raise ValueError('out must be a C-contiguous float32 array of shape {}'.format((B, 7, T, self.freq_dim)))
         p = self._make_params(B, N)
         _native.check(_native.lib().salsa_lite_extract_host(
             ctypes.byref(p), self.cutoff_bin, self.mode, ctypes.c_void_p(a.ctypes.data),
@@ -330,7 +344,9 @@ class FeatureScaler:
             self._sums = torch.zeros((self.n_feature_channels, F, 2), dtype=torch.float64, device=features.device)
         elif self._sums.shape[1] != F:
             raise ValueError('feature dimension changed from {} to {}'.format(self._sums.shape[1], F))
-        _native.check(_native.lib().salsa_scaler_accumulate(_ptr(features), B, C, T, F, _ptr(self._sums), _stream()))
+        _native.same_device(features, self._sums)
+        with _native.device_of(features) as st:
+            _native.check(_native.lib().salsa_scaler_accumulate(_ptr(features), B, C, T, F, _ptr(self._sums), st))
         self._frames += B * T
         return self
 

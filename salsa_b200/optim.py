@@ -48,7 +48,8 @@ class Adam:
             raise ValueError('flat_grads must match the parameter buffer')
         self.step_count += 1
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
-        _native.check(_native.lib().crnn_adam_step(vp(self.params), vp(flat_grads.contiguous()), vp(self.exp_avg), vp(self.exp_avg_sq),
-                                                   self.params.numel(), ctypes.c_double(self.lr), ctypes.c_double(self.betas[0]),
-                                                   ctypes.c_double(self.betas[1]), ctypes.c_double(self.eps), self.step_count,
-                                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        _native.same_device(self.params, flat_grads)
+        with _native.device_of(self.params) as st:
+            _native.check(_native.lib().crnn_adam_step(vp(self.params), vp(flat_grads.contiguous()), vp(self.exp_avg), vp(self.exp_avg_sq),
+                                                       self.params.numel(), ctypes.c_double(self.lr), ctypes.c_double(self.betas[0]),
+                                                       ctypes.c_double(self.betas[1]), ctypes.c_double(self.eps), self.step_count, st))

@@ -200,6 +200,68 @@ def test_salsa_clip_other_ranges_and_thresholds(sb, fmt, fmin, fmax, cond):
     close(out[4:][sel], ref[4:][sel], 'spatial')
 
 
+def test_salsa_clip_bins_reach_past_the_last_full_tile(sb):
+    """fmax_doa 9300 Hz -> upper_bin 198: 197 spatial bins, i.e. 7 tiles of 32 = 224 > the 200 feature columns.  The last
+    tile's row store must stop at the feature width (it used to spill into the next row); more spatial bins than feature
+    columns is the reference's broadcast error (salsa_feature_extraction.py:373-374) -> ValueError."""
+    from oracle import salsa as osalsa, synth
+    audio = synth.make_clip(23, 'foa', seconds=2.0)
+    ref = osalsa.salsa_clip(audio, 'foa', fmax_doa=9300)
+    ex = sb.SalsaExtractor('foa', fmax_doa=9300)
+    assert ex.upper_bin - ex.lower_bin == 197
+    guard = torch.full((2, 7, ref.shape[1], 200), 7.0, device='cuda')          # clip 1 is a canary behind clip 0
+    ex.extract(torch.from_numpy(audio)[None].cuda(), out=guard[:1])
+    assert torch.all(guard[1] == 7.0), 'the eigenvector kernel wrote past the feature tensor'
+    check_feature(guard[0].cpu().numpy(), ref, what='197 spatial bins')
+    with pytest.raises(ValueError):
+        sb.SalsaExtractor('foa', fmax_doa=9600).extract(torch.from_numpy(audio)[None].cuda())      # 203 bins > 200 columns
+
+
+def test_salsa_clip_win_len_applies_to_the_spectrogram_only(sb):
+    """win_len configures MagStftExtractor only (:324-325); the spectrum behind the spatial channels is librosa's default
+    full-length Hann whatever win_len is (:359-361)."""
+    from oracle import salsa as osalsa, synth
+    audio = synth.make_clip(29, 'foa', seconds=2.0)
+    ref = osalsa.salsa_clip(audio, 'foa', win_length=400)
+    base = osalsa.salsa_clip(audio, 'foa')
+    assert np.array_equal(ref[4:], base[4:]) and not np.array_equal(ref[:4], base[:4])
+    out = sb.SalsaExtractor('foa', win_len=400).extract(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
+    check_feature(out, ref, what='win_len 400')
+    # SALSA-Lite reads win_len from the config and never uses it (salsa_lite_feature_extraction.py:44, :97-98)
+    a = torch.from_numpy(audio)[None].cuda()
+    assert torch.equal(sb.SalsaLiteExtractor(win_len=400).extract(a), sb.SalsaLiteExtractor().extract(a))
+
+
+def test_tracker_word_count_not_a_multiple_of_the_block(sb):
+    """op-level seam with 300 bins: 10 mask words = one full block of 8 warps + a block with 6 surplus warps, which must
+    not write mask words past their row."""
+    from oracle import salsa as osalsa
+    rng = np.random.default_rng(5)
+    amp = rng.standard_normal((300, 40, 1)) + 1j * rng.standard_normal((300, 40, 1))
+    amp[:, 10:25] *= 30.0                                              # a burst the tracker selects
+    steer = rng.standard_normal((300, 1, 4)) + 1j * rng.standard_normal((300, 1, 4))
+    X = amp * steer + 0.05 * (rng.standard_normal((300, 40, 4)) + 1j * rng.standard_normal((300, 40, 4)))
+    X = X.astype(np.complex64).astype(np.complex128)
+    kw = dict(audio_format='foa', fs=24000, n_fft=1024, lower_bin=1)
+    ref = osalsa.extract_normalized_eigenvector(X, **kw)
+    out = sb.extract_normalized_eigenvector(X, **kw)
+    assert np.array_equal(out != 0, ref != 0) and (ref != 0).mean() > 0.1
+    close(out, ref, '300-bin eigenvector op')
+
+
+def test_out_buffers_are_validated(sb):
+    lite = sb.SalsaLiteExtractor()
+    a = torch.zeros((1, 4, 24000), device='cuda')
+    with pytest.raises(ValueError):
+        lite.extract(a, out=torch.empty((1, 7, 81, 190), device='cuda'))
+    with pytest.raises(ValueError):
+        lite.extract(a, out=torch.empty((1, 7, 81, 191), dtype=torch.float64, device='cuda'))
+    with pytest.raises(ValueError):
+        lite.extract_host(np.zeros((1, 4, 24000), np.float32), out=np.empty((1, 7, 80, 191), np.float32))
+    with pytest.raises(ValueError):
+        sb.SalsaExtractor('foa').extract(a, out=torch.empty((1, 7, 81, 200)))             # not on the device
+
+
 def test_salsa_no_tracking_matches_oracle(sb, golden):
     from oracle import salsa as osalsa
     g = golden('clip_cases')
