@@ -92,7 +92,9 @@ def make_clips(torch, n_clips, audio_format, device, seed, n_samples=N_SAMPLES, 
                     ph = torch.exp(-2j * 3.141592653589793 * f[None] * tau[:, m:m + 1])
                     mix[:, m] += torch.fft.irfft(S * ph, n_samples)
         mix += 1e-3 * torch.randn(mix.shape, generator=g, device=device)
-        out[c0:c0 + b] = mix
+        # the dataset's clips are 16-bit wav files (librosa.load -> sample / 32768, salsa_feature_extraction.py:353):
+        # the synthetic clips live on the same grid, so the float32 and the 16-bit PCM entry points see the same audio
+        out[c0:c0 + b] = torch.round(mix * 32768.0).clamp_(-32768.0, 32767.0) / 32768.0
     return out
 
 
@@ -200,15 +202,37 @@ def env_int(name, default):
         return default
 
 
+def reference_sample_clips(args, cores):
+    """The bounded sample both arms time on the CPU: one window of --cpu-seconds per host core, cut at offsets spread over
+    the clip length out of the FIRST clips of the benchmark batch (rank 0's generator, first chunk of 40 clips: the same
+    audio the CUDA arm processes).  Falls back to the host generator (same recipe, other draws) without a CUDA device."""
+    import numpy as np
+    n_win = int(args.cpu_seconds * FS)
+    n = min(cores, 40)
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('no CUDA device')
+        audio = make_clips(torch, 40, args.format, torch.device('cuda', 0), seed=0)[:n]
+        clips = []
+        for i in range(n):
+            off = int((i + 0.5) / n * max(1, N_SAMPLES - n_win))
+            clips.append(np.ascontiguousarray(audio[i, :, off:off + n_win].cpu().numpy()))
+        del audio
+        torch.cuda.empty_cache()
+        return clips, 'windows of the first {} benchmark clips'.format(n)
+    except Exception as exc:                                   # noqa: BLE001 -- a CPU-only box still gets its baseline
+        return host_sample_clips(n, args.cpu_seconds, args.format), 'oracle.synth clips ({})'.format(repr(exc)[:60])
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python
-    that cannot travel to the GPU box) on all host cores.  Each step = one bounded sample."""
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python + librosa and cannot
+    travel to the GPU box) on all host cores.  Each step = one bounded sample of the benchmark workload."""
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    seconds = args.cpu_seconds
     fmax = 9000 if args.format == 'foa' else 4000
-    clips = host_sample_clips(cores, seconds, args.format)
+    clips, origin = reference_sample_clips(args, cores)
     vals = []
     for step in range(args.warmup + args.steps):
         v, wall, used, valid = cpu_baseline(clips, args.format, fmax, batched=False, cores=cores)
@@ -216,13 +240,14 @@ def run_reference(args, rank, world):
             vals.append((v, wall))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(w for _, w in vals) / len(vals)
-    sample = '{} clips x {} s per step (one per core), oracle loop form = reference algorithm (1 LAPACK SVD per bin)'.format(
-        len(clips), seconds)
+    sample = ('{} x {:.0f} s {} per step (one per core, offsets spread over the clip), valid-bin fraction {:.2f}; oracle loop '
+              'form = the reference algorithm (1 LAPACK SVD per selected bin); rate extrapolates linearly to the 600-clip batch'
+              ).format(len(clips), args.cpu_seconds, origin, valid)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args, world, None),
+        'config': workload_config(args, world),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -231,21 +256,18 @@ def run_reference(args, rank, world):
     return 0
 
 
-def workload_config(args, world, valid_frac):
-    cfg = {
+def workload_config(args, world):
+    """Identical in both arms (the driver compares them): the workload, and how the CPU arm samples it."""
+    lite = getattr(args, 'feature', 'salsa') == 'salsa_lite'
+    return {
         'workload': '{} {} batch: {} synthetic 4-ch 24 kHz 60 s clips per GPU, n_fft=512 hop=300 '
-                    '(BASELINE.json configs[{}])'.format('SALSA-Lite' if getattr(args, 'feature', 'salsa') == 'salsa_lite' else 'SALSA',
-                                                         args.format.upper(), args.clips,
-                                                         2 if getattr(args, 'feature', 'salsa') == 'salsa_lite' else 1),
+                    '(BASELINE.json configs[{}])'.format('SALSA-Lite' if lite else 'SALSA', args.format.upper(), args.clips, 2 if lite else 1),
         'clips_per_gpu': args.clips, 'clips_total': args.clips * world, 'audio_format': args.format,
         'stft_precision': args.stft_precision,
-        'l2_policy': 'inputs larger than L2 ({:.1f} GB audio per GPU per step)'.format(
-            args.clips * AUDIO_BYTES_PER_CLIP / 1e9),
-        'parallelism': 'clips sharded over {} GPU(s), no data-path collective'.format(world),
+        'l2_policy': 'inputs larger than L2 ({:.1f} GB audio per GPU per step)'.format(args.clips * AUDIO_BYTES_PER_CLIP / 1e9),
+        'parallelism': 'clips sharded over {} GPU(s), no data-path collective in the headline step'.format(world),
+        'cpu_arm_sample': '{:.0f} s windows of the first benchmark clips, one per host core per step (rate extrapolated)'.format(args.cpu_seconds),
     }
-    if valid_frac is not None:
-        cfg['valid_bin_fraction'] = round(valid_frac, 4)
-    return cfg
 
 
 # ------------------------------------------------------------------------------------------------
@@ -504,6 +526,133 @@ def bench_crnn(args, torch, dist, feat, rank, world, dev, peaks):
     return res
 
 
+def time_steps(torch, dist, world, dev, fn, warmup, steps):
+    """W warm-up calls, then K calls between two CUDA events on the current stream, bracketed by barrier + synchronize;
+    returns the max over ranks of the milliseconds per step."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        fn()
+    stop.record()
+    barrier()
+    t = torch.tensor([start.elapsed_time(stop) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_host_link(torch, dist, world, dev, ne, feat_bytes, chunk_clips, steps):
+    """Ceiling of the end-to-end leg: the same bytes as one `extract_host` step (ne clips of audio in, ne clips of features
+    out, in chunks of `chunk_clips`) as plain pinned cudaMemcpyAsync on two streams with NO kernels, all ranks at once."""
+    out = {}
+    for label, in_bytes in (('pcm16', AUDIO_BYTES_PER_CLIP // 2), ('f32', AUDIO_BYTES_PER_CLIP)):
+        with numa_local(dev.index or 0):
+            h_in = torch.empty(ne * in_bytes, dtype=torch.uint8, pin_memory=True)
+            h_out = torch.empty(ne * feat_bytes, dtype=torch.uint8, pin_memory=True)
+            h_in.zero_()
+            h_out.zero_()
+        d_in = torch.empty(chunk_clips * in_bytes, dtype=torch.uint8, device=dev)
+        d_out = torch.empty(chunk_clips * feat_bytes, dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def step():
+            for c0 in range(0, ne, chunk_clips):
+                n = min(chunk_clips, ne - c0)
+                with torch.cuda.stream(s_in):
+                    d_in[:n * in_bytes].copy_(h_in[c0 * in_bytes:(c0 + n) * in_bytes], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    h_out[c0 * feat_bytes:(c0 + n) * feat_bytes].copy_(d_out[:n * feat_bytes], non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+
+        step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        sec = float(te.item()) / steps
+        out[label] = {'clips_per_s_ceiling': ne * world / sec, 'h2d_gbs_per_gpu': ne * in_bytes / sec / 1e9,
+                      'd2h_gbs_per_gpu': ne * feat_bytes / sec / 1e9}
+        del h_in, h_out, d_in, d_out
+    return out
+
+
+def bench_other_configs(args, torch, dist, rank, world, dev, peak):
+    """BASELINE.json configs[2] (SALSA-Lite MIC), the MIC full-eigenvector path of configs[3] on this GPU count, and -- with
+    more than one rank -- configs[3]'s data plane: every rank's features all-gathered over NVLink (NCCL) in chunks of clips,
+    the gather of chunk i overlapped with the extraction of chunk i + 1; reported with and without the gather."""
+    import salsa_b200
+    n = args.clips
+    audio = make_clips(torch, n, 'mic', dev, seed=7000 + 1000 * rank)
+    res = {}
+    # ---- configs[2]: SALSA-Lite MIC
+    lite = salsa_b200.SalsaLiteExtractor('salsa_lite')
+    feat = torch.empty((n, 7, N_FRAMES, lite.freq_dim), dtype=torch.float32, device=dev)
+    ms = time_steps(torch, dist, world, dev, lambda: lite.extract(audio, out=feat), 2, max(3, args.steps // 4))
+    lite_bytes = AUDIO_BYTES_PER_CLIP + feature_bytes_per_clip(lite.freq_dim)
+    res['salsa_lite_mic'] = {'config': 'configs[2]: SALSA-Lite MIC, {} clips per GPU'.format(n), 'value': n * world / (ms / 1e3),
+                             'unit': UNIT, 'ms_per_step': ms, 'roofline_frac': n * lite_bytes / (ms / 1e3) / 1e9 / peak}
+    del feat
+    # ---- configs[3] without the gather: SALSA MIC full eigenvector
+    ex = salsa_b200.SalsaExtractor('mic', fmax_doa=4000)
+    feat = torch.empty((n, 7, N_FRAMES, ex.freq_dim), dtype=torch.float32, device=dev)
+    ms = time_steps(torch, dist, world, dev, lambda: ex.extract(audio, out=feat), 2, max(3, args.steps // 4))
+    fbytes = feature_bytes_per_clip(ex.freq_dim)
+    res['salsa_mic'] = {'config': 'configs[3] compute: SALSA MIC full eigenvector, {} clips per GPU, no gather'.format(n),
+                        'value': n * world / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms,
+                        'roofline_frac': n * (AUDIO_BYTES_PER_CLIP + fbytes) / (ms / 1e3) / 1e9 / peak}
+    del feat
+    torch.cuda.empty_cache()
+    if world == 1:
+        return res
+    # ---- configs[3] with its data plane
+    from salsa_b200.sharding import ChunkedFeatureGather
+    chunk = min(args.gather_chunk, n)
+    n_chunks = (n + chunk - 1) // chunk
+    recv = (world - 1) * n * fbytes
+    ms_plain = None
+    for transport in ('auto', 'nccl'):
+        gather = ChunkedFeatureGather(ex, chunk, N_SAMPLES, dev, transport=transport)
+        if transport == 'auto' and gather.transport == 'nccl':
+            res['salsa_mic_gather_p2p'] = {'unavailable': gather.fallback_reason}
+            del gather
+            continue
+        ok = gather.verify(audio[:chunk])                    # bit-level checksum of every rank's chunk after the exchange
+
+        def chunked(with_gather):
+            for c in range(n_chunks):
+                gather.step(audio[c * chunk:(c + 1) * chunk], gather=with_gather)
+            gather.finish()
+
+        if ms_plain is None:
+            ms_plain = time_steps(torch, dist, world, dev, lambda: chunked(False), 1, 3)
+        ms_gather = time_steps(torch, dist, world, dev, lambda: chunked(True), 1, 3)
+        res['salsa_mic_gather_' + gather.transport] = {
+            'config': 'configs[3]: SALSA MIC full eigenvector, {} clips over {} GPUs, features of every rank gathered on every rank in '
+                      'chunks of {} clips, the exchange of chunk i overlapped with the extraction of chunk i + 1'.format(n * world, world, chunk),
+            'transport': 'copy-engine pushes into symmetric (peer-mapped) buffers over NVLink' if gather.transport == 'p2p'
+                         else 'NCCL all_gather_into_tensor',
+            'value': n * world / (ms_gather / 1e3), 'unit': UNIT, 'ms_per_step': ms_gather,
+            'value_without_gather': n * world / (ms_plain / 1e3), 'ms_per_step_without_gather': ms_plain,
+            'nvlink_bytes_received_per_gpu': recv, 'gather_gbs_received_per_gpu': recv / (ms_gather / 1e3) / 1e9,
+            'gathered_checksums_match': bool(ok)}
+        del gather
+        torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -517,10 +666,13 @@ def main():
     ap.add_argument('--stft-precision', type=int, default=64, choices=[32, 64])
     ap.add_argument('--e2e-clips', type=int, default=120, help='clips per GPU per end-to-end step (host buffers)')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-chunk', type=int, default=8, help='clips per chunk of the host pipeline')
     ap.add_argument('--cpu-seconds', type=float, default=5.0, help='clip length of the CPU baseline sample')
+    ap.add_argument('--gather-chunk', type=int, default=50, help='clips per all-gather chunk of the configs[3] leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-crnn', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the SALSA-Lite / MIC / gather legs')
     ap.add_argument('--no-fast-mode', action='store_true', help='skip the float32-FFT comparison run')
     ap.add_argument('--crnn-batch', type=int, default=32, help='clips per CRNN forward per GPU')
     args = ap.parse_args()
@@ -541,9 +693,16 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    peaks = json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {}
+    if 'hbm_gbs' in peaks:
+        peak, peak_src = float(peaks['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+
     fmax = 9000 if args.format == 'foa' else 4000
     if args.feature == 'salsa_lite':
-        args.format, args.no_crnn, args.no_cpu_baseline = 'mic', True, True
+        args.format, args.no_crnn, args.no_cpu_baseline, args.no_other_configs = 'mic', True, True, True
         ex_kwargs = dict(feature_type='salsa_lite', stft_precision=args.stft_precision)
         ex = salsa_b200.SalsaLiteExtractor(**ex_kwargs)
     else:
@@ -588,78 +747,95 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = n_clips * world / (ms_per_step / 1e3)
     valid_frac = float((feat[: min(n_clips, 8), 4:, :, :ex.upper_bin - ex.lower_bin] != 0).float().mean().item())
-    feat_bytes = feature_bytes_per_clip(ex.freq_dim)
 
     # ---- the float32-FFT variant, for the record: speed and how far it is from the float64-FFT features ----
     fast = None
     if args.stft_precision == 64 and not args.no_fast_mode:
         ex32 = type(ex)(**{**ex_kwargs, 'stft_precision': 32})
         feat32 = torch.empty_like(feat)
-        ex32.extract(audio, out=feat32)
-        barrier()
-        start.record()
-        for _ in range(2):
-            ex32.extract(audio, out=feat32)
-        stop.record()
-        barrier()
-        t32 = torch.tensor([start.elapsed_time(stop) / 2], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+        t32 = time_steps(torch, dist, world, dev, lambda: ex32.extract(audio, out=feat32), 1, 2)
         n_sp = 4
         mism = int(((feat32[:, n_sp:] != 0) != (feat[:, n_sp:] != 0)).sum().item())
         both = (feat32[:, n_sp:] != 0) & (feat[:, n_sp:] != 0)
-        fast = {'stft_precision': 32, 'value': n_clips * world / (float(t32.item()) / 1e3), 'unit': UNIT,
-                'ms_per_step': float(t32.item()),
+        fast = {'stft_precision': 32, 'value': n_clips * world / (t32 / 1e3), 'unit': UNIT, 'ms_per_step': t32,
                 'valid_bin_mask_mismatches_vs_fp64_fft': mism, 'bins_compared': int(feat[:, n_sp:].numel()),
                 'max_abs_diff_spectrogram_db': float((feat32[:, :n_sp] - feat[:, :n_sp]).abs().max().item()),
                 'max_abs_diff_spatial_on_common_bins': float(((feat32[:, n_sp:] - feat[:, n_sp:]).abs() * both).max().item())}
-        del feat32
+        del feat32, both
 
-    # ---- end to end through the host-buffer entry point ---------------------------------------
+    # ---- end to end through the host-buffer entry points --------------------------------------
     e2e = None
     if not args.no_e2e:
         ne = min(args.e2e_clips, n_clips)
+        is_salsa = args.feature == 'salsa'
         with numa_local(dev.index or 0):
             h_audio = torch.empty((ne, 4, N_SAMPLES), dtype=torch.float32, pin_memory=True)
             h_audio.copy_(audio[:ne])
+            h_pcm = torch.empty((ne, 4, N_SAMPLES), dtype=torch.int16, pin_memory=True)
+            h_pcm.copy_(torch.round(audio[:ne] * 32768.0).to(torch.int16))          # exact: the clips live on the 16-bit grid
             h_feat = torch.empty((ne, 7, N_FRAMES, ex.freq_dim), dtype=torch.float32, pin_memory=True)
             h_feat.zero_()                                                   # first touch under the local affinity
-        ex.extract_host(h_audio, out=h_feat, clips_per_chunk=8)             # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            ex.extract_host(h_audio, out=h_feat, clips_per_chunk=8)        # synchronous
-        torch.cuda.synchronize()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        same = bool(torch.equal(h_feat[0].to(dev), feat[0]) or
-                    torch.allclose(h_feat[0].to(dev), feat[0], equal_nan=True))
-        e2e = {'value': ne * world * args.e2e_steps / float(te.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': ne * AUDIO_BYTES_PER_CLIP, 'd2h_bytes_per_step': ne * feat_bytes,
-               'clips_per_step_per_gpu': ne, 'steps': args.e2e_steps, 'matches_device_path': same,
-               'api': 'SalsaExtractor.extract_host -> salsa_extract_host (pinned host buffers, 3-stream pipeline)'}
-        del h_audio, h_feat
 
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    peaks = json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {}
+        def e2e_run(h_in):
+            ex.extract_host(h_in, out=h_feat, clips_per_chunk=args.e2e_chunk)             # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                ex.extract_host(h_in, out=h_feat, clips_per_chunk=args.e2e_chunk)        # synchronous
+            torch.cuda.synchronize()
+            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(h_feat[0].to(dev), feat[0]) or torch.allclose(h_feat[0].to(dev), feat[0], equal_nan=True))
+            return ne * world * args.e2e_steps / float(te.item()), same
+
+        v32, same32 = e2e_run(h_audio)
+        if is_salsa:
+            v16, same16 = e2e_run(h_pcm)
+        link = bench_host_link(torch, dist, world, dev, ne, feat_bytes, args.e2e_chunk, args.e2e_steps)
+        if is_salsa:
+            e2e = {'value': v16, 'unit': UNIT, 'h2d_bytes_per_step': ne * AUDIO_BYTES_PER_CLIP // 2, 'd2h_bytes_per_step': ne * feat_bytes,
+                   'clips_per_step_per_gpu': ne, 'steps': args.e2e_steps, 'matches_device_path': same16 and same32,
+                   'api': 'SalsaExtractor.extract_host(int16 PCM) -> salsa_extract_host_pcm16 (pinned host buffers: the wav files\' 16-bit '
+                          'samples in, float32 features out; 3-stream pipeline)',
+                   'value_f32_input': v32, 'h2d_bytes_per_step_f32_input': ne * AUDIO_BYTES_PER_CLIP,
+                   'host_link_ceiling': link['pcm16']['clips_per_s_ceiling'], 'frac_of_host_link': v16 / link['pcm16']['clips_per_s_ceiling'],
+                   'host_link': link}
+        else:
+            e2e = {'value': v32, 'unit': UNIT, 'h2d_bytes_per_step': ne * AUDIO_BYTES_PER_CLIP, 'd2h_bytes_per_step': ne * feat_bytes,
+                   'clips_per_step_per_gpu': ne, 'steps': args.e2e_steps, 'matches_device_path': same32,
+                   'api': 'SalsaLiteExtractor.extract_host -> salsa_lite_extract_host (pinned host buffers, 3-stream pipeline)',
+                   'host_link_ceiling': link['f32']['clips_per_s_ceiling'], 'frac_of_host_link': v32 / link['f32']['clips_per_s_ceiling'],
+                   'host_link': link}
+        del h_audio, h_feat, h_pcm
+        _native.lib().salsa_host_release()
+
     cpu_clips = None
     if rank == 0 and not args.no_cpu_baseline:
         # bounded CPU sample: one window of cpu_seconds per host core, taken at offsets spread over the
         # clip length (clip starts are often silent, which would flatter the CPU's masked-bin loop)
         cores = os.cpu_count() or 1
         n_win = int(args.cpu_seconds * FS)
+        nc = min(cores, n_clips, 40)
         cpu_clips = []
-        for i in range(min(cores, n_clips)):
-            off = int((i + 0.5) / cores * max(1, N_SAMPLES - n_win))
+        for i in range(nc):
+            off = int((i + 0.5) / nc * max(1, N_SAMPLES - n_win))
             cpu_clips.append(np.ascontiguousarray(audio[i, :, off:off + n_win].cpu().numpy()))
     crnn = None
+    pipeline = None
     if not args.no_crnn:
         pipeline = bench_pipeline(args, torch, dist, audio, rank, world, dev) if args.feature == 'salsa' else None
-        del audio
-        torch.cuda.empty_cache()
+    del audio
+    ex._workspace = None
+    torch.cuda.empty_cache()
+    if not args.no_crnn:
         crnn = bench_crnn(args, torch, dist, feat, rank, world, dev, peaks)
         crnn['pipeline'] = pipeline
+    del feat
+    torch.cuda.empty_cache()
+    other = None
+    if not args.no_other_configs:
+        other = bench_other_configs(args, torch, dist, rank, world, dev, peak)
 
     if rank != 0:
         if world > 1:
@@ -668,18 +844,16 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
-    if 'hbm_gbs' in peaks:
-        peak, peak_src = float(peaks['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     dom = max(kernels.items(), key=lambda kv: kv[1][0]) if kernels else (None, (0.0, 0))
     total_kernel_ms = sum(v[0] for v in kernels.values())
     # algorithmic bytes (audio read once + features written once, 49 925 600 B per SALSA clip) split over the
     # kernels that move them: stft_kernel reads the audio and writes the 4 spectrogram channels, eig_tile_kernel writes
     # the 3 spatial channels; the fused kernels move everything.  X and the masks between the kernels are NOT counted.
     path_bytes = n_clips * (AUDIO_BYTES_PER_CLIP + feat_bytes)
-    share = {'stft_kernel': (AUDIO_BYTES_PER_CLIP + feat_bytes * 4 // 7) if 'eig_tile_kernel' in kernels else 0,
-             'eig_tile_kernel': feat_bytes * 3 // 7}
+    eig_name = next((k for k in kernels if k.startswith('eig_') and k != 'eig_redo_kernel'), None)
+    share = {'stft_kernel': (AUDIO_BYTES_PER_CLIP + feat_bytes * 4 // 7) if eig_name else 0}
+    if eig_name:
+        share[eig_name] = feat_bytes * 3 // 7
     roofline = None
     if dom[0]:
         avg_ms = dom[1][0] / dom[1][1]
@@ -690,9 +864,10 @@ def main():
                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': avg_ms,
                     'share_of_step': dom[1][0] / total_kernel_ms,
-                    'kernels_ms_per_step': {k: v[0] / args.steps for k, v in kernels.items()},
-                    'path': {'algorithmic_bytes_per_step': path_bytes, 'achieved': path_achieved, 'frac': path_achieved / peak,
-                             'note': 'all kernels of the step: audio read once + features written once over ms_per_step'}}
+                    # the whole step (all kernels): audio read once + features written once over ms_per_step
+                    'path_bytes_per_step': path_bytes, 'path_achieved': path_achieved, 'path_frac': path_achieved / peak}
+        for k, v in kernels.items():
+            roofline['ms_' + k] = round(v[0] / args.steps, 4)
         traffic_path = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.isfile(traffic_path):
             try:
@@ -700,29 +875,28 @@ def main():
                 if tr:
                     # ncu measured bytes per clip at its own (smaller) batch; scaled to this launch
                     roofline['traffic'] = tr['dram_bytes_per_clip'] * n_clips
-                    roofline['traffic_source'] = tr.get('source')
+                    roofline['traffic_note'] = 'ncu capture of {} clips scaled to {}'.format(tr.get('clips', '?'), n_clips)
             except (ValueError, KeyError):
                 pass
 
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        clips = cpu_clips
-        v, wall, used, vfrac = cpu_baseline(clips, args.format, fmax, batched=False, cores=cores)
-        vb, wallb, _, _ = cpu_baseline(clips, args.format, fmax, batched=True, cores=cores)
+        v, wall, used, vfrac = cpu_baseline(cpu_clips, args.format, fmax, batched=False, cores=cores)
+        vb, wallb, _, _ = cpu_baseline(cpu_clips, args.format, fmax, batched=True, cores=cores)
         cpu = {'value': v, 'unit': UNIT, 'cores': used, 'kind': 'port',
                'sample': '{:.0f} s windows of {} of the benchmark clips (offsets spread over the clip), one per core, '
                          '{:.1f} s wall, valid-bin fraction {:.2f}; oracle loop form (1 LAPACK SVD per selected bin, as the '
-                         'reference)'.format(args.cpu_seconds, len(clips), wall, vfrac),
+                         'reference)'.format(args.cpu_seconds, len(cpu_clips), wall, vfrac),
                'value_stacked_lapack': vb}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32 (covariance/eigenvector) + f64 (STFT, tracker)' if args.stft_precision == 64 else 'f32 (+ f64 tracker)',
-        'data': 'synthetic', 'config': workload_config(args, world, valid_frac),
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-        'fp32_fft_mode': fast, 'crnn': crnn,
+        'data': 'synthetic', 'config': workload_config(args, world), 'valid_bin_fraction': round(valid_frac, 4),
+        'clocks': clocks, 'gpu_launches': launches, 'fp32_fft_mode': fast, 'crnn': crnn, 'other_configs': other,
+        'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
     }
     print(json.dumps(line))
     if world > 1:

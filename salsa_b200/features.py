@@ -235,12 +235,12 @@ class SalsaExtractor:
         return out
 
     def extract_host(self, audio: np.ndarray, out: np.ndarray = None, clips_per_chunk: int = 16) -> np.ndarray:
-        """Host buffers in and out ((B, 4, N) float32 -> (B, 7, T, freq_dim) float32); the library
+        """Host buffers in and out ((B, 4, N) float32 or int16 PCM -> (B, 7, T, freq_dim) float32); the library
         streams chunks of clips through the GPU.  Accepts NumPy arrays or pinned CPU torch tensors."""
         _require_cuda()
         a = audio.numpy() if isinstance(audio, torch.Tensor) else audio
-        if a.ndim != 3 or a.shape[1] != 4 or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
-            raise ValueError('audio must be a C-contiguous float32 array of shape (B, 4, N)')
+        if a.ndim != 3 or a.shape[1] != 4 or a.dtype not in (np.float32, np.int16) or not a.flags['C_CONTIGUOUS']:
+            raise ValueError('audio must be a C-contiguous float32 (or int16 PCM) array of shape (B, 4, N)')
         B, _, N = a.shape
         T = self.n_frames(N)
         if out is None:
@@ -249,8 +249,9 @@ class SalsaExtractor:
         if o.shape != (B, 7, T, self.freq_dim) or o.dtype != np.float32 or not o.flags['C_CONTIGUOUS']:
             raise ValueError('out must be a C-contiguous float32 array of shape {}'.format((B, 7, T, self.freq_dim)))
         p = self._make_params(B, N)
-        _native.check(_native.lib().salsa_extract_host(ctypes.byref(p), ctypes.c_void_p(a.ctypes.data),
-                                                       ctypes.c_void_p(o.ctypes.data), int(clips_per_chunk)))
+        # int16: the wav files' own samples (what librosa.load divides by 32768, :353); half the bytes over PCIe
+        fn = _native.lib().salsa_extract_host_pcm16 if a.dtype == np.int16 else _native.lib().salsa_extract_host
+        _native.check(fn(ctypes.byref(p), ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(o.ctypes.data), int(clips_per_chunk)))
         return out
 
 

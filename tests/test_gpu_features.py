@@ -294,6 +294,20 @@ def test_batch_equals_single_and_host_path(sb):
     assert np.array_equal(lite.extract_host(clips, clips_per_chunk=3), lb)
 
 
+def test_pcm16_host_input_is_bit_identical(sb):
+    """16-bit PCM in (the wav files' samples; librosa.load returns sample / 32768, salsa_feature_extraction.py:353) ==
+    float32 in, bit for bit; odd sample counts exercise the tail of the conversion kernel."""
+    from oracle import synth
+    clips = np.stack([synth.make_clip(60 + i, 'foa', seconds=1.0)[:, :23997] for i in range(3)])
+    pcm = np.clip(np.round(clips * 32768.0), -32768, 32767).astype(np.int16)
+    as_float = (pcm.astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+    ex = sb.SalsaExtractor('foa')
+    ref = ex.extract_host(as_float, clips_per_chunk=2)
+    out = ex.extract_host(pcm, clips_per_chunk=2)
+    assert np.array_equal(out, ref, equal_nan=True) and (ref[:, 4:] != 0).mean() > 0.05
+    assert np.array_equal(ref, ex.extract(torch.from_numpy(as_float).cuda()).cpu().numpy(), equal_nan=True)
+
+
 def test_empty_batch_and_bad_shapes(sb):
     ex = sb.SalsaExtractor('foa')
     out = ex.extract(torch.empty((0, 4, 24000), device='cuda'))

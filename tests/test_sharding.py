@@ -81,3 +81,61 @@ def test_gather_single_process():
     assert sharding.gather_clip_outputs(x, 4) is x
     with pytest.raises(ValueError):
         sharding.gather_clip_outputs(x, 5)
+
+
+class _FakeExtractor:
+    """The SalsaExtractor surface on CPU tensors: 'features' that identify (rank, clip) so that a gather can be checked."""
+    freq_dim = 5
+
+    def __init__(self, rank):
+        self.rank = rank
+
+    def n_frames(self, n_samples):
+        return 1 + n_samples // 300
+
+    def extract(self, audio, out=None):
+        out[:] = audio[:, :1, :1, None].expand_as(out) + 1000.0 * self.rank
+        return out
+
+
+def _chunk_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        n, chunk, n_samples = 7, 3, 900                         # 3 chunks, the last one short
+        audio = torch.arange(n, dtype=torch.float32)[:, None, None].expand(n, 4, n_samples).contiguous()
+        cg = sharding.ChunkedFeatureGather(_FakeExtractor(rank), chunk, n_samples, torch.device('cpu'))
+        ok = cg.verify(audio[:chunk])
+        seen = []
+        pending = []
+        for c in range(0, n, chunk):
+            a = audio[c:c + chunk]
+            pending.append((a.shape[0], c, cg.step(a)[1]))
+            if len(pending) == 2:                                # chunk i is complete once step i + 1 returned and was waited:
+                cg.work[(cg.i - 2) & 1].wait()                   # the consumer waits for the older gather, then reads it
+                m, c0, buf = pending.pop(0)
+                seen.append((c0, buf[:, :m, 0, 0, 0].clone()))
+        cg.finish()
+        for m, c0, buf in pending:
+            seen.append((c0, buf[:, :m, 0, 0, 0].clone()))
+        for c0, vals in seen:
+            want = torch.stack([torch.arange(c0, c0 + vals.shape[1], dtype=torch.float32) + 1000.0 * r for r in range(world)])
+            ok = ok and torch.equal(vals, want)
+        q.put((rank, bool(ok) and len(seen) == 3))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chunked_feature_gather_world_size_2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chunk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == {0: True, 1: True}
