@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsalsa_b200.so')
+# SALSA_B200_LIB: another build of the same library (A/B runs of kernel variants, scripts/build_variant.sh)
+LIB_PATH = os.environ.get('SALSA_B200_LIB') or os.path.join(_HERE, 'libsalsa_b200.so')
 
 SALSA_OK, SALSA_EINVAL, SALSA_ECUDA, SALSA_ENOMEM = 0, -1, -2, -3
 FORMAT_FOA, FORMAT_MIC = 0, 1

@@ -113,12 +113,33 @@ struct LaneTwiddles {
     Cx<T> w256;   // W256^lane          pass 1 -> 2
     Cx<T> w32;    // W32^(lane & 3)     pass 2 -> 3
     Cx<T> w512h;  // W512^lane / 2      real split (the 1/2 of the odd part folded in)
+    // Optional tables in shared memory (null: the powers are multiplied out in registers).
+    //   tab_a + 32 k1 = W256^(lane k1), k1 = 1..7: one conflict-free 16-byte load per power
+    //   tab_b +  4 j1 = W32^((lane & 3) j1), j1 = 1..7: four distinct addresses inside one 64-byte line per load
+    // Which of them are used is a template parameter of the transform (TAB: bit 0 = tab_a, bit 1 = tab_b).
+    const Cx<T>* tab_a;
+    const Cx<T>* tab_b;
 };
+
+constexpr int kTwiddleTabElems = 8 * 32 + 8 * 4;   // complex values of FftSmem's twiddle tables
 
 template <typename T>
 __device__ __forceinline__ LaneTwiddles<T> lane_twiddles(const FftTables<T>& tb, int lane) {
     const Cx<T> r = tb.tw_r[lane];
-    return {tb.tw_a[32 + lane], tb.tw_b[32 + lane], {(T)0.5 * r.re, (T)0.5 * r.im}};
+    return {tb.tw_a[32 + lane], tb.tw_b[32 + lane], {(T)0.5 * r.re, (T)0.5 * r.im}, nullptr, nullptr};
+}
+
+// Fills the shared-memory twiddle tables (`tab`: kTwiddleTabElems values; call by the whole CTA, barrier afterwards) ...
+template <typename T>
+__device__ __forceinline__ void load_twiddle_tables(Cx<T>* tab, const FftTables<T>& tb) {
+    for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) tab[i] = tb.tw_a[i];                      // [k1][lane]
+    for (int i = threadIdx.x; i < 8 * 4; i += blockDim.x) tab[8 * 32 + i] = tb.tw_b[(i >> 2) * 32 + (i & 3)];   // [j1][m2]
+}
+// ... and points a lane's constants at them.
+template <typename T>
+__device__ __forceinline__ void use_twiddle_tables(LaneTwiddles<T>& tw, const Cx<T>* tab, int lane) {
+    tw.tab_a = tab + lane;
+    tw.tab_b = tab + 8 * 32 + (lane & 3);
 }
 
 template <typename T> __device__ __forceinline__ Cx<T> shfl_cx(Cx<T> v, int src) {
@@ -153,16 +174,17 @@ __device__ __forceinline__ void window_frame(const float2 (&raw)[8], const T* __
     }
 }
 
-// One warp: the 512-point real transform of the windowed, packed frame in v (see window_frame).
-// X[j] = bin lane + 32 j (j = 0..7) of this lane; `nyq` = bin 256 (valid in lane 0 only).
-// `scratch` points to kScratchElems complex values of per-warp shared memory used by the two exchanges between the
-// three butterfly passes.
-template <typename T>
-__device__ __forceinline__ void warp_fft_passes(Cx<T> (&v)[8], const LaneTwiddles<T>& tw, Cx<T>* scratch, int lane, Cx<T> (&X)[8],
-                                                T& nyq) {
+// One warp: passes 1-3 of the 256-point complex transform of the windowed, packed frame in v (see window_frame).
+// z[i] = Z[lane + 32 i].  `scratch` points to kScratchElems complex values of per-warp shared memory used by the two
+// exchanges between the three butterfly passes.
+template <typename T, int TAB>
+__device__ __forceinline__ void warp_fft_core(Cx<T> (&v)[8], const LaneTwiddles<T>& tw, Cx<T>* scratch, int lane, Cx<T> (&z)[8]) {
     // ---- pass 1: 8-point DFT over n1 (stride 32), twiddle W256^(lane*k1) = w256^k1
     dft8(v);
-    {
+    if (TAB & 1) {
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) v[k1] = cmul(v[k1], tw.tab_a[32 * k1]);
+    } else {
         const Cx<T> w1 = tw.w256, w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
         v[1] = cmul(v[1], w1);
         v[2] = cmul(v[2], w2);
@@ -181,7 +203,10 @@ __device__ __forceinline__ void warp_fft_passes(Cx<T> (&v)[8], const LaneTwiddle
     for (int m1 = 0; m1 < 8; ++m1) v[m1] = scratch[k1 * kScratchPad + 4 * m1 + m2];
     __syncwarp();
     dft8(v);
-    {
+    if (TAB & 2) {
+#pragma unroll
+        for (int j1 = 1; j1 < 8; ++j1) v[j1] = cmul(v[j1], tw.tab_b[4 * j1]);
+    } else {
         const Cx<T> u1 = tw.w32, u2 = cmul(u1, u1), u3 = cmul(u2, u1), u4 = cmul(u2, u2);
         v[1] = cmul(v[1], u1);
         v[2] = cmul(v[2], u2);
@@ -197,7 +222,6 @@ __device__ __forceinline__ void warp_fft_passes(Cx<T> (&v)[8], const LaneTwiddle
     __syncwarp();
     // ---- pass 3: lane owns (k1 = lane&7, j1 = (lane>>3) + 4p), p = 0,1; 4-point DFT over m2
     //      -> z[p + 2 j2] = Z[k1 + 8 j1 + 64 j2] = Z[lane + 32 (p + 2 j2)]
-    Cx<T> z[8];
     const int pk1 = lane & 7;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -210,6 +234,15 @@ __device__ __forceinline__ void warp_fft_passes(Cx<T> (&v)[8], const LaneTwiddle
         for (int j2 = 0; j2 < 4; ++j2) z[p + 2 * j2] = w[j2];
     }
     __syncwarp();      // scratch may be reused by the caller / the next transform
+}
+
+// One warp: the 512-point real transform of the windowed, packed frame in v (see window_frame).
+// X[j] = bin lane + 32 j (j = 0..7) of this lane; `nyq` = bin 256 (valid in lane 0 only).
+template <typename T, int TAB = 0>
+__device__ __forceinline__ void warp_fft_passes(Cx<T> (&v)[8], const LaneTwiddles<T>& tw, Cx<T>* scratch, int lane, Cx<T> (&X)[8],
+                                                T& nyq) {
+    Cx<T> z[8];
+    warp_fft_core<T, TAB>(v, tw, scratch, lane, z);
     // ---- real split, in registers: X[k] = E + W512^k O with E = (Z[k] + conj Z[256-k]) / 2,
     //      O = -i (Z[k] - conj Z[256-k]) / 2.  For k = lane + 32 j the partner Z[256 - k] is z[7 - j] of lane
     //      32 - lane (lane 0: its own z[(8 - j) & 7]); W512^k = w512 * W16^j with W16^j a constant.  The factor 1/2
@@ -231,6 +264,48 @@ __device__ __forceinline__ void warp_fft_passes(Cx<T> (&v)[8], const LaneTwiddle
         const T tr = dr * wh.re - di * wh.im, ti = dr * wh.im + di * wh.re;
         X[j] = {(T)0.5 * sr + tr, (T)0.5 * si + ti};
     }
+}
+
+// The same transform with the real split done on PAIRS of bins: with E, O as above and T = W512^k O,
+//     X[k] = E + T          X[256 - k] = conj(E - T),
+// so one partner exchange and one twiddle product serve two bins (12 operations per pair instead of 2 x 10, half the
+// shuffles).  The price is the order of the upper half of the spectrum:
+//     lo[j] = X[lane + 32 j]                 j = 0..3   (bins 0..127, natural lane order)
+//     hr[j] = X[256 - lane - 32 j]           j = 0..3   (lanes 1..31: bins 129..255 except 160, 192, 224; lane 0: bins
+//                                                        256 (Nyquist), 224, 192, 160)
+//     x128  = X[128]                         (valid in lane 0)
+// upper_group() below turns (hr, x128) into "group g = bins 32 g .. 32 g + 31 in REVERSED lane order".
+template <typename T, int TAB>
+__device__ __forceinline__ void warp_fft_passes_paired(Cx<T> (&v)[8], const LaneTwiddles<T>& tw, Cx<T>* scratch, int lane,
+                                                       Cx<T> (&lo)[4], Cx<T> (&hr)[4], Cx<T>& x128) {
+    Cx<T> z[8];
+    warp_fft_core<T, TAB>(v, tw, scratch, lane, z);
+    x128 = {z[4].re, -z[4].im};                 // k = 128 pairs with itself: E = Re Z, T = -i Im Z
+    const int partner_lane = (32 - lane) & 31;
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+    const Cx<T> w16[4] = {{(T)1, (T)0}, {c1, -s1}, {h, -h}, {s1, -c1}};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // partner Z[256 - k] of k = lane + 32 j: z[7 - j] of lane 32 - lane; lane 0 (which reads from itself) pairs
+        // with its own z[(8 - j) & 7]
+        const Cx<T> send = lane == 0 ? z[(8 - j) & 7] : z[7 - j];
+        const Cx<T> b = shfl_cx(send, partner_lane);
+        const Cx<T> a = z[j];
+        const T sr = a.re + b.re, si = a.im - b.im;          // 2 E
+        const T dr = a.im + b.im, di = b.re - a.re;          // 2 O
+        const Cx<T> wh = j == 0 ? tw.w512h : cmul(tw.w512h, w16[j]);
+        const T tr = dr * wh.re - di * wh.im, ti = dr * wh.im + di * wh.re;
+        lo[j] = {(T)0.5 * sr + tr, (T)0.5 * si + ti};
+        hr[j] = {(T)0.5 * sr - tr, ti - (T)0.5 * si};
+    }
+}
+
+// Value this lane holds of upper group g = 4..7 (bin 32 g + ((32 - lane) & 31)) given hr[] / x128 of
+// warp_fft_passes_paired, already converted to whatever type V the caller works in.
+template <typename V>
+__device__ __forceinline__ V upper_group(const V (&hr)[4], V x128, int g, int lane) {
+    const V first = g == 4 ? x128 : hr[(8 - g) & 3];       // lane 0: bins 128, 160, 192, 224
+    return lane == 0 ? first : hr[7 - g];
 }
 
 // window + passes in one call

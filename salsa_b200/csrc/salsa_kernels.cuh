@@ -18,6 +18,15 @@
 
 namespace salsa {
 
+#ifndef STFT_MINB
+#define STFT_MINB 2                      // resident CTAs per SM stft_kernel is compiled for (register budget 65536 / (256 MINB))
+#endif
+#ifndef STFT_TAB
+#define STFT_TAB 2                       // pass twiddles of the transform from shared-memory tables: bit 0 pass 1, bit 1 pass 2
+#endif
+#ifndef STFT_PREFETCH
+#define STFT_PREFETCH 1                  // stft_kernel requests a warp's next frame while it transforms the current one
+#endif
 constexpr int kWarps = 8;                // warps per CTA in the STFT-bearing kernels
 constexpr int kThreads = kWarps * 32;
 constexpr float kAmin = 1e-10f;          // power_to_db amin (salsa_feature_extraction.py:195)
@@ -56,12 +65,14 @@ template <typename T>
 struct FftSmem {
     T win[kNfft];
     Cx<T> scratch[kWarps][kScratchElems];
+    Cx<T> twiddles[kTwiddleTabElems];      // pass twiddles of the TAB variants of the transform (fft.cuh)
 };
 
 template <typename T>
 __device__ __forceinline__ void load_fft_smem(FftSmem<T>& s, const FftTables<T>& tb) {
     if (tb.window)
         for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s.win[i] = tb.window[i];
+    load_twiddle_tables(s.twiddles, tb);
 }
 
 // Warp index as a value the compiler KNOWS is the same in every lane (a shuffle from lane 0): with `threadIdx.x >> 5`
@@ -72,7 +83,11 @@ __device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xfffff
 // power_to_db(ref=1, amin=1e-10, top_db=None): 10 log10(max(amin, p)) (:195).  The argument is never
 // denormal (>= amin), so the MUFU.LG2 approximation applies directly; its error (<= 2^-22 absolute
 // plus 2 ulp) is below 2e-5 dB over the whole [-100, +100] dB range.
-__device__ __forceinline__ float power_db(float p) { return 3.01029995663981195f * __log2f(fmaxf(kAmin, p)); }
+__device__ __forceinline__ float power_db(float p) {
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(kAmin, p)));     // bare MUFU.LG2: no denormal pre-scaling
+    return 3.01029995663981195f * l;
+}
 
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     float2 v;
@@ -121,6 +136,41 @@ __device__ __forceinline__ void write_logspec_row(const float (&p)[8], float p_n
     if (lane < 8) row[bands.n_lin + lane] = power_db(0.125f * (lane < 4 ? v6 : v7));
 }
 
+// The same for the layout of warp_fft_passes_paired: p[g] for g < 4 is the power of bin lane + 32 g, for g >= 4 of bin
+// 32 g + rl with rl = (32 - lane) & 31 (upper groups in reversed lane order).  In that order the 8 bins of a compressed
+// band are the 8 lanes of an aligned octet: bins 193..200 are lanes 31..24 of group 6, ..., bins 217..223 + 224 are lanes
+// 7..1 of group 6 + lane 0 of group 7, bins 225..232 lanes 31..24 of group 7, ..., bins 249..255 lanes 7..1.
+__device__ __forceinline__ void write_logspec_row_paired(const float (&p)[8], float p_nyq, float* row, BandLayout bands, int lane,
+                                                         int rl) {
+    const bool compress = bands.n_out > bands.n_lin;
+    if (!compress) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int band = (g < 4 ? lane : rl) + 32 * g - 1;
+            if (band >= 0) row[band] = power_db(p[g]);
+        }
+        if (lane == 0) row[kHalf - 1] = power_db(p_nyq);
+        return;
+    }
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+        const int band = (g < 4 ? lane : rl) + 32 * g - 1;
+        if (g > 0 || lane > 0) row[band] = power_db(p[g]);
+    }
+    if (lane == 0) row[191] = power_db(p[6]);           // bin 192
+    float r6 = lane == 0 ? p[7] : p[6];                  // lane 0: bin 224 closes the band of bins 217..224
+    float r7 = lane == 0 ? 0.0f : p[7];                  // the last band has 7 bins (249..255)
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+        r6 += __shfl_xor_sync(0xffffffffu, r6, m);
+        r7 += __shfl_xor_sync(0xffffffffu, r7, m);
+    }
+    // band 192 + i (i = 0..3) = octet 3 - i of r6, band 196 + i = octet 3 - i of r7
+    const int src = 8 * (3 - (lane & 3));
+    const float v6 = __shfl_sync(0xffffffffu, r6, src), v7 = __shfl_sync(0xffffffffu, r7, src);
+    if (lane < 8) row[bands.n_lin + lane] = power_db(0.125f * (lane < 4 ? v6 : v7));
+}
+
 // ------------------------------------------------------------------------------------------------
 // stft_kernel: grid (frame blocks, clips); one warp per (frame, channel) item.
 // ------------------------------------------------------------------------------------------------
@@ -131,13 +181,14 @@ constexpr int kStftX = 1, kStftPower0 = 2, kStftSpec = 4, kStftAny = -1;
 constexpr int kStftTiled = 8, kStftTiledAny = 16;
 
 template <typename T, int CH, int OUT>
-__global__ void __launch_bounds__(kThreads, 2) stft_kernel(StftArgs a, FftTables<T> tb) {
+__global__ void __launch_bounds__(kThreads, STFT_MINB) stft_kernel(StftArgs a, FftTables<T> tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
     load_fft_smem(s, tb);
     __syncthreads();
     const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
-    const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
+    LaneTwiddles<T> tw = lane_twiddles(tb, lane);
+    use_twiddle_tables(tw, s.twiddles, lane);
     const int clip = blockIdx.y;
     const int f0 = blockIdx.x * a.frames_per_block;
     const int f1 = min(a.n_frames, f0 + a.frames_per_block);
@@ -146,53 +197,65 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(StftArgs a, FftTables
     const bool has_p0 = OUT == kStftAny ? a.power0 != nullptr : (OUT & kStftPower0) != 0;
     const bool has_spec = OUT == kStftAny ? a.spec != nullptr : (OUT & kStftSpec) != 0;
     constexpr bool tiled = OUT != kStftAny && (OUT & (kStftTiled | kStftTiledAny)) != 0;
-    const float* clip_audio = a.audio + (long long)clip * a.n_chans * a.n_samples;
+    // a warp keeps its channel: items (frame, channel) are dealt frame-major, so warp w walks the frames
+    // f0 + w / CH, + kWarps / CH, ... of channel w % CH
+    static_assert(kWarps % CH == 0, "channels divide the warps of a CTA");
+    constexpr int kFrameStep = kWarps / CH;
+    const int ch = warp % CH;
+    const float* chan_audio = a.audio + ((long long)clip * a.n_chans + ch) * a.n_samples;
     Cx<T>* scratch = s.scratch[warp];
     const T* win = tb.window ? s.win : nullptr;
-    const int n_items = (f1 - f0) * CH;             // CH = channels transformed (a.ch_count)
-    const int lane_off = lane - a.lower + (lane < a.lower ? kTileBins - kTileFrameElems : 0);
+    const int rl = (32 - lane) & 31;             // position of this lane's bins in the upper groups (reversed order)
+    const int lo_off = lane - a.lower + (lane < a.lower ? kTileBins - kTileFrameElems : 0);
+    const int hi_off = rl - a.lower + (rl < a.lower ? kTileBins - kTileFrameElems : 0);
     float2 raw[8];
-    int t = f0 + warp / CH, ch = warp % CH;
-    if (warp < n_items) load_frame(clip_audio + (long long)ch * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, lane, raw);
-    for (int item = warp; item < n_items; item += kWarps) {
+    int t = f0 + warp / CH;
+    if (STFT_PREFETCH && t < f1) load_frame(chan_audio, a.n_samples, t * a.hop - kNfft / 2, lane, raw);
+    for (; t < f1; t += kFrameStep) {
         Cx<T> v[8];
+        if (!STFT_PREFETCH) load_frame(chan_audio, a.n_samples, t * a.hop - kNfft / 2, lane, raw);
         window_frame<T>(raw, win, tw, lane, v);
-        // `raw` is consumed: the samples of this warp's next (frame, channel) item are requested before the passes
-        const int nxt = item + kWarps;
-        const int tn = f0 + nxt / CH, chn = nxt % CH;
-        if (nxt < n_items) load_frame(clip_audio + (long long)chn * a.n_samples, a.n_samples, tn * a.hop - kNfft / 2, lane, raw);
-        Cx<T> X[8];
-        T nyq;
-        warp_fft_passes<T>(v, tw, scratch, lane, X, nyq);
+        // `raw` is consumed: the samples of this warp's next frame are requested before the passes
+        if (STFT_PREFETCH && t + kFrameStep < f1) load_frame(chan_audio, a.n_samples, (t + kFrameStep) * a.hop - kNfft / 2, lane, raw);
+        Cx<T> lo[4], hr[4], x128;
+        warp_fft_passes_paired<T, STFT_TAB>(v, tw, scratch, lane, lo, hr, x128);
+        // librosa stores complex64: round, then put the upper half into groups (reversed lane order, fft.cuh)
+        float2 hf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hf[j] = make_float2((float)hr[j].re, (float)hr[j].im);
+        const float2 x128f = make_float2((float)x128.re, (float)x128.im);
+        float2 xf[8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xf[g] = make_float2((float)lo[g].re, (float)lo[g].im);
+#pragma unroll
+        for (int g = 4; g < 8; ++g) xf[g] = upper_group(hf, x128f, g, lane);
         const long long o = ((long long)clip * a.n_frames + t);
         float2* xrow = a.X + (o * a.n_chans + ch) * a.x_pitch - a.lower;
         double* prow = a.power0 + o * nb - a.lower;
         float2* xtile = a.X + o * a.x_tiles * kTileFrameElems + ch * kTileBins;
         float p[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = lane + 32 * j;
-            const float re = (float)X[j].re, im = (float)X[j].im;     // librosa stores complex64
-            p[j] = power_f32(re, im);
+        for (int g = 0; g < 8; ++g) {
+            const int k = 32 * g + (g < 4 ? lane : rl);
+            const float re = xf[g].x, im = xf[g].y;
+            p[g] = power_f32(re, im);
             if (tiled && (unsigned)(k - a.lower) < (unsigned)nb) {
-                // tiled layout: spatial bin b = k - lower -> tile b / 32, position b % 32.  With lower < 32 that is tile j
-                // (j - 1 for the first `lower` lanes) at a per-lane offset that does not depend on j
-                if (OUT & kStftTiled) xtile[j * kTileFrameElems + lane_off] = make_float2(re, im);
-                else xtile[((k - a.lower) >> 5) * kTileFrameElems + ((k - a.lower) & 31)] = make_float2(re, im);
+                // tiled layout: spatial bin b = k - lower -> tile b / 32, position b % 32.  With lower < 32 that is tile g
+                // (g - 1 for the `lower` lanes at the bottom of the group) at a per-lane offset that does not depend on g
+                if (OUT & kStftTiled) xtile[g * kTileFrameElems + (g < 4 ? lo_off : hi_off)] = xf[g];
+                else xtile[((k - a.lower) >> 5) * kTileFrameElems + ((k - a.lower) & 31)] = xf[g];
             }
             if (!tiled && (has_x || has_p0) && (unsigned)(k - a.lower) < (unsigned)nb) {
-                if (has_x) xrow[k] = make_float2(re, im);
+                if (has_x) xrow[k] = xf[g];
                 // np.abs(complex128) ** 2 (:53-55) up to one float64 ulp
                 if (has_p0 && ch == 0) prow[k] = fma((double)re, (double)re, (double)im * (double)im);
             }
         }
         if (has_spec) {
-            const float p_nyq = power_f32((float)nyq, 0.0f);
+            const float p_nyq = hf[0].x * hf[0].x;        // lane 0: hr[0] = X[256], real
             float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
-            write_logspec_row(p, p_nyq, row, a.bands, lane);
+            write_logspec_row_paired(p, p_nyq, row, a.bands, lane, rl);
         }
-        t = tn;
-        ch = chn;
     }
 }
 
@@ -395,12 +458,12 @@ __host__ __device__ constexpr size_t eig_tile_smem_bytes() {
            (size_t)FT * kTileBins * sizeof(uint16_t) + 2 * FT * sizeof(uint32_t) + 16;
 }
 
-template <int FT, int MINB, int NSQ, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, MINB) eig_tile_kernel(EigTileArgs a) {
+// One tile: frames t0 .. t0 + nt - 1 (nt <= FT) of bin tile bt of clip `clip`; `phase` is the parity of the mbarrier
+// phase this copy completes.
+template <int FT, int NSQ, int WARPS>
+__device__ __forceinline__ void eig_tile_body(const EigTileArgs& a, unsigned char* smem_raw, int clip, int bt, int t0, int nt,
+                                              uint32_t phase, int warp, int lane) {
     constexpr int BB = kTileBins, R = FT + 2 * kHop, NT = WARPS * 32;
-    static_assert(FT % WARPS == 0 && NT >= R, "frames dealt to the warps; one copy-issuing thread per frame");
-    static_assert(FT == 32, "one mask word per lane in the compaction scan (24 frames per tile measured 7 % slower)");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);                                     // [R][4][BB]
     float* stage = reinterpret_cast<float*>(xs + R * kTileFrameElems);                    // [3][FT][BB]
     uint16_t* list = reinterpret_cast<uint16_t*>(stage + 3 * FT * BB);                    // [FT * BB]
@@ -408,18 +471,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) eig_tile_kernel(EigTileArgs 
     uint32_t* sredo = smask + FT;                                                          // [FT]
     uint64_t* bar = reinterpret_cast<uint64_t*>(sredo + FT);
     int* n_items = reinterpret_cast<int*>(bar + 1);
-    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
-    const int clip = blockIdx.z, bt = blockIdx.y;
-    const int t0 = blockIdx.x * FT;
-    const int nt = min(FT, a.n_frames - t0);
-    if (threadIdx.x == 0) {
-        tc::mbar_init(bar, 1);
-        tc::fence_barrier_init();
-    }
     if (threadIdx.x < FT) sredo[threadIdx.x] = 0u;
-    __syncthreads();
     // ---- 1
     const int n_rows = nt + 2 * kHop;
+    // (the phase cannot complete before thread 0's arrival, whatever the order in which the copies below land)
     if (threadIdx.x == 0) tc::mbar_expect_tx(bar, (uint32_t)(n_rows * kTileFrameElems * sizeof(float2)));
     if (threadIdx.x < n_rows) {
         int f = (t0 - kHop + (int)threadIdx.x) % a.n_frames;             // wrap padding of the frame axis (:43)
@@ -454,7 +509,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) eig_tile_kernel(EigTileArgs 
             if ((w >> lane) & 1u) list[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((tl << 5) | lane);
         }
     }
-    if (warp == 0) tc::mbar_wait(bar, 0);      // one warp polls the mbarrier, the others sleep at the barrier below
+    if (warp == 0) tc::mbar_wait(bar, phase);      // one warp polls the mbarrier, the others sleep at the barrier below
     __syncthreads();
     // ---- 2
     const int count = *n_items;
@@ -501,6 +556,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) eig_tile_kernel(EigTileArgs 
                 make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
     }
+}
+
+// grid (frame tiles of FT, bin tiles, clips)
+template <int FT, int MINB, int NSQ, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, MINB) eig_tile_kernel(EigTileArgs a) {
+    static_assert(FT % WARPS == 0 && WARPS * 32 >= FT + 2 * kHop, "frames dealt to the warps; one copy-issuing thread per frame");
+    static_assert(FT == 32, "one mask word per lane in the compaction scan (24 frames per tile measured 7 % slower)");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + eig_tile_smem_bytes<FT>() - 16);
+    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar, 1);
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int t0 = blockIdx.x * FT;
+    eig_tile_body<FT, NSQ, WARPS>(a, smem_raw, blockIdx.z, blockIdx.y, t0, min(FT, a.n_frames - t0), 0u, warp, lane);
 }
 
 // eig_redo_kernel: float64 re-evaluation of the bins eig_tile_kernel marked (a few per 100 000); one thread per
@@ -743,7 +815,8 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
     load_fft_smem(s, tb);
     __syncthreads();
     const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
-    const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
+    LaneTwiddles<T> tw = lane_twiddles(tb, lane);
+    use_twiddle_tables(tw, s.twiddles, lane);
     const int clip = blockIdx.y;
     const int f0 = blockIdx.x * a.frames_per_block;
     const int f1 = min(a.n_frames, f0 + a.frames_per_block);
@@ -754,6 +827,7 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
     Cx<T>* scratch = s.scratch[warp];
     const T* win = tb.window ? s.win : nullptr;
     const float inv_pi = 0.318309886183790671538f;
+    const int rl = (32 - lane) & 31;             // position of this lane's bins in the upper groups (reversed order, fft.cuh)
     float2 raw[8];
     if (f0 + warp < f1) load_frame(clip_audio, a.n_samples, (f0 + warp) * a.hop - kNfft / 2, lane, raw);
     for (int t = f0 + warp; t < f1; t += kWarps) {
@@ -765,24 +839,29 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
             // `raw` is consumed: request the next channel of this frame (or channel 0 of this warp's next frame)
             if (ch < 3) load_frame(clip_audio + (long long)(ch + 1) * a.n_samples, a.n_samples, t * a.hop - kNfft / 2, lane, raw);
             else if (t + kWarps < f1) load_frame(clip_audio, a.n_samples, (t + kWarps) * a.hop - kNfft / 2, lane, raw);
-            Cx<T> X[8];
-            T nyq;
-            warp_fft_passes<T>(v, tw, scratch, lane, X, nyq);
+            Cx<T> lo[4], hr[4], x128;
+            warp_fft_passes_paired<T, STFT_TAB>(v, tw, scratch, lane, lo, hr, x128);
+            float2 hf[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hf[j] = make_float2((float)hr[j].re, (float)hr[j].im);
+            const float2 x128f = make_float2((float)x128.re, (float)x128.im);
             float* srow = clip_feat + ch * chan_stride + (long long)t * width - a.lower;         // indexed by the bin
             float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width - a.lower;   // used for ch >= 1
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = lane + 32 * j;
-                const float re = (float)X[j].re, im = (float)X[j].im;
-                if (ch == 0 && j < NJ) x0[j] = make_float2(re, im);
+            for (int g = 0; g < 8; ++g) {
+                const int k = 32 * g + (g < 4 ? lane : rl);
+                const float2 x = g < 4 ? make_float2((float)lo[g & 3].re, (float)lo[g & 3].im) : upper_group(hf, x128f, g, lane);
+                const float re = x.x, im = x.y;
+                if (ch == 0 && g < NJ) x0[g < NJ ? g : 0] = x;
                 if ((unsigned)(k - a.lower) < (unsigned)width) {
                     srow[k] = power_db(power_f32(re, im));     // (np.abs(stft) ** 2).T -> power_to_db (:104-105)
                     if (ch > 0) {
                         float ph = 0.0f;
-                        if (j < NJ && k - a.lower < a.upper_cropped) {
+                        if (g < NJ && k - a.lower < a.upper_cropped) {
                             // X_ch conj(X_0) with exact float64 products (:111), angle in float32
-                            const double pr = (double)re * x0[j].x + (double)im * x0[j].y;
-                            const double pi = (double)im * x0[j].x - (double)re * x0[j].y;
+                            const float2 r = x0[g < NJ ? g : 0];
+                            const double pr = (double)re * r.x + (double)im * r.y;
+                            const double pi = (double)im * r.x - (double)re * r.y;
                             const float ang = atan2f((float)pi, (float)pr);
                             ph = a.mode == SALSA_LITE_IPD ? ang * inv_pi
                                                           : ang * (float)(a.inv_delta / (double)max(k, 1));
