@@ -423,7 +423,7 @@ def bench_crnn(args, torch, dist, feat, rank, world, dev, peaks):
     value = B * world / (ms / 1e3)
     # end to end: pinned host features in, host logits out; the copy of step i+1 runs on a second stream while
     # step i computes (two device input buffers)
-    nb = min(B, 16)
+    nb = B
     with numa_local(dev.index or 0):
         h_x = torch.empty((nb,) + tuple(x.shape[1:]), dtype=torch.float32, pin_memory=True)
         h_x.copy_(x[:nb])

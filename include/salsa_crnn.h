@@ -27,6 +27,46 @@
 extern "C" {
 #endif
 
+/* ---- model level: one call per batch ------------------------------------------------------------------------------
+ * What a non-Python host needs from models.seld_models.SeldModel (models/seld_models.py:39-49) and the checkpoint
+ * loading of experiments/inference.py:102-116. */
+
+/* One tensor of the reference's state dict (Lightning checkpoint ['state_dict'], keys `encoder.*` / `decoder.*`):
+ * HOST pointer to contiguous float32 values in the reference's own layout (nn.Conv2d weight (Cout, Cin, k, k),
+ * BatchNorm weight / bias / running_mean / running_var, nn.GRU weight_ih_l* / weight_hh_l* / bias_*, nn.Linear weight / bias). */
+typedef struct crnn_tensor {
+    const char *name;
+    const float *data;
+    int64_t numel;
+} crnn_tensor_t;
+
+/* Builds the inference model on the current device: folds every eval-mode BatchNorm into its convolution, packs the
+ * weights for the tensor-core kernels (planes = 1: bf16; planes = 3: three bf16 planes per value, float32-grade), stacks
+ * the two GRU directions and fuses the four heads.  Entries the model does not use (num_batches_tracked, ...) are
+ * ignored; a missing or mis-sized entry is SALSA_EINVAL.  PannResNet22(n_input_channels=7) + SeldDecoder(512, n_classes,
+ * 'reg_xyz', 'bigru', 'avg', 256).  *model_out is released with crnn_free_model(). */
+int crnn_load_weights(const crnn_tensor_t *tensors, int32_t n_tensors, int32_t planes, int32_t n_classes, void **model_out);
+int crnn_free_model(void *model);
+
+/* Bytes of device scratch crnn_forward needs for a (B, 7, T, F) batch (T = the frames actually used). */
+size_t crnn_workspace_bytes(const void *model, int32_t B, int32_t T, int32_t F);
+
+/* SeldModel.forward (models/seld_models.py:39-49): feat float32 [B][7][T_in][F] (the h5 'feature' layout; the first
+ * T_use <= T_in frames of every clip are used: dataset/database.py:205-207 trims 4801 -> 4800) ->
+ * logits float32 [B][T'][n_classes] ('event_frame_logit'), doa float32 [B][T'][3 n_classes] ('doa_frame_output', x | y | z),
+ * T' = T_use / 16 (four 2x2 poolings, floor).  mean / std float32 [n_scaled][F] (or NULL with n_scaled = 0): the data
+ * layer's (x - mean) / std on the first n_scaled channels (dataset/database.py:196-202), fused into the first kernel.
+ * All pointers are device pointers owned by the caller; nothing is allocated.  The ~30 kernels of the forward are captured
+ * into a CUDA graph the second time the same set of buffers is seen and replayed from then on (asynchronous on `stream`). */
+int crnn_forward(void *model, const float *feat, int32_t B, int32_t T_in, int32_t T_use, int32_t F, const float *mean,
+                 const float *std, int32_t n_scaled, float *logits, float *doa, void *workspace, size_t workspace_bytes,
+                 void *stream);
+
+/* "graph" (0 / 1): replay a captured CUDA graph (default) or launch the kernels one by one. */
+int crnn_model_option(const char *name, int32_t value);
+
+/* ---- operator level ------------------------------------------------------------------------------------------------ */
+
 /* nn.Conv2d(k=3, pad=1 | k=1, stride 1, bias=False) + eval-mode BatchNorm2d (+ residual add) (+ ReLU):
  * ConvBlock.forward (models/model_utils.py:213-216), _ResnetBasicBlock.forward (:352-365), the
  * downsample branch (:474-481).  tcgen05 implicit GEMM, fp32 accumulation.

@@ -29,6 +29,11 @@ class SalsaParams(ctypes.Structure):
     ]
 
 
+class CrnnTensor(ctypes.Structure):
+    """crnn_tensor_t"""
+    _fields_ = [('name', ctypes.c_char_p), ('data', ctypes.POINTER(ctypes.c_float)), ('numel', ctypes.c_int64)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -61,6 +66,11 @@ SIGNATURES = {
     'salsa_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'salsa_profile_read': (ctypes.c_int, [_i32, _vp, _vp, _vp]),
     # include/salsa_crnn.h
+    'crnn_load_weights': (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp]),
+    'crnn_free_model': (ctypes.c_int, [_vp]),
+    'crnn_workspace_bytes': (_sz, [_vp, _i32, _i32, _i32]),
+    'crnn_forward': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    'crnn_model_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),
     'crnn_conv2d': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_conv_first': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_set_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),

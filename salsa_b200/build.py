@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libsalsa_b200.so')
-SOURCES = ['salsa_abi.cu', 'crnn_abi.cu']
+SOURCES = ['salsa_abi.cu', 'crnn_abi.cu', 'crnn_model.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
 
@@ -23,13 +23,16 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, 'include', f) for f in os.listdir(os.path.join(ROOT, 'include'))]
     if not force and os.path.isfile(OUT) and os.path.getmtime(OUT) >= _newest(deps):
         return OUT
-    objs = []
-    for src in srcs:
+    objs, procs = [], []
+    for src in srcs:                      # one nvcc per translation unit, side by side
         obj = os.path.join(HERE, '_build', os.path.basename(src) + '.o')
         os.makedirs(os.path.dirname(obj), exist_ok=True)
         cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
-        subprocess.run(cmd, check=True)
+        procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
+    for cmd, proc in procs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
     subprocess.run([nvcc, '-shared', '-o', OUT] + objs + ['-lcudart'], check=True)
     return OUT
 

@@ -10,9 +10,12 @@ Eval mode only: BatchNorm uses running statistics (folded into the convolution w
 dict is loaded) and dropout is the identity.  All compute happens in the CUDA library; there is no
 PyTorch / CPU fallback.  Arithmetic: bf16 operands, fp32 accumulation (tensor cores), fp32 GRU state.
 """
+import ctypes
+
 import numpy as np
 import torch
 
+from . import _native
 from . import crnn_ops as ops
 
 BN_EPS = 1e-5
@@ -113,6 +116,20 @@ class SeldModel:
         self.training = False
         self._w = None
         self._scaler = None
+        self._native_model = None          # crnn_load_weights handle (the one-call forward)
+        self._workspace = None
+        self._out = None
+
+    def __del__(self):
+        self._release_native()
+
+    def _release_native(self):
+        if getattr(self, '_native_model', None):
+            try:
+                _native.lib().crnn_free_model(self._native_model)
+            except Exception:              # noqa: BLE001 -- interpreter shutdown
+                pass
+            self._native_model = None
 
     # ---- nn.Module-like surface -----------------------------------------------------------------
     def eval(self):
@@ -131,7 +148,10 @@ class SeldModel:
     def _fold(self, sd, conv_key, bn_prefix, pad_to=64):
         """conv weight (Cout,Cin,k,k) + eval BatchNorm -> bf16 (k*k, Cout, planes*Cin_pad), fp32 bias (Cout,)."""
         w = _t(sd[conv_key])
-        scale = _t(sd[bn_prefix + '.weight']) / torch.sqrt(_t(sd[bn_prefix + '.running_var']) + BN_EPS)
+        # float32 arithmetic with a correctly rounded square root (NumPy; torch's vectorised CPU sqrt is off by an ulp for
+        # some inputs), so that the library's own folding (crnn_model.cu: fold_conv) gives the same bits
+        var = _t(sd[bn_prefix + '.running_var']).numpy()
+        scale = torch.from_numpy(_t(sd[bn_prefix + '.weight']).numpy() / np.sqrt(var + np.float32(BN_EPS)))
         bias = _t(sd[bn_prefix + '.bias']) - _t(sd[bn_prefix + '.running_mean']) * scale
         w = w * scale[:, None, None, None]
         cout, cin, k, _ = w.shape
@@ -172,7 +192,26 @@ class SeldModel:
         W['fc1'] = (ops.split_planes(w1, self.planes).to(dev), b1.contiguous().to(dev))
         W['fc2'] = (ops.split_planes(w2, self.planes).to(dev), b2.contiguous().to(dev))
         self._w = W
+        self._load_native(sd)
         return self
+
+    def _load_native(self, sd):
+        """The same state dict through `crnn_load_weights` (include/salsa_crnn.h): the library folds and packs the weights
+        itself and keeps them for `crnn_forward`, the one-call forward a non-Python host uses."""
+        self._release_native()
+        keep, table = [], []
+        for name, value in sd.items():
+            if not (name.startswith('encoder.') or name.startswith('decoder.')) or name.endswith('num_batches_tracked'):
+                continue
+            arr = np.ascontiguousarray(_t(value).numpy(), dtype=np.float32)
+            keep.append(arr)
+            table.append(_native.CrnnTensor(name.encode(), arr.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), arr.size))
+        arr_t = (_native.CrnnTensor * len(table))(*table)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().crnn_load_weights(ctypes.cast(arr_t, ctypes.c_void_p), len(table), self.planes, self.n_classes,
+                                                          ctypes.byref(handle)))
+        self._native_model = handle
 
     # ---- forward ----------------------------------------------------------------------------------
     def set_scaler(self, mean, std):
@@ -230,7 +269,45 @@ class SeldModel:
                 'doa_frame_output': doa.reshape(B, T, 3 * self.n_classes)}
 
     def forward(self, x, n_frames=None):
-        """x: (batch_size, n_channels, n_timesteps, n_features) -> the reference's output dict (seld_models.py:39-49)."""
+        """x: (batch_size, n_channels, n_timesteps, n_features) -> the reference's output dict (seld_models.py:39-49).
+        One native call (`crnn_forward`: the whole layer schedule on a workspace this object owns, replayed as a CUDA graph)."""
+        if self._native_model is None:
+            raise RuntimeError('load_state_dict() first')
+        if x.dim() != 4 or x.shape[1] != self.encoder.n_input_channels or self.encoder.n_input_channels != 7:
+            raise ValueError('x must be (batch_size, 7, n_timesteps, n_features)')
+        if not x.is_cuda:
+            raise ValueError('x must be a CUDA tensor (salsa_b200 has no CPU fallback)')
+        x = x.to(self.device, torch.float32).contiguous()
+        B, _, T_in, F = x.shape
+        T = T_in if n_frames is None else int(n_frames)
+        lib = _native.lib()
+        with _native.device_of(x) as st:
+            need = lib.crnn_workspace_bytes(self._native_model, B, T, F)
+            if need == 0:
+                _native.check(_native.SALSA_EINVAL)
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != x.device:
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+            Tp = T // 16
+            # persistent output buffers (stable pointers keep the captured graph valid); the caller gets copies
+            if self._out is None or self._out[0].shape[:2] != (B, Tp) or self._out[0].device != x.device:
+                self._out = (torch.empty((B, Tp, self.n_classes), dtype=torch.float32, device=x.device),
+                             torch.empty((B, Tp, 3 * self.n_classes), dtype=torch.float32, device=x.device))
+            logits, doa = self._out
+            mean = std = None
+            n_scaled = 0
+            if self._scaler is not None:
+                mean = self._scaler[0].to(x.device, torch.float32).reshape(-1, F).contiguous()
+                std = self._scaler[1].to(x.device, torch.float32).reshape(-1, F).contiguous()
+                n_scaled = mean.shape[0]
+            p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+            _native.check(lib.crnn_forward(self._native_model, p(x), B, T_in, T, F, p(mean), p(std), n_scaled, p(logits), p(doa),
+                                           p(self._workspace), self._workspace.numel(), st))
+            self._keep = (x, mean, std)          # the asynchronous call reads them
+            return {'event_frame_logit': logits.clone(), 'doa_frame_output': doa.clone()}
+
+    def forward_ops(self, x, n_frames=None):
+        """The same forward operator by operator (`encode` + `decode`): every layer is its own native call on torch-allocated
+        tensors.  Bit-identical to `forward`; kept for per-layer tests and profiling."""
         return self.decode(self.encode(x, n_frames))
 
     def predict(self, x, n_frames=None):

@@ -190,3 +190,81 @@ def test_pipeline_audio_to_outputs():
     assert tuple(pred['event_frame_logit'].shape) == (2, 32, 12)          # 16 * 10 / 80 -> ratio 2
     rows = pipe.events(audio)
     assert len(rows) == 2 and all(len(r) == 5 for clip in rows for r in clip)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+def test_one_call_forward_equals_operator_by_operator(precision):
+    """`forward` = crnn_forward (the library runs the whole layer schedule on one workspace, as a CUDA graph from the second
+    call on) must be bit-identical to `forward_ops` (every layer its own call on torch-allocated tensors), which also pins
+    the library's own BatchNorm folding / weight packing (crnn_load_weights) to the Python one."""
+    import salsa_b200
+    from oracle import crnn as ocrnn
+    m = salsa_b200.SeldModel(salsa_b200.PannResNet22(7), salsa_b200.SeldDecoder(512, decoder_type='bigru', freq_pool='avg', decoder_size=256),
+                             precision=precision)
+    m.load_state_dict(ocrnn.make_state_dict(5))
+    for shape in ((2, 7, 96, 200), (1, 7, 81, 191)):            # 81 frames: odd sizes through the four floor-mode poolings
+        x = ocrnn.model_input(13, shape).cuda()
+        n_frames = 80 if shape[2] == 81 else None                # the data layer's trim (database.py:205-207)
+        want = m.forward_ops(x, n_frames=n_frames)
+        outs = [m.forward(x, n_frames=n_frames) for _ in range(3)]       # direct, captured, replayed
+        for got in outs:
+            for k in want:
+                assert torch.equal(got[k], want[k]), (precision, shape, k)
+    mean = torch.full((4, 1, 200), -50.0)
+    std = torch.full((4, 1, 200), 12.0)
+    x = ocrnn.model_input(14, (1, 7, 64, 200)).cuda()
+    m.set_scaler(mean.numpy(), std.numpy())
+    try:
+        a, b = m.forward(x), m.forward_ops(x)
+    finally:
+        m.set_scaler(None, None)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+
+
+def test_c_abi_model_entry_points_with_caller_owned_workspace():
+    """crnn_load_weights / crnn_workspace_bytes / crnn_forward through ctypes alone, as a non-Python host would call them
+    (include/salsa_crnn.h; torch only lends device memory): nothing is allocated inside the forward, a too small workspace
+    and a missing tensor are reported, results equal the Python-side model."""
+    import ctypes
+    import salsa_b200
+    from salsa_b200 import _native
+    from oracle import crnn as ocrnn
+    lib = _native.lib()
+    sd = ocrnn.make_state_dict(0)
+    arrays = {k: np.ascontiguousarray(v.detach().float().numpy()) for k, v in sd.items() if not k.endswith('num_batches_tracked')}
+
+    def table(names):
+        entries = [_native.CrnnTensor(k.encode(), arrays[k].ctypes.data_as(ctypes.POINTER(ctypes.c_float)), arrays[k].size) for k in names]
+        return (_native.CrnnTensor * len(entries))(*entries), len(entries)
+
+    t, n = table([k for k in arrays if k != 'decoder.gru.weight_hh_l1'])
+    handle = ctypes.c_void_p()
+    assert lib.crnn_load_weights(ctypes.cast(t, ctypes.c_void_p), n, 1, 12, ctypes.byref(handle)) == _native.SALSA_EINVAL
+    assert b'decoder.gru.weight_hh_l1' in lib.salsa_last_error()
+    t, n = table(list(arrays))
+    _native.check(lib.crnn_load_weights(ctypes.cast(t, ctypes.c_void_p), n, 1, 12, ctypes.byref(handle)))
+    B, T, F = 2, 128, 200
+    x = ocrnn.model_input(2, (B, 7, T, F)).cuda()
+    need = lib.crnn_workspace_bytes(handle, B, T, F)
+    assert need > 0
+    work = torch.empty(need, dtype=torch.uint8, device='cuda')
+    logits = torch.empty((B, T // 16, 12), device='cuda')
+    doa = torch.empty((B, T // 16, 36), device='cuda')
+    p = lambda a: ctypes.c_void_p(a.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    args = (handle, p(x), B, T, T, F, None, None, 0, p(logits), p(doa))
+    assert lib.crnn_forward(*args, p(work), need - 1, st) == _native.SALSA_ENOMEM
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    free_before = torch.cuda.mem_get_info()[0]
+    for _ in range(3):
+        _native.check(lib.crnn_forward(*args, p(work), need, st))
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() == before
+    assert free_before - torch.cuda.mem_get_info()[0] < 64 << 20          # graph / module bookkeeping only, no activations
+    m = salsa_b200.SeldModel(salsa_b200.PannResNet22(7), salsa_b200.SeldDecoder(512, decoder_type='bigru', freq_pool='avg', decoder_size=256))
+    m.load_state_dict(sd)
+    want = m.forward_ops(x)
+    assert torch.equal(logits, want['event_frame_logit']) and torch.equal(doa, want['doa_frame_output'])
+    _native.check(lib.crnn_free_model(handle))
