@@ -124,6 +124,14 @@ int salsa_extract(const salsa_params_t *p, const float *audio, float *feature, v
 int salsa_lite_extract(const salsa_params_t *p, int32_t cutoff_bin, int32_t mode, const float *audio,
                        float *feature, void *stream);
 
+/* LinSpecIvExtractor.extract (dataset/feature_extraction.py:273-358), the FOA "linspeciv" feature family on the same STFT
+ * front-end: audio -> feature [n_clips][7][n_frames][200] = four log-linear spectrogram channels (as salsa_extract) + the
+ * three intensity-vector channels W (Re(conj(X0) Xc) / (|IV| + 1e-8)).  lower_bin / upper_bin / audio_format of `p` are
+ * ignored; win_len / window apply to both parts, as in the reference.  Scratch: the complex64 spectrum (39 MB per 60 s clip). */
+size_t salsa_linspec_iv_workspace_bytes(const salsa_params_t *p);
+int salsa_linspec_iv(const salsa_params_t *p, const float *audio, float *feature, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
 /* Same two entry points for HOST buffers (pinned memory recommended): clips are streamed through
  * the GPU in chunks, overlapping host->device copy, kernels and device->host copy.  Synchronous. */
 int salsa_extract_host(const salsa_params_t *p, const float *audio_host, float *feature_host,

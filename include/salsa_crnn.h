@@ -139,6 +139,18 @@ int crnn_gather_time(const float *in, const int32_t *idx, float *out, int32_t B,
 int crnn_augment(const float *x, float *out, const float *y_doa, float *y_out, const int32_t *ops, int32_t B,
                  int32_t T, int32_t F, int32_t Ty, int32_t n_classes, void *stream);
 
+/* CompositeCutout.apply (utilities/transforms.py:257-283; composed behind the frequency shift for MIC SALSA features,
+ * dataset/datamodule.py:76-82) on a device batch, IN PLACE: whichever of RandomCutoutNp (:58-125), SpecAugmentNp (:128-196)
+ * or RandomCutoutHoleNp (:199-254) the host drew is a list of at most 8 rectangles per sample:
+ *   rects   int32 [B][8][4] = {first frame, end frame, first frequency, end frequency} (ends exclusive), applied in order
+ *   n_rects int32 [B]       (0 = transform skipped for this sample)
+ *   u       float64 [B][8]  the uniform [0, 1) draw behind each rectangle's fill value
+ *   minmax  fp32 [B][2]     scratch: np.min / np.max of each sample before any cut, computed here
+ * A rectangle sets channels 0 .. C - n_zero_channels - 1 to float32(min + (max - min) * u) and the last n_zero_channels
+ * channels to 0 (is_filled_last_channels = True): the reference's arithmetic, bit for bit. */
+int crnn_cutout(float *x, const int32_t *rects, const int32_t *n_rects, const double *u, float *minmax, int32_t B, int32_t C,
+                int32_t T, int32_t F, int32_t n_zero_channels, void *stream);
+
 /* BaseModel.compute_loss for output_format='reg_xyz' (models/interfaces.py:273-355; SURVEY.md 8 f1, loss row):
  * sed_loss = mean BCE-with-logits over [rows][n_classes]; doa_loss = sum over x, y, z of sum(|pred - gt| * event_gt) /
  * sum(event_gt); loss = w_sed * sed_loss + w_doa * doa_loss (seld.yml:53-55: 0.3 / 0.7).

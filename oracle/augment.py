@@ -108,3 +108,19 @@ def shift_updown(x: np.ndarray, shift_len: int, direction: str, n_last_channels:
         return shifted
     new[:-n_last_channels] = shifted
     return new
+
+
+def cutout_rects(x: np.ndarray, rects, n_zero_channels: int = None):
+    """The fill step shared by RandomCutoutNp (:100-123), SpecAugmentNp (:170-194) and RandomCutoutHoleNp (:233-252),
+    is_filled_last_channels=True: rects = [(top, bottom, left, right, u)] in order; the value of a rectangle is
+    np.random.uniform(min, max) = min + (max - min) * u with min / max of x BEFORE any cut, stored into the float32 array."""
+    lo, hi = np.min(x), np.max(x)
+    out = x.copy()
+    for top, bottom, left, right, u in rects:
+        c = float(lo) + (float(hi) - float(lo)) * u
+        if n_zero_channels is None:
+            out[:, top:bottom, left:right] = c
+        else:
+            out[:-n_zero_channels, top:bottom, left:right] = c
+            out[-n_zero_channels:, top:bottom, left:right] = 0.0
+    return out

@@ -132,6 +132,32 @@ def augment_cases():
     return out
 
 
+def extras_cases():
+    """Round-2 additions, again from the unmodified reference: the MIC training transforms with CompositeCutout behind the
+    frequency shift (dataset/datamodule.py:76-82) under np.random.seed, and LinSpecIvExtractor (dataset/feature_extraction.py:
+    273-358) on the golden FOA clip."""
+    T = ref_import.transforms_module()
+    out = {}
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal((7, 32, 48)) * 10.0 - 40.0).astype(np.float32)
+    y_sed = (rng.random((6, 12)) > 0.5).astype(np.float32)
+    y_doa = rng.standard_normal((6, 36)).astype(np.float32)
+    out['cut_x'], out['cut_y_sed'], out['cut_y_doa'] = x, y_sed, y_doa
+    joint = T.ComposeMapTransform([T.TfmapRandomSwapChannelMic(n_classes=12)])
+    single = T.ComposeTransformNp([T.RandomShiftUpDownNp(freq_shift_range=10),
+                                   T.CompositeCutout(image_aspect_ratio=32 / 48, n_zero_channels=3)])
+    for seed in range(30):
+        np.random.seed(seed)
+        xa, _, ya_doa = joint(x, y_sed, y_doa)
+        xa = single(xa)
+        out['cut_{}_x'.format(seed)] = np.ascontiguousarray(xa)
+        out['cut_{}_y_doa'.format(seed)] = np.ascontiguousarray(ya_doa)
+    fe = ref_import.other_features_module()
+    foa = np.load(os.path.join(GOLDEN_DIR, 'clip_cases.npz'))['audio_foa']
+    out['linspeciv_foa'] = fe.LinSpecIvExtractor(n_fft=512, hop_length=300, win_length=512).extract(foa).astype(np.float32)
+    return out
+
+
 def main(argv=None):
     if not ref_import.available():
         print('reference checkout not found; golden vectors can only be generated in the build container')
@@ -145,6 +171,8 @@ def main(argv=None):
         np.savez_compressed(os.path.join(GOLDEN_DIR, 'model_cases.npz'), **model_cases())
     if argv and 'augment' in argv:
         np.savez_compressed(os.path.join(GOLDEN_DIR, 'augment_cases.npz'), **augment_cases())
+    if argv and 'extras' in argv:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'extras_cases.npz'), **extras_cases())
     for fn in sorted(os.listdir(GOLDEN_DIR)):
         print('{:32s} {:10d} B'.format(fn, os.path.getsize(os.path.join(GOLDEN_DIR, fn))))
     return 0

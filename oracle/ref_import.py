@@ -50,6 +50,14 @@ def features_module():
     return importlib.import_module('dataset.salsa_feature_extraction')
 
 
+def other_features_module():
+    """-> the reference module `dataset.feature_extraction` (verbatim): the IV / GCC-PHAT / mel families.  Only the
+    classes that need nothing from librosa but `stft` / `power_to_db` can be instantiated (no `librosa.filters`)."""
+    features_module()                      # installs the stubs
+    import importlib
+    return importlib.import_module('dataset.feature_extraction')
+
+
 def transforms_module():
     """-> the reference module `utilities.transforms` (verbatim; NumPy only)."""
     _ensure_path()

@@ -56,6 +56,8 @@ SIGNATURES = {
     'salsa_workspace_bytes': (_sz, [_P]),
     'salsa_extract': (ctypes.c_int, [_P, _vp, _vp, _vp, _sz, _vp]),
     'salsa_lite_extract': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _vp]),
+    'salsa_linspec_iv_workspace_bytes': (_sz, [_P]),
+    'salsa_linspec_iv': (ctypes.c_int, [_P, _vp, _vp, _vp, _sz, _vp]),
     'salsa_extract_host': (ctypes.c_int, [_P, _vp, _vp, _i32]),
     'salsa_lite_extract_host': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _i32]),
     'salsa_extract_host_pcm16': (ctypes.c_int, [_P, _vp, _vp, _i32]),
@@ -83,6 +85,7 @@ SIGNATURES = {
     'crnn_decode_events': (ctypes.c_int, [_vp, _vp, _i32, _i32, ctypes.c_float, _vp, _vp, _vp, _vp]),
     'crnn_gather_time': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'crnn_augment': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_cutout': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _i32, _vp]),
     'crnn_seld_loss': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, _i32, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),
 }

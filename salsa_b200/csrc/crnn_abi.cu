@@ -329,6 +329,22 @@ int crnn_augment(const float* x, float* out, const float* y_doa, float* y_out, c
     return check_cuda(cudaGetLastError(), "augment_doa_kernel");
 }
 
+int crnn_cutout(float* x, const int32_t* rects, const int32_t* n_rects, const double* u, float* minmax, int32_t B, int32_t C,
+                int32_t T, int32_t F, int32_t n_zero_channels, void* stream) {
+    if (!x || !rects || !n_rects || !u || !minmax) return fail(SALSA_EINVAL, "cutout: null pointer");
+    if (n_zero_channels < 0 || n_zero_channels > C) return fail(SALSA_EINVAL, "cutout: n_zero_channels out of range");
+    if (B <= 0 || C <= 0 || T <= 0 || F <= 0) return SALSA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    sample_minmax_kernel<<<B, 1024, 0, st>>>(x, (long long)C * T * F, minmax);
+    count_launch();
+    int rc = check_cuda(cudaGetLastError(), "sample_minmax_kernel");
+    if (rc) return rc;
+    cutout_kernel<<<grid_for((long long)B * T * F, 256), 256, 0, st>>>(x, reinterpret_cast<const int4*>(rects), n_rects, u, minmax, B, C, T, F,
+                                                                      n_zero_channels);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "cutout_kernel");
+}
+
 int crnn_seld_loss(const float* logit, const float* doa, const float* event_gt, const float* doa_gt, int64_t rows, int32_t n_classes,
                    float w_sed, float w_doa, double* sums, float* loss, float* g_logit, float* g_doa, void* stream) {
     if (!logit || !doa || !event_gt || !doa_gt || !sums || !loss) return fail(SALSA_EINVAL, "seld_loss: null pointer");

@@ -472,6 +472,75 @@ __global__ void augment_kernel(const float* __restrict__ x, float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CompositeCutout (utilities/transforms.py:257-283): RandomCutoutNp (:58-125), SpecAugmentNp (:128-196) or
+// RandomCutoutHoleNp (:199-254) all reduce to "up to 8 rectangles (time x frequency) per sample, filled in order with a
+// value drawn between the sample's min and max; the last n_zero_channels channels get 0 instead".
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxCutRects = 8;
+
+// min / max of every sample (np.min(x), np.max(x) before any cut): one block per sample
+__global__ void __launch_bounds__(1024) sample_minmax_kernel(const float* __restrict__ x, long long n_per_sample, float* __restrict__ minmax) {
+    const float* p = x + (long long)blockIdx.x * n_per_sample;
+    float lo = INFINITY, hi = -INFINITY;
+    for (long long i = threadIdx.x; i < n_per_sample; i += blockDim.x) {
+        const float v = p[i];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    __shared__ float s_lo[32], s_hi[32];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, m));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, m));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_lo[threadIdx.x >> 5] = lo;
+        s_hi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        lo = threadIdx.x < (blockDim.x >> 5) ? s_lo[threadIdx.x] : INFINITY;
+        hi = threadIdx.x < (blockDim.x >> 5) ? s_hi[threadIdx.x] : -INFINITY;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, m));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, m));
+        }
+        if (threadIdx.x == 0) {
+            minmax[2 * blockIdx.x] = lo;
+            minmax[2 * blockIdx.x + 1] = hi;
+        }
+    }
+}
+
+// one thread per (sample, frame, frequency): the LAST rectangle that covers the position decides its value
+__global__ void cutout_kernel(float* __restrict__ x, const int4* __restrict__ rects, const int* __restrict__ n_rects,
+                              const double* __restrict__ u, const float* __restrict__ minmax, int B, int C, int T, int F,
+                              int n_zero_channels) {
+    const long long total = (long long)B * T * F;
+    const long long plane = (long long)T * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const long long r = i / F;
+        const int t = (int)(r % T), b = (int)(r / T);
+        int hit = -1;
+        for (int k = n_rects[b] - 1; k >= 0; --k) {
+            const int4 q = rects[b * kMaxCutRects + k];           // {top, bottom, left, right}, exclusive ends
+            if (t >= q.x && t < q.y && f >= q.z && f < q.w) {
+                hit = k;
+                break;
+            }
+        }
+        if (hit < 0) continue;
+        // np.random.uniform(min, max) = min + (max - min) * u in float64, stored into the float32 array
+        const double lo = (double)minmax[2 * b], hi = (double)minmax[2 * b + 1];
+        const float fill = (float)(lo + (hi - lo) * u[b * kMaxCutRects + hit]);
+        float* dst = x + (long long)b * C * plane + (long long)t * F + f;
+        for (int c = 0; c < C; ++c) dst[c * plane] = c < C - n_zero_channels ? fill : 0.0f;
+    }
+}
+
 // y_doa [B][Ty][3 n] = x | y | z per class: the label side of the two channel swaps
 __global__ void augment_doa_kernel(const float* __restrict__ y, float* __restrict__ out, const int4* __restrict__ ops, int B, int Ty, int n) {
     const long long total = (long long)B * Ty * n;

@@ -673,6 +673,41 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
     return check_launch("lite_kernel");
 }
 
+size_t salsa_linspec_iv_workspace_bytes(const salsa_params_t* p) {
+    if (!p || p->n_clips < 0 || p->hop_len <= 0) return 0;
+    return round256((size_t)p->n_clips * salsa_n_frames(p->n_samples, p->hop_len) * 4 * (kHalf - 1) * sizeof(float2)) + 256;
+}
+
+int salsa_linspec_iv(const salsa_params_t* p, const float* audio, float* feature, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p) return fail(SALSA_EINVAL, "params is NULL");
+    salsa_params_t q = *p;
+    q.lower_bin = 1;                       // every bin the band matrix touches: 1 .. n_fft/2 - 1
+    q.upper_bin = kHalf;
+    q.audio_format = SALSA_FORMAT_FOA;
+    int rc = validate_params(&q);
+    if (rc) return rc;
+    if (!q.is_compress_high_freq)
+        return fail(SALSA_EINVAL, "linspec_iv: only the compressed 200-band layout is implemented (the uncompressed one needs the Nyquist bin)");
+    if (q.n_clips == 0) return SALSA_OK;
+    if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    if (!workspace || workspace_bytes < salsa_linspec_iv_workspace_bytes(&q)) return fail(SALSA_ENOMEM, "workspace smaller than salsa_linspec_iv_workspace_bytes()");
+    double win[kNfft];
+    const bool builtin_hann = !q.window && q.win_len == q.n_fft;
+    if (!builtin_hann) host_window(&q, win);
+    DeviceTables tb;
+    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_frames = salsa_n_frames(q.n_samples, q.hop_len);
+    const BandLayout bands = band_layout(&q);
+    float2* X = reinterpret_cast<float2*>(workspace);
+    // one transform per (frame, channel): log-linear spectrogram rows into channels 0..3, the complex64 spectrum (one
+    // window for both, as the reference: :325-340) into the workspace
+    if ((rc = launch_stft(&q, tb, audio, X, kHalf - 1, 0, feature, 7LL * n_frames * bands.n_out, nullptr, 4, st))) return rc;
+    ProfScope prof("iv_kernel", st);
+    iv_kernel<<<dim3(n_frames, q.n_clips), 256, 0, st>>>(X, feature, n_frames, kHalf - 1, bands);
+    return check_launch("iv_kernel");
+}
+
 int salsa_pcm16_to_float(const int16_t* pcm, float* audio, int64_t n, void* stream) {
     if (!pcm || !audio) return fail(SALSA_EINVAL, "pcm16_to_float: null pointer");
     if (n <= 0) return SALSA_OK;

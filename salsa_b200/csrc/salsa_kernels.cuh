@@ -875,6 +875,54 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
 }
 
 // ------------------------------------------------------------------------------------------------
+// iv_kernel: the intensity-vector channels of LinSpecIvExtractor.extract (dataset/feature_extraction.py:342-351), FOA:
+//     IV_c = Re(conj(X_0) X_c), c = 1..3;  normal = sqrt(IVx^2 + IVy^2 + IVz^2) + 1e-8;  feature = W (IV_c / normal)
+// in float32 like the reference's complex64 arithmetic, with W the log-linear band matrix of the spectrogram (:273-300:
+// 192 single bins, then 8 bands of 8 bins -- the last of 7 -- weighted 1/8).  grid (frames, clips), thread = bin - 1;
+// X rows [clip][frame][4][x_pitch] hold bins 1 .. x_pitch (written by stft_kernel's row layout).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) iv_kernel(const float2* __restrict__ X, float* __restrict__ feature, int n_frames, int x_pitch,
+                                                 BandLayout bands) {
+    __shared__ float s_iv[3][256];
+    const int t = blockIdx.x, clip = blockIdx.y, k = threadIdx.x;          // k = bin - 1
+    const float2* row = X + ((long long)clip * n_frames + t) * 4 * x_pitch;
+    float iv[3] = {0.0f, 0.0f, 0.0f};
+    if (k < x_pitch) {
+        const float2 x0 = __ldg(row + k);
+        float sq = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 xc = __ldg(row + (c + 1) * x_pitch + k);
+            iv[c] = fmaf(x0.x, xc.x, x0.y * xc.y);
+            sq = fmaf(iv[c], iv[c], sq);
+        }
+        const float normal = sqrtf(sq) + 1e-8f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) iv[c] = iv[c] / normal;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s_iv[c][k] = iv[c];
+    __syncthreads();
+    const long long chan_stride = (long long)n_frames * bands.n_out;
+    float* out = feature + (long long)clip * 7 * chan_stride + 4 * chan_stride + (long long)t * bands.n_out;
+    if (k < bands.n_out) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v;
+            if (k < bands.n_lin) {
+                v = s_iv[c][k];                                   // band k = bin k + 1
+            } else {
+                const int first = bands.n_lin + 8 * (k - bands.n_lin);      // bins first + 1 .. first + 8, clipped below the Nyquist bin
+                v = 0.0f;
+                for (int j = 0; j < 8; ++j)
+                    if (first + j < kHalf - 1) v += 0.125f * s_iv[c][first + j];
+            }
+            out[c * chan_stride + k] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pcm16_to_float_kernel: 16-bit PCM samples -> float32, sample / 32768 (exact), as soundfile / librosa.load hand the wav
 // files of the dataset to the reference (salsa_feature_extraction.py:353).  8 samples per thread and step.
 // ------------------------------------------------------------------------------------------------

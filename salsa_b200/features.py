@@ -16,7 +16,7 @@ import torch
 from . import _native
 from ._native import SalsaParams
 
-__all__ = ['doa_bins', 'MagStftExtractor', 'extract_normalized_eigenvector', 'SalsaExtractor',
+__all__ = ['doa_bins', 'MagStftExtractor', 'LinSpecIvExtractor', 'extract_normalized_eigenvector', 'SalsaExtractor',
            'SalsaLiteExtractor', 'stft', 'FeatureScaler', 'compute_scaler']
 
 
@@ -138,6 +138,53 @@ class MagStftExtractor:
         spec = torch.empty((4, T, self.n_bands), dtype=torch.float32, device='cuda')
         _native.check(lib.salsa_stft(ctypes.byref(p), _ptr(d_audio), None, _ptr(spec), None, _stream()))
         return spec.cpu().numpy()
+
+
+class LinSpecIvExtractor:
+    """Log-linear spectrogram + intensity vector (FOA), same constructor and `extract` contract as the reference class
+    (dataset/feature_extraction.py:273-358).  `extract_batch` is the device-resident batch form."""
+
+    def __init__(self, n_fft: int, hop_length: int, win_length: int = None, window: str = 'hann',
+                 is_compress_high_freq: bool = True, stft_precision: int = 64):
+        self.n_fft, self.hop_length, self.window = n_fft, hop_length, window
+        self.eps = 1e-8
+        self.win_length = self.n_fft if win_length is None else win_length
+        assert self.win_length <= self.n_fft, 'Windown length is greater than nfft!'
+        assert n_fft == 512 or n_fft == 256, 'nfft is not 512 or 256'
+        if n_fft != 512 or not is_compress_high_freq:
+            raise NotImplementedError('salsa_b200 implements n_fft = 512 with is_compress_high_freq=True')
+        self.stft_precision = stft_precision
+        self.n_bands = 200
+        self._workspace = None
+
+    def extract_batch(self, audio: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """audio (B, 4, N) float32 CUDA -> (B, 7, T, 200) float32 CUDA, asynchronous on the current stream."""
+        _require_cuda()
+        if audio.dim() != 3 or audio.shape[1] != 4 or audio.dtype != torch.float32 or not audio.is_cuda:
+            raise ValueError('audio must be a CUDA float32 tensor of shape (B, 4, N)')
+        audio = audio.contiguous()
+        B, _, N = audio.shape
+        p = _params(B, N, n_fft=self.n_fft, hop_len=self.hop_length, win_len=self.win_length, stft_precision=self.stft_precision,
+                    window_table=_window_table(self.window, self.win_length, self.n_fft))
+        lib = _native.lib()
+        T = lib.salsa_n_frames(N, self.hop_length)
+        if out is None:
+            out = torch.empty((B, 7, T, self.n_bands), dtype=torch.float32, device=audio.device)
+        else:
+            _check_out(out, (B, 7, T, self.n_bands), audio.device)
+        need = lib.salsa_linspec_iv_workspace_bytes(ctypes.byref(p))
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != audio.device:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=audio.device)
+        with _native.device_of(audio) as st:
+            _native.check(lib.salsa_linspec_iv(ctypes.byref(p), _ptr(audio), _ptr(out), _ptr(self._workspace), self._workspace.numel(), st))
+        return out
+
+    def extract(self, audio_input: np.ndarray) -> np.ndarray:
+        """(4, n_samples) float32 -> (7, n_timeframes, 200) float32, like the reference."""
+        audio = np.ascontiguousarray(audio_input, dtype=np.float32)
+        if audio.ndim != 2 or audio.shape[0] != 4:
+            raise ValueError('audio_input must be (4, n_samples), got {}'.format(audio.shape))
+        return self.extract_batch(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
 
 
 def extract_normalized_eigenvector(X, condition_number: float = 5.0, n_hopframes: int = 3, is_tracking: bool = True,

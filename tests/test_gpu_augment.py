@@ -64,3 +64,30 @@ def test_augment_argument_checks(aug):
         aug.RandomShiftUpDownNp(n_last_channels=6)
     out, _, y = aug.BatchAugment()(x, None)                   # nothing configured: identity, labels untouched
     assert torch.equal(out, x) and y is None
+
+
+def test_composite_cutout_reproduces_the_reference(aug, golden):
+    """swap -> shift -> CompositeCutout on the device (crnn_augment + crnn_cutout), seeded like the reference's loader: the
+    arrays of the unmodified reference classes, bit for bit (fill value = float32(min + (max - min) u) with the sample's
+    min / max found on the device)."""
+    g = golden('extras_cases')
+    x = torch.from_numpy(g['cut_x'])[None].cuda()
+    y_doa = torch.from_numpy(g['cut_y_doa'])[None].cuda()
+    batch = aug.BatchAugment(aug.TfmapRandomSwapChannelMic(n_classes=12), aug.RandomShiftUpDownNp(freq_shift_range=10),
+                             aug.CompositeCutout(image_aspect_ratio=32 / 48, n_zero_channels=3))
+    for seed in range(30):
+        np.random.seed(seed)
+        xa, _, ya = batch(x, None, y_doa)
+        assert np.array_equal(xa.cpu().numpy()[0], g['cut_{}_x'.format(seed)]), seed
+        assert np.array_equal(ya.cpu().numpy()[0], g['cut_{}_y_doa'.format(seed)]), seed
+    # a batch at the training chunk size against the oracle: every sample its own rectangles
+    from oracle import augment as oaug
+    rng = np.random.default_rng(8)
+    xb = (rng.standard_normal((6, 7, 640, 200)) * 12 - 50).astype(np.float32)
+    np.random.seed(123)
+    cut = aug.CompositeCutout(always_apply=True, image_aspect_ratio=640 / 200, n_zero_channels=3)
+    b2 = aug.BatchAugment(None, None, cut)
+    ops, cuts = b2.draw(6, 200, 640)
+    out, _, _ = b2(torch.from_numpy(xb).cuda(), None, None, ops=(ops, cuts))
+    for b in range(6):
+        assert np.array_equal(out[b].cpu().numpy(), oaug.cutout_rects(xb[b], cuts[b], n_zero_channels=3)), b

@@ -358,3 +358,26 @@ def test_scaler_matches_oracle_and_sklearn(sb):
     np.testing.assert_allclose(std, ostd, rtol=1e-5, atol=1e-5)
     m2, s2 = sb.compute_scaler([feats])
     assert np.array_equal(m2, mean) and np.array_equal(s2, std)
+
+
+def test_linspec_iv_matches_golden_and_oracle(sb, golden):
+    """LinSpecIvExtractor (dataset/feature_extraction.py:273-358) on the shared STFT front-end: spectrogram channels to
+    1e-4 max(1, |ref|), intensity-vector channels (values in [-1, 1]) to 1e-4 absolute."""
+    from oracle import salsa as osalsa, synth
+    ref = golden('extras_cases')['linspeciv_foa']
+    ex = sb.LinSpecIvExtractor(n_fft=512, hop_length=300, win_length=512)
+    out = ex.extract(golden('clip_cases')['audio_foa'])
+    assert out.shape == ref.shape and out.dtype == np.float32
+    close(out[:4], ref[:4], 'linspeciv spectrogram')
+    err = np.abs(out[4:] - ref[4:])
+    print('linspeciv golden: IV max |err| {:.2e}'.format(err.max()))
+    assert err.max() <= 1e-4
+    clips = np.stack([synth.make_clip(70 + i, 'foa', seconds=3.0) for i in range(2)])
+    batch = ex.extract_batch(torch.from_numpy(clips).cuda()).cpu().numpy()
+    for i in range(2):
+        want = osalsa.linspec_iv_clip(clips[i])
+        close(batch[i, :4], want[:4], 'linspeciv spectrogram (3 s)')
+        assert np.abs(batch[i, 4:] - want[4:]).max() <= 1e-4
+        assert np.all(np.abs(batch[i, 4:]) <= 1.0 + 1e-6)
+    with pytest.raises(NotImplementedError):
+        sb.LinSpecIvExtractor(n_fft=512, hop_length=300, is_compress_high_freq=False)

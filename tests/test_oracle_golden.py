@@ -214,3 +214,40 @@ def test_augment_oracle_matches_reference_golden(golden, fmt):
         assert np.array_equal(xa, g['{}_{}_x'.format(fmt, seed)]), (fmt, seed)          # bit-exact: permutations, signs, one subtraction
         assert np.array_equal(ya, g['{}_{}_y_doa'.format(fmt, seed)]), (fmt, seed)
     assert len(seen) > 12                            # the seeds exercise many different draws
+
+
+def test_composite_cutout_draws_and_fill_match_reference_golden(golden):
+    """MIC training transforms with CompositeCutout behind the shift (dataset/datamodule.py:76-82): the host-side draws of
+    salsa_b200.augment (same NumPy calls in the same order as utilities/transforms.py:58-283) + the oracle's fill reproduce
+    the arrays the unmodified reference classes produced under np.random.seed.  No GPU involved."""
+    from oracle import augment as oaug
+    from salsa_b200 import augment
+    g = golden('extras_cases')
+    x, y_doa = g['cut_x'], g['cut_y_doa']
+    batch = augment.BatchAugment(augment.TfmapRandomSwapChannelMic(n_classes=12), augment.RandomShiftUpDownNp(freq_shift_range=10),
+                                 augment.CompositeCutout(image_aspect_ratio=32 / 48, n_zero_channels=3))
+    kinds = set()
+    for seed in range(30):
+        np.random.seed(seed)
+        ops, cuts = batch.draw(1, x.shape[2], x.shape[1])
+        m = [(ops[0, 1] >> i) & 1 for i in range(3)]
+        xa, ya = oaug.swap_mic(x, y_doa, m)
+        if ops[0, 2]:
+            xa = oaug.shift_updown(xa, int(ops[0, 2]), 'up' if ops[0, 3] == 0 else 'down')
+        xa = oaug.cutout_rects(xa, cuts[0], n_zero_channels=3)
+        kinds.add(len(cuts[0]))
+        assert np.array_equal(xa, g['cut_{}_x'.format(seed)]), seed
+        assert np.array_equal(ya, g['cut_{}_y_doa'.format(seed)]), seed
+    assert kinds == {0, 1, 2, 8}                     # skipped, random cutout, SpecAugment stripes, holes
+
+
+def test_linspec_iv_oracle_matches_reference_golden(golden):
+    """oracle.salsa.linspec_iv_clip restates LinSpecIvExtractor.extract (dataset/feature_extraction.py:316-358); the golden array
+    is the unmodified class's output on the golden FOA clip."""
+    from oracle import salsa as osalsa
+    out = osalsa.linspec_iv_clip(golden('clip_cases')['audio_foa'])
+    ref = golden('extras_cases')['linspeciv_foa']
+    assert out.shape == ref.shape == (7, 81, 200)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
+    # the spectrogram part is MagStftExtractor's (same W, same window): identical to the SALSA golden
+    np.testing.assert_allclose(ref[:4], golden('clip_cases')['logspec_foa'], rtol=0, atol=1e-6)
