@@ -474,49 +474,48 @@ def bench_crnn(args, torch, dist, feat, rank, world, dev, peaks):
                      'frac': achieved / peaks.get('bf16_tflops_sustained', 1400.0), 'traffic': None,
                      'note': 'algorithmic conv FLOPs (335.5 GFLOP per clip) over the whole forward time, GRU and heads included in the time'},
     }
-    # the float32-parity mode (three bf16 planes per operand, six plane products per MAC), for the record
+    # the float32-parity modes (operands as sums of bf16 planes on the same tensor-core kernels), for the record:
+    # bf16x2 = two planes, three plane products per MAC; bf16x3 = three planes, six products
     del model, out
     torch.cuda.empty_cache()
-    m3 = salsa_b200.SeldModel(salsa_b200.PannResNet22(n_input_channels=7),
-                              salsa_b200.SeldDecoder(512, n_classes=12, output_format='reg_xyz', decoder_type='bigru',
-                                                     freq_pool='avg', decoder_size=256), precision='bf16x3')
-    m3.load_state_dict(salsa_b200.crnn.random_state_dict(0))
-    b3 = min(B, 8)
-    m3.forward(x[:b3], n_frames=T)
-    barrier()
-    start.record()
-    for _ in range(2):
-        m3.forward(x[:b3], n_frames=T)
-    stop.record()
-    barrier()
-    res['bf16x3_parity_mode'] = {'value': b3 * world * 2 / (start.elapsed_time(stop) / 1e3), 'unit': 'clips/s', 'batch_per_gpu': b3,
-                                 'note': 'logits within 1e-4 of the float32 reference (tests/test_gpu_crnn_model.py), 6x the MMA work'}
-    del m3
+    for precision, bp, note in (('bf16x2', min(B, 16), 'logits 6-8e-5 of the output scale from the float32 reference (bar 1e-4), 3x the MMA work'),
+                                ('bf16x3', min(B, 8), 'logits 3-4e-5 from the float32 reference, 6x the MMA work')):
+        mp = salsa_b200.SeldModel(salsa_b200.PannResNet22(n_input_channels=7),
+                                  salsa_b200.SeldDecoder(512, n_classes=12, output_format='reg_xyz', decoder_type='bigru',
+                                                         freq_pool='avg', decoder_size=256), precision=precision)
+        mp.load_state_dict(salsa_b200.crnn.random_state_dict(0))
+        xp = x[:bp]
+        msp = time_steps(torch, dist, world, dev, lambda: mp.forward(xp, n_frames=T), 2, 3)
+        res[precision + '_parity_mode'] = {'value': bp * world / (msp / 1e3), 'unit': 'clips/s', 'batch_per_gpu': bp, 'note': note}
+        del mp
+        torch.cuda.empty_cache()
     if rank == 0 and not args.no_cpu_baseline:
-        # stock PyTorch / cuDNN under bf16 autocast on the same GPU, for the convolution stack only (the
-        # encoder holds 99.5 % of the FLOPs; the oracle's step-by-step GRU is a Python loop and would be unfair).
-        # A baseline beside the number, like the CPU leg: it executes the oracle's functional encoder, not the product.
+        # stock PyTorch / cuDNN on the same GPU, for the convolution stack only (the encoder holds 99.5 % of
+        # the FLOPs; the oracle's step-by-step GRU is a Python loop and would be unfair), channels_last tensors, in the
+        # three arithmetic modes that sit beside ours: bf16 autocast (beside bf16), TF32 and strict fp32 (beside the
+        # parity modes).  Baselines beside the number, like the CPU leg: they execute the oracle's functional encoder.
         try:
             from oracle import crnn as ocrnn
             sd = {k: v.to(dev) for k, v in salsa_b200.crnn.random_state_dict(0).items() if k.startswith('encoder.')}
+            sd = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
             bc = min(B, 8)
-            xc = x[:bc, :, :T].contiguous()
-            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
-                ocrnn.encoder_forward(sd, xc)
-                torch.cuda.synchronize()
-                start.record()
-                for _ in range(3):
-                    ocrnn.encoder_forward(sd, xc)
-                stop.record()
-                torch.cuda.synchronize()
-            res['cudnn_bf16_encoder_baseline'] = {
-                'value': bc * 3 / (start.elapsed_time(stop) / 1e3), 'unit': 'clips/s', 'batch': bc,
-                'note': 'torch {} eager F.conv2d / batch_norm / avg_pool2d under bf16 autocast, encoder only (no GRU, no heads)'.format(
+            xc = x[:bc, :, :T].contiguous(memory_format=torch.channels_last)
+            base = {}
+            for label, tf32, autocast in (('bf16_autocast', True, True), ('tf32', True, False), ('fp32', False, False)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.benchmark = True
+                with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+                    msb = time_steps(torch, dist, 1, dev, lambda: ocrnn.encoder_forward(sd, xc), 2, 3)
+                base[label] = bc / (msb / 1e3)
+            res['cudnn_encoder_baselines'] = {
+                'clips_per_s': base, 'batch': bc,
+                'note': 'torch {} F.conv2d / batch_norm / avg_pool2d, channels_last, cudnn.benchmark on, encoder only (no GRU, no heads)'.format(
                     torch.__version__)}
             del sd, xc
             torch.cuda.empty_cache()
         except Exception as exc:          # the baseline must never take the product line down
-            res['cudnn_bf16_encoder_baseline'] = {'unavailable': repr(exc)[:200]}
+            res['cudnn_encoder_baselines'] = {'unavailable': repr(exc)[:200]}
         import torch as _t
         tc = _crnn_cpu_chunk(None)
         tc = min(tc, _crnn_cpu_chunk(None))

@@ -12,10 +12,11 @@
  *   GEMM weights bf16       [N][K]              (nn.Linear.weight layout)
  *   bias         fp32       [Cout] / [N]        (folded BatchNorm shift or nn.Linear.bias)
  *
- * Precision: `planes` = 1 is plain bf16 operands with fp32 accumulation.  `planes` = 3 ("bf16x3") stores every
- * activation and weight as the sum of three bf16 planes laid side by side along the channel axis
- * ([..][3][C], hi | mid | lo) and accumulates the six plane products whose weight is above 2^-24 on the same
- * tensor-core path: float32-grade results at six times the MMA work, used for parity with the reference.
+ * Precision: `planes` = 1 is plain bf16 operands with fp32 accumulation.  `planes` = 2 / 3 ("bf16x2" / "bf16x3") store every
+ * activation and weight as the sum of two / three bf16 planes laid side by side along the channel axis ([..][planes][C],
+ * hi | mid | lo) and accumulate the plane products that matter (3 for two planes: hi hi, hi lo, lo hi; 6 for three) on the
+ * same tensor-core path: float32-grade results (logits 6-8e-5 / 3-4e-5 of the output scale from the float32 reference) at
+ * three / six times the MMA work, used for parity with the reference.
  */
 #ifndef SALSA_CRNN_H
 #define SALSA_CRNN_H
@@ -41,7 +42,7 @@ typedef struct crnn_tensor {
 } crnn_tensor_t;
 
 /* Builds the inference model on the current device: folds every eval-mode BatchNorm into its convolution, packs the
- * weights for the tensor-core kernels (planes = 1: bf16; planes = 3: three bf16 planes per value, float32-grade), stacks
+ * weights for the tensor-core kernels (planes = 1: bf16; 2 / 3: two / three bf16 planes per value, float32-grade), stacks
  * the two GRU directions and fuses the four heads.  Entries the model does not use (num_batches_tracked, ...) are
  * ignored; a missing or mis-sized entry is SALSA_EINVAL.  PannResNet22(n_input_channels=7) + SeldDecoder(512, n_classes,
  * 'reg_xyz', 'bigru', 'avg', 256).  *model_out is released with crnn_free_model(). */

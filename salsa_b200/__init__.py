@@ -14,5 +14,6 @@ from . import crnn_ops  # noqa: F401
 from . import augment  # noqa: F401
 from . import optim  # noqa: F401
 from .pipeline import SeldPipeline  # noqa: F401
+from . import driver  # noqa: F401
 
 __version__ = '0.1.0'

@@ -103,10 +103,10 @@ class SeldModel:
         """precision: 'bf16' (bf16 operands, fp32 accumulation: the fast mode) or 'bf16x3' (every operand is the
         sum of three bf16 planes, six plane products per MAC on the same tensor-core kernels: float32-grade
         results, used for parity with the float32 reference)."""
-        if precision not in ('bf16', 'bf16x3'):
-            raise ValueError('precision must be bf16 or bf16x3')
+        if precision not in ('bf16', 'bf16x2', 'bf16x3'):
+            raise ValueError('precision must be bf16, bf16x2 or bf16x3')
         self.precision = precision
-        self.planes = 3 if precision == 'bf16x3' else 1
+        self.planes = {'bf16': 1, 'bf16x2': 2, 'bf16x3': 3}[precision]
         self.encoder, self.decoder = encoder, decoder
         self.label_rate, self.feature_rate = label_rate, feature_rate
         self.time_downsample_ratio = float(encoder.time_downsample_ratio)

@@ -80,7 +80,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
 static int conv_generic(const void* x, const void* w, const float* bias, const void* residual, void* out, float* out_f32, int B,
                         int H, int W, int Cin, int Cout, int taps, int relu, int planes, int pool, long long pix_limit,
                         cudaStream_t st) {
-    if (planes != 1 && planes != 3) return fail(SALSA_EINVAL, "conv: planes must be 1 (bf16) or 3 (bf16x3)");
+    if (planes < 1 || planes > 3) return fail(SALSA_EINVAL, "conv: planes must be 1 (bf16), 2 (bf16x2) or 3 (bf16x3)");
     if (!x || !w || (!out && !out_f32)) return fail(SALSA_EINVAL, "conv: null pointer");
     if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv: bad dimensions");
     if (Cin % kKC != 0 || Cin <= 0) return fail(SALSA_EINVAL, "conv: Cin must be a multiple of 64");
@@ -137,7 +137,7 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
 static int conv_first(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int relu, int planes,
                       cudaStream_t st) {
     if (!x || !w || !out) return fail(SALSA_EINVAL, "conv_first: null pointer");
-    if (planes != 1 && planes != 3) return fail(SALSA_EINVAL, "conv_first: planes must be 1 or 3");
+    if (planes < 1 || planes > 3) return fail(SALSA_EINVAL, "conv_first: planes must be 1, 2 or 3");
     CUtensorMap ta, tw;
     {
         const cuuint64_t cp = (cuuint64_t)kC1 * planes;

@@ -76,7 +76,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // Epilogue of one tile for one warp (32 output pixels): TMEM -> registers -> + bias (+ residual) -> ReLU ->
 // fp32 and / or bf16 (one or three planes) NHWC stores.  `taddr0` = accumulator stage address of this warp's
-// lane quarter; with planes == 3 the correction accumulator sits N_TILE columns further.
+// lane quarter; with planes > 1 the correction accumulator sits N_TILE columns further.
 template <int N_TILE>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0, int n0, size_t pix, bool valid) {
 #pragma unroll 1
@@ -85,7 +85,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t taddr0
         const uint32_t taddr = taddr0 + (uint32_t)(j * 32);
         tc::tmem_ld32(taddr, r);
         tc::tmem_ld_wait();
-        if (a.planes == 3) {
+        if (a.planes > 1) {
             uint32_t r2[32];
             tc::tmem_ld32(taddr + (uint32_t)N_TILE, r2);
             tc::tmem_ld_wait();
@@ -320,8 +320,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
         tc::fence_barrier_init();
     }
-    // planes == 3 keeps the small correction products in their own accumulator (see the MMA issuer)
-    const int acc_cols = a.planes == 3 ? 2 * N_TILE : N_TILE;      // TMEM columns per accumulator stage
+    // planes > 1 keeps the small correction products in their own accumulator (see the MMA issuer)
+    const int acc_cols = a.planes > 1 ? 2 * N_TILE : N_TILE;      // TMEM columns per accumulator stage
     if (warp == 2) tc::tmem_alloc(tmem_slot, (uint32_t)(2 * acc_cols));
     tc::fence_before_sync();
     __syncthreads();
@@ -535,7 +535,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
         }
         tc::fence_barrier_init();
     }
-    const int acc_cols = a.planes == 3 ? 2 * N_TILE : N_TILE;
+    const int acc_cols = a.planes > 1 ? 2 * N_TILE : N_TILE;
     if (warp == 2) tc::tmem_alloc(tmem_slot, (uint32_t)(2 * acc_cols));
     tc::fence_before_sync();
     __syncthreads();

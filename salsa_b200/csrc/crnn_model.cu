@@ -307,7 +307,7 @@ extern "C" {
 
 int crnn_load_weights(const crnn_tensor_t* tensors, int32_t n_tensors, int32_t planes, int32_t n_classes, void** model_out) {
     if (!tensors || !model_out || n_tensors <= 0) return fail(SALSA_EINVAL, "crnn_load_weights: null argument");
-    if (planes != 1 && planes != 3) return fail(SALSA_EINVAL, "crnn_load_weights: planes must be 1 (bf16) or 3 (bf16x3)");
+    if (planes < 1 || planes > 3) return fail(SALSA_EINVAL, "crnn_load_weights: planes must be 1 (bf16), 2 (bf16x2) or 3 (bf16x3)");
     if (n_classes <= 0 || 4 * n_classes > 64) return fail(SALSA_EINVAL, "crnn_load_weights: at most 16 classes");
     Table t;
     for (int i = 0; i < n_tensors; ++i)

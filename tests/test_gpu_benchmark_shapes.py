@@ -46,10 +46,10 @@ def oracle_outputs():
     return out
 
 
-# bars: bf16x3 is the float32-parity mode (north_star: 1e-4 relative); bf16 rounds every activation to 8 mantissa bits, its
-# envelope is a few 1e-2 of the output scale and is measured, not hidden
+# bars: bf16x3 and bf16x2 are the float32-parity modes (north_star: 1e-4 relative; measured 3-4e-5 and 6-8e-5); bf16 rounds
+# every activation to 8 mantissa bits, its envelope is a few 1e-2 of the output scale and is measured, not hidden
 @pytest.mark.parametrize('shape', [(2, 7, 640, 200), (1, 7, 4800, 200)])
-@pytest.mark.parametrize('precision,bar', [('bf16x3', 1e-4), ('bf16', 6e-2)])
+@pytest.mark.parametrize('precision,bar', [('bf16x3', 1e-4), ('bf16x2', 1e-4), ('bf16', 6e-2)])
 def test_crnn_forward_at_benchmark_shapes(oracle_outputs, shape, precision, bar):
     m, _ = _model(precision)
     x, ref = oracle_outputs[shape]

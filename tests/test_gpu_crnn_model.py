@@ -192,7 +192,7 @@ def test_pipeline_audio_to_outputs():
     assert len(rows) == 2 and all(len(r) == 5 for clip in rows for r in clip)
 
 
-@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+@pytest.mark.parametrize('precision', ['bf16', 'bf16x2', 'bf16x3'])
 def test_one_call_forward_equals_operator_by_operator(precision):
     """`forward` = crnn_forward (the library runs the whole layer schedule on one workspace, as a CUDA graph from the second
     call on) must be bit-identical to `forward_ops` (every layer its own call on torch-allocated tensors), which also pins

@@ -381,3 +381,42 @@ def test_linspec_iv_matches_golden_and_oracle(sb, golden):
         assert np.all(np.abs(batch[i, 4:]) <= 1.0 + 1e-6)
     with pytest.raises(NotImplementedError):
         sb.LinSpecIvExtractor(n_fft=512, hop_length=300, is_compress_high_freq=False)
+
+
+def test_script_level_seam_writes_the_reference_layout(sb, tmp_path):
+    """extract_features(data_config, ...) (dataset/salsa_feature_extraction.py:265-385): wav directory in, the reference's
+    directory layout out, features equal to the oracle on the same 16-bit audio, scaler = compute_scaler of the dev split."""
+    import wave
+    from oracle import salsa as osalsa, synth
+    from salsa_b200 import driver
+    data_dir, feat_dir = tmp_path / 'data', tmp_path / 'feat'
+    clips = {}
+    for split, n in (('foa_dev', 3), ('foa_eval', 1)):
+        (data_dir / split).mkdir(parents=True)
+        for i in range(n):
+            pcm = np.clip(np.round(synth.make_clip(90 + 10 * len(clips) + i, 'foa', seconds=1.0 + 0.5 * (i == 2)) * 32768), -32768, 32767).astype(np.int16)
+            name = 'fold1_room1_mix{:03d}.wav'.format(i)
+            with wave.open(str(data_dir / split / name), 'wb') as w:
+                w.setnchannels(4)
+                w.setsampwidth(2)
+                w.setframerate(24000)
+                w.writeframes(np.ascontiguousarray(pcm.T).tobytes())
+            clips[(split, name)] = pcm.astype(np.float32) / np.float32(32768.0)
+    cfg = {'data_dir': str(data_dir), 'feature_dir': str(feat_dir),
+           'data': dict(format='foa', fs=24000, n_fft=512, hop_len=300, win_len=512, fmin_doa=50, fmax_doa=9000)}
+    written = {}
+    root = driver.extract_features(cfg, batch_clips=2, writer=lambda path, arrays: written.__setitem__(path, arrays))
+    assert root == str(feat_dir / 'salsa' / 'foa' / '24000fs_512nfft_300nhop_5cond_9000fmaxdoa')
+    dev_feats = []
+    for (split, name), audio in clips.items():
+        f = written[str(feat_dir / 'salsa' / 'foa' / '24000fs_512nfft_300nhop_5cond_9000fmaxdoa' / split / name.replace('wav', 'h5'))]['feature']
+        ref = osalsa.salsa_clip(audio, 'foa')
+        check_feature(f, ref, what='{}/{}'.format(split, name))
+        if split == 'foa_dev':
+            dev_feats.append(ref)
+    sc = written[str(feat_dir / 'salsa' / 'foa' / '24000fs_512nfft_300nhop_5cond_9000fmaxdoa' / 'foa_feature_scaler.h5')]
+    mean, std = osalsa.compute_scaler(dev_feats)
+    assert sc['mean'].shape == (4, 1, 200) and sc['mean'].dtype == np.float32
+    np.testing.assert_allclose(sc['mean'], mean, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(sc['std'], std, rtol=0, atol=2e-4)
+    assert (feat_dir / 'salsa' / 'foa' / '24000fs_512nfft_300nhop_5cond_9000fmaxdoa' / 'foa_eval').is_dir()

@@ -47,3 +47,28 @@ def test_learning_rate_schedule_matches_np_interp():
     assert lr == pytest.approx((1e-4 + 1e-2) / 2) and mom == pytest.approx(0.85)
     assert s.at(49, 99)[0] == pytest.approx(np.interp(4999, [0, 2250, 4500, 5000], (1e-4, 1e-2, 1e-3, 1e-4)))
     assert s.at(60, 0) == (1e-4, 0.9)                           # beyond the last milestone np.interp holds the end value
+
+
+def test_driver_descriptions_and_wav_reader(tmp_path):
+    """Directory names of the script-level seam (dataset/salsa_feature_extraction.py:315-321, salsa_lite...:69) and the 16-bit
+    wav reader behind it."""
+    import wave
+    import numpy as np
+    from salsa_b200 import driver
+    cfg = {'data': dict(format='foa', fs=24000, n_fft=512, hop_len=300, win_len=512, fmin_doa=50, fmax_doa=9000)}
+    assert driver.feature_description(cfg) == '24000fs_512nfft_300nhop_5cond_9000fmaxdoa'
+    assert driver.feature_description(cfg, cond_num=0, is_tracking=False, is_compress_high_freq=False) == \
+        '24000fs_512nfft_300nhop_0cond_9000fmaxdoa_notracking_nocompress'
+    cfg['data']['fmax_doa'] = 20000                               # clipped at fs / 2 (:299)
+    assert driver.feature_description(cfg, 'salsa_lite') == '24000fs_512nfft_300nhop_12000fmaxdoa'
+    pcm = (np.random.default_rng(0).integers(-3000, 3000, size=(4, 1000))).astype(np.int16)
+    path = str(tmp_path / 'a.wav')
+    with wave.open(path, 'wb') as w:
+        w.setnchannels(4)
+        w.setsampwidth(2)
+        w.setframerate(24000)
+        w.writeframes(np.ascontiguousarray(pcm.T).tobytes())
+    assert np.array_equal(driver.read_wav_pcm16(path, 24000), pcm)
+    import pytest
+    with pytest.raises(ValueError):
+        driver.read_wav_pcm16(path, 16000)
