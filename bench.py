@@ -652,6 +652,47 @@ def bench_other_configs(args, torch, dist, rank, world, dev, peak):
     return res
 
 
+def bench_train(args, torch, dist, rank, world, dev):
+    """BASELINE.json configs[4]: CRNN training on on-the-fly SALSA features, bf16, data-parallel.  Per step and rank: 32 audio
+    chunks of 8 s -> SALSA FOA features (native) -> channel-swap / frequency-shift augmentation (native) -> forward + backward
+    (3x3 convolutions forward + input gradient native; weight gradients, BatchNorm, GRU, heads: torch / cuDNN autograd) ->
+    loss (native) -> bucketed bf16 gradient all-reduce overlapped with the backward pass (NCCL) -> Adam (native)."""
+    import numpy as np
+    import salsa_b200
+    from salsa_b200 import augment, train
+    B, n_samp = args.train_batch, 8 * FS
+    audio = make_clips(torch, B, 'foa', dev, seed=9000 + 1000 * rank, n_samples=n_samp, chunk=B)
+    ex = salsa_b200.SalsaExtractor('foa')
+    aug = augment.BatchAugment(augment.TfmapRandomSwapChannelFoa(n_classes=12), augment.RandomShiftUpDownNp(freq_shift_range=10))
+    sched = salsa_b200.optim.LearningRateScheduler(steps_per_epoch=100, max_epochs=50)
+    tr = train.SeldTrainer(salsa_b200.crnn.random_state_dict(0), scheduler=sched, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(77 + rank)
+    tgt = {'event_frame_gt': (torch.rand((B, 80, 12), generator=g, device=dev) > 0.8).float(),
+           'doa_frame_gt': torch.rand((B, 80, 36), generator=g, device=dev) * 2 - 1}
+    np.random.seed(1234 + rank)
+    losses = []
+
+    def step():
+        feat = ex.extract(audio)[:, :, :640]                 # 641 -> 640 frames (database.py:205-207)
+        x, _, y_doa = aug(feat, tgt['event_frame_gt'], tgt['doa_frame_gt'])
+        losses.append(tr.step(x, {'event_frame_gt': tgt['event_frame_gt'], 'doa_frame_gt': y_doa}))
+
+    ms = time_steps(torch, dist, world, dev, step, 3, max(3, args.steps))
+    first, last = float(losses[0][0].item()), float(losses[-1][0].item())
+    # the feature part alone, for the split
+    ms_feat = time_steps(torch, dist, world, dev, lambda: ex.extract(audio), 1, 3)
+    n_params = int(tr.flat.numel())
+    return {'config': 'configs[4]: CRNN (ResNet22 + BiGRU) training step on on-the-fly SALSA FOA features, bf16 autocast, batch {} x (7, 640, 200) '
+                      'per GPU, {} GPU(s) data-parallel'.format(B, world),
+            'value': B * world / (ms / 1e3), 'unit': 'chunks/s (8 s each)', 'audio_min_per_s': B * world * 8 / 60.0 / (ms / 1e3),
+            'ms_per_step': ms, 'ms_features': ms_feat, 'loss_first_step': first, 'loss_last_step': last, 'parameters': n_params,
+            'allreduce': 'bucketed bf16 all-reduce of the flat gradient ({:.1f} MB on the wire per step), launched per bucket during the '
+                         'backward pass'.format(n_params * 2 / 1e6) if world > 1 else 'single rank: none',
+            'native': 'SALSA features, augmentation, 3x3 convolution forward + input gradient (tcgen05), loss, Adam',
+            'library': 'convolution weight gradients, BatchNorm (batch statistics), pooling, dropout, BiGRU, heads: torch / cuDNN autograd'}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -674,6 +715,8 @@ def main():
     ap.add_argument('--no-other-configs', action='store_true', help='skip the SALSA-Lite / MIC / gather legs')
     ap.add_argument('--no-fast-mode', action='store_true', help='skip the float32-FFT comparison run')
     ap.add_argument('--crnn-batch', type=int, default=32, help='clips per CRNN forward per GPU')
+    ap.add_argument('--train-batch', type=int, default=32, help='8 s chunks per training step per GPU')
+    ap.add_argument('--no-train', action='store_true', help='skip the configs[4] training-step leg')
     args = ap.parse_args()
 
     rank, world, local_rank = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
@@ -835,6 +878,10 @@ def main():
     other = None
     if not args.no_other_configs:
         other = bench_other_configs(args, torch, dist, rank, world, dev, peak)
+    train_leg = None
+    if not args.no_train and args.feature == 'salsa':
+        torch.cuda.empty_cache()
+        train_leg = bench_train(args, torch, dist, rank, world, dev)
 
     if rank != 0:
         if world > 1:
@@ -894,7 +941,7 @@ def main():
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32 (covariance/eigenvector) + f64 (STFT, tracker)' if args.stft_precision == 64 else 'f32 (+ f64 tracker)',
         'data': 'synthetic', 'config': workload_config(args, world), 'valid_bin_fraction': round(valid_frac, 4),
-        'clocks': clocks, 'gpu_launches': launches, 'fp32_fft_mode': fast, 'crnn': crnn, 'other_configs': other,
+        'clocks': clocks, 'gpu_launches': launches, 'fp32_fft_mode': fast, 'crnn': crnn, 'other_configs': other, 'train_step': train_leg,
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
     }
     print(json.dumps(line))

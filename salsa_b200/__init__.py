@@ -15,5 +15,6 @@ from . import augment  # noqa: F401
 from . import optim  # noqa: F401
 from .pipeline import SeldPipeline  # noqa: F401
 from . import driver  # noqa: F401
+from . import train  # noqa: F401
 
 __version__ = '0.1.0'

@@ -338,6 +338,18 @@ SALSA_HD int principal_eigenvector(const Herm4<T>& Rin, int n_sq_rt, bool second
             c[i] = {sel(c0.re, c1.re, c2.re, c3.re) * cs, sel(c0.im, c1.im, c2.im, c3.im) * cs};
         }
         herm_matvec(B, c, v);
+        if (!second_product && NSQ == 2) {
+            // B = R^4 exactly here (no rescaling between two squarings) and c = R^4 e_p / B_pp, v = B c: the Rayleigh quotient
+            // of B at c is a lower bound of lambda1^4, exact to O((lambda2/lambda1)^8) -- 2.6e-6 at the coherence threshold 5,
+            // i.e. 6e-7 in lambda1, two orders below the certification margin 4 tau of the rank-1 test
+            Cx<T> num = {(T)0, (T)0}, den = {(T)0, (T)0};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dot_pair_acc(num, c[i], v[i]);
+                abs2_pair_acc(den, c[i]);
+            }
+            lam1_pow4 = (num.re + num.im) * rcp_scale<T>(den.re + den.im);
+        }
         if (second_product) {                // exponent 3 * 2^n_sq instead of 2 * 2^n_sq for half the price of a squaring
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[i] = v[i];

@@ -196,7 +196,10 @@ static EigArgs eig_args(const salsa_params_t* p) {
     // Without a usable gap (no test, cond <= 1) iterate longer.
     int n_sq = 10, n_mv = 1;
     if (e.test && p->cond_num > 1.0) {
-        const double need = log(1e7) / log(p->cond_num);
+#ifndef EIG_CONTAMINATION
+#define EIG_CONTAMINATION 1e-7
+#endif
+        const double need = log(1.0 / EIG_CONTAMINATION) / log(p->cond_num);
         n_sq = (int)ceil(log2(need)) - 1;
         n_sq = std::max(2, std::min(10, n_sq));
         if (n_sq > 2 && 3.0 * ldexp(1.0, n_sq - 1) >= need) {

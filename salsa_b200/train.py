@@ -1,0 +1,228 @@
+"""On-the-fly training step of the SELD CRNN (BASELINE.json configs[4]).
+
+The reference trains through PyTorch Lightning: `training_step` (models/seld_models.py:51-76) = forward in train mode ->
+`interpolate_tensor` to the label rate -> `compute_loss` (models/interfaces.py:273-355), Adam with the piecewise-linear
+lr / beta1 schedule (utilities/learning_utils.py:17-52), DDP gradient all-reduce (experiments/train.py:98-104).  Here:
+
+  native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 convolutions' forward and input gradient
+                              (the tcgen05 implicit-GEMM kernel; dgrad = the same kernel on flipped / transposed weights),
+                              the loss with its output gradients (`crnn_seld_loss`), the Adam step (`crnn_adam_step`)
+  torch / cuDNN (library)     the convolutions' weight gradient, BatchNorm with batch statistics, pooling, dropout, the
+                              BiGRU and the heads, through autograd -- not native yet, and said so wherever a number is quoted
+  torch.distributed           bucketed bf16 all-reduce of the flat gradient buffer, started per bucket while the backward
+                              pass is still running (`GradAllReduce`; NCCL on the GPU box, gloo in the CPU tests)
+
+Parameters live in ONE flat float32 buffer (the optimiser's view) with per-tensor views carrying the reference's state-dict
+names, so `state_dict()` interchanges with reference checkpoints and with the inference model (`SeldModel.load_state_dict`).
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import crnn_ops as ops
+from .optim import Adam, LearningRateScheduler
+
+__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3']
+
+
+class NativeConv3x3(torch.autograd.Function):
+    """3x3 / pad 1 / stride 1 convolution without bias on channels_last bf16 tensors.  forward: `crnn_conv2d`.  backward:
+    input gradient = `crnn_conv2d` of the output gradient with the taps flipped and Cin / Cout exchanged; weight gradient =
+    torch.nn.grad.conv2d_weight (cuDNN) until the native wgrad exists."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wp = w.detach().permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
+        out = ops.conv2d(xb.permute(0, 2, 3, 1), wp)                       # NHWC view of the channels_last tensor
+        ctx.save_for_backward(xb, w)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, w = ctx.saved_tensors
+        gyb = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wt = w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
+            dx = ops.conv2d(gyb.permute(0, 2, 3, 1), wt).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            dw = torch.nn.grad.conv2d_weight(xb, w.shape, gyb, padding=1).to(w.dtype)
+        return dx, dw
+
+
+class GradAllReduce:
+    """Averages a flat gradient buffer over the process group in buckets, each bucket's all-reduce started (asynchronously,
+    bf16 on the wire by default) as soon as every parameter inside it has its gradient, i.e. while the backward pass of the
+    earlier layers is still running.  `params` are the per-tensor views in FORWARD order; the backward pass fills them back
+    to front, so buckets are cut from the end."""
+
+    def __init__(self, flat_grad: torch.Tensor, offsets, bucket_bytes: int = 8 << 20, wire_dtype=torch.bfloat16, group=None):
+        self.flat, self.group, self.wire = flat_grad, group, wire_dtype
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # buckets = runs of whole parameters, cut from the last parameter backwards
+        self.buckets = []                      # (lo, hi) element ranges
+        self.bucket_of = {}                    # parameter index -> bucket index
+        hi = offsets[-1][1] if offsets else 0
+        cur = []
+        for i in range(len(offsets) - 1, -1, -1):
+            cur.append(i)
+            lo = offsets[i][0]
+            if (hi - lo) * 4 >= bucket_bytes or i == 0:
+                for j in cur:
+                    self.bucket_of[j] = len(self.buckets)
+                self.buckets.append((lo, hi))
+                hi, cur = lo, []
+        self.pending = [0] * len(self.buckets)
+        self.sizes = [sum(1 for j in self.bucket_of.values() if j == b) for b in range(len(self.buckets))]
+        self.work = []
+
+    def reset(self):
+        self.pending = list(self.sizes)
+        self.work = []
+
+    def ready(self, param_index: int):
+        """Call when parameter `param_index` has its final gradient (a post-accumulate-grad hook)."""
+        b = self.bucket_of[param_index]
+        self.pending[b] -= 1
+        if self.pending[b] == 0 and self.world > 1:
+            lo, hi = self.buckets[b]
+            chunk = self.flat[lo:hi]
+            wire = chunk if self.wire is None or chunk.dtype == self.wire else chunk.to(self.wire)
+            self.work.append((dist.all_reduce(wire, group=self.group, async_op=True), wire, chunk))
+
+    def finish(self):
+        """Waits for the buckets in flight and writes the averages back into the flat buffer."""
+        for b, n in enumerate(self.pending):          # parameters that received no gradient this step
+            if n > 0 and self.world > 1:
+                self.pending[b] = 1
+                self.ready(next(j for j, bb in self.bucket_of.items() if bb == b))
+        for work, wire, chunk in self.work:
+            work.wait()
+            if wire is not chunk:
+                chunk.copy_(wire)
+            chunk.div_(self.world)
+        self.work = []
+
+
+class SeldTrainer:
+    """PannResNet22 + SeldDecoder(bigru, avg) in train mode with the reference's state-dict names, one flat parameter buffer,
+    and `step(x, target_dict)` = the reference's training step."""
+
+    def __init__(self, state_dict, n_classes: int = 12, label_rate: int = 10, feature_rate: float = 80.0, loss_weight=(0.3, 0.7),
+                 lr: float = 1e-3, device='cuda', native_conv: bool = True, group=None, scheduler: LearningRateScheduler = None,
+                 bucket_bytes: int = 8 << 20, wire_dtype=torch.bfloat16, autocast: bool = True, dropout: bool = True):
+        """native_conv / autocast / dropout = False are for tests (a pure torch float32 reference of the same step);
+        wire_dtype None sends float32 gradients."""
+        self.device = torch.device(device)
+        self.n_classes, self.loss_weight = n_classes, tuple(loss_weight)
+        self.ratio = 16.0 * label_rate / feature_rate                 # time_downsample_ratio * label_rate / feature_rate
+        self.native_conv = native_conv and self.device.type == 'cuda'
+        self.autocast = autocast and self.device.type == 'cuda'
+        self.dropout = dropout
+        self.scheduler = scheduler
+        names = [k for k, v in state_dict.items() if not (k.endswith('running_mean') or k.endswith('running_var') or k.endswith('num_batches_tracked'))]
+        sizes = [int(torch.as_tensor(state_dict[k]).numel()) for k in names]
+        total = sum(sizes)
+        self.flat = torch.empty(total, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.params, self.offsets, at = {}, [], 0
+        for k, n in zip(names, sizes):
+            src = torch.as_tensor(state_dict[k]).detach().to(self.device, torch.float32)
+            self.flat[at:at + n].copy_(src.reshape(-1))
+            p = self.flat[at:at + n].view(src.shape).requires_grad_(True)
+            p.grad = self.flat_grad[at:at + n].view(src.shape)        # autograd accumulates in place into the flat gradient
+            self.params[k] = p
+            self.offsets.append((at, at + n))
+            at += n
+        self.buffers = {k: torch.as_tensor(v).detach().clone().to(self.device) for k, v in state_dict.items() if k not in self.params}
+        self.reducer = GradAllReduce(self.flat_grad, self.offsets, bucket_bytes=bucket_bytes, wire_dtype=wire_dtype, group=group)
+        for i, p in enumerate(self.params.values()):
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self.reducer.ready(i))
+        self.optimizer = Adam(self.flat, lr=lr) if self.device.type == 'cuda' else None
+        self.gru = torch.nn.GRU(input_size=512, hidden_size=256, num_layers=2, batch_first=True, bidirectional=True, dropout=0.3).to(self.device)
+        self.training = True
+        self.epoch, self.batch_idx = 0, 0
+
+    # ---- state ------------------------------------------------------------------------------------------------------
+    def state_dict(self):
+        out = {k: v.detach().clone() for k, v in self.params.items()}
+        out.update({k: v.clone() for k, v in self.buffers.items()})
+        return out
+
+    # ---- forward (train mode) ---------------------------------------------------------------------------------------
+    def _conv3(self, x, key):
+        w = self.params[key]
+        if self.native_conv and w.shape[1] % 64 == 0:
+            return NativeConv3x3.apply(x, w)
+        return F.conv2d(x, w, padding=1)
+
+    def _bn(self, x, prefix):
+        return F.batch_norm(x, self.buffers[prefix + '.running_mean'], self.buffers[prefix + '.running_var'], self.params[prefix + '.weight'],
+                            self.params[prefix + '.bias'], training=self.training, momentum=0.1, eps=1e-5)
+
+    def forward(self, x):
+        """x (B, 7, T, F) float32 -> {'event_frame_logit': (B, T/16, n), 'doa_frame_output': (B, T/16, 3n)}, with autograd."""
+        tr = self.training and self.dropout
+        x = x.contiguous(memory_format=torch.channels_last)
+        with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast):
+            p = 'encoder.conv_block1'
+            x = F.relu(self._bn(F.conv2d(x, self.params[p + '.conv1.weight'], padding=1), p + '.bn1'))      # 7 input channels: cuDNN
+            x = F.relu(self._bn(self._conv3(x, p + '.conv2.weight'), p + '.bn2'))
+            x = F.avg_pool2d(x, 2)                                            # ConvBlock.forward (models/model_utils.py:213-220)
+            for li in range(1, 5):
+                for bi in range(2):
+                    q = 'encoder.resnet.layer{}.{}'.format(li, bi)
+                    identity = x
+                    out = F.avg_pool2d(x, 2) if (li > 1 and bi == 0) else x   # _ResnetBasicBlock.forward (:345-367)
+                    out = F.relu(self._bn(self._conv3(out, q + '.conv1.weight'), q + '.bn1'))
+                    out = F.dropout(out, p=0.1, training=tr)
+                    out = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2')
+                    if li > 1 and bi == 0:
+                        identity = F.avg_pool2d(identity, 2)
+                        identity = self._bn(F.conv2d(identity, self.params[q + '.downsample.1.weight']), q + '.downsample.2')
+                    x = F.relu(out + identity)
+            x = torch.mean(x.float(), dim=3).transpose(1, 2)                  # SeldDecoder.forward (models/decoders.py:106-154)
+            gru_params = {k[len('decoder.gru.'):]: v for k, v in self.params.items() if k.startswith('decoder.gru.')}
+            self.gru.train(self.training)
+            self.gru.dropout = 0.3 if tr else 0.0                             # inter-layer dropout (models/decoders.py:44-46)
+            x, _ = torch.func.functional_call(self.gru, gru_params, (x,))
+
+            def head(name, act=None):
+                h = F.relu(F.linear(F.dropout(x, 0.2, tr), self.params['decoder.{}_fc_1.weight'.format(name)], self.params['decoder.{}_fc_1.bias'.format(name)]))
+                h = F.linear(F.dropout(h, 0.2, tr), self.params['decoder.{}_fc_2.weight'.format(name)], self.params['decoder.{}_fc_2.bias'.format(name)])
+                return h if act is None else act(h)
+
+            logit = head('event')
+            doa = torch.cat([head('x', torch.tanh), head('y', torch.tanh), head('z', torch.tanh)], dim=-1)
+        return {'event_frame_logit': logit.float(), 'doa_frame_output': doa.float()}
+
+    # ---- one training step ------------------------------------------------------------------------------------------
+    def step(self, x, target_dict):
+        """forward -> interpolate to the label rate -> loss -> backward (bucketed all-reduce overlapped) -> Adam.
+        Returns (loss, sed_loss, doa_loss) as a float32 tensor (3,)."""
+        self.flat_grad.zero_()
+        self.reducer.reset()
+        out = self.forward(x)
+        idx = torch.as_tensor(ops.interpolate_index(out['event_frame_logit'].shape[1], self.ratio), device=self.device)
+        logit, doa = out['event_frame_logit'][:, idx], out['doa_frame_output'][:, idx]      # interpolate_tensor (model_utils.py:57-75)
+        n = min(logit.shape[1], target_dict['event_frame_gt'].shape[1])
+        logit, doa = logit[:, :n], doa[:, :n]
+        egt, dgt = target_dict['event_frame_gt'][:, :n], target_dict['doa_frame_gt'][:, :n]
+        if self.device.type == 'cuda':
+            loss, g_logit, g_doa = ops.seld_loss(logit.detach(), doa.detach(), egt, dgt, loss_weight=self.loss_weight, with_grad=True)
+            torch.autograd.backward([logit, doa], [g_logit, g_doa])
+        else:                                                                 # CPU tests of the host logic: the same loss in torch
+            sed = F.binary_cross_entropy_with_logits(logit, egt)
+            d = sum(((doa[..., i * self.n_classes:(i + 1) * self.n_classes] - dgt[..., i * self.n_classes:(i + 1) * self.n_classes]).abs() * egt).sum()
+                    / egt.sum().clamp(min=1e-12) for i in range(3))
+            total = self.loss_weight[0] * sed + self.loss_weight[1] * d
+            total.backward()
+            loss = torch.stack([total.detach(), sed.detach(), d.detach()])
+        self.reducer.finish()
+        if self.scheduler is not None and self.optimizer is not None:
+            self.scheduler.apply(self.optimizer, self.epoch, self.batch_idx)
+        if self.optimizer is not None:
+            self.optimizer.step(self.flat_grad)
+        self.batch_idx += 1
+        return loss

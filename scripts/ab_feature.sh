@@ -3,7 +3,7 @@
 for tag in "$@"; do
   lib=salsa_b200/_build/libsalsa_$tag.so
   [ "$tag" = default ] && lib=salsa_b200/libsalsa_b200.so
-  SALSA_B200_LIB=$PWD/$lib python bench.py --no-crnn --no-cpu-baseline --no-e2e --no-other-configs --no-fast-mode --steps 5 --warmup 2 > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  SALSA_B200_LIB=$PWD/$lib python bench.py --no-crnn --no-cpu-baseline --no-e2e --no-other-configs --no-fast-mode --no-train --steps 5 --warmup 2 > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
   python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]

@@ -139,3 +139,51 @@ def test_chunked_feature_gather_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert results == {0: True, 1: True}
+
+
+def _train_worker(rank, world, port, q):
+    """SeldTrainer's gradient plane on gloo: after `step` every rank holds the AVERAGE of the per-rank gradients (buckets
+    all-reduced while the backward pass runs), hence identical parameters."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from salsa_b200 import train
+        from salsa_b200.crnn import random_state_dict
+        torch.manual_seed(0)
+        torch.set_num_threads(2)
+        sd = random_state_dict(0)
+        tr = train.SeldTrainer(sd, device='cpu', wire_dtype=None, dropout=False, bucket_bytes=4 << 20)
+        assert len(tr.reducer.buckets) > 3
+        g = torch.Generator().manual_seed(100 + rank)                 # every rank its own batch
+        x = torch.randn(1, 7, 32, 32, generator=g)
+        tgt = {'event_frame_gt': (torch.rand(1, 4, 12, generator=g) > 0.5).float(), 'doa_frame_gt': torch.randn(1, 4, 36, generator=g)}
+        loss = tr.step(x, tgt)
+        mine = tr.flat_grad.clone()
+        # the same gradients without the reducer, averaged by hand
+        solo = train.SeldTrainer(sd, device='cpu', wire_dtype=None, dropout=False)
+        solo.reducer.world = 1
+        solo.step(x, tgt)
+        local = solo.flat_grad.clone()
+        both = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(both, local)
+        want = sum(both) / world
+        ok = bool(torch.allclose(mine, want, rtol=1e-5, atol=1e-7)) and bool(torch.isfinite(loss).all()) and float(mine.abs().max()) > 0
+        ok = ok and not torch.allclose(local, want, rtol=1e-3, atol=1e-6)          # the ranks really saw different data
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_gradient_allreduce_world_size_2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == {0: True, 1: True}
