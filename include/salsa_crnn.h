@@ -77,6 +77,14 @@ int crnn_conv2d(const void *x, const void *w, const float *bias, const void *res
                 int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t relu, int32_t planes,
                 int32_t pool, void *stream);
 
+/* Weight gradient of nn.Conv2d(k=3, pad=1, stride 1, bias=False) (the backward pass of models/model_utils.py:192-200,
+ * :301-304 in the training step, models/seld_models.py:68-76): x bf16 NHWC [B][H][W][Cin], gy = dLoss/dOutput bf16 NHWC
+ * [B][H][W][Cout] -> dw fp32 [9][Cout][Cin] (tap-major like the packed weights; overwritten).  tcgen05 GEMMs over the pixel
+ * axis on MN-major operands, split over the grid, accumulated with fp32 atomics.  (The input gradient is crnn_conv2d itself
+ * on gy with the taps flipped and Cin / Cout exchanged.) */
+int crnn_conv_wgrad(const void *x, const void *gy, float *dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                    void *stream);
+
 /* The first convolution of the encoder (conv_block1.conv1 + bn1 + ReLU, models/model_utils.py:213-215) on an input
  * padded to 16 channels: x bf16 NHWC [B][H][W][planes*16], w bf16 [9][64][planes*16] -> out bf16 [B][H][W][planes*64]. */
 int crnn_conv_first(const void *x, const void *w, const float *bias, void *out, int32_t B, int32_t H, int32_t W,

@@ -74,6 +74,7 @@ SIGNATURES = {
     'crnn_forward': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     'crnn_model_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),
     'crnn_conv2d': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_conv_wgrad': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_conv_first': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_set_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),
     'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -75,6 +75,20 @@ def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, 
     return out
 
 
+def conv_wgrad(x, gy):
+    """x (B,H,W,Cin) bf16 NHWC, gy (B,H,W,Cout) bf16 NHWC -> dW (9, Cout, Cin) fp32: the weight gradient of the 3x3 / pad 1
+    convolution y = conv(x, w), tap-major like the packed weights."""
+    _check_act(x)
+    _check_act(gy)
+    B, H, W, Cin = x.shape
+    if tuple(gy.shape[:3]) != (B, H, W):
+        raise ValueError('x and gy must share batch and spatial dimensions')
+    Cout = gy.shape[3]
+    dw = torch.empty((9, Cout, Cin), dtype=torch.float32, device=x.device)
+    _call('crnn_conv_wgrad', x, _p(x), _p(gy), _p(dw), B, H, W, Cin, Cout)
+    return dw
+
+
 def conv_first(x, w, bias=None, relu=True, planes=1):
     """First convolution: x (B,H,W,planes*16) bf16, w (9,64,planes*16) bf16 -> (B,H,W,planes*64) bf16."""
     _check_act(x)

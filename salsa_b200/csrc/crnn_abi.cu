@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "crnn_conv.cuh"
 #include "crnn_kernels.cuh"
+#include "crnn_wgrad.cuh"
 #include "salsa_crnn.h"
 
 namespace salsa {
@@ -327,6 +328,47 @@ int crnn_augment(const float* x, float* out, const float* y_doa, float* y_out, c
         y_doa, y_out, reinterpret_cast<const int4*>(ops), B, Ty, n_classes);
     count_launch();
     return check_cuda(cudaGetLastError(), "augment_doa_kernel");
+}
+
+int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream) {
+    if (!x || !gy || !dw) return fail(SALSA_EINVAL, "conv_wgrad: null pointer");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv_wgrad: bad dimensions");
+    if (Cin % 64 != 0 || Cout % 64 != 0 || Cin <= 0 || Cout <= 0) return fail(SALSA_EINVAL, "conv_wgrad: Cin and Cout must be multiples of 64");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return fail(SALSA_EINVAL, "conv_wgrad: unaligned pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tx, tg;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + 2), 1};
+        int rc = make_tmap(&tx, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+        int rc = make_tmap(&tg, gy, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    WgradArgs a;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+    a.tiles_w = (W + kTileW - 1) / kTileW;
+    a.tiles_h = (H + kTileH - 1) / kTileH;
+    a.n_ktiles = B * a.tiles_h * a.tiles_w;
+    a.dw = dw;
+    SALSA_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * Cout * Cin * sizeof(float), st));
+    SALSA_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int pairs = (Cout / 64) * (Cin / 64);
+    // split the pixel tiles over enough CTAs to fill the GPU about twice (one CTA per SM: the three-stage ring takes the
+    // whole shared memory); every split adds one pass of 9 x 64 x 64 atomic adds
+    const int splits = std::max(1, std::min(a.n_ktiles, (2 * sms + pairs - 1) / pairs));
+    conv_wgrad_kernel<<<dim3(splits, pairs), kWgThreads, kWgSmemBytes, st>>>(tx, tg, a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "conv_wgrad_kernel");
 }
 
 int crnn_cutout(float* x, const int32_t* rects, const int32_t* n_rects, const double* u, float* minmax, int32_t B, int32_t C,

@@ -4,11 +4,12 @@ The reference trains through PyTorch Lightning: `training_step` (models/seld_mod
 `interpolate_tensor` to the label rate -> `compute_loss` (models/interfaces.py:273-355), Adam with the piecewise-linear
 lr / beta1 schedule (utilities/learning_utils.py:17-52), DDP gradient all-reduce (experiments/train.py:98-104).  Here:
 
-  native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 convolutions' forward and input gradient
-                              (the tcgen05 implicit-GEMM kernel; dgrad = the same kernel on flipped / transposed weights),
-                              the loss with its output gradients (`crnn_seld_loss`), the Adam step (`crnn_adam_step`)
-  torch / cuDNN (library)     the convolutions' weight gradient, BatchNorm with batch statistics, pooling, dropout, the
-                              BiGRU and the heads, through autograd -- not native yet, and said so wherever a number is quoted
+  native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 convolutions' forward, input gradient (the
+                              tcgen05 implicit-GEMM kernel on flipped / transposed weights) and weight gradient
+                              (`crnn_conv_wgrad`), the loss with its output gradients (`crnn_seld_loss`), the Adam step
+  torch / cuDNN (library)     the first (7-channel) and the 1x1 convolutions, BatchNorm with batch statistics, pooling,
+                              dropout, the BiGRU and the heads, through autograd -- not native yet, and said so wherever a
+                              number is quoted
   torch.distributed           bucketed bf16 all-reduce of the flat gradient buffer, started per bucket while the backward
                               pass is still running (`GradAllReduce`; NCCL on the GPU box, gloo in the CPU tests)
 
@@ -28,7 +29,9 @@ __all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3']
 class NativeConv3x3(torch.autograd.Function):
     """3x3 / pad 1 / stride 1 convolution without bias on channels_last bf16 tensors.  forward: `crnn_conv2d`.  backward:
     input gradient = `crnn_conv2d` of the output gradient with the taps flipped and Cin / Cout exchanged; weight gradient =
-    torch.nn.grad.conv2d_weight (cuDNN) until the native wgrad exists."""
+    `crnn_conv_wgrad` (tcgen05 GEMMs over the pixel axis on MN-major operands).  `native_wgrad = False` switches the weight
+    gradient to torch.nn.grad.conv2d_weight (cuDNN) for A/B runs."""
+    native_wgrad = True
 
     @staticmethod
     def forward(ctx, x, w):
@@ -47,7 +50,11 @@ class NativeConv3x3(torch.autograd.Function):
             wt = w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
             dx = ops.conv2d(gyb.permute(0, 2, 3, 1), wt).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
-            dw = torch.nn.grad.conv2d_weight(xb, w.shape, gyb, padding=1).to(w.dtype)
+            if NativeConv3x3.native_wgrad:
+                dw = ops.conv_wgrad(xb.permute(0, 2, 3, 1), gyb.permute(0, 2, 3, 1))          # (9, Cout, Cin) fp32
+                dw = dw.reshape(3, 3, w.shape[0], w.shape[1]).permute(2, 3, 0, 1).to(w.dtype)
+            else:
+                dw = torch.nn.grad.conv2d_weight(xb, w.shape, gyb, padding=1).to(w.dtype)
         return dx, dw
 
 
