@@ -85,6 +85,22 @@ int crnn_conv2d(const void *x, const void *w, const float *bias, const void *res
 int crnn_conv_wgrad(const void *x, const void *gy, float *dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                     void *stream);
 
+/* nn.BatchNorm2d in TRAIN mode (batch statistics; models/model_utils.py:202-203, :216, :356 in the training step), fused with
+ * the residual add and the ReLU around it, on NHWC bf16 activations viewed as [n_pix][C] (C = 64, 128, 256 or 512):
+ *   z = relu?(gamma (y - mean) / sqrt(var + eps) + beta (+ residual)),  mean / var = biased statistics of y over the pixels
+ *   stat fp32 [C][2] receives (mean, 1 / std) for the backward pass; sums float64 [C][2] is scratch; running_mean /
+ *   running_var fp32 [C] (both or neither) are updated with `momentum` (unbiased variance), like nn.BatchNorm2d. */
+int crnn_bn_train_forward(const void *y, const float *gamma, const float *beta, const void *residual, void *z, float *stat,
+                          double *sums, float *running_mean, float *running_var, int64_t n_pix, int32_t C, float eps,
+                          float momentum, int32_t relu, void *stream);
+
+/* Its backward pass: dz = dLoss/dz (bf16), z / y / stat from the forward ->
+ *   dy bf16 = gamma / std (g - mean(g) - xhat mean(g xhat)),  g = dz (z > 0 when relu),  xhat = (y - mean) / std
+ *   d_residual bf16 (optional) = g;  dgamma fp32 [C] = sum g xhat;  dbeta fp32 [C] = sum g;  sums float64 [C][2] scratch. */
+int crnn_bn_train_backward(const void *dz, const void *z, const void *y, const float *stat, const float *gamma, void *dy,
+                           void *d_residual, double *sums, float *dgamma, float *dbeta, int64_t n_pix, int32_t C, int32_t relu,
+                           void *stream);
+
 /* The first convolution of the encoder (conv_block1.conv1 + bn1 + ReLU, models/model_utils.py:213-215) on an input
  * padded to 16 channels: x bf16 NHWC [B][H][W][planes*16], w bf16 [9][64][planes*16] -> out bf16 [B][H][W][planes*64]. */
 int crnn_conv_first(const void *x, const void *w, const float *bias, void *out, int32_t B, int32_t H, int32_t W,

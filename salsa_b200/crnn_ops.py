@@ -89,6 +89,43 @@ def conv_wgrad(x, gy):
     return dw
 
 
+def bn_train_forward(y, gamma, beta, residual=None, relu=True, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
+    """Train-mode BatchNorm2d (+ residual) (+ ReLU) on NHWC bf16: y (..., C) -> (z bf16 like y, stat fp32 (C, 2) = mean | 1/std).
+    running_mean / running_var (fp32 (C,), both or neither) are updated in place like nn.BatchNorm2d does."""
+    _check_act(y)
+    C = y.shape[-1]
+    n_pix = y.numel() // C
+    if residual is not None:
+        _check_act(residual)
+        if residual.shape != y.shape:
+            raise ValueError('residual shape mismatch')
+    for t in (gamma, beta):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == C):
+            raise ValueError('gamma / beta must be contiguous CUDA float32 (C,)')
+    z = torch.empty_like(y)
+    stat = torch.empty((C, 2), dtype=torch.float32, device=y.device)
+    sums = torch.empty((C, 2), dtype=torch.float64, device=y.device)
+    _call('crnn_bn_train_forward', y, _p(y), _p(gamma), _p(beta), _p(residual), _p(z), _p(stat), _p(sums), _p(running_mean), _p(running_var),
+          n_pix, C, ctypes.c_float(eps), ctypes.c_float(momentum), int(bool(relu)))
+    return z, stat
+
+
+def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False):
+    """-> (dy bf16, d_residual bf16 or None, dgamma fp32 (C,), dbeta fp32 (C,))."""
+    _check_act(dz)
+    _check_act(y)
+    C = y.shape[-1]
+    n_pix = y.numel() // C
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if want_residual_grad else None
+    sums = torch.empty((C, 2), dtype=torch.float64, device=y.device)
+    dgamma = torch.empty((C,), dtype=torch.float32, device=y.device)
+    dbeta = torch.empty((C,), dtype=torch.float32, device=y.device)
+    _call('crnn_bn_train_backward', dz, _p(dz), _p(z), _p(y), _p(stat), _p(gamma), _p(dy), _p(dres), _p(sums), _p(dgamma), _p(dbeta), n_pix, C,
+          int(bool(relu)))
+    return dy, dres, dgamma, dbeta
+
+
 def conv_first(x, w, bias=None, relu=True, planes=1):
     """First convolution: x (B,H,W,planes*16) bf16, w (9,64,planes*16) bf16 -> (B,H,W,planes*64) bf16."""
     _check_act(x)

@@ -371,6 +371,51 @@ int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t
     return check_cuda(cudaGetLastError(), "conv_wgrad_kernel");
 }
 
+int crnn_bn_train_forward(const void* y, const float* gamma, const float* beta, const void* residual, void* z, float* stat,
+                          double* sums, float* running_mean, float* running_var, int64_t n_pix, int32_t C, float eps, float momentum,
+                          int32_t relu, void* stream) {
+    if (!y || !gamma || !beta || !z || !stat || !sums) return fail(SALSA_EINVAL, "bn_train_forward: null pointer");
+    if (C <= 0 || C % 8 != 0 || C > 512 || 256 % (C / 8) != 0) return fail(SALSA_EINVAL, "bn_train_forward: C must be 64, 128, 256 or 512");
+    if (n_pix <= 0) return fail(SALSA_EINVAL, "bn_train_forward: empty input");
+    if ((running_mean == nullptr) != (running_var == nullptr)) return fail(SALSA_EINVAL, "bn_train_forward: running statistics go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    SALSA_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(double), st));
+    const int lanes = 256 / (C / 8);
+    const int blocks = (int)std::min<long long>((n_pix + lanes * 32 - 1) / (lanes * 32), 148LL * 8);
+    bn_stats_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(y), n_pix, C, sums);
+    count_launch();
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, n_pix, C, eps, momentum, stat, running_mean, running_var);
+    count_launch();
+    bn_apply_kernel<<<grid_for(n_pix * (C / 8), 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(y), stat, gamma, beta,
+                                                                     reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                                     reinterpret_cast<__nv_bfloat16*>(z), n_pix, C, relu);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "bn_train_forward");
+}
+
+int crnn_bn_train_backward(const void* dz, const void* z, const void* y, const float* stat, const float* gamma, void* dy,
+                           void* d_residual, double* sums, float* dgamma, float* dbeta, int64_t n_pix, int32_t C, int32_t relu,
+                           void* stream) {
+    if (!dz || !y || !stat || !gamma || !dy || !sums || !dgamma || !dbeta) return fail(SALSA_EINVAL, "bn_train_backward: null pointer");
+    if (relu && !z) return fail(SALSA_EINVAL, "bn_train_backward: the ReLU mask needs the forward output");
+    if (C <= 0 || C % 8 != 0 || C > 512 || 256 % (C / 8) != 0) return fail(SALSA_EINVAL, "bn_train_backward: C must be 64, 128, 256 or 512");
+    if (n_pix <= 0) return fail(SALSA_EINVAL, "bn_train_backward: empty input");
+    cudaStream_t st = (cudaStream_t)stream;
+    SALSA_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(double), st));
+    const int lanes = 256 / (C / 8);
+    const int blocks = (int)std::min<long long>((n_pix + lanes * 32 - 1) / (lanes * 32), 148LL * 8);
+    bn_bwd_reduce_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), reinterpret_cast<const __nv_bfloat16*>(z),
+                                                              reinterpret_cast<const __nv_bfloat16*>(y), stat, n_pix, C, relu, sums);
+    count_launch();
+    bn_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dz), reinterpret_cast<const __nv_bfloat16*>(z), reinterpret_cast<const __nv_bfloat16*>(y), stat,
+        gamma, sums, reinterpret_cast<__nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(d_residual), n_pix, C, relu);
+    count_launch();
+    bn_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "bn_train_backward");
+}
+
 int crnn_cutout(float* x, const int32_t* rects, const int32_t* n_rects, const double* u, float* minmax, int32_t B, int32_t C,
                 int32_t T, int32_t F, int32_t n_zero_channels, void* stream) {
     if (!x || !rects || !n_rects || !u || !minmax) return fail(SALSA_EINVAL, "cutout: null pointer");

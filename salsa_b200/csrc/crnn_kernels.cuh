@@ -473,6 +473,172 @@ __global__ void augment_kernel(const float* __restrict__ x, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Train-mode BatchNorm2d on NHWC bf16 activations (nn.BatchNorm2d with batch statistics, models/model_utils.py:202-203, :216,
+// :356 in the training step), fused with what surrounds it in ConvBlock / _ResnetBasicBlock: the residual add and the ReLU.
+//   forward   bn_stats_kernel (per-channel sum, sum of squares) -> bn_finalize_kernel (mean, 1/std, running statistics)
+//             -> bn_apply_kernel: z = relu?(gamma (y - mean) / std + beta (+ residual))
+//   backward  bn_bwd_reduce_kernel: g = dz * (z > 0); dbeta = sum g, dgamma = sum g * xhat
+//             -> bn_bwd_apply_kernel: dy = gamma / std * (g - dbeta / N - xhat * dgamma / N); the residual branch receives g
+// Thread = 8 consecutive channels (one 16-byte load) of a strided set of pixels; C is a multiple of 8, at most 512.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+        v[2 * e] = __low2float(h2);
+        v[2 * e + 1] = __high2float(h2);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        w4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    return make_uint4(w4[0], w4[1], w4[2], w4[3]);
+}
+
+// Per-channel reduction of two quantities over the pixels: every thread accumulates its channels over its pixels in fp32
+// (at most a few hundred values), threads that share a channel group are combined through shared memory in fp64, one
+// atomicAdd(double) per channel and block.  `f(pix, c8, a, b)` adds the contributions of pixel `pix`, channels 8 c8 .. 8 c8 + 7.
+template <typename F>
+__device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* __restrict__ out /* [C][2] */, F f) {
+    __shared__ double s_red[256][2];
+    const int groups = C >> 3;                        // channel groups of 8
+    const int lanes = blockDim.x / groups;            // threads per channel group (pixel lanes)
+    const int c8 = threadIdx.x % groups, pl = threadIdx.x / groups;
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.0f;
+    if (pl < lanes)
+        for (long long p = (long long)blockIdx.x * lanes + pl; p < n_pix; p += (long long)gridDim.x * lanes) f(p, c8, a, b);
+    // combine the pixel lanes of a channel group: one channel at a time through shared memory
+    for (int i = 0; i < 8; ++i) {
+        __syncthreads();
+        s_red[threadIdx.x][0] = pl < lanes ? (double)a[i] : 0.0;
+        s_red[threadIdx.x][1] = pl < lanes ? (double)b[i] : 0.0;
+        __syncthreads();
+        if (pl == 0) {
+            double sa = 0.0, sb = 0.0;
+            for (int l = 0; l < lanes; ++l) {
+                sa += s_red[l * groups + c8][0];
+                sb += s_red[l * groups + c8][1];
+            }
+            atomicAdd(out + (size_t)(c8 * 8 + i) * 2, sa);
+            atomicAdd(out + (size_t)(c8 * 8 + i) * 2 + 1, sb);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long n_pix, int C, double* __restrict__ sums) {
+    channel_reduce2(n_pix, C, sums, [&](long long p, int c8, float (&a)[8], float (&b)[8]) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y + p * C) + c8), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[i] += v[i];
+            b[i] = fmaf(v[i], v[i], b[i]);
+        }
+    });
+}
+
+// sums [C][2] -> stat [C][2] = (mean, 1 / sqrt(var + eps)) with the biased batch variance; running statistics updated like
+// nn.BatchNorm2d (momentum on the mean and on the UNBIASED variance)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long n_pix, int C, float eps, float momentum,
+                                   float* __restrict__ stat, float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double n = (double)n_pix;
+    const double mean = sums[2 * c] / n;
+    const double var = fmax(sums[2 * c + 1] / n - mean * mean, 0.0);
+    stat[2 * c] = (float)mean;
+    stat[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(n > 1.0 ? var * n / (n - 1.0) : var);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ z,
+                                                       long long n_pix, int C, int relu) {
+    const int groups = C >> 3;
+    const long long total = n_pix * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % groups) * 8;
+        float v[8], r[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), v);
+        if (residual) unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + k;
+            float o = fmaf((v[k] - stat[2 * c]) * stat[2 * c + 1], gamma[c], beta[c]);
+            if (residual) o += r[k];
+            v[k] = relu ? fmaxf(o, 0.0f) : o;
+        }
+        reinterpret_cast<uint4*>(z)[i] = pack8(v);
+    }
+}
+
+// sums [C][2] += (sum g, sum g * xhat) with g = dz * (z > 0) when relu, xhat = (y - mean) / std
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
+                                                            const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
+                                                            long long n_pix, int C, int relu, double* __restrict__ sums) {
+    channel_reduce2(n_pix, C, sums, [&](long long p, int c8, float (&a)[8], float (&b)[8]) {
+        float g[8], zz[8], yy[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dz + p * C) + c8), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y + p * C) + c8), yy);
+        if (relu) unpack8(__ldg(reinterpret_cast<const uint4*>(z + p * C) + c8), zz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c8 * 8 + i;
+            const float gi = (relu && !(zz[i] > 0.0f)) ? 0.0f : g[i];
+            a[i] += gi;
+            b[i] = fmaf(gi, (yy[i] - stat[2 * c]) * stat[2 * c + 1], b[i]);
+        }
+    });
+}
+
+// dy = gamma / std * (g - dbeta / N - xhat * dgamma / N); d_residual (optional) = g
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
+                                                           const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
+                                                           const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                           __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ d_residual,
+                                                           long long n_pix, int C, int relu) {
+    const int groups = C >> 3;
+    const long long total = n_pix * groups;
+    const float inv_n = (float)(1.0 / (double)n_pix);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % groups) * 8;
+        float g[8], zz[8], yy[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dz) + i), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
+        if (relu) unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + k;
+            if (relu && !(zz[k] > 0.0f)) g[k] = 0.0f;
+            const float xhat = (yy[k] - stat[2 * c]) * stat[2 * c + 1];
+            const float dbeta = (float)sums[2 * c], dgamma = (float)sums[2 * c + 1];
+            o[k] = gamma[c] * stat[2 * c + 1] * (g[k] - dbeta * inv_n - xhat * dgamma * inv_n);
+        }
+        reinterpret_cast<uint4*>(dy)[i] = pack8(o);
+        if (d_residual) reinterpret_cast<uint4*>(d_residual)[i] = pack8(g);
+    }
+}
+
+// sums [C][2] = (dbeta, dgamma) in float64 -> the float32 parameter gradients
+__global__ void bn_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    dbeta[c] = (float)sums[2 * c];
+    dgamma[c] = (float)sums[2 * c + 1];
+}
+
+// ------------------------------------------------------------------------------------------------
 // CompositeCutout (utilities/transforms.py:257-283): RandomCutoutNp (:58-125), SpecAugmentNp (:128-196) or
 // RandomCutoutHoleNp (:199-254) all reduce to "up to 8 rectangles (time x frequency) per sample, filled in order with a
 // value drawn between the sample's min and max; the last n_zero_channels channels get 0 instead".

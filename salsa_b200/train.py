@@ -7,9 +7,10 @@ lr / beta1 schedule (utilities/learning_utils.py:17-52), DDP gradient all-reduce
   native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 convolutions' forward, input gradient (the
                               tcgen05 implicit-GEMM kernel on flipped / transposed weights) and weight gradient
                               (`crnn_conv_wgrad`), the loss with its output gradients (`crnn_seld_loss`), the Adam step
-  torch / cuDNN (library)     the first (7-channel) and the 1x1 convolutions, BatchNorm with batch statistics, pooling,
-                              dropout, the BiGRU and the heads, through autograd -- not native yet, and said so wherever a
-                              number is quoted
+                              train-mode BatchNorm fused with the residual add and the ReLU, forward and backward
+                              (`crnn_bn_train_forward` / `_backward`)
+  torch / cuDNN (library)     the first (7-channel) and the 1x1 convolutions, pooling, dropout, the BiGRU and the heads,
+                              through autograd -- not native yet, and said so wherever a number is quoted
   torch.distributed           bucketed bf16 all-reduce of the flat gradient buffer, started per bucket while the backward
                               pass is still running (`GradAllReduce`; NCCL on the GPU box, gloo in the CPU tests)
 
@@ -23,7 +24,7 @@ import torch.nn.functional as F
 from . import crnn_ops as ops
 from .optim import Adam, LearningRateScheduler
 
-__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3']
+__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeBnAct']
 
 
 class NativeConv3x3(torch.autograd.Function):
@@ -56,6 +57,30 @@ class NativeConv3x3(torch.autograd.Function):
             else:
                 dw = torch.nn.grad.conv2d_weight(xb, w.shape, gyb, padding=1).to(w.dtype)
         return dx, dw
+
+
+class NativeBnAct(torch.autograd.Function):
+    """Train-mode BatchNorm2d (+ residual add) (+ ReLU) on channels_last bf16 tensors: `crnn_bn_train_forward` /
+    `crnn_bn_train_backward`.  Running statistics are updated in place in the forward pass."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, residual, running_mean, running_var, relu):
+        yb = y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        rb = None if residual is None else residual.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        g, b = gamma.detach().contiguous(), beta.detach().contiguous()
+        z, stat = ops.bn_train_forward(yb.permute(0, 2, 3, 1), g, b, None if rb is None else rb.permute(0, 2, 3, 1), relu=relu,
+                                       running_mean=running_mean, running_var=running_var)
+        ctx.save_for_backward(yb, z, stat, g)
+        ctx.relu, ctx.has_res = relu, residual is not None
+        return z.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dz):
+        yb, z, stat, g = ctx.saved_tensors
+        dzb = dz.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dy, dres, dgamma, dbeta = ops.bn_train_backward(dzb.permute(0, 2, 3, 1), z, yb.permute(0, 2, 3, 1), stat, g, relu=ctx.relu,
+                                                        want_residual_grad=ctx.has_res and ctx.needs_input_grad[3])
+        return (dy.permute(0, 3, 1, 2), dgamma, dbeta, None if dres is None else dres.permute(0, 3, 1, 2), None, None, None)
 
 
 class GradAllReduce:
@@ -118,13 +143,15 @@ class SeldTrainer:
 
     def __init__(self, state_dict, n_classes: int = 12, label_rate: int = 10, feature_rate: float = 80.0, loss_weight=(0.3, 0.7),
                  lr: float = 1e-3, device='cuda', native_conv: bool = True, group=None, scheduler: LearningRateScheduler = None,
-                 bucket_bytes: int = 8 << 20, wire_dtype=torch.bfloat16, autocast: bool = True, dropout: bool = True):
-        """native_conv / autocast / dropout = False are for tests (a pure torch float32 reference of the same step);
+                 bucket_bytes: int = 8 << 20, wire_dtype=torch.bfloat16, autocast: bool = True, dropout: bool = True,
+                 native_bn: bool = True):
+        """native_conv / native_bn / autocast / dropout = False are for tests (a pure torch float32 reference of the same step);
         wire_dtype None sends float32 gradients."""
         self.device = torch.device(device)
         self.n_classes, self.loss_weight = n_classes, tuple(loss_weight)
         self.ratio = 16.0 * label_rate / feature_rate                 # time_downsample_ratio * label_rate / feature_rate
         self.native_conv = native_conv and self.device.type == 'cuda'
+        self.native_bn = native_bn and self.device.type == 'cuda'
         self.autocast = autocast and self.device.type == 'cuda'
         self.dropout = dropout
         self.scheduler = scheduler
@@ -164,9 +191,16 @@ class SeldTrainer:
             return NativeConv3x3.apply(x, w)
         return F.conv2d(x, w, padding=1)
 
-    def _bn(self, x, prefix):
-        return F.batch_norm(x, self.buffers[prefix + '.running_mean'], self.buffers[prefix + '.running_var'], self.params[prefix + '.weight'],
-                            self.params[prefix + '.bias'], training=self.training, momentum=0.1, eps=1e-5)
+    def _bn(self, x, prefix, relu=False, residual=None):
+        """BatchNorm2d (+ residual) (+ ReLU): one native pass each way in train mode, torch ops otherwise."""
+        rm, rv = self.buffers[prefix + '.running_mean'], self.buffers[prefix + '.running_var']
+        w, b = self.params[prefix + '.weight'], self.params[prefix + '.bias']
+        if self.native_bn and self.training and x.is_cuda and x.shape[1] in (64, 128, 256, 512):
+            return NativeBnAct.apply(x, w, b, residual, rm, rv, relu)
+        out = F.batch_norm(x, rm, rv, w, b, training=self.training, momentum=0.1, eps=1e-5)
+        if residual is not None:
+            out = out + residual
+        return F.relu(out) if relu else out
 
     def forward(self, x):
         """x (B, 7, T, F) float32 -> {'event_frame_logit': (B, T/16, n), 'doa_frame_output': (B, T/16, 3n)}, with autograd."""
@@ -174,21 +208,20 @@ class SeldTrainer:
         x = x.contiguous(memory_format=torch.channels_last)
         with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast):
             p = 'encoder.conv_block1'
-            x = F.relu(self._bn(F.conv2d(x, self.params[p + '.conv1.weight'], padding=1), p + '.bn1'))      # 7 input channels: cuDNN
-            x = F.relu(self._bn(self._conv3(x, p + '.conv2.weight'), p + '.bn2'))
+            x = self._bn(F.conv2d(x, self.params[p + '.conv1.weight'], padding=1), p + '.bn1', relu=True)     # 7 input channels: cuDNN
+            x = self._bn(self._conv3(x, p + '.conv2.weight'), p + '.bn2', relu=True)
             x = F.avg_pool2d(x, 2)                                            # ConvBlock.forward (models/model_utils.py:213-220)
             for li in range(1, 5):
                 for bi in range(2):
                     q = 'encoder.resnet.layer{}.{}'.format(li, bi)
                     identity = x
                     out = F.avg_pool2d(x, 2) if (li > 1 and bi == 0) else x   # _ResnetBasicBlock.forward (:345-367)
-                    out = F.relu(self._bn(self._conv3(out, q + '.conv1.weight'), q + '.bn1'))
+                    out = self._bn(self._conv3(out, q + '.conv1.weight'), q + '.bn1', relu=True)
                     out = F.dropout(out, p=0.1, training=tr)
-                    out = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2')
                     if li > 1 and bi == 0:
                         identity = F.avg_pool2d(identity, 2)
                         identity = self._bn(F.conv2d(identity, self.params[q + '.downsample.1.weight']), q + '.downsample.2')
-                    x = F.relu(out + identity)
+                    x = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2', relu=True, residual=identity)   # relu(bn2(.) + identity)
             x = torch.mean(x.float(), dim=3).transpose(1, 2)                  # SeldDecoder.forward (models/decoders.py:106-154)
             gru_params = {k[len('decoder.gru.'):]: v for k, v in self.params.items() if k.startswith('decoder.gru.')}
             self.gru.train(self.training)

@@ -44,6 +44,38 @@ def test_native_conv_weight_gradient(B, H, W, Cin, Cout):
     assert rel(dw, ref) < 1e-4
 
 
+@pytest.mark.parametrize('C,relu,with_res', [(64, True, False), (128, True, True), (512, False, False), (256, True, True)])
+def test_native_batchnorm_train_forward_and_backward(C, relu, with_res):
+    """crnn_bn_train_forward / _backward (batch statistics, fused residual add and ReLU) against torch's F.batch_norm +
+    autograd in float32 on the same bf16 inputs: outputs and input gradients to bf16 rounding, parameter gradients and
+    running statistics to 1e-3 / 1e-5."""
+    from salsa_b200.train import NativeBnAct
+    g = torch.Generator().manual_seed(C)
+    B, H, W = 3, 20, 13
+    y = (torch.randn(B, C, H, W, generator=g) * 2 + 0.5).bfloat16().float().cuda().requires_grad_(True)
+    res = torch.randn(B, C, H, W, generator=g).bfloat16().float().cuda().requires_grad_(True) if with_res else None
+    gamma = torch.empty(C).uniform_(0.5, 1.5, generator=g).cuda().requires_grad_(True)
+    beta = torch.empty(C).uniform_(-0.3, 0.3, generator=g).cuda().requires_grad_(True)
+    dz = torch.randn(B, C, H, W, generator=g).bfloat16().float().cuda()
+    rm_ref, rv_ref = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    rm, rv = rm_ref.clone(), rv_ref.clone()
+    ref = F.batch_norm(y, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+    if with_res:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    inputs = (y, gamma, beta) + ((res,) if with_res else ())
+    grads_ref = torch.autograd.grad(ref, inputs, dz)
+    out = NativeBnAct.apply(y, gamma, beta, res, rm, rv, relu)
+    grads = torch.autograd.grad(out, inputs, dz)
+    assert rel(out, ref) < 1e-2
+    assert torch.allclose(rm, rm_ref, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    assert rel(grads[0], grads_ref[0]) < 2e-2                     # dy (bf16 output, relu mask taken from the bf16 z)
+    assert rel(grads[1], grads_ref[1]) < 1e-2 and rel(grads[2], grads_ref[2]) < 1e-2
+    if with_res:
+        assert rel(grads[3], grads_ref[3]) < 1e-2
+
+
 def _batch(seed=3, B=2, T=128):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, 7, T, 200, generator=g).cuda()
@@ -53,10 +85,12 @@ def _batch(seed=3, B=2, T=128):
 
 
 def test_training_step_matches_pure_torch_steps():
-    """Same weights, same batch, dropout off.  Against the same step with cuDNN convolutions under bf16 autocast (the same
-    arithmetic class): gradient cosine > 0.9999 -- the native forward / dgrad are drop-ins.  Against the float32 step
-    (autocast off): the loss to 1e-3; the gradient direction is only as close as bf16 leaves it with a sign-gradient (MAE)
-    loss and batch statistics over two samples (measured 0.96, the same for the cuDNN bf16 step): printed, loose bar."""
+    """Same weights, same batch, dropout off.
+      * native convolutions only (BatchNorm through torch) against the same step with cuDNN convolutions under bf16 autocast:
+        identical rounding points, gradient cosine > 0.9999 -- forward, dgrad and wgrad are drop-ins;
+      * everything native (convolutions + fused BatchNorm / residual / ReLU) against the float32 step (autocast off): loss to
+        2e-3; the gradient direction is only as close as bf16 leaves it with a sign-gradient (MAE) loss and batch statistics
+        over two samples -- the bar is "at least as close to float32 as the cuDNN bf16 step is" (both ~0.96-0.97)."""
     import salsa_b200
     from salsa_b200 import train
     sd = salsa_b200.crnn.random_state_dict(1)
@@ -67,17 +101,16 @@ def test_training_step_matches_pure_torch_steps():
         t.optimizer = None                                    # gradients only
         return t
 
-    nat, t16, t32 = make(), make(native_conv=False), make(native_conv=False, autocast=False)
-    l_nat, l_16, l_32 = nat.step(x, tgt), t16.step(x, tgt), t32.step(x, tgt)
-    assert torch.allclose(l_nat, l_16, rtol=1e-3, atol=1e-4), (l_nat, l_16)
+    nat, conv_only = make(), make(native_bn=False)
+    t16, t32 = make(native_conv=False, native_bn=False), make(native_conv=False, native_bn=False, autocast=False)
+    l_nat, l_conv, l_16, l_32 = nat.step(x, tgt), conv_only.step(x, tgt), t16.step(x, tgt), t32.step(x, tgt)
+    cos = lambda a, b: F.cosine_similarity(a.flat_grad, b.flat_grad, dim=0).item()
+    print('train step: loss native {} float32 {}; gradient cosine: native-conv vs cuDNN-bf16 {:.6f}; vs float32: all-native {:.4f}, '
+          'native-conv {:.4f}, cuDNN-bf16 {:.4f}'.format(l_nat.tolist(), l_32.tolist(), cos(conv_only, t16), cos(nat, t32), cos(conv_only, t32), cos(t16, t32)))
+    assert torch.allclose(l_conv, l_16, rtol=1e-3, atol=1e-4), (l_conv, l_16)
+    assert cos(conv_only, t16) > 0.9999
     assert torch.allclose(l_nat, l_32, rtol=2e-3, atol=2e-3), (l_nat, l_32)
-    cos16 = F.cosine_similarity(nat.flat_grad, t16.flat_grad, dim=0).item()
-    cos32 = F.cosine_similarity(nat.flat_grad, t32.flat_grad, dim=0).item()
-    ref32 = F.cosine_similarity(t16.flat_grad, t32.flat_grad, dim=0).item()
-    print('train step: loss {}; gradient cosine native vs cuDNN-bf16 {:.6f}, native vs float32 {:.4f} (cuDNN-bf16 vs float32 {:.4f})'.format(
-        l_nat.tolist(), cos16, cos32, ref32))
-    assert cos16 > 0.9999
-    assert cos32 > 0.9 and abs(cos32 - ref32) < 5e-3
+    assert cos(nat, t32) > cos(t16, t32) - 0.01 and cos(nat, t32) > 0.9
     out = t32.forward(x)
     assert tuple(out['event_frame_logit'].shape) == (2, 8, 12) and tuple(out['doa_frame_output'].shape) == (2, 8, 36)
 
