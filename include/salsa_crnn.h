@@ -127,6 +127,10 @@ int crnn_pack_input(const float *x, void *y, int32_t B, int32_t C, int32_t T, in
 /* F.avg_pool2d(x, kernel_size=(2, 2)) (models/model_utils.py:220, :349; nn.AvgPool2d :476), floor mode. */
 int crnn_avgpool2(const void *x, void *y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t planes, void *stream);
 
+/* Backward of that pooling (training step): dy bf16 [B][H/2][W/2][C] -> dx bf16 [B][H][W][C] = dy / 4 under every 2x2 window,
+ * 0 in an odd last row / column. */
+int crnn_avgpool2_backward(const void *dy, void *dx, int32_t B, int32_t H, int32_t W, int32_t C, void *stream);
+
 /* torch.mean(x, dim=3) + transpose (models/decoders.py:111, :123): [B*H][W][C] -> [B*H][C]. */
 int crnn_freq_mean(const void *x, void *y, int32_t BH, int32_t W, int32_t C, int32_t planes, void *stream);
 

@@ -82,6 +82,7 @@ SIGNATURES = {
     'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_pack_input': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
     'crnn_avgpool2': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'crnn_avgpool2_backward': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'crnn_freq_mean': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'crnn_gru_layer': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     'crnn_head_finish': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),

@@ -190,6 +190,17 @@ def avgpool2(x, planes=1):
     return y
 
 
+def avgpool2_backward(dy, H, W):
+    """dy (B,H//2,W//2,C) bf16 -> dx (B,H,W,C) bf16."""
+    _check_act(dy)
+    B, Ho, Wo, C = dy.shape
+    if (Ho, Wo) != (H // 2, W // 2):
+        raise ValueError('dy does not belong to an input of {} x {}'.format(H, W))
+    dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dy.device)
+    _call('crnn_avgpool2_backward', dy, _p(dy), _p(dx), B, H, W, C)
+    return dx
+
+
 def freq_mean(x, planes=1):
     """(B,H,W,C) -> (pad_rows(B*H), C), mean over W; padding rows are zero."""
     _check_act(x)

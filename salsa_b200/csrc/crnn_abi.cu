@@ -252,6 +252,16 @@ int crnn_avgpool2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32
     return check_cuda(cudaGetLastError(), "avgpool2_kernel");
 }
 
+int crnn_avgpool2_backward(const void* dy, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+    if (!dy || !dx) return fail(SALSA_EINVAL, "avgpool2_backward: null pointer");
+    if (C % 8 != 0 || H < 2 || W < 2 || B <= 0) return fail(SALSA_EINVAL, "avgpool2_backward: bad dimensions");
+    const long long n = (long long)B * H * W * (C / 8);
+    avgpool2_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                             reinterpret_cast<__nv_bfloat16*>(dx), B, H, W, C);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "avgpool2_bwd_kernel");
+}
+
 int crnn_freq_mean(const void* x, void* y, int32_t BH, int32_t W, int32_t C, int32_t planes, void* stream) {
     if (!x || !y) return fail(SALSA_EINVAL, "freq_mean: null pointer");
     if (C % 8 != 0 || W <= 0) return fail(SALSA_EINVAL, "freq_mean: bad dimensions");

@@ -630,6 +630,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     }
 }
 
+// backward of F.avg_pool2d(2x2), floor mode, on NHWC bf16: dx[b][h][w][c] = dy[b][h/2][w/2][c] / 4 (0 in the odd last row / column)
+__global__ void avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+    const long long total = (long long)B * H * W * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        long long p = i / C8;
+        const int w = (int)(p % W);
+        p /= W;
+        const int h = (int)(p % H), b = (int)(p / H);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if ((h >> 1) < Ho && (w >> 1) < Wo) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((((long long)b * Ho + (h >> 1)) * Wo + (w >> 1)) * C)) + c8), v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] *= 0.25f;
+        }
+        reinterpret_cast<uint4*>(dx)[i] = pack8(v);
+    }
+}
+
 // sums [C][2] = (dbeta, dgamma) in float64 -> the float32 parameter gradients
 __global__ void bn_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;

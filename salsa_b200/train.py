@@ -8,8 +8,8 @@ lr / beta1 schedule (utilities/learning_utils.py:17-52), DDP gradient all-reduce
                               tcgen05 implicit-GEMM kernel on flipped / transposed weights) and weight gradient
                               (`crnn_conv_wgrad`), the loss with its output gradients (`crnn_seld_loss`), the Adam step
                               train-mode BatchNorm fused with the residual add and the ReLU, forward and backward
-                              (`crnn_bn_train_forward` / `_backward`)
-  torch / cuDNN (library)     the first (7-channel) and the 1x1 convolutions, pooling, dropout, the BiGRU and the heads,
+                              (`crnn_bn_train_forward` / `_backward`), 2x2 average pooling forward and backward
+  torch / cuDNN (library)     the first (7-channel) and the 1x1 convolutions, dropout, the BiGRU and the heads,
                               through autograd -- not native yet, and said so wherever a number is quoted
   torch.distributed           bucketed bf16 all-reduce of the flat gradient buffer, started per bucket while the backward
                               pass is still running (`GradAllReduce`; NCCL on the GPU box, gloo in the CPU tests)
@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from . import crnn_ops as ops
 from .optim import Adam, LearningRateScheduler
 
-__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeBnAct']
+__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeBnAct', 'NativeAvgPool2']
 
 
 class NativeConv3x3(torch.autograd.Function):
@@ -81,6 +81,22 @@ class NativeBnAct(torch.autograd.Function):
         dy, dres, dgamma, dbeta = ops.bn_train_backward(dzb.permute(0, 2, 3, 1), z, yb.permute(0, 2, 3, 1), stat, g, relu=ctx.relu,
                                                         want_residual_grad=ctx.has_res and ctx.needs_input_grad[3])
         return (dy.permute(0, 3, 1, 2), dgamma, dbeta, None if dres is None else dres.permute(0, 3, 1, 2), None, None, None)
+
+
+class NativeAvgPool2(torch.autograd.Function):
+    """F.avg_pool2d(x, 2) on channels_last bf16 tensors: `crnn_avgpool2` / `crnn_avgpool2_backward` (torch's NHWC pooling
+    kernels took a third of the training step)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ctx.hw = (xb.shape[2], xb.shape[3])
+        return ops.avgpool2(xb.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dyb = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        return ops.avgpool2_backward(dyb.permute(0, 2, 3, 1), *ctx.hw).permute(0, 3, 1, 2)
 
 
 class GradAllReduce:
@@ -191,6 +207,11 @@ class SeldTrainer:
             return NativeConv3x3.apply(x, w)
         return F.conv2d(x, w, padding=1)
 
+    def _pool(self, x):
+        if self.native_bn and x.is_cuda and x.shape[1] % 8 == 0:
+            return NativeAvgPool2.apply(x)
+        return F.avg_pool2d(x, 2)
+
     def _bn(self, x, prefix, relu=False, residual=None):
         """BatchNorm2d (+ residual) (+ ReLU): one native pass each way in train mode, torch ops otherwise."""
         rm, rv = self.buffers[prefix + '.running_mean'], self.buffers[prefix + '.running_var']
@@ -210,17 +231,16 @@ class SeldTrainer:
             p = 'encoder.conv_block1'
             x = self._bn(F.conv2d(x, self.params[p + '.conv1.weight'], padding=1), p + '.bn1', relu=True)     # 7 input channels: cuDNN
             x = self._bn(self._conv3(x, p + '.conv2.weight'), p + '.bn2', relu=True)
-            x = F.avg_pool2d(x, 2)                                            # ConvBlock.forward (models/model_utils.py:213-220)
+            x = self._pool(x)                                                 # ConvBlock.forward (models/model_utils.py:213-220)
             for li in range(1, 5):
                 for bi in range(2):
                     q = 'encoder.resnet.layer{}.{}'.format(li, bi)
                     identity = x
-                    out = F.avg_pool2d(x, 2) if (li > 1 and bi == 0) else x   # _ResnetBasicBlock.forward (:345-367)
-                    out = self._bn(self._conv3(out, q + '.conv1.weight'), q + '.bn1', relu=True)
+                    pooled = self._pool(x) if (li > 1 and bi == 0) else x     # _ResnetBasicBlock.forward (:345-367)
+                    out = self._bn(self._conv3(pooled, q + '.conv1.weight'), q + '.bn1', relu=True)
                     out = F.dropout(out, p=0.1, training=tr)
-                    if li > 1 and bi == 0:
-                        identity = F.avg_pool2d(identity, 2)
-                        identity = self._bn(F.conv2d(identity, self.params[q + '.downsample.1.weight']), q + '.downsample.2')
+                    if li > 1 and bi == 0:                                     # downsample = AvgPool2d(2) + 1x1 conv + BN (:474-481): the same pooled tensor
+                        identity = self._bn(F.conv2d(pooled, self.params[q + '.downsample.1.weight']), q + '.downsample.2')
                     x = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2', relu=True, residual=identity)   # relu(bn2(.) + identity)
             x = torch.mean(x.float(), dim=3).transpose(1, 2)                  # SeldDecoder.forward (models/decoders.py:106-154)
             gru_params = {k[len('decoder.gru.'):]: v for k, v in self.params.items() if k.startswith('decoder.gru.')}

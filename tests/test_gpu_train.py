@@ -76,6 +76,18 @@ def test_native_batchnorm_train_forward_and_backward(C, relu, with_res):
         assert rel(grads[3], grads_ref[3]) < 1e-2
 
 
+def test_native_avgpool_forward_and_backward():
+    from salsa_b200.train import NativeAvgPool2
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 64, 21, 13, generator=g).bfloat16().float().cuda().requires_grad_(True)         # odd sizes: floor mode
+    dy = torch.randn(2, 64, 10, 6, generator=g).bfloat16().float().cuda()
+    ref = F.avg_pool2d(x, 2)
+    gx_ref, = torch.autograd.grad(ref, x, dy)
+    out = NativeAvgPool2.apply(x)
+    gx, = torch.autograd.grad(out, x, dy)
+    assert rel(out, ref) < 1e-2 and torch.equal(gx.float(), (gx_ref).bfloat16().float())
+
+
 def _batch(seed=3, B=2, T=128):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, 7, T, 200, generator=g).cuda()
