@@ -561,21 +561,28 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long n_
     }
 }
 
+// z = relu?(scale y + shift (+ residual)) with scale = gamma / std, shift = beta - mean scale.  blockDim (256) is a multiple
+// of the channel groups, so a thread keeps its 8 channels for the whole grid-stride loop: coefficients live in registers.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ z,
                                                        long long n_pix, int C, int relu) {
     const int groups = C >> 3;
     const long long total = n_pix * groups;
+    const int c0 = (int)(threadIdx.x % groups) * 8;
+    float scale[8], shift[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        scale[k] = gamma[c0 + k] * stat[2 * (c0 + k) + 1];
+        shift[k] = fmaf(-stat[2 * (c0 + k)], scale[k], beta[c0 + k]);
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % groups) * 8;
         float v[8], r[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), v);
         if (residual) unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int c = c0 + k;
-            float o = fmaf((v[k] - stat[2 * c]) * stat[2 * c + 1], gamma[c], beta[c]);
+            float o = fmaf(v[k], scale[k], shift[k]);
             if (residual) o += r[k];
             v[k] = relu ? fmaxf(o, 0.0f) : o;
         }
@@ -587,6 +594,14 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                             const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
                                                             long long n_pix, int C, int relu, double* __restrict__ sums) {
+    // a thread keeps its channel group: mean / (1 / std) of its 8 channels live in registers
+    const int c0 = (int)(threadIdx.x % (C >> 3)) * 8;
+    float mean[8], inv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        mean[k] = stat[2 * (c0 + k)];
+        inv[k] = stat[2 * (c0 + k) + 1];
+    }
     channel_reduce2(n_pix, C, sums, [&](long long p, int c8, float (&a)[8], float (&b)[8]) {
         float g[8], zz[8], yy[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(dz + p * C) + c8), g);
@@ -594,15 +609,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
         if (relu) unpack8(__ldg(reinterpret_cast<const uint4*>(z + p * C) + c8), zz);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int c = c8 * 8 + i;
             const float gi = (relu && !(zz[i] > 0.0f)) ? 0.0f : g[i];
             a[i] += gi;
-            b[i] = fmaf(gi, (yy[i] - stat[2 * c]) * stat[2 * c + 1], b[i]);
+            b[i] = fmaf(gi, (yy[i] - mean[i]) * inv[i], b[i]);
         }
     });
 }
 
-// dy = gamma / std * (g - dbeta / N - xhat * dgamma / N); d_residual (optional) = g
+// dy = gamma / std * (g - dbeta / N - xhat * dgamma / N) = ca g + cy y + c0 per channel; d_residual (optional) = g
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                            const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
                                                            const float* __restrict__ gamma, const double* __restrict__ sums,
@@ -611,19 +625,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     const int groups = C >> 3;
     const long long total = n_pix * groups;
     const float inv_n = (float)(1.0 / (double)n_pix);
+    const int c0 = (int)(threadIdx.x % groups) * 8;
+    float ca[8], cy[8], cc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        const float mean = stat[2 * c], inv = stat[2 * c + 1];
+        const float dbeta = (float)sums[2 * c], dgamma = (float)sums[2 * c + 1];
+        ca[k] = gamma[c] * inv;
+        cy[k] = -ca[k] * dgamma * inv_n * inv;                  // coefficient of y
+        cc[k] = -ca[k] * dbeta * inv_n - cy[k] * mean;          // constant
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % groups) * 8;
         float g[8], zz[8], yy[8], o[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(dz) + i), g);
         unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
         if (relu) unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int c = c0 + k;
             if (relu && !(zz[k] > 0.0f)) g[k] = 0.0f;
-            const float xhat = (yy[k] - stat[2 * c]) * stat[2 * c + 1];
-            const float dbeta = (float)sums[2 * c], dgamma = (float)sums[2 * c + 1];
-            o[k] = gamma[c] * stat[2 * c + 1] * (g[k] - dbeta * inv_n - xhat * dgamma * inv_n);
+            o[k] = fmaf(ca[k], g[k], fmaf(cy[k], yy[k], cc[k]));
         }
         reinterpret_cast<uint4*>(dy)[i] = pack8(o);
         if (d_residual) reinterpret_cast<uint4*>(d_residual)[i] = pack8(g);
