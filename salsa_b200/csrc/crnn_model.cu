@@ -8,6 +8,7 @@
 // no per-layer tensor-map encoding, no allocation, no host work between the ~30 kernels.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -85,7 +86,11 @@ struct Model {
     std::mutex mutex;
 };
 
-int g_use_graph = 1;
+// SALSA_B200_CRNN_GRAPH=0 (read once) or crnn_model_option("graph", 0): launch the kernels one by one (profilers list them)
+int g_use_graph = [] {
+    const char* e = getenv("SALSA_B200_CRNN_GRAPH");
+    return (e && e[0] == '0') ? 0 : 1;
+}();
 
 using Table = std::map<std::string, std::pair<const float*, int64_t>>;
 
