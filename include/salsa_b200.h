@@ -132,6 +132,15 @@ size_t salsa_linspec_iv_workspace_bytes(const salsa_params_t *p);
 int salsa_linspec_iv(const salsa_params_t *p, const float *audio, float *feature, void *workspace, size_t workspace_bytes,
                      void *stream);
 
+/* LogSpecGccExtractor.extract (dataset/feature_extraction.py:362-482), the MIC "linspecgcc" family: audio -> feature
+ * [n_clips][10][n_frames][200] = four log-linear spectrogram channels + GCC-PHAT of the six channel pairs (sig m, ref n,
+ * n < m; the 200 lags -100 .. 99 of the inverse transform of the cross-spectrum phase of a 1024-point STFT).  Needs the
+ * compressed layout, win_len = n_fft = 512 and the built-in Hann window.  The workspace (236 MB + 148 MB per 60 s clip) holds the
+ * three 512-point spectra that make up the 1024-point one and the GEMM operand of the inverse transform: split large batches. */
+size_t salsa_logspec_gcc_workspace_bytes(const salsa_params_t *p);
+int salsa_logspec_gcc(const salsa_params_t *p, const float *audio, float *feature, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
 /* Same two entry points for HOST buffers (pinned memory recommended): clips are streamed through
  * the GPU in chunks, overlapping host->device copy, kernels and device->host copy.  Synchronous. */
 int salsa_extract_host(const salsa_params_t *p, const float *audio_host, float *feature_host,

@@ -155,6 +155,8 @@ def extras_cases():
     fe = ref_import.other_features_module()
     foa = np.load(os.path.join(GOLDEN_DIR, 'clip_cases.npz'))['audio_foa']
     out['linspeciv_foa'] = fe.LinSpecIvExtractor(n_fft=512, hop_length=300, win_length=512).extract(foa).astype(np.float32)
+    mic = np.load(os.path.join(GOLDEN_DIR, 'clip_cases.npz'))['audio_mic'][:, :12000]          # 0.5 s: 41 frames
+    out['linspecgcc_mic'] = fe.LogSpecGccExtractor(n_fft=512, hop_length=300, win_length=512).extract(mic).astype(np.float32)
     return out
 
 

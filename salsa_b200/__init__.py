@@ -6,7 +6,7 @@ All compute runs in libsalsa_b200.so (hand-written CUDA behind a C ABI, include/
 this package is the thin host side.  There is no CPU fallback.
 """
 from . import _native  # noqa: F401
-from .features import (FeatureScaler, LinSpecIvExtractor, MagStftExtractor, SalsaExtractor, SalsaLiteExtractor, compute_scaler,  # noqa: F401
+from .features import (FeatureScaler, LinSpecIvExtractor, LogSpecGccExtractor, MagStftExtractor, SalsaExtractor, SalsaLiteExtractor, compute_scaler,  # noqa: F401
                        doa_bins, extract_normalized_eigenvector, stft)
 
 from .crnn import PannResNet22, SeldDecoder, SeldModel  # noqa: F401

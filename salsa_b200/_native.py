@@ -58,6 +58,8 @@ SIGNATURES = {
     'salsa_lite_extract': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _vp]),
     'salsa_linspec_iv_workspace_bytes': (_sz, [_P]),
     'salsa_linspec_iv': (ctypes.c_int, [_P, _vp, _vp, _vp, _sz, _vp]),
+    'salsa_logspec_gcc_workspace_bytes': (_sz, [_P]),
+    'salsa_logspec_gcc': (ctypes.c_int, [_P, _vp, _vp, _vp, _sz, _vp]),
     'salsa_extract_host': (ctypes.c_int, [_P, _vp, _vp, _i32]),
     'salsa_lite_extract_host': (ctypes.c_int, [_P, _i32, _i32, _vp, _vp, _i32]),
     'salsa_extract_host_pcm16': (ctypes.c_int, [_P, _vp, _vp, _i32]),

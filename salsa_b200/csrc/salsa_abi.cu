@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "salsa_crnn.h"
 #include "salsa_kernels.cuh"
 
 namespace salsa {
@@ -239,10 +240,10 @@ static int set_smem(K kernel, size_t bytes) {
 // ---------------------------------------------------------------------------------------------
 template <typename T, int CH, int OUT>
 static int launch_stft_t(const StftArgs& a, const FftTables<T>& tb, dim3 grid, cudaStream_t st) {
-    const size_t smem = sizeof(FftSmem<T>);
+    const size_t smem = sizeof(FftSmemW<T, kStftWarps>);
     int rc = set_smem(stft_kernel<T, CH, OUT>, smem);
     if (rc) return rc;
-    stft_kernel<T, CH, OUT><<<grid, kThreads, smem, st>>>(a, tb);
+    stft_kernel<T, CH, OUT><<<grid, kStftThreads, smem, st>>>(a, tb);
     return SALSA_OK;
 }
 
@@ -259,7 +260,8 @@ static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const fl
     a.lower = p->lower_bin;
     a.upper = p->upper_bin;
     a.ch_count = ch_count;
-    a.frames_per_block = 32;
+    // every warp of a CTA transforms 16 (frame, channel) items: 32 frames per CTA with 8 warps and 4 channels
+    a.frames_per_block = 16 * kStftWarps / ch_count;
     a.bands = band_layout(p);
     a.X = X;
     a.x_pitch = x_pitch;
@@ -674,6 +676,145 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
         }
     }
     return check_launch("lite_kernel");
+}
+
+// ---- LogSpecGccExtractor (dataset/feature_extraction.py:362-482) --------------------------------------------------
+namespace {
+// bf16 bits, round to nearest even
+uint16_t bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float bf16_val(uint16_t b) {
+    const uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+std::mutex g_gcc_mutex;
+void* g_gcc_table[64] = {};          // per device: the inverse-transform table, bf16x2 planes [256][2][1024]
+
+// row n = lag n - 100 (cc[-100:] then cc[:100], :439): cc[lag] = (1/N) (U0 + (-1)^lag U512 + 2 sum_k Re(U_k e^{2 pi i k lag / N}))
+int gcc_table(void** out) {
+    int dev = 0;
+    SALSA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_gcc_mutex);
+    if (!g_gcc_table[dev]) {
+        const int N = 1024;
+        std::vector<uint16_t> h((size_t)kGccLagsPad * 2 * kGccK, 0);
+        for (int n = 0; n < kGccLags; ++n) {
+            const int lag = n - kGccLags / 2;
+            for (int col = 0; col < kGccK; ++col) {
+                double v;
+                if (col == 0) v = 1.0 / N;
+                else if (col == 1) v = ((lag & 1) ? -1.0 : 1.0) / N;
+                else {
+                    const int k = col >> 1;
+                    const double ang = 2.0 * M_PI * (double)((long long)k * lag % N) / N;
+                    v = (col & 1) ? -2.0 * sin(ang) / N : 2.0 * cos(ang) / N;
+                }
+                const uint16_t hi = bf16_rne((float)v);
+                h[((size_t)n * 2) * kGccK + col] = hi;
+                h[((size_t)n * 2 + 1) * kGccK + col] = bf16_rne((float)(v - (double)bf16_val(hi)));
+            }
+        }
+        void* d = nullptr;
+        SALSA_CUDA(cudaMalloc(&d, h.size() * sizeof(uint16_t)));
+        SALSA_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        g_gcc_table[dev] = d;
+    }
+    *out = g_gcc_table[dev];
+    return SALSA_OK;
+}
+
+struct GccWorkspace {
+    float2 *XE, *XC, *XS;
+    void* A;          // bf16 [rows_pad][2][1024]
+    float* G;         // fp32 [rows_pad][256]
+    size_t bytes;
+};
+GccWorkspace carve_gcc(const salsa_params_t* p, void* base) {
+    const size_t T = (size_t)salsa_n_frames(p->n_samples, p->hop_len), B = (size_t)p->n_clips;
+    const size_t rows = (B * 6 * T + 7) / 8 * 8;
+    char* at = reinterpret_cast<char*>(base);
+    GccWorkspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* ptr = at + off;
+        off += round256(bytes);
+        return ptr;
+    };
+    w.XE = reinterpret_cast<float2*>(take(B * T * 4 * (kHalf + 1) * sizeof(float2)));
+    w.XC = reinterpret_cast<float2*>(take(B * T * 4 * kHalf * sizeof(float2)));
+    w.XS = reinterpret_cast<float2*>(take(B * T * 4 * kHalf * sizeof(float2)));
+    w.A = take(rows * 2 * kGccK * 2);
+    w.G = reinterpret_cast<float*>(take(rows * kGccLagsPad * sizeof(float)));
+    w.bytes = off + 256;
+    return w;
+}
+}  // namespace
+
+size_t salsa_logspec_gcc_workspace_bytes(const salsa_params_t* p) {
+    if (!p || p->n_clips < 0 || p->hop_len <= 0) return 0;
+    return carve_gcc(p, nullptr).bytes;
+}
+
+int salsa_logspec_gcc(const salsa_params_t* p, const float* audio, float* feature, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!p) return fail(SALSA_EINVAL, "params is NULL");
+    salsa_params_t q = *p;
+    q.lower_bin = 1;
+    q.upper_bin = kHalf;
+    q.audio_format = SALSA_FORMAT_MIC;
+    int rc = validate_params(&q);
+    if (rc) return rc;
+    if (!q.is_compress_high_freq) return fail(SALSA_EINVAL, "logspec_gcc: only the compressed 200-band layout is implemented");
+    if (q.window) return fail(SALSA_EINVAL, "logspec_gcc: a Hann window of win_len samples is built in");
+    if (q.win_len != q.n_fft) return fail(SALSA_EINVAL, "logspec_gcc: win_len must equal n_fft (512)");
+    if (q.n_clips == 0) return SALSA_OK;
+    if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
+    const GccWorkspace w = carve_gcc(&q, workspace);
+    if (!workspace || workspace_bytes < w.bytes) return fail(SALSA_ENOMEM, "workspace smaller than salsa_logspec_gcc_workspace_bytes()");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_frames = salsa_n_frames(q.n_samples, q.hop_len);
+    const BandLayout bands = band_layout(&q);
+    // three transforms per (frame, channel): the Hann window w (even bins of the 1024-point spectrum, and the log-linear
+    // spectrogram channels 0..3), w cos(pi j / 512) and w sin(pi j / 512) (odd bins)
+    double win[3][kNfft];
+    for (int j = 0; j < kNfft; ++j) {
+        const double wj = 0.5 - 0.5 * cos(2.0 * M_PI * (double)j / kNfft);
+        win[0][j] = wj;
+        win[1][j] = wj * cos(M_PI * (double)j / kNfft);
+        win[2][j] = wj * sin(M_PI * (double)j / kNfft);
+    }
+    salsa_params_t qe = q;
+    qe.lower_bin = 0;
+    qe.upper_bin = kHalf + 1;                  // bins 0 .. 256
+    salsa_params_t qo = q;
+    qo.lower_bin = 0;
+    qo.upper_bin = kHalf;                      // bins 0 .. 255
+    DeviceTables tb;
+    if ((rc = get_tables(nullptr, &tb))) return rc;
+    const long long spec_stride = 10LL * n_frames * bands.n_out;
+    if ((rc = launch_stft(&qe, tb, audio, w.XE, kHalf + 1, 0, feature, spec_stride, nullptr, 4, st))) return rc;
+    if ((rc = get_tables(win[1], &tb))) return rc;
+    if ((rc = launch_stft(&qo, tb, audio, w.XC, kHalf, 0, nullptr, 0, nullptr, 4, st))) return rc;
+    if ((rc = get_tables(win[2], &tb))) return rc;
+    if ((rc = launch_stft(&qo, tb, audio, w.XS, kHalf, 0, nullptr, 0, nullptr, 4, st))) return rc;
+    {
+        ProfScope prof("gcc_unit_kernel", st);
+        gcc_unit_kernel<<<dim3(n_frames, q.n_clips), 256, 0, st>>>(w.XE, w.XC, w.XS, reinterpret_cast<__nv_bfloat16*>(w.A), n_frames);
+        if ((rc = check_launch("gcc_unit_kernel"))) return rc;
+    }
+    void* table = nullptr;
+    if ((rc = gcc_table(&table))) return rc;
+    const long long rows = (long long)q.n_clips * 6 * n_frames;
+    if (rows > 0x7fffffffLL) return fail(SALSA_EINVAL, "logspec_gcc: too many rows for one call, split the batch");
+    if ((rc = crnn_gemm(w.A, table, nullptr, nullptr, w.G, (int32_t)rows, kGccLagsPad, kGccK, 0, 2, stream))) return rc;
+    ProfScope prof("gcc_scatter_kernel", st);
+    gcc_scatter_kernel<<<dim3(n_frames, 6, q.n_clips), 256, 0, st>>>(w.G, feature, n_frames, bands.n_out);
+    return check_launch("gcc_scatter_kernel");
 }
 
 size_t salsa_linspec_iv_workspace_bytes(const salsa_params_t* p) {

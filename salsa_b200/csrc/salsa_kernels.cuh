@@ -14,6 +14,8 @@
 #pragma once
 #include "eig.cuh"
 #include "fft.cuh"
+#include <cuda_bf16.h>
+
 #include "tc_ptx.cuh"
 
 namespace salsa {
@@ -61,15 +63,23 @@ struct StftArgs {
     double* power0;       // [clip][frame][upper-lower] or null
 };
 
-template <typename T>
-struct FftSmem {
+template <typename T, int WARPS>
+struct FftSmemW {
     T win[kNfft];
-    Cx<T> scratch[kWarps][kScratchElems];
+    Cx<T> scratch[WARPS][kScratchElems];
     Cx<T> twiddles[kTwiddleTabElems];      // pass twiddles of the TAB variants of the transform (fft.cuh)
 };
-
 template <typename T>
-__device__ __forceinline__ void load_fft_smem(FftSmem<T>& s, const FftTables<T>& tb) {
+using FftSmem = FftSmemW<T, kWarps>;
+
+#ifndef STFT_WARPS
+#define STFT_WARPS 8                     // warps per CTA of stft_kernel (a multiple of the channel count)
+#endif
+constexpr int kStftWarps = STFT_WARPS;
+constexpr int kStftThreads = kStftWarps * 32;
+
+template <typename S, typename T>
+__device__ __forceinline__ void load_fft_smem(S& s, const FftTables<T>& tb) {
     if (tb.window)
         for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s.win[i] = tb.window[i];
     load_twiddle_tables(s.twiddles, tb);
@@ -181,9 +191,10 @@ constexpr int kStftX = 1, kStftPower0 = 2, kStftSpec = 4, kStftAny = -1;
 constexpr int kStftTiled = 8, kStftTiledAny = 16;
 
 template <typename T, int CH, int OUT>
-__global__ void __launch_bounds__(kThreads, STFT_MINB) stft_kernel(StftArgs a, FftTables<T> tb) {
+__global__ void __launch_bounds__(kStftThreads, STFT_MINB) stft_kernel(StftArgs a, FftTables<T> tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
+    using Smem = FftSmemW<T, kStftWarps>;
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     load_fft_smem(s, tb);
     __syncthreads();
     const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
@@ -199,8 +210,8 @@ __global__ void __launch_bounds__(kThreads, STFT_MINB) stft_kernel(StftArgs a, F
     constexpr bool tiled = OUT != kStftAny && (OUT & (kStftTiled | kStftTiledAny)) != 0;
     // a warp keeps its channel: items (frame, channel) are dealt frame-major, so warp w walks the frames
     // f0 + w / CH, + kWarps / CH, ... of channel w % CH
-    static_assert(kWarps % CH == 0, "channels divide the warps of a CTA");
-    constexpr int kFrameStep = kWarps / CH;
+    static_assert(kStftWarps % CH == 0, "channels divide the warps of a CTA");
+    constexpr int kFrameStep = kStftWarps / CH;
     const int ch = warp % CH;
     const float* chan_audio = a.audio + ((long long)clip * a.n_chans + ch) * a.n_samples;
     Cx<T>* scratch = s.scratch[warp];
@@ -251,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, STFT_MINB) stft_kernel(StftArgs a, F
                 if (has_p0 && ch == 0) prow[k] = fma((double)re, (double)re, (double)im * (double)im);
             }
         }
+        if (!tiled && has_x && a.upper > kHalf && lane == 0) xrow[kHalf] = make_float2(hf[0].x, 0.0f);     // the Nyquist bin (real)
         if (has_spec) {
             const float p_nyq = hf[0].x * hf[0].x;        // lane 0: hr[0] = X[256], real
             float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
@@ -920,6 +932,78 @@ __global__ void __launch_bounds__(256) iv_kernel(const float2* __restrict__ X, f
             out[c * chan_stride + k] = v;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GCC-PHAT of LogSpecGccExtractor (dataset/feature_extraction.py:411-445): per channel pair the inverse real FFT of the
+// unit phasors of the cross spectrum of a 1024-point STFT (the 512-sample window zero-padded to 1024, librosa's
+// win_length < n_fft), of which the 200 lags -100 .. 99 are kept.
+//   * the 1024-point spectrum of a zero-padded 512-sample frame is two 512-point transforms: even bins 2m = F[m] with
+//     F = DFT512(w x); odd bins 2m+1 = S[m] + i C[m] (up to a sign common to all channels) with C / S = DFT512(w x cos(pi j/512))
+//     / DFT512(w x sin(pi j/512)): three passes of stft_kernel with three windows (XE bins 0..256, XC / XS bins 0..255);
+//   * gcc_unit_kernel: U[k] = R / |R|, R = X_sig[k] conj(X_ref[k]) (= exp(i angle(R)), 1 where R = 0) for the six pairs,
+//     written as the bf16x2-split rows of a GEMM operand: row (clip, pair, frame), columns [Re U0, Re U512, Re U1, Im U1, ...];
+//   * the inverse transform restricted to 200 lags is that row times a constant 1024 x 200 cosine / sine table: crnn_gemm
+//     (tcgen05, two bf16 planes per operand = float32-grade), then gcc_scatter_kernel puts the rows into the feature layout.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGccK = 1024;          // GEMM K: 2 real + 2 x 511 (re, im) values per row
+constexpr int kGccLags = 200, kGccLagsPad = 256;
+
+__global__ void __launch_bounds__(256) gcc_unit_kernel(const float2* __restrict__ XE, const float2* __restrict__ XC,
+                                                       const float2* __restrict__ XS, __nv_bfloat16* __restrict__ A, int n_frames) {
+    const int t = blockIdx.x, clip = blockIdx.y;
+    const long long ft = (long long)clip * n_frames + t;
+    const float2* e = XE + ft * 4 * (kHalf + 1);
+    const float2* c = XC + ft * 4 * kHalf;
+    const float2* sn = XS + ft * 4 * kHalf;
+    for (int k = threadIdx.x; k <= 2 * kHalf; k += blockDim.x) {
+        float2 x[4];
+        const int m = k >> 1;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            if (k & 1) {
+                const float2 cc = __ldg(c + ch * kHalf + m), ss = __ldg(sn + ch * kHalf + m);
+                x[ch] = make_float2(ss.x - cc.y, ss.y + cc.x);           // S + i C
+            } else {
+                x[ch] = __ldg(e + ch * (kHalf + 1) + m);
+            }
+        }
+        int pair = 0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int mm = n + 1; mm < 4; ++mm, ++pair) {
+                // R = X_sig conj(X_ref), sig = mm, ref = n (:135-136, :431)
+                const float re = fmaf(x[mm].x, x[n].x, x[mm].y * x[n].y), im = fmaf(x[mm].y, x[n].x, -x[mm].x * x[n].y);
+                const float mag2 = fmaf(re, re, im * im);
+                float ur = 1.0f, ui = 0.0f;                               // angle(0) = 0
+                if (mag2 > 0.0f) {
+                    const float inv = rsqrtf(mag2);
+                    ur = re * inv;
+                    ui = im * inv;
+                }
+                __nv_bfloat16* row = A + (((long long)clip * 6 + pair) * n_frames + t) * (2 * kGccK);
+                auto put = [&](int col, float v) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                    row[col] = hi;
+                    row[kGccK + col] = __float2bfloat16_rn(v - __bfloat162float(hi));
+                };
+                if (k == 0) put(0, ur);
+                else if (k == 2 * kHalf) put(1, ur);
+                else {
+                    put(2 * k, ur);
+                    put(2 * k + 1, ui);
+                }
+            }
+    }
+}
+
+// G [rows = (clip, pair, frame)][256] fp32 -> feature [clip][10][T][200], channels 4 + pair
+__global__ void __launch_bounds__(256) gcc_scatter_kernel(const float* __restrict__ G, float* __restrict__ feature, int n_frames, int feat_dim) {
+    const int t = blockIdx.x, pair = blockIdx.y, clip = blockIdx.z;
+    const float* src = G + (((long long)clip * 6 + pair) * n_frames + t) * kGccLagsPad;
+    float* dst = feature + (((long long)clip * 10 + 4 + pair) * n_frames + t) * feat_dim;
+    for (int i = threadIdx.x; i < feat_dim; i += blockDim.x) dst[i] = i < kGccLags ? src[i] : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------------

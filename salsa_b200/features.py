@@ -16,7 +16,7 @@ import torch
 from . import _native
 from ._native import SalsaParams
 
-__all__ = ['doa_bins', 'MagStftExtractor', 'LinSpecIvExtractor', 'extract_normalized_eigenvector', 'SalsaExtractor',
+__all__ = ['doa_bins', 'MagStftExtractor', 'LinSpecIvExtractor', 'LogSpecGccExtractor', 'extract_normalized_eigenvector', 'SalsaExtractor',
            'SalsaLiteExtractor', 'stft', 'FeatureScaler', 'compute_scaler']
 
 
@@ -181,6 +181,55 @@ class LinSpecIvExtractor:
 
     def extract(self, audio_input: np.ndarray) -> np.ndarray:
         """(4, n_samples) float32 -> (7, n_timeframes, 200) float32, like the reference."""
+        audio = np.ascontiguousarray(audio_input, dtype=np.float32)
+        if audio.ndim != 2 or audio.shape[0] != 4:
+            raise ValueError('audio_input must be (4, n_samples), got {}'.format(audio.shape))
+        return self.extract_batch(torch.from_numpy(audio)[None].cuda()).cpu().numpy()[0]
+
+
+class LogSpecGccExtractor:
+    """Log-linear spectrogram + GCC-PHAT of the six microphone pairs (MIC format), same constructor and `extract` contract
+    as the reference class (dataset/feature_extraction.py:362-482): (4, n_samples) -> (10, n_timeframes, 200).
+    `extract_batch` is the device-resident batch form (it walks the batch in chunks: the workspace is ~0.4 GB per 60 s clip)."""
+
+    def __init__(self, n_fft: int, hop_length: int, win_length: int = None, window: str = 'hann',
+                 is_compress_high_freq: bool = True, stft_precision: int = 64, clips_per_chunk: int = 16):
+        self.n_fft, self.hop_length, self.window = n_fft, hop_length, window
+        self.win_length = self.n_fft if win_length is None else win_length
+        assert self.win_length <= self.n_fft, 'Windown length is greater than nfft!'
+        assert n_fft == 512 or n_fft == 256, 'nfft is not 512 or 256'
+        if n_fft != 512 or not is_compress_high_freq or self.win_length != n_fft or window != 'hann':
+            raise NotImplementedError('salsa_b200 implements n_fft = win_length = 512, window="hann", is_compress_high_freq=True')
+        self.stft_precision = stft_precision
+        self.n_freqs = 200
+        self.clips_per_chunk = int(clips_per_chunk)
+        self._workspace = None
+
+    def extract_batch(self, audio: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """audio (B, 4, N) float32 CUDA -> (B, 10, T, 200) float32 CUDA."""
+        _require_cuda()
+        if audio.dim() != 3 or audio.shape[1] != 4 or audio.dtype != torch.float32 or not audio.is_cuda:
+            raise ValueError('audio must be a CUDA float32 tensor of shape (B, 4, N)')
+        audio = audio.contiguous()
+        B, _, N = audio.shape
+        lib = _native.lib()
+        T = lib.salsa_n_frames(N, self.hop_length)
+        if out is None:
+            out = torch.empty((B, 10, T, self.n_freqs), dtype=torch.float32, device=audio.device)
+        else:
+            _check_out(out, (B, 10, T, self.n_freqs), audio.device)
+        for c0 in range(0, B, self.clips_per_chunk):
+            n = min(self.clips_per_chunk, B - c0)
+            p = _params(n, N, n_fft=self.n_fft, hop_len=self.hop_length, win_len=self.win_length, stft_precision=self.stft_precision)
+            need = lib.salsa_logspec_gcc_workspace_bytes(ctypes.byref(p))
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != audio.device:
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=audio.device)
+            with _native.device_of(audio) as st:
+                _native.check(lib.salsa_logspec_gcc(ctypes.byref(p), _ptr(audio[c0:c0 + n]), _ptr(out[c0:c0 + n]), _ptr(self._workspace),
+                                                    self._workspace.numel(), st))
+        return out
+
+    def extract(self, audio_input: np.ndarray) -> np.ndarray:
         audio = np.ascontiguousarray(audio_input, dtype=np.float32)
         if audio.ndim != 2 or audio.shape[0] != 4:
             raise ValueError('audio_input must be (4, n_samples), got {}'.format(audio.shape))

@@ -420,3 +420,27 @@ def test_script_level_seam_writes_the_reference_layout(sb, tmp_path):
     np.testing.assert_allclose(sc['mean'], mean, rtol=0, atol=2e-4)
     np.testing.assert_allclose(sc['std'], std, rtol=0, atol=2e-4)
     assert (feat_dir / 'salsa' / 'foa' / '24000fs_512nfft_300nhop_5cond_9000fmaxdoa' / 'foa_eval').is_dir()
+
+
+def test_linspec_gcc_matches_golden_and_oracle(sb, golden):
+    """LogSpecGccExtractor (dataset/feature_extraction.py:362-482): the 1024-point zero-padded STFT assembled from three
+    512-point transforms, unit cross-spectrum phasors, and the inverse transform restricted to 200 lags as a tcgen05 GEMM
+    (two bf16 planes per operand).  Spectrogram channels to 1e-4 max(1, |ref|), GCC channels (|values| <= 1) to 1e-4."""
+    from oracle import salsa as osalsa, synth
+    ref = golden('extras_cases')['linspecgcc_mic']
+    ex = sb.LogSpecGccExtractor(n_fft=512, hop_length=300, win_length=512)
+    out = ex.extract(golden('clip_cases')['audio_mic'][:, :12000])
+    assert out.shape == ref.shape == (10, 41, 200) and out.dtype == np.float32
+    close(out[:4], ref[:4], 'linspecgcc spectrogram')
+    err = np.abs(out[4:] - ref[4:])
+    print('linspecgcc golden: GCC max |err| {:.2e} (peak {:.2f})'.format(err.max(), np.abs(ref[4:]).max()))
+    assert err.max() <= 1e-4
+    clips = np.stack([synth.make_clip(75 + i, 'mic', seconds=2.0) for i in range(3)])
+    ex2 = sb.LogSpecGccExtractor(n_fft=512, hop_length=300, clips_per_chunk=2)          # two chunks
+    batch = ex2.extract_batch(torch.from_numpy(clips).cuda()).cpu().numpy()
+    for i in range(3):
+        want = osalsa.linspec_gcc_clip(clips[i])
+        close(batch[i, :4], want[:4], 'linspecgcc spectrogram (2 s)')
+        assert np.abs(batch[i, 4:] - want[4:]).max() <= 1e-4
+    with pytest.raises(NotImplementedError):
+        sb.LogSpecGccExtractor(n_fft=512, hop_length=300, win_length=400)

@@ -251,3 +251,14 @@ def test_linspec_iv_oracle_matches_reference_golden(golden):
     np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
     # the spectrogram part is MagStftExtractor's (same W, same window): identical to the SALSA golden
     np.testing.assert_allclose(ref[:4], golden('clip_cases')['logspec_foa'], rtol=0, atol=1e-6)
+
+
+def test_linspec_gcc_oracle_matches_reference_golden(golden):
+    """oracle.salsa.linspec_gcc_clip restates LogSpecGccExtractor (dataset/feature_extraction.py:362-482); the golden array is the
+    unmodified class's output on the first 0.5 s of the golden MIC clip."""
+    from oracle import salsa as osalsa
+    out = osalsa.linspec_gcc_clip(golden('clip_cases')['audio_mic'][:, :12000])
+    ref = golden('extras_cases')['linspecgcc_mic']
+    assert out.shape == ref.shape == (10, 41, 200)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
+    assert np.abs(ref[4:]).max() > 0.3               # real correlation peaks, not noise
