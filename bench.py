@@ -666,7 +666,7 @@ def bench_train(args, torch, dist, rank, world, dev):
     ex = salsa_b200.SalsaExtractor('foa')
     aug = augment.BatchAugment(augment.TfmapRandomSwapChannelFoa(n_classes=12), augment.RandomShiftUpDownNp(freq_shift_range=10))
     sched = salsa_b200.optim.LearningRateScheduler(steps_per_epoch=100, max_epochs=50)
-    tr = train.SeldTrainer(salsa_b200.crnn.random_state_dict(0), scheduler=sched, device=dev)
+    tr = train.SeldTrainer(salsa_b200.crnn.random_state_dict(0), scheduler=sched, device=dev, use_graph=not args.no_train_graph)
     g = torch.Generator(device=dev)
     g.manual_seed(77 + rank)
     tgt = {'event_frame_gt': (torch.rand((B, 80, 12), generator=g, device=dev) > 0.8).float(),
@@ -687,7 +687,7 @@ def bench_train(args, torch, dist, rank, world, dev):
     return {'config': 'configs[4]: CRNN (ResNet22 + BiGRU) training step on on-the-fly SALSA FOA features, bf16 autocast, batch {} x (7, 640, 200) '
                       'per GPU, {} GPU(s) data-parallel'.format(B, world),
             'value': B * world / (ms / 1e3), 'unit': 'chunks/s (8 s each)', 'audio_min_per_s': B * world * 8 / 60.0 / (ms / 1e3),
-            'ms_per_step': ms, 'ms_features': ms_feat, 'loss_first_step': first, 'loss_last_step': last, 'parameters': n_params,
+            'ms_per_step': ms, 'ms_features': ms_feat, 'cuda_graph': ('off' if args.no_train_graph else (tr.graph_error or 'forward + loss + backward + all-reduce + Adam replayed as one CUDA graph')), 'loss_first_step': first, 'loss_last_step': last, 'parameters': n_params,
             'allreduce': 'bucketed bf16 all-reduce of the flat gradient ({:.1f} MB on the wire per step), launched per bucket during the '
                          'backward pass'.format(n_params * 2 / 1e6) if world > 1 else 'single rank: none',
             'native': 'SALSA features, augmentation, 3x3 convolution forward + input gradient + weight gradient (tcgen05), train-mode BatchNorm + residual + ReLU and 2x2 pooling forward / backward, loss, Adam',
@@ -718,6 +718,7 @@ def main():
     ap.add_argument('--crnn-batch', type=int, default=32, help='clips per CRNN forward per GPU')
     ap.add_argument('--train-batch', type=int, default=32, help='8 s chunks per training step per GPU')
     ap.add_argument('--no-train', action='store_true', help='skip the configs[4] training-step leg')
+    ap.add_argument('--no-train-graph', action='store_true', help='training step as single launches instead of one CUDA graph replay')
     args = ap.parse_args()
 
     rank, world, local_rank = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)

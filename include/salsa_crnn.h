@@ -197,6 +197,14 @@ int crnn_seld_loss(const float *logit, const float *doa, const float *event_gt, 
 int crnn_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr, double beta1,
                    double beta2, double eps, int32_t step, void *stream);
 
+/* The same step with its per-batch scalars in DEVICE memory, for a training step replayed as a CUDA graph (the reference
+ * changes lr / beta1 every batch, utilities/learning_utils.py:44-52): crnn_adam_hyper fills hyper_host[6] = {1 - beta1, beta2,
+ * 1 - beta2, eps, lr / (1 - beta1^step), sqrt(1 - beta2^step)} exactly as crnn_adam_step forms them; the caller copies the 24
+ * bytes to the device (stream-ordered) before crnn_adam_step_hyper, which reads them from hyper_dev. */
+int crnn_adam_hyper(double lr, double beta1, double beta2, double eps, int32_t step, float *hyper_host);
+int crnn_adam_step_hyper(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                         const float *hyper_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,8 @@ SIGNATURES = {
     'crnn_augment': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_cutout': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _i32, _vp]),
+    'crnn_adam_hyper': (ctypes.c_int, [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _i32, _vp]),
+    'crnn_adam_step_hyper': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, _vp, _vp]),
     'crnn_seld_loss': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, _i32, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),
 }
 

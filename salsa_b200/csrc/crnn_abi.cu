@@ -474,4 +474,27 @@ int crnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
     return check_cuda(cudaGetLastError(), "adam_step_kernel");
 }
 
+int crnn_adam_hyper(double lr, double beta1, double beta2, double eps, int32_t step, float* hyper_host) {
+    if (!hyper_host) return fail(SALSA_EINVAL, "adam_hyper: null pointer");
+    if (step < 1) return fail(SALSA_EINVAL, "adam_hyper: step counts from 1");
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    hyper_host[0] = (float)(1.0 - beta1);
+    hyper_host[1] = (float)beta2;
+    hyper_host[2] = (float)(1.0 - beta2);
+    hyper_host[3] = (float)eps;
+    hyper_host[4] = (float)(lr / bc1);
+    hyper_host[5] = (float)sqrt(bc2);
+    return SALSA_OK;
+}
+
+int crnn_adam_step_hyper(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper_dev,
+                         void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper_dev) return fail(SALSA_EINVAL, "adam_step_hyper: null pointer");
+    if (n <= 0) return SALSA_OK;
+    adam_step_hyper_kernel<<<std::min(grid_for(n, 256), 4096), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n,
+                                                                                             hyper_dev);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "adam_step_hyper_kernel");
+}
+
 }  // extern "C"

@@ -873,5 +873,25 @@ __global__ void adam_step_kernel(float* __restrict__ param, const float* __restr
     }
 }
 
+// The same update with the six per-step scalars read from device memory (hyper = {1 - beta1, beta2, 1 - beta2, eps,
+// step_size, bias2_sqrt}, filled by crnn_adam_hyper): a CUDA graph of the training step can be replayed with a new
+// learning rate / beta1 / step count by rewriting 24 bytes.
+__global__ void adam_step_hyper_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
+                                       float* __restrict__ exp_avg_sq, long long n, const float* __restrict__ hyper) {
+    const float w = hyper[0], beta2 = hyper[1], one_minus_beta2 = hyper[2], eps = hyper[3], step_size = hyper[4], bias2_sqrt = hyper[5];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float g = grad[i];
+        float m = exp_avg[i];
+        const float diff = g - m;
+        m = w < 0.5f ? fmaf(w, diff, m) : g - diff * (1.0f - w);
+        float v = exp_avg_sq[i] * beta2;
+        v = fmaf(one_minus_beta2 * g, g, v);
+        exp_avg[i] = m;
+        exp_avg_sq[i] = v;
+        const float denom = sqrtf(v) / bias2_sqrt + eps;
+        param[i] = param[i] - step_size * (m / denom);
+    }
+}
+
 }  // namespace crnn
 }  // namespace salsa

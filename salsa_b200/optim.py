@@ -1,8 +1,8 @@
 """Optimiser side of the reference's training step, for parameters that live in one flat CUDA
 buffer: `Adam` = torch.optim.Adam as `BaseModel.configure_optimizers` builds it (models/interfaces.py:85-95) and
 `LearningRateScheduler` = the piecewise-linear learning-rate / beta1 schedule of utilities/learning_utils.py:17-52
-(same constructor arguments, `np.interp` over the same step milestones).  The backward pass that would produce the
-gradients is not part of this package yet."""
+(same constructor arguments, `np.interp` over the same step milestones).  The training step that produces the gradients
+is salsa_b200.train.SeldTrainer."""
 import ctypes
 
 import numpy as np
@@ -42,6 +42,25 @@ class Adam:
         self.exp_avg = torch.zeros_like(flat_params)
         self.exp_avg_sq = torch.zeros_like(flat_params)
         self.step_count = 0
+
+    # ---- the same step for a CUDA-graph replayed training step: the scalars of this batch travel through device memory
+    def stage_hyper(self):
+        """Advances the step count, forms this batch's scalars on the host (crnn_adam_hyper: the same arithmetic as
+        crnn_adam_step) and copies them, stream-ordered, into the device buffer `step_staged` reads."""
+        if not hasattr(self, '_hyper_host'):
+            self._hyper_host = torch.empty(6, dtype=torch.float32).pin_memory()
+            self._hyper_dev = torch.zeros(6, dtype=torch.float32, device=self.params.device)
+        self.step_count += 1
+        _native.check(_native.lib().crnn_adam_hyper(ctypes.c_double(self.lr), ctypes.c_double(self.betas[0]), ctypes.c_double(self.betas[1]),
+                                                    ctypes.c_double(self.eps), self.step_count, ctypes.c_void_p(self._hyper_host.data_ptr())))
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+
+    def step_staged(self, flat_grads: torch.Tensor):
+        """The update with the scalars staged by `stage_hyper` (one kernel launch, no host state: capturable)."""
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        with _native.device_of(self.params) as st:
+            _native.check(_native.lib().crnn_adam_step_hyper(vp(self.params), vp(flat_grads), vp(self.exp_avg), vp(self.exp_avg_sq),
+                                                             self.params.numel(), vp(self._hyper_dev), st))
 
     def step(self, flat_grads: torch.Tensor):
         if flat_grads.shape != self.params.shape or flat_grads.dtype != torch.float32 or not flat_grads.is_cuda:

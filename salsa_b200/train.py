@@ -160,9 +160,11 @@ class SeldTrainer:
     def __init__(self, state_dict, n_classes: int = 12, label_rate: int = 10, feature_rate: float = 80.0, loss_weight=(0.3, 0.7),
                  lr: float = 1e-3, device='cuda', native_conv: bool = True, group=None, scheduler: LearningRateScheduler = None,
                  bucket_bytes: int = 8 << 20, wire_dtype=torch.bfloat16, autocast: bool = True, dropout: bool = True,
-                 native_bn: bool = True):
+                 native_bn: bool = True, use_graph: bool = False):
         """native_conv / native_bn / autocast / dropout = False are for tests (a pure torch float32 reference of the same step);
-        wire_dtype None sends float32 gradients."""
+        wire_dtype None sends float32 gradients.  use_graph: `step` captures forward + loss + backward (+ all-reduce) + Adam as
+        ONE CUDA graph at the first sighting of a batch shape and replays it afterwards (about 1000 launches per step
+        otherwise: the step is host-bound without it); lr / beta1 / the step count reach the replay through device memory."""
         self.device = torch.device(device)
         self.n_classes, self.loss_weight = n_classes, tuple(loss_weight)
         self.ratio = 16.0 * label_rate / feature_rate                 # time_downsample_ratio * label_rate / feature_rate
@@ -193,6 +195,10 @@ class SeldTrainer:
         self.gru = torch.nn.GRU(input_size=512, hidden_size=256, num_layers=2, batch_first=True, bidirectional=True, dropout=0.3).to(self.device)
         self.training = True
         self.epoch, self.batch_idx = 0, 0
+        self.use_graph = use_graph and self.device.type == 'cuda'
+        self._graphs = {}                    # batch shape -> (graph, static inputs, static loss)
+        self._index_cache = {}
+        self.graph_error = None              # why a capture fell back to eager launches (None: it did not)
 
     # ---- state ------------------------------------------------------------------------------------------------------
     def state_dict(self):
@@ -258,13 +264,75 @@ class SeldTrainer:
         return {'event_frame_logit': logit.float(), 'doa_frame_output': doa.float()}
 
     # ---- one training step ------------------------------------------------------------------------------------------
+    def _label_index(self, n_frames):
+        """Index map of interpolate_tensor on the device, built once per sequence length (no host copy inside a capture)."""
+        key = (n_frames, self.ratio)
+        if key not in self._index_cache:
+            self._index_cache[key] = torch.as_tensor(ops.interpolate_index(n_frames, self.ratio), device=self.device)
+        return self._index_cache[key]
+
     def step(self, x, target_dict):
         """forward -> interpolate to the label rate -> loss -> backward (bucketed all-reduce overlapped) -> Adam.
         Returns (loss, sed_loss, doa_loss) as a float32 tensor (3,)."""
+        if self.use_graph and self.graph_error is None:
+            return self._step_graph(x, target_dict)
+        return self._step_eager(x, target_dict)
+
+    # ---- the step as one CUDA graph ---------------------------------------------------------------------------------------
+    def _mutable_state(self):
+        return [self.flat, self.optimizer.exp_avg, self.optimizer.exp_avg_sq] + list(self.buffers.values())
+
+    def _step_graph(self, x, target_dict):
+        egt, dgt = target_dict['event_frame_gt'], target_dict['doa_frame_gt']
+        key = (tuple(x.shape), tuple(egt.shape), tuple(dgt.shape))
+        if key not in self._graphs:
+            static = [torch.empty_like(x, memory_format=torch.contiguous_format), torch.empty_like(egt), torch.empty_like(dgt)]
+            for s_, t_ in zip(static, (x, egt, dgt)):
+                s_.copy_(t_)
+            body = lambda: self._step_eager(static[0], {'event_frame_gt': static[1], 'doa_frame_gt': static[2]}, staged=True)
+            # warm-up on a side stream (lazy initialisation of cuDNN / autograd / the allocator must not be captured), with
+            # the trainer's state put back afterwards so that it is not part of the training trajectory
+            saved = [t.clone() for t in self._mutable_state()]
+            saved_count, saved_idx = self.optimizer.step_count, self.batch_idx
+            try:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        self.optimizer.stage_hyper()
+                        body()
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    loss = body()
+            except Exception as e:                      # capture refused (a library call that is not capturable): eager launches
+                self.graph_error = '{}: {}'.format(type(e).__name__, str(e).splitlines()[0] if str(e) else '')
+                torch.cuda.synchronize(self.device)
+                graph = None
+            for t, sv in zip(self._mutable_state(), saved):
+                t.copy_(sv)
+            self.optimizer.step_count, self.batch_idx = saved_count, saved_idx
+            if graph is None:
+                return self._step_eager(x, target_dict)
+            self._graphs[key] = (graph, static, loss)
+        graph, static, loss = self._graphs[key]
+        for s_, t_ in zip(static, (x, egt, dgt)):
+            s_.copy_(t_)
+        if self.scheduler is not None:
+            self.scheduler.apply(self.optimizer, self.epoch, self.batch_idx)
+        self.optimizer.stage_hyper()
+        graph.replay()
+        self.batch_idx += 1
+        return loss.clone()
+
+    def _step_eager(self, x, target_dict, staged=False):
+        """The launches of one step; `staged`: Adam reads this batch's scalars from device memory (stage_hyper) and the
+        schedule / counters are advanced by the caller (the body a CUDA graph is captured from)."""
         self.flat_grad.zero_()
         self.reducer.reset()
         out = self.forward(x)
-        idx = torch.as_tensor(ops.interpolate_index(out['event_frame_logit'].shape[1], self.ratio), device=self.device)
+        idx = self._label_index(out['event_frame_logit'].shape[1])
         logit, doa = out['event_frame_logit'][:, idx], out['doa_frame_output'][:, idx]      # interpolate_tensor (model_utils.py:57-75)
         n = min(logit.shape[1], target_dict['event_frame_gt'].shape[1])
         logit, doa = logit[:, :n], doa[:, :n]
@@ -280,6 +348,9 @@ class SeldTrainer:
             total.backward()
             loss = torch.stack([total.detach(), sed.detach(), d.detach()])
         self.reducer.finish()
+        if staged:
+            self.optimizer.step_staged(self.flat_grad)
+            return loss
         if self.scheduler is not None and self.optimizer is not None:
             self.scheduler.apply(self.optimizer, self.epoch, self.batch_idx)
         if self.optimizer is not None:

@@ -148,3 +148,42 @@ def test_steps_reduce_the_loss_and_weights_hand_over_to_inference():
     for k in want:
         print('hand-over to the inference model:', k, 'rel-to-scale difference {:.3e}'.format(rel(got[k], want[k])))
         assert rel(got[k], want[k]) < 1e-1, k
+
+
+def test_graph_replayed_step_follows_the_eager_step():
+    """use_graph=True: forward + loss + backward + Adam captured once and replayed, lr / beta1 / step count through device
+    memory.  With dropout off both trajectories differ only by the summation order of the weight gradient's atomics (which a
+    large learning rate amplifies within a few steps: the schedule here stays below 5e-4); the
+    warm-up runs of the capture must not leak into the training state (first loss identical to the eager trainer's)."""
+    import salsa_b200
+    from salsa_b200 import train
+    sd = salsa_b200.crnn.random_state_dict(4)
+    x, tgt = _batch(seed=11)
+    mk = lambda **kw: train.SeldTrainer(sd, lr=1e-3, dropout=False,
+                                        scheduler=salsa_b200.optim.LearningRateScheduler(steps_per_epoch=4, max_epochs=2, lrs=(1e-4, 5e-4, 2e-4, 1e-4)), **kw)
+    eager, graphed = mk(), mk(use_graph=True)
+    le = [eager.step(x, tgt) for _ in range(6)]
+    lg = [graphed.step(x, tgt) for _ in range(6)]
+    assert graphed.graph_error is None, graphed.graph_error
+    assert len(graphed._graphs) == 1
+    le, lg = torch.stack(le).cpu(), torch.stack(lg).cpu()
+    print('eager', le[:, 0].tolist(), 'graph', lg[:, 0].tolist())
+    assert torch.allclose(le[0], lg[0], rtol=1e-4, atol=1e-5)            # same state at the first step
+    assert torch.allclose(le, lg, rtol=5e-2, atol=5e-3)                   # the same trajectory (schedule crossing a milestone)
+    assert eager.optimizer.step_count == graphed.optimizer.step_count == 6 and graphed.batch_idx == 6
+    # running statistics advanced exactly six times
+    k = 'encoder.conv_block1.bn1.running_mean'
+    assert rel(graphed.buffers[k], eager.buffers[k]) < 1e-2
+
+
+def test_adam_step_with_device_scalars_equals_the_scalar_call():
+    import salsa_b200
+    g = torch.Generator().manual_seed(0)
+    p0, grad = torch.randn(10007, generator=g).cuda(), torch.randn(10007, generator=g).cuda()
+    a, b = salsa_b200.optim.Adam(p0.clone(), lr=3e-3, betas=(0.85, 0.999)), salsa_b200.optim.Adam(p0.clone(), lr=3e-3, betas=(0.85, 0.999))
+    for i in range(3):
+        a.lr = b.lr = 3e-3 * (i + 1)
+        a.step(grad * (i + 1))
+        b.stage_hyper()
+        b.step_staged(grad * (i + 1))
+    assert torch.equal(a.params, b.params) and torch.equal(a.exp_avg_sq, b.exp_avg_sq) and a.step_count == b.step_count == 3
