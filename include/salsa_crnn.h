@@ -95,11 +95,14 @@ int crnn_bn_train_forward(const void *y, const float *gamma, const float *beta, 
                           float momentum, int32_t relu, void *stream);
 
 /* Its backward pass: dz = dLoss/dz (bf16), z / y / stat from the forward ->
- *   dy bf16 = gamma / std (g - mean(g) - xhat mean(g xhat)),  g = dz (z > 0 when relu),  xhat = (y - mean) / std
- *   d_residual bf16 (optional) = g;  dgamma fp32 [C] = sum g xhat;  dbeta fp32 [C] = sum g;  sums float64 [C][2] scratch. */
-int crnn_bn_train_backward(const void *dz, const void *z, const void *y, const float *stat, const float *gamma, void *dy,
-                           void *d_residual, double *sums, float *dgamma, float *dbeta, int64_t n_pix, int32_t C, int32_t relu,
-                           void *stream);
+ *   dy bf16 = gamma / std (g - mean(g) - xhat mean(g xhat)),  g = dz * mask,  xhat = (y - mean) / std
+ *   d_residual bf16 (optional) = g;  dgamma fp32 [C] = sum g xhat;  dbeta fp32 [C] = sum g;  sums float64 [C][2] scratch.
+ *   relu = 0: no ReLU in the forward (mask = 1);  1: mask = z > 0, read from z;  2: the forward had NO residual, so the mask
+ *   is recomputed from y, gamma, beta and stat with the forward's own expression (bit-identical to z > 0; z may be NULL and
+ *   one tensor less is read).  beta is only used by relu = 2. */
+int crnn_bn_train_backward(const void *dz, const void *z, const void *y, const float *stat, const float *gamma,
+                           const float *beta, void *dy, void *d_residual, double *sums, float *dgamma, float *dbeta,
+                           int64_t n_pix, int32_t C, int32_t relu, void *stream);
 
 /* The first convolution of the encoder (conv_block1.conv1 + bn1 + ReLU, models/model_utils.py:213-215) on an input
  * padded to 16 channels: x bf16 NHWC [B][H][W][planes*16], w bf16 [9][64][planes*16] -> out bf16 [B][H][W][planes*64]. */

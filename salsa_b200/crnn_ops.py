@@ -110,8 +110,9 @@ def bn_train_forward(y, gamma, beta, residual=None, relu=True, running_mean=None
     return z, stat
 
 
-def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False):
-    """-> (dy bf16, d_residual bf16 or None, dgamma fp32 (C,), dbeta fp32 (C,))."""
+def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False, beta=None):
+    """-> (dy bf16, d_residual bf16 or None, dgamma fp32 (C,), dbeta fp32 (C,)).  With `relu` and `beta` given and z None, the
+    forward had no residual and the ReLU mask is recomputed from y (one tensor less to read)."""
     _check_act(dz)
     _check_act(y)
     C = y.shape[-1]
@@ -121,8 +122,9 @@ def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False
     sums = torch.empty((C, 2), dtype=torch.float64, device=y.device)
     dgamma = torch.empty((C,), dtype=torch.float32, device=y.device)
     dbeta = torch.empty((C,), dtype=torch.float32, device=y.device)
-    _call('crnn_bn_train_backward', dz, _p(dz), _p(z), _p(y), _p(stat), _p(gamma), _p(dy), _p(dres), _p(sums), _p(dgamma), _p(dbeta), n_pix, C,
-          int(bool(relu)))
+    mode = 0 if not relu else (2 if (z is None and beta is not None) else 1)
+    _call('crnn_bn_train_backward', dz, _p(dz), _p(z), _p(y), _p(stat), _p(gamma), _p(beta), _p(dy), _p(dres), _p(sums), _p(dgamma), _p(dbeta),
+          n_pix, C, mode)
     return dy, dres, dgamma, dbeta
 
 

@@ -350,14 +350,14 @@ int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + 2), 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
         int rc = make_tmap(&tx, x, 4, dims, str, box);
         if (rc) return rc;
     }
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + 2), 1};      // the halo is taken on dY
         int rc = make_tmap(&tg, gy, 4, dims, str, box);
         if (rc) return rc;
     }
@@ -403,23 +403,34 @@ int crnn_bn_train_forward(const void* y, const float* gamma, const float* beta, 
     return check_cuda(cudaGetLastError(), "bn_train_forward");
 }
 
-int crnn_bn_train_backward(const void* dz, const void* z, const void* y, const float* stat, const float* gamma, void* dy,
-                           void* d_residual, double* sums, float* dgamma, float* dbeta, int64_t n_pix, int32_t C, int32_t relu,
-                           void* stream) {
+int crnn_bn_train_backward(const void* dz, const void* z, const void* y, const float* stat, const float* gamma, const float* beta,
+                           void* dy, void* d_residual, double* sums, float* dgamma, float* dbeta, int64_t n_pix, int32_t C,
+                           int32_t relu, void* stream) {
     if (!dz || !y || !stat || !gamma || !dy || !sums || !dgamma || !dbeta) return fail(SALSA_EINVAL, "bn_train_backward: null pointer");
-    if (relu && !z) return fail(SALSA_EINVAL, "bn_train_backward: the ReLU mask needs the forward output");
+    if (relu < 0 || relu > 2) return fail(SALSA_EINVAL, "bn_train_backward: relu is 0 (none), 1 (mask from z) or 2 (mask recomputed from y)");
+    if (relu == 1 && !z) return fail(SALSA_EINVAL, "bn_train_backward: the ReLU mask needs the forward output");
+    if (relu == 2 && !beta) return fail(SALSA_EINVAL, "bn_train_backward: recomputing the ReLU mask needs beta");
     if (C <= 0 || C % 8 != 0 || C > 512 || 256 % (C / 8) != 0) return fail(SALSA_EINVAL, "bn_train_backward: C must be 64, 128, 256 or 512");
     if (n_pix <= 0) return fail(SALSA_EINVAL, "bn_train_backward: empty input");
     cudaStream_t st = (cudaStream_t)stream;
     SALSA_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(double), st));
     const int lanes = 256 / (C / 8);
-    const int blocks = (int)std::min<long long>((n_pix + lanes * 32 - 1) / (lanes * 32), 148LL * 8);
-    bn_bwd_reduce_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), reinterpret_cast<const __nv_bfloat16*>(z),
-                                                              reinterpret_cast<const __nv_bfloat16*>(y), stat, n_pix, C, relu, sums);
+    const int blocks = std::max(1, (int)std::min<long long>((n_pix + lanes * 32 - 1) / (lanes * 32), 148LL * 8));
+    const int grid2 = grid_for((n_pix * (C / 8) + 1) / 2, 256);
+    const __nv_bfloat16 *pdz = reinterpret_cast<const __nv_bfloat16*>(dz), *pz = reinterpret_cast<const __nv_bfloat16*>(z),
+                        *py = reinterpret_cast<const __nv_bfloat16*>(y);
+    __nv_bfloat16 *pdy = reinterpret_cast<__nv_bfloat16*>(dy), *pdr = reinterpret_cast<__nv_bfloat16*>(d_residual);
+    if (relu == 0) {
+        bn_bwd_reduce_kernel<0><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums);
+        bn_bwd_apply_kernel<0><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C);
+    } else if (relu == 1) {
+        bn_bwd_reduce_kernel<1><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums);
+        bn_bwd_apply_kernel<1><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C);
+    } else {
+        bn_bwd_reduce_kernel<2><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums);
+        bn_bwd_apply_kernel<2><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C);
+    }
     count_launch();
-    bn_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dz), reinterpret_cast<const __nv_bfloat16*>(z), reinterpret_cast<const __nv_bfloat16*>(y), stat,
-        gamma, sums, reinterpret_cast<__nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(d_residual), n_pix, C, relu);
     count_launch();
     bn_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
     count_launch();

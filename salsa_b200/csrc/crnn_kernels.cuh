@@ -477,7 +477,8 @@ __global__ void augment_kernel(const float* __restrict__ x, float* __restrict__ 
 // :356 in the training step), fused with what surrounds it in ConvBlock / _ResnetBasicBlock: the residual add and the ReLU.
 //   forward   bn_stats_kernel (per-channel sum, sum of squares) -> bn_finalize_kernel (mean, 1/std, running statistics)
 //             -> bn_apply_kernel: z = relu?(gamma (y - mean) / std + beta (+ residual))
-//   backward  bn_bwd_reduce_kernel: g = dz * (z > 0); dbeta = sum g, dgamma = sum g * xhat
+//   backward  bn_bwd_reduce_kernel: g = dz * (z > 0) (the mask read from z, or recomputed from y when there was no residual);
+//             dbeta = sum g, dgamma = sum g * xhat
 //             -> bn_bwd_apply_kernel: dy = gamma / std * (g - dbeta / N - xhat * dgamma / N); the residual branch receives g
 // Thread = 8 consecutive channels (one 16-byte load) of a strided set of pixels; C is a multiple of 8, at most 512.
 // ------------------------------------------------------------------------------------------------
@@ -502,18 +503,35 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 
 // Per-channel reduction of two quantities over the pixels: every thread accumulates its channels over its pixels in fp32
 // (at most a few hundred values), threads that share a channel group are combined through shared memory in fp64, one
-// atomicAdd(double) per channel and block.  `f(pix, c8, a, b)` adds the contributions of pixel `pix`, channels 8 c8 .. 8 c8 + 7.
-template <typename F>
-__device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* __restrict__ out /* [C][2] */, F f) {
+// atomicAdd(double) per channel and block.  `load(pix, c8, q)` fetches the NT 16-byte words of pixel `pix`, channels
+// 8 c8 .. 8 c8 + 7; `acc(q, a, b)` adds their contributions.  Four pixels' loads are issued before the first is consumed
+// (the reductions are pure streaming reads: bytes in flight are what the bandwidth depends on).
+template <int NT, typename L, typename A>
+__device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* __restrict__ out /* [C][2] */, L load, A acc) {
     __shared__ double s_red[256][2];
+    constexpr int U = 4;
     const int groups = C >> 3;                        // channel groups of 8
     const int lanes = blockDim.x / groups;            // threads per channel group (pixel lanes)
     const int c8 = threadIdx.x % groups, pl = threadIdx.x / groups;
     float a[8], b[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.0f;
-    if (pl < lanes)
-        for (long long p = (long long)blockIdx.x * lanes + pl; p < n_pix; p += (long long)gridDim.x * lanes) f(p, c8, a, b);
+    if (pl < lanes) {
+        const long long stride = (long long)gridDim.x * lanes;
+        long long p = (long long)blockIdx.x * lanes + pl;
+        for (; p + (U - 1) * stride < n_pix; p += U * stride) {
+            uint4 q[U][NT];
+#pragma unroll
+            for (int u = 0; u < U; ++u) load(p + u * stride, c8, q[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc(q[u], a, b);
+        }
+        for (; p < n_pix; p += stride) {
+            uint4 q[NT];
+            load(p, c8, q);
+            acc(q, a, b);
+        }
+    }
     // combine the pixel lanes of a channel group: one channel at a time through shared memory
     for (int i = 0; i < 8; ++i) {
         __syncthreads();
@@ -533,15 +551,17 @@ __device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* 
 }
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long n_pix, int C, double* __restrict__ sums) {
-    channel_reduce2(n_pix, C, sums, [&](long long p, int c8, float (&a)[8], float (&b)[8]) {
-        float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(y + p * C) + c8), v);
+    channel_reduce2<1>(n_pix, C, sums,
+        [&](long long p, int c8, uint4 (&q)[1]) { q[0] = __ldg(reinterpret_cast<const uint4*>(y + p * C) + c8); },
+        [&](const uint4 (&q)[1], float (&a)[8], float (&b)[8]) {
+            float v[8];
+            unpack8(q[0], v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            a[i] += v[i];
-            b[i] = fmaf(v[i], v[i], b[i]);
-        }
-    });
+            for (int i = 0; i < 8; ++i) {
+                a[i] += v[i];
+                b[i] = fmaf(v[i], v[i], b[i]);
+            }
+        });
 }
 
 // sums [C][2] -> stat [C][2] = (mean, 1 / sqrt(var + eps)) with the biased batch variance; running statistics updated like
@@ -590,10 +610,30 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
     }
 }
 
-// sums [C][2] += (sum g, sum g * xhat) with g = dz * (z > 0) when relu, xhat = (y - mean) / std
+// ReLU mask of the backward pass.  relu = 0: none; 1: z > 0 read from the forward output; 2: the forward had no residual, so
+// z = relu(scale y + shift) is a function of y alone and the mask is RECOMPUTED from y with bn_apply_kernel's own expression
+// (bit-identical to z > 0; one tensor less to read).
+struct BnMaskCoef {
+    float scale[8], shift[8];
+};
+__device__ __forceinline__ void bn_mask_coef(const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             int c0, BnMaskCoef& m) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        m.scale[k] = gamma[c0 + k] * stat[2 * (c0 + k) + 1];
+        m.shift[k] = fmaf(-stat[2 * (c0 + k)], m.scale[k], beta[c0 + k]);
+    }
+}
+__device__ __forceinline__ bool bn_mask_from_y(float y, float scale, float shift) {
+    return __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(y, scale, shift), 0.0f))) > 0.0f;
+}
+
+// sums [C][2] += (sum g, sum g * xhat) with g = dz * mask, xhat = (y - mean) / std
+template <int RELU>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                             const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
-                                                            long long n_pix, int C, int relu, double* __restrict__ sums) {
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            long long n_pix, int C, double* __restrict__ sums) {
     // a thread keeps its channel group: mean / (1 / std) of its 8 channels live in registers
     const int c0 = (int)(threadIdx.x % (C >> 3)) * 8;
     float mean[8], inv[8];
@@ -602,26 +642,38 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
         mean[k] = stat[2 * (c0 + k)];
         inv[k] = stat[2 * (c0 + k) + 1];
     }
-    channel_reduce2(n_pix, C, sums, [&](long long p, int c8, float (&a)[8], float (&b)[8]) {
-        float g[8], zz[8], yy[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dz + p * C) + c8), g);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(y + p * C) + c8), yy);
-        if (relu) unpack8(__ldg(reinterpret_cast<const uint4*>(z + p * C) + c8), zz);
+    BnMaskCoef mc;
+    if (RELU == 2) bn_mask_coef(stat, gamma, beta, c0, mc);
+    constexpr int NT = RELU == 1 ? 3 : 2;
+    channel_reduce2<NT>(n_pix, C, sums,
+        [&](long long p, int c8, uint4 (&q)[NT]) {
+            q[0] = __ldg(reinterpret_cast<const uint4*>(dz + p * C) + c8);
+            q[1] = __ldg(reinterpret_cast<const uint4*>(y + p * C) + c8);
+            if (RELU == 1) q[NT - 1] = __ldg(reinterpret_cast<const uint4*>(z + p * C) + c8);
+        },
+        [&](const uint4 (&q)[NT], float (&a)[8], float (&b)[8]) {
+            float g[8], zz[8], yy[8];
+            unpack8(q[0], g);
+            unpack8(q[1], yy);
+            if (RELU == 1) unpack8(q[NT - 1], zz);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float gi = (relu && !(zz[i] > 0.0f)) ? 0.0f : g[i];
-            a[i] += gi;
-            b[i] = fmaf(gi, (yy[i] - mean[i]) * inv[i], b[i]);
-        }
-    });
+            for (int i = 0; i < 8; ++i) {
+                const bool on = RELU == 0 ? true : (RELU == 1 ? zz[i] > 0.0f : bn_mask_from_y(yy[i], mc.scale[i], mc.shift[i]));
+                const float gi = on ? g[i] : 0.0f;
+                a[i] += gi;
+                b[i] = fmaf(gi, (yy[i] - mean[i]) * inv[i], b[i]);
+            }
+        });
 }
 
 // dy = gamma / std * (g - dbeta / N - xhat * dgamma / N) = ca g + cy y + c0 per channel; d_residual (optional) = g
+template <int RELU>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                            const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
-                                                           const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const double* __restrict__ sums,
                                                            __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ d_residual,
-                                                           long long n_pix, int C, int relu) {
+                                                           long long n_pix, int C) {
     const int groups = C >> 3;
     const long long total = n_pix * groups;
     const float inv_n = (float)(1.0 / (double)n_pix);
@@ -636,18 +688,39 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
         cy[k] = -ca[k] * dgamma * inv_n * inv;                  // coefficient of y
         cc[k] = -ca[k] * dbeta * inv_n - cy[k] * mean;          // constant
     }
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    BnMaskCoef mc;
+    if (RELU == 2) bn_mask_coef(stat, gamma, beta, c0, mc);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto one = [&](long long i, const uint4& qg, const uint4& qy, const uint4& qz) {
         float g[8], zz[8], yy[8], o[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dz) + i), g);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
-        if (relu) unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
+        unpack8(qg, g);
+        unpack8(qy, yy);
+        if (RELU == 1) unpack8(qz, zz);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if (relu && !(zz[k] > 0.0f)) g[k] = 0.0f;
+            const bool on = RELU == 0 ? true : (RELU == 1 ? zz[k] > 0.0f : bn_mask_from_y(yy[k], mc.scale[k], mc.shift[k]));
+            if (!on) g[k] = 0.0f;
             o[k] = fmaf(ca[k], g[k], fmaf(cy[k], yy[k], cc[k]));
         }
         reinterpret_cast<uint4*>(dy)[i] = pack8(o);
         if (d_residual) reinterpret_cast<uint4*>(d_residual)[i] = pack8(g);
+    };
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {               // two positions' loads in flight
+        const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dz) + i), g1 = __ldg(reinterpret_cast<const uint4*>(dz) + i + stride);
+        const uint4 y0 = __ldg(reinterpret_cast<const uint4*>(y) + i), y1 = __ldg(reinterpret_cast<const uint4*>(y) + i + stride);
+        uint4 z0 = make_uint4(0, 0, 0, 0), z1 = z0;
+        if (RELU == 1) {
+            z0 = __ldg(reinterpret_cast<const uint4*>(z) + i);
+            z1 = __ldg(reinterpret_cast<const uint4*>(z) + i + stride);
+        }
+        one(i, g0, y0, z0);
+        one(i + stride, g1, y1, z1);
+    }
+    if (i < total) {
+        const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dz) + i), y0 = __ldg(reinterpret_cast<const uint4*>(y) + i);
+        const uint4 z0 = RELU == 1 ? __ldg(reinterpret_cast<const uint4*>(z) + i) : make_uint4(0, 0, 0, 0);
+        one(i, g0, y0, z0);
     }
 }
 

@@ -1,21 +1,29 @@
 // Weight gradient of the 3x3 / pad 1 / stride 1 convolution on the Blackwell tensor cores (training step).
 //
 //   dW[tap][co][ci] = sum over pixels p of  dY[p][co] * X[p + offset(tap)][ci]          (zero padding outside the image)
+//                   = sum over pixels q of  dY[q - offset(tap)][co] * X[q][ci]
 //
 // i.e. per tap a GEMM whose reduction runs over the PIXELS.  Both operands are NHWC activations, pixel-major in memory:
 // exactly what tcgen05 calls "MN-major" operands (the M / N index is the contiguous one).  A TMA box of [64 channels] x
 // [16 x 8 pixels] with 128-byte swizzle lands in shared memory as 128 rows (pixels = K) of 128 bytes (64 channels = M or N),
 // which is the canonical MN-major SWIZZLE_128B layout: 8-row groups 1024 bytes apart (SBO), one MMA (K = 16) per two groups.
 //
+// The halo is taken on dY (second form above): per pixel tile one plain X box and three column-shifted 18-row boxes of dY,
+// in which tap (dy, dx) is the box shifted by 2 - dx columns, read from row 2 - dy on (a 1024-byte offset).  A 64 x 64 block
+// of one tap would be an M = 64 MMA, which runs at half the tensor rate; an M = 128 MN-major operand is TWO 64-channel
+// groups a "leading byte offset" apart, and nothing says the second group has to be other channels: with LBO = 1024 bytes it
+// is the same 64 output channels one pixel row further down, i.e. the neighbouring tap.  So TWO TAPS are stacked into one
+// M = 128 MMA (rows 0-63 of the accumulator = one tap, rows 64-127 = the other): (dy 2, dy 1) of each of the three boxes,
+// then (box 0, dy 0) with (box 1, dy 0) at LBO = one box; the ninth tap stays an M = 64 MMA.  5 instead of 9 MMAs per
+// 16 pixels at the same cycles each.
+//
 // One CTA owns one (64 output channels) x (64 input channels) block of all nine taps and a strided share of the pixel tiles
 // (split-K over the grid's x dimension):
-//   warp 0   TMA producer: per pixel tile the dY box and three column-shifted 18-row halo boxes of X (the same loads as
-//            the forward kernel's: the nine taps are row offsets of 1024 bytes into them; out-of-image pixels arrive as zeros)
-//   warp 1   MMA issuer: 9 taps x 8 tcgen05.mma (M = 64, N = 64, K = 16) per pixel tile into nine accumulators that live in
-//            TMEM for the whole kernel: 64-row accumulators use 16 lanes of each TMEM quarter, so taps 2j and 2j+1 share the
-//            columns 64 j .. 64 j + 63 at lane offsets 0 and 16 (5 x 64 = 320 of the 512 columns)
+//   warp 0   TMA producer: per pixel tile the X box and the three dY halo boxes (out-of-image pixels arrive as zeros)
+//   warp 1   MMA issuer: 8 x (4 MMAs M = 128 + 1 MMA M = 64, N = 64, K = 16) per pixel tile into five accumulators that live
+//            in TMEM for the whole kernel (4 x 64 columns on all 128 lanes + 64 columns on 16 lanes of each quarter)
 //   warp 2   TMEM allocation
-//   warps 4-7 epilogue, once: tcgen05.ld -> red.global.add.f32 into dW (fp32 [9][Cout][Cin], zeroed by the host)
+//   warps 4-7 epilogue, once: tcgen05.ld -> red.global.add.v4.f32 into dW (fp32 [9][Cout][Cin], zeroed by the host)
 #pragma once
 #include "crnn_conv.cuh"
 
@@ -23,8 +31,8 @@ namespace salsa {
 namespace crnn {
 
 constexpr int kWgStages = 3;
-constexpr int kWgGyBytes = kTileH * kTileW * 128;                 // dY tile: 128 pixels x 64 channels
-constexpr int kWgStageBytes = kWgGyBytes + 3 * kHaloBytes;
+constexpr int kWgXBytes = kTileH * kTileW * 128;                  // X tile: 128 pixels x 64 channels
+constexpr int kWgStageBytes = kWgXBytes + 3 * kHaloBytes;
 constexpr int kWgThreads = 256;
 constexpr size_t kWgSmemBytes = 1024 + (size_t)kWgStages * kWgStageBytes + 256;
 
@@ -45,9 +53,15 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t start, uint32_t 
     return d;
 }
 
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands MN-major, M = 64, N = 64
-__host__ __device__ constexpr uint32_t idesc_bf16_mn_m64_n64() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands MN-major, N = 64
+__host__ __device__ constexpr uint32_t idesc_bf16_mn_n64(uint32_t m) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((m >> 4) << 24);
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+                 "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+                 : "memory");
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -89,31 +103,37 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 tc::mbar_wait(empty + s, ph ^ 1);
                 tc::mbar_expect_tx(full + s, (uint32_t)kWgStageBytes);
                 unsigned char* dst = smem + s * kWgStageBytes;
-                tc::tma_load_4d(dst, &tm_gy, full + s, co0, w0, h0, b);
-                for (int kw = 0; kw < 3; ++kw)
-                    tc::tma_load_4d(dst + kWgGyBytes + kw * kHaloBytes, &tm_x, full + s, ci0, w0 - 1 + kw, h0 - 1, b);
+                tc::tma_load_4d(dst, &tm_x, full + s, ci0, w0, h0, b);
+                for (int sh = 0; sh < 3; ++sh)
+                    tc::tma_load_4d(dst + kWgXBytes + sh * kHaloBytes, &tm_gy, full + s, co0, w0 - 1 + sh, h0 - 1, b);
                 if (++s == kWgStages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = idesc_bf16_mn_m64_n64();
-            const uint64_t desc_fixed = smem_desc_mn_sw128(0, 1024, 1024);
+            constexpr uint32_t idesc128 = idesc_bf16_mn_n64(128), idesc64 = idesc_bf16_mn_n64(64);
+            const uint64_t desc_rows = smem_desc_mn_sw128(0, 1024, 1024);                     // second M group: one pixel row down
+            const uint64_t desc_boxes = smem_desc_mn_sw128(0, (uint32_t)kHaloBytes, 1024);    // second M group: the next box
             int s = 0;
             uint32_t ph = 0, accumulate = 0;
             for (int kt = blockIdx.x; kt < a.n_ktiles; kt += gridDim.x) {
                 tc::mbar_wait(full + s, ph);
                 tc::fence_after_sync();
                 const uint32_t base = tc::smem_u32(smem + s * kWgStageBytes);
-                const uint64_t a_desc = desc_fixed + (uint64_t)(base >> 4);
+                const uint32_t gy = base + kWgXBytes;
+                const uint64_t b_desc = desc_rows + (uint64_t)(base >> 4);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    // tap (dy, dx) = (t / 3, t % 3): X rows start dy * 8 pixels = dy * 1024 bytes into the halo box shifted by dx
-                    const uint64_t b_desc = desc_fixed + (uint64_t)((base + kWgGyBytes + (t % 3) * kHaloBytes + (t / 3) * kTileW * 128) >> 4);
-                    const uint32_t tmem_d = tmem_base + (uint32_t)((t >> 1) * 64) + ((uint32_t)((t & 1) * 16) << 16);
+                for (int k = 0; k < (kTileH * kTileW) / 16; ++k) {          // 16 pixels = 16 rows of 128 bytes per MMA
+                    const uint32_t acc = (k == 0) ? accumulate : 1u;
+                    const uint64_t kb = (uint64_t)(k * 128);
 #pragma unroll
-                    for (int k = 0; k < (kTileH * kTileW) / 16; ++k)       // 16 pixels = 16 rows of 128 bytes per MMA
-                        tc::mma_bf16(tmem_d, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc, (k == 0) ? accumulate : 1u);
+                    for (int sh = 0; sh < 3; ++sh)      // box sh (dx = 2 - sh): rows 0-63 <- dy = 2 (row offset 0), rows 64-127 <- dy = 1
+                        tc::mma_bf16(tmem_base + (uint32_t)(sh * 64), desc_rows + (uint64_t)((gy + sh * kHaloBytes) >> 4) + kb, b_desc + kb,
+                                     idesc128, acc);
+                    // dy = 0 (row offset 2): boxes 0 and 1 stacked, box 2 alone
+                    tc::mma_bf16(tmem_base + 192u, desc_boxes + (uint64_t)((gy + 2 * kTileW * 128) >> 4) + kb, b_desc + kb, idesc128, acc);
+                    tc::mma_bf16(tmem_base + 256u, desc_rows + (uint64_t)((gy + 2 * kHaloBytes + 2 * kTileW * 128) >> 4) + kb, b_desc + kb,
+                                 idesc64, acc);
                 }
                 accumulate = 1;
                 tc::mma_commit(empty + s);
@@ -122,23 +142,36 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             tc::mma_commit(acc_full);
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;                               // TMEM lane quarter: rows 16 q .. 16 q + 15 of every accumulator
+        const int q = warp - 4;                               // TMEM lane quarter
         tc::mbar_wait(acc_full, 0);
         tc::fence_after_sync();
-        const int row = co0 + 16 * q + (lane & 15);
+        // M = 128 accumulators: lane = row; rows 0-63 / 64-127 are the two stacked taps
+        const int row128 = co0 + ((32 * q + lane) & 63), upper = q >> 1;
 #pragma unroll 1
-        for (int j = 0; j < 5; ++j) {
-            const int tap = 2 * j + (lane >> 4);              // lanes 0-15: tap 2j, lanes 16-31: tap 2j + 1
+        for (int j = 0; j < 4; ++j) {
+            // j < 3: box j, (dy 2 | dy 1), dx = 2 - j;   j = 3: dy 0, (box 0 -> dx 2 | box 1 -> dx 1)
+            const int tap = j < 3 ? (upper ? 3 : 6) + (2 - j) : (upper ? 1 : 2);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 uint32_t r[32];
                 tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(j * 64 + half * 32), r);
                 tc::tmem_ld_wait();
-                if (tap < 9) {
-                    float* dst = a.dw + ((size_t)tap * a.Cout + row) * a.Cin + ci0 + half * 32;
+                float* dst = a.dw + ((size_t)tap * a.Cout + row128) * a.Cin + ci0 + half * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(r[i]));
-                }
+                for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+            }
+        }
+        // M = 64 accumulator (tap 0 = dy 0, dx 0): rows 16 q .. 16 q + 15 on lanes 0-15 of this quarter
+        const int row64 = co0 + 16 * q + (lane & 15);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + half * 32), r);
+            tc::tmem_ld_wait();
+            if (lane < 16) {
+                float* dst = a.dw + (size_t)row64 * a.Cin + ci0 + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
             }
         }
     }

@@ -70,15 +70,16 @@ class NativeBnAct(torch.autograd.Function):
         g, b = gamma.detach().contiguous(), beta.detach().contiguous()
         z, stat = ops.bn_train_forward(yb.permute(0, 2, 3, 1), g, b, None if rb is None else rb.permute(0, 2, 3, 1), relu=relu,
                                        running_mean=running_mean, running_var=running_var)
-        ctx.save_for_backward(yb, z, stat, g)
         ctx.relu, ctx.has_res = relu, residual is not None
+        # without a residual the ReLU mask is a function of y: the backward pass recomputes it instead of reading z
+        ctx.save_for_backward(yb, z if (relu and ctx.has_res) else None, stat, g, b)
         return z.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dz):
-        yb, z, stat, g = ctx.saved_tensors
+        yb, z, stat, g, b = ctx.saved_tensors
         dzb = dz.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        dy, dres, dgamma, dbeta = ops.bn_train_backward(dzb.permute(0, 2, 3, 1), z, yb.permute(0, 2, 3, 1), stat, g, relu=ctx.relu,
+        dy, dres, dgamma, dbeta = ops.bn_train_backward(dzb.permute(0, 2, 3, 1), z, yb.permute(0, 2, 3, 1), stat, g, relu=ctx.relu, beta=b,
                                                         want_residual_grad=ctx.has_res and ctx.needs_input_grad[3])
         return (dy.permute(0, 3, 1, 2), dgamma, dbeta, None if dres is None else dres.permute(0, 3, 1, 2), None, None, None)
 
