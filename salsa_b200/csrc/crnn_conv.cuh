@@ -298,7 +298,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // ping-pong pays when the epilogue has a residual to fetch (measured: 0.28 -> 0.25 ms on the 64-channel residual
     // layers, 0.16 -> 0.20 ms on the plain ones), see epilogue_tile_tma
-    const bool pingpong = a.tma_store && S::kStgBufs == 2 && a.residual != nullptr;
+#ifndef CONV_PINGPONG_ALWAYS
+#define CONV_PINGPONG_ALWAYS 0
+#endif
+    const bool pingpong = a.tma_store && S::kStgBufs == 2 && (CONV_PINGPONG_ALWAYS || a.residual != nullptr);
     if (a.Cout * (int)sizeof(float) > S::kBiasBytes) bias_s = nullptr;      // wide GEMMs read the bias from global memory
     if (a.tma_store && bias_s)
         for (int i = threadIdx.x; i < a.Cout; i += kConvThreads) bias_s[i] = a.bias ? a.bias[i] : 0.0f;
@@ -518,7 +521,12 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool pingpong = false;       // no residual here: both warp groups split every tile
+#ifndef CONV_FIRST_PINGPONG
+#define CONV_FIRST_PINGPONG 1
+#endif
+    // the two epilogue warp groups alternate tiles (1) or split every tile (0): the kernel is bound by its epilogue's fixed
+    // latencies (accumulator wait, TMEM load, proxy fence, barriers, TMA issue), which ping-pong overlaps: 0.90 -> 0.66 ms per 16 clips
+    const bool pingpong = CONV_FIRST_PINGPONG && a.tma_store;
     if (threadIdx.x < 64) bias_s[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tm_act);
