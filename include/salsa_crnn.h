@@ -78,12 +78,13 @@ int crnn_conv2d(const void *x, const void *w, const float *bias, const void *res
                 int32_t pool, void *stream);
 
 /* Weight gradient of nn.Conv2d(k=3, pad=1, stride 1, bias=False) (the backward pass of models/model_utils.py:192-200,
- * :301-304 in the training step, models/seld_models.py:68-76): x bf16 NHWC [B][H][W][Cin], gy = dLoss/dOutput bf16 NHWC
- * [B][H][W][Cout] -> dw fp32 [9][Cout][Cin] (tap-major like the packed weights; overwritten).  tcgen05 GEMMs over the pixel
- * axis on MN-major operands, split over the grid, accumulated with fp32 atomics.  (The input gradient is crnn_conv2d itself
- * on gy with the taps flipped and Cin / Cout exchanged.) */
+ * :301-304 in the training step, models/seld_models.py:68-76) or, with ksize = 1, of the 1x1 downsample convolutions
+ * (:307-309): x bf16 NHWC [B][H][W][Cin], gy = dLoss/dOutput bf16 NHWC [B][H][W][Cout] -> dw fp32 [ksize^2][Cout][Cin]
+ * (tap-major like the packed weights; overwritten).  tcgen05 GEMMs over the pixel axis on MN-major operands, two taps
+ * stacked per M = 128 MMA, split over the grid, accumulated with fp32 vector atomics.  (The input gradient is crnn_conv2d
+ * itself on gy with the taps flipped and Cin / Cout exchanged.) */
 int crnn_conv_wgrad(const void *x, const void *gy, float *dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                    void *stream);
+                    int32_t ksize, void *stream);
 
 /* nn.BatchNorm2d in TRAIN mode (batch statistics; models/model_utils.py:202-203, :216, :356 in the training step), fused with
  * the residual add and the ReLU around it, on NHWC bf16 activations viewed as [n_pix][C] (C = 64, 128, 256 or 512):

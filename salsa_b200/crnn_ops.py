@@ -75,17 +75,17 @@ def conv2d(x, w, bias=None, residual=None, relu=False, out=None, out_f32=False, 
     return out
 
 
-def conv_wgrad(x, gy):
-    """x (B,H,W,Cin) bf16 NHWC, gy (B,H,W,Cout) bf16 NHWC -> dW (9, Cout, Cin) fp32: the weight gradient of the 3x3 / pad 1
-    convolution y = conv(x, w), tap-major like the packed weights."""
+def conv_wgrad(x, gy, ksize=3):
+    """x (B,H,W,Cin) bf16 NHWC, gy (B,H,W,Cout) bf16 NHWC -> dW (ksize^2, Cout, Cin) fp32: the weight gradient of the 3x3 / pad 1
+    (or 1x1) convolution y = conv(x, w), tap-major like the packed weights."""
     _check_act(x)
     _check_act(gy)
     B, H, W, Cin = x.shape
     if tuple(gy.shape[:3]) != (B, H, W):
         raise ValueError('x and gy must share batch and spatial dimensions')
     Cout = gy.shape[3]
-    dw = torch.empty((9, Cout, Cin), dtype=torch.float32, device=x.device)
-    _call('crnn_conv_wgrad', x, _p(x), _p(gy), _p(dw), B, H, W, Cin, Cout)
+    dw = torch.empty((ksize * ksize, Cout, Cin), dtype=torch.float32, device=x.device)
+    _call('crnn_conv_wgrad', x, _p(x), _p(gy), _p(dw), B, H, W, Cin, Cout, ksize)
     return dw
 
 

@@ -340,9 +340,11 @@ int crnn_augment(const float* x, float* out, const float* y_doa, float* y_out, c
     return check_cuda(cudaGetLastError(), "augment_doa_kernel");
 }
 
-int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream) {
+int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize,
+                    void* stream) {
     if (!x || !gy || !dw) return fail(SALSA_EINVAL, "conv_wgrad: null pointer");
     if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv_wgrad: bad dimensions");
+    if (ksize != 3 && ksize != 1) return fail(SALSA_EINVAL, "conv_wgrad: ksize must be 3 or 1");
     if (Cin % 64 != 0 || Cout % 64 != 0 || Cin <= 0 || Cout <= 0) return fail(SALSA_EINVAL, "conv_wgrad: Cin and Cout must be multiples of 64");
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return fail(SALSA_EINVAL, "conv_wgrad: unaligned pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -367,7 +369,8 @@ int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t
     a.tiles_h = (H + kTileH - 1) / kTileH;
     a.n_ktiles = B * a.tiles_h * a.tiles_w;
     a.dw = dw;
-    SALSA_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * Cout * Cin * sizeof(float), st));
+    a.taps = ksize * ksize;
+    SALSA_CUDA(cudaMemsetAsync(dw, 0, (size_t)a.taps * Cout * Cin * sizeof(float), st));
     SALSA_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -39,7 +39,8 @@ constexpr size_t kWgSmemBytes = 1024 + (size_t)kWgStages * kWgStageBytes + 256;
 struct WgradArgs {
     int B, H, W, Cin, Cout;
     int tiles_w, tiles_h, n_ktiles;     // pixel tiles = B * tiles_h * tiles_w
-    float* dw;                          // [9][Cout][Cin]
+    int taps;                           // 9 (3x3, pad 1) or 1 (1x1: only the centre tap = box 1, row offset 1, as one M = 64 MMA)
+    float* dw;                          // [taps][Cout][Cin]
 };
 
 // shared-memory descriptor of an MN-major operand tile with 128-byte swizzle: rows (K) of 128 bytes, 8-row groups `sbo` apart
@@ -101,10 +102,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const int tw = kt % a.tiles_w, th = (kt / a.tiles_w) % a.tiles_h, b = kt / (a.tiles_w * a.tiles_h);
                 const int h0 = th * kTileH, w0 = tw * kTileW;
                 tc::mbar_wait(empty + s, ph ^ 1);
-                tc::mbar_expect_tx(full + s, (uint32_t)kWgStageBytes);
+                tc::mbar_expect_tx(full + s, (uint32_t)(a.taps == 9 ? kWgStageBytes : kWgXBytes + kHaloBytes));
                 unsigned char* dst = smem + s * kWgStageBytes;
                 tc::tma_load_4d(dst, &tm_x, full + s, ci0, w0, h0, b);
-                for (int sh = 0; sh < 3; ++sh)
+                for (int sh = (a.taps == 9 ? 0 : 1); sh < (a.taps == 9 ? 3 : 2); ++sh)
                     tc::tma_load_4d(dst + kWgXBytes + sh * kHaloBytes, &tm_gy, full + s, co0, w0 - 1 + sh, h0 - 1, b);
                 if (++s == kWgStages) { s = 0; ph ^= 1; }
             }
@@ -122,6 +123,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const uint32_t base = tc::smem_u32(smem + s * kWgStageBytes);
                 const uint32_t gy = base + kWgXBytes;
                 const uint64_t b_desc = desc_rows + (uint64_t)(base >> 4);
+                if (a.taps == 1) {
+#pragma unroll
+                    for (int k = 0; k < (kTileH * kTileW) / 16; ++k)
+                        tc::mma_bf16(tmem_base + 256u, desc_rows + (uint64_t)((gy + kHaloBytes + kTileW * 128) >> 4) + (uint64_t)(k * 128),
+                                     b_desc + (uint64_t)(k * 128), idesc64, (k == 0) ? accumulate : 1u);
+                } else
 #pragma unroll
                 for (int k = 0; k < (kTileH * kTileW) / 16; ++k) {          // 16 pixels = 16 rows of 128 bytes per MMA
                     const uint32_t acc = (k == 0) ? accumulate : 1u;
@@ -148,7 +155,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // M = 128 accumulators: lane = row; rows 0-63 / 64-127 are the two stacked taps
         const int row128 = co0 + ((32 * q + lane) & 63), upper = q >> 1;
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < (a.taps == 9 ? 4 : 0); ++j) {
             // j < 3: box j, (dy 2 | dy 1), dx = 2 - j;   j = 3: dy 0, (box 0 -> dx 2 | box 1 -> dx 1)
             const int tap = j < 3 ? (upper ? 3 : 6) + (2 - j) : (upper ? 1 : 2);
 #pragma unroll 1
@@ -161,7 +168,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
             }
         }
-        // M = 64 accumulator (tap 0 = dy 0, dx 0): rows 16 q .. 16 q + 15 on lanes 0-15 of this quarter
+        // M = 64 accumulator (tap 0 = dy 0, dx 0; the only tap of a 1x1): rows 16 q .. 16 q + 15 on lanes 0-15 of this quarter
         const int row64 = co0 + 16 * q + (lane & 15);
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {

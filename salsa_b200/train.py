@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from . import crnn_ops as ops
 from .optim import Adam, LearningRateScheduler
 
-__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeBnAct', 'NativeAvgPool2']
+__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeConv1x1', 'NativeBnAct', 'NativeAvgPool2']
 
 
 class NativeConv3x3(torch.autograd.Function):
@@ -56,6 +56,31 @@ class NativeConv3x3(torch.autograd.Function):
                 dw = dw.reshape(3, 3, w.shape[0], w.shape[1]).permute(2, 3, 0, 1).to(w.dtype)
             else:
                 dw = torch.nn.grad.conv2d_weight(xb, w.shape, gyb, padding=1).to(w.dtype)
+        return dx, dw
+
+
+class NativeConv1x1(torch.autograd.Function):
+    """1x1 convolution without bias (the downsample branch, models/model_utils.py:307-309) on channels_last bf16 tensors:
+    forward and input gradient = `crnn_conv2d` with one tap (weights transposed for the gradient), weight gradient =
+    `crnn_conv_wgrad(ksize=1)`."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wp = w.detach().reshape(1, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
+        ctx.save_for_backward(xb, w)
+        return ops.conv2d(xb.permute(0, 2, 3, 1), wp).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, w = ctx.saved_tensors
+        gyb = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wt = w.detach().reshape(w.shape[0], w.shape[1]).t().reshape(1, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
+            dx = ops.conv2d(gyb.permute(0, 2, 3, 1), wt).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad(xb.permute(0, 2, 3, 1), gyb.permute(0, 2, 3, 1), ksize=1).reshape(w.shape).to(w.dtype)
         return dx, dw
 
 
@@ -247,7 +272,9 @@ class SeldTrainer:
                     out = self._bn(self._conv3(pooled, q + '.conv1.weight'), q + '.bn1', relu=True)
                     out = F.dropout(out, p=0.1, training=tr)
                     if li > 1 and bi == 0:                                     # downsample = AvgPool2d(2) + 1x1 conv + BN (:474-481): the same pooled tensor
-                        identity = self._bn(F.conv2d(pooled, self.params[q + '.downsample.1.weight']), q + '.downsample.2')
+                        wd = self.params[q + '.downsample.1.weight']
+                        ds = NativeConv1x1.apply(pooled, wd) if self.native_conv else F.conv2d(pooled, wd)
+                        identity = self._bn(ds, q + '.downsample.2')
                     x = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2', relu=True, residual=identity)   # relu(bn2(.) + identity)
             x = torch.mean(x.float(), dim=3).transpose(1, 2)                  # SeldDecoder.forward (models/decoders.py:106-154)
             gru_params = {k[len('decoder.gru.'):]: v for k, v in self.params.items() if k.startswith('decoder.gru.')}

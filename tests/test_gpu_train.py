@@ -187,3 +187,19 @@ def test_adam_step_with_device_scalars_equals_the_scalar_call():
         b.stage_hyper()
         b.step_staged(grad * (i + 1))
     assert torch.equal(a.params, b.params) and torch.equal(a.exp_avg_sq, b.exp_avg_sq) and a.step_count == b.step_count == 3
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 40, 25, 64, 128), (1, 33, 12, 256, 512)])
+def test_native_conv1x1_all_three_directions(B, H, W, Cin, Cout):
+    """The downsample branch's 1x1 convolution: forward / input gradient on the tcgen05 kernel with one tap, weight gradient
+    = crnn_conv_wgrad(ksize=1) (the centre tap alone), against float32 F.conv2d + autograd on the same bf16 operands."""
+    from salsa_b200.train import NativeConv1x1
+    g = torch.Generator().manual_seed(Cin + H)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16().float().cuda().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).bfloat16().float().cuda().requires_grad_(True)
+    gy = torch.randn(B, Cout, H, W, generator=g).bfloat16().float().cuda()
+    y_ref = F.conv2d(x, w)
+    gx_ref, gw_ref = torch.autograd.grad(y_ref, (x, w), gy)
+    y = NativeConv1x1.apply(x, w)
+    gx, gw = torch.autograd.grad(y, (x, w), gy)
+    assert rel(y, y_ref) < 1e-2 and rel(gx, gx_ref) < 1e-2 and rel(gw, gw_ref) < 1e-4
