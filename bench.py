@@ -655,8 +655,8 @@ def bench_other_configs(args, torch, dist, rank, world, dev, peak):
 def bench_train(args, torch, dist, rank, world, dev):
     """BASELINE.json configs[4]: CRNN training on on-the-fly SALSA features, bf16, data-parallel.  Per step and rank: 32 audio
     chunks of 8 s -> SALSA FOA features (native) -> channel-swap / frequency-shift augmentation (native) -> forward + backward
-    (3x3 convolutions in all three directions, train-mode BatchNorm + residual + ReLU and pooling native; first / 1x1
-    convolutions, dropout, GRU, heads: torch / cuDNN autograd) ->
+    (3x3 and 1x1 convolutions in all three directions, train-mode BatchNorm + residual + ReLU and pooling native; first
+    convolution, dropout, GRU, heads: torch / cuDNN autograd) ->
     loss (native) -> bucketed bf16 gradient all-reduce overlapped with the backward pass (NCCL) -> Adam (native)."""
     import numpy as np
     import salsa_b200
@@ -687,11 +687,12 @@ def bench_train(args, torch, dist, rank, world, dev):
     return {'config': 'configs[4]: CRNN (ResNet22 + BiGRU) training step on on-the-fly SALSA FOA features, bf16 autocast, batch {} x (7, 640, 200) '
                       'per GPU, {} GPU(s) data-parallel'.format(B, world),
             'value': B * world / (ms / 1e3), 'unit': 'chunks/s (8 s each)', 'audio_min_per_s': B * world * 8 / 60.0 / (ms / 1e3),
-            'ms_per_step': ms, 'ms_features': ms_feat, 'cuda_graph': ('off' if args.no_train_graph else (tr.graph_error or 'forward + loss + backward + all-reduce + Adam replayed as one CUDA graph')), 'loss_first_step': first, 'loss_last_step': last, 'parameters': n_params,
-            'allreduce': 'bucketed bf16 all-reduce of the flat gradient ({:.1f} MB on the wire per step), launched per bucket during the '
-                         'backward pass'.format(n_params * 2 / 1e6) if world > 1 else 'single rank: none',
-            'native': 'SALSA features, augmentation, 3x3 convolution forward + input gradient + weight gradient (tcgen05), train-mode BatchNorm + residual + ReLU and 2x2 pooling forward / backward, loss, Adam',
-            'library': 'first (7-channel) and 1x1 convolutions, dropout, BiGRU, heads: torch / cuDNN autograd'}
+            'ms_per_step': ms, 'ms_features': ms_feat, 'cuda_graph': ('off' if args.no_train_graph else (tr.graph_error or 'forward + loss + backward replayed as one CUDA graph; all-reduce of the flat gradient (one NCCL call) and Adam follow it')), 'loss_first_step': first, 'loss_last_step': last, 'parameters': n_params,
+            'allreduce': ('bf16 all-reduce of the flat gradient ({:.1f} MB on the wire per step), '.format(n_params * 2 / 1e6) +
+                          ('one call after the graph replay' if (tr.use_graph and tr.graph_error is None) else 'launched per bucket during the backward pass'))
+                         if world > 1 else 'single rank: none',
+            'native': 'SALSA features, augmentation, 3x3 and 1x1 convolutions forward + input gradient + weight gradient (tcgen05), train-mode BatchNorm + residual + ReLU and 2x2 pooling forward / backward, loss, Adam',
+            'library': 'first (7-channel) convolution, dropout, BiGRU, heads: torch / cuDNN autograd'}
 
 
 def main():

@@ -4,15 +4,16 @@ The reference trains through PyTorch Lightning: `training_step` (models/seld_mod
 `interpolate_tensor` to the label rate -> `compute_loss` (models/interfaces.py:273-355), Adam with the piecewise-linear
 lr / beta1 schedule (utilities/learning_utils.py:17-52), DDP gradient all-reduce (experiments/train.py:98-104).  Here:
 
-  native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 convolutions' forward, input gradient (the
-                              tcgen05 implicit-GEMM kernel on flipped / transposed weights) and weight gradient
-                              (`crnn_conv_wgrad`), the loss with its output gradients (`crnn_seld_loss`), the Adam step
+  native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 and 1x1 convolutions' forward, input gradient
+                              (the tcgen05 implicit-GEMM kernel on flipped / transposed weights) and weight gradient
+                              (`crnn_conv_wgrad`), the loss with its output gradients (`crnn_seld_loss`), the Adam step,
                               train-mode BatchNorm fused with the residual add and the ReLU, forward and backward
                               (`crnn_bn_train_forward` / `_backward`), 2x2 average pooling forward and backward
-  torch / cuDNN (library)     the first (7-channel) and the 1x1 convolutions, dropout, the BiGRU and the heads,
-                              through autograd -- not native yet, and said so wherever a number is quoted
-  torch.distributed           bucketed bf16 all-reduce of the flat gradient buffer, started per bucket while the backward
-                              pass is still running (`GradAllReduce`; NCCL on the GPU box, gloo in the CPU tests)
+  torch / cuDNN (library)     the first (7-channel) convolution, dropout, the BiGRU and the heads, through autograd -- not
+                              native yet, and said so wherever a number is quoted
+  torch.distributed           bf16 all-reduce of the flat gradient buffer (`GradAllReduce`; NCCL on the GPU box, gloo in the
+                              CPU tests): per bucket while the backward pass is still running (eager step), or one call after
+                              the replay when forward + loss + backward run as ONE CUDA graph (`use_graph=True`)
 
 Parameters live in ONE flat float32 buffer (the optimiser's view) with per-tensor views carrying the reference's state-dict
 names, so `state_dict()` interchanges with reference checkpoints and with the inference model (`SeldModel.load_state_dict`).
@@ -150,6 +151,7 @@ class GradAllReduce:
         self.pending = [0] * len(self.buckets)
         self.sizes = [sum(1 for j in self.bucket_of.values() if j == b) for b in range(len(self.buckets))]
         self.work = []
+        self.enabled = True            # False: the hooks do nothing (a CUDA graph capture must not contain the collective)
 
     def reset(self):
         self.pending = list(self.sizes)
@@ -157,6 +159,8 @@ class GradAllReduce:
 
     def ready(self, param_index: int):
         """Call when parameter `param_index` has its final gradient (a post-accumulate-grad hook)."""
+        if not self.enabled:
+            return
         b = self.bucket_of[param_index]
         self.pending[b] -= 1
         if self.pending[b] == 0 and self.world > 1:
@@ -167,6 +171,8 @@ class GradAllReduce:
 
     def finish(self):
         """Waits for the buckets in flight and writes the averages back into the flat buffer."""
+        if not self.enabled:
+            return
         for b, n in enumerate(self.pending):          # parameters that received no gradient this step
             if n > 0 and self.world > 1:
                 self.pending[b] = 1
@@ -179,6 +185,18 @@ class GradAllReduce:
         self.work = []
 
 
+    def reduce_all(self):
+        """The whole flat gradient in ONE all-reduce (28 MB in bf16: a fraction of a millisecond over NVLink), for a step whose
+        backward pass is replayed as a CUDA graph and therefore cannot start bucket collectives from hooks."""
+        if self.world == 1:
+            return
+        wire = self.flat if self.wire is None or self.flat.dtype == self.wire else self.flat.to(self.wire)
+        dist.all_reduce(wire, group=self.group)
+        if wire is not self.flat:
+            self.flat.copy_(wire)
+        self.flat.div_(self.world)
+
+
 class SeldTrainer:
     """PannResNet22 + SeldDecoder(bigru, avg) in train mode with the reference's state-dict names, one flat parameter buffer,
     and `step(x, target_dict)` = the reference's training step."""
@@ -188,9 +206,10 @@ class SeldTrainer:
                  bucket_bytes: int = 8 << 20, wire_dtype=torch.bfloat16, autocast: bool = True, dropout: bool = True,
                  native_bn: bool = True, use_graph: bool = False):
         """native_conv / native_bn / autocast / dropout = False are for tests (a pure torch float32 reference of the same step);
-        wire_dtype None sends float32 gradients.  use_graph: `step` captures forward + loss + backward (+ all-reduce) + Adam as
-        ONE CUDA graph at the first sighting of a batch shape and replays it afterwards (about 1000 launches per step
-        otherwise: the step is host-bound without it); lr / beta1 / the step count reach the replay through device memory."""
+        wire_dtype None sends float32 gradients.  use_graph: `step` captures forward + loss + backward as ONE CUDA graph at the
+        first sighting of a batch shape and replays it afterwards (about 1000 launches per step otherwise: the step is
+        host-bound without it); the gradient all-reduce (one NCCL call on the flat buffer) and Adam follow the replay as
+        ordinary launches -- a collective inside a capture is not portable across NCCL versions."""
         self.device = torch.device(device)
         self.n_classes, self.loss_weight = n_classes, tuple(loss_weight)
         self.ratio = 16.0 * label_rate / feature_rate                 # time_downsample_ratio * label_rate / feature_rate
@@ -317,17 +336,16 @@ class SeldTrainer:
             static = [torch.empty_like(x, memory_format=torch.contiguous_format), torch.empty_like(egt), torch.empty_like(dgt)]
             for s_, t_ in zip(static, (x, egt, dgt)):
                 s_.copy_(t_)
-            body = lambda: self._step_eager(static[0], {'event_frame_gt': static[1], 'doa_frame_gt': static[2]}, staged=True)
+            body = lambda: self._step_eager(static[0], {'event_frame_gt': static[1], 'doa_frame_gt': static[2]}, gradients_only=True)
             # warm-up on a side stream (lazy initialisation of cuDNN / autograd / the allocator must not be captured), with
-            # the trainer's state put back afterwards so that it is not part of the training trajectory
+            # the trainer's state (BatchNorm running statistics) put back afterwards so that it is not part of the trajectory
             saved = [t.clone() for t in self._mutable_state()]
-            saved_count, saved_idx = self.optimizer.step_count, self.batch_idx
+            self.reducer.enabled = False
             try:
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):
                     for _ in range(2):
-                        self.optimizer.stage_hyper()
                         body()
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 torch.cuda.synchronize(self.device)
@@ -338,25 +356,26 @@ class SeldTrainer:
                 self.graph_error = '{}: {}'.format(type(e).__name__, str(e).splitlines()[0] if str(e) else '')
                 torch.cuda.synchronize(self.device)
                 graph = None
+            self.reducer.enabled = True
             for t, sv in zip(self._mutable_state(), saved):
                 t.copy_(sv)
-            self.optimizer.step_count, self.batch_idx = saved_count, saved_idx
             if graph is None:
                 return self._step_eager(x, target_dict)
             self._graphs[key] = (graph, static, loss)
         graph, static, loss = self._graphs[key]
         for s_, t_ in zip(static, (x, egt, dgt)):
             s_.copy_(t_)
+        graph.replay()                                   # zero gradients, forward, loss, backward
+        self.reducer.reduce_all()
         if self.scheduler is not None:
             self.scheduler.apply(self.optimizer, self.epoch, self.batch_idx)
-        self.optimizer.stage_hyper()
-        graph.replay()
+        self.optimizer.step(self.flat_grad)
         self.batch_idx += 1
         return loss.clone()
 
-    def _step_eager(self, x, target_dict, staged=False):
-        """The launches of one step; `staged`: Adam reads this batch's scalars from device memory (stage_hyper) and the
-        schedule / counters are advanced by the caller (the body a CUDA graph is captured from)."""
+    def _step_eager(self, x, target_dict, gradients_only=False):
+        """The launches of one step; `gradients_only`: stop after the backward pass (the body a CUDA graph is captured from;
+        all-reduce, schedule and Adam are the caller's)."""
         self.flat_grad.zero_()
         self.reducer.reset()
         out = self.forward(x)
@@ -375,10 +394,9 @@ class SeldTrainer:
             total = self.loss_weight[0] * sed + self.loss_weight[1] * d
             total.backward()
             loss = torch.stack([total.detach(), sed.detach(), d.detach()])
-        self.reducer.finish()
-        if staged:
-            self.optimizer.step_staged(self.flat_grad)
+        if gradients_only:
             return loss
+        self.reducer.finish()
         if self.scheduler is not None and self.optimizer is not None:
             self.scheduler.apply(self.optimizer, self.epoch, self.batch_idx)
         if self.optimizer is not None:

@@ -170,6 +170,13 @@ def _train_worker(rank, world, port, q):
         want = sum(both) / world
         ok = bool(torch.allclose(mine, want, rtol=1e-5, atol=1e-7)) and bool(torch.isfinite(loss).all()) and float(mine.abs().max()) > 0
         ok = ok and not torch.allclose(local, want, rtol=1e-3, atol=1e-6)          # the ranks really saw different data
+        # the single-call variant used after a CUDA-graph replay of the backward pass: hooks off, one all-reduce of the flat buffer
+        solo.reducer.world = world
+        solo.reducer.enabled = False
+        solo._step_eager(x, tgt, gradients_only=True)
+        ok = ok and bool(torch.allclose(solo.flat_grad, local, rtol=1e-5, atol=1e-7))      # nothing reduced yet
+        solo.reducer.reduce_all()
+        ok = ok and bool(torch.allclose(solo.flat_grad, want, rtol=1e-5, atol=1e-7))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
