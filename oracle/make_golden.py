@@ -160,6 +160,23 @@ def extras_cases():
     return out
 
 
+def nfft256_cases():
+    """The n_fft = 256 configuration the reference accepts (salsa_feature_extraction.py:151-152, :163-170, :300-306), from
+    the unmodified reference on the first 0.5 s of the golden clips: MagStftExtractor (both band layouts, a shorter window) and
+    the per-clip SALSA body, FOA and MIC, at hop 150."""
+    ref = ref_import.features_module()
+    clips = np.load(os.path.join(GOLDEN_DIR, 'clip_cases.npz'))
+    foa, mic = clips['audio_foa'][:, :12000], clips['audio_mic'][:, :12000]
+    cfg = lambda base: dict(DATA_CFG[base], n_fft=256, win_len=256, hop_len=150)
+    out = {}
+    out['salsa_foa'] = ref_import.run_driver_body('salsa', foa, cfg('foa'))
+    out['salsa_mic'] = ref_import.run_driver_body('salsa', mic, cfg('mic'))
+    out['logspec_foa'] = ref.MagStftExtractor(n_fft=256, hop_length=150, win_length=256).extract(foa)
+    out['logspec_foa_nocompress'] = ref.MagStftExtractor(n_fft=256, hop_length=150, win_length=256, is_compress_high_freq=False).extract(foa)
+    out['logspec_foa_win200'] = ref.MagStftExtractor(n_fft=256, hop_length=150, win_length=200).extract(foa)
+    return out
+
+
 def main(argv=None):
     if not ref_import.available():
         print('reference checkout not found; golden vectors can only be generated in the build container')
@@ -175,6 +192,8 @@ def main(argv=None):
         np.savez_compressed(os.path.join(GOLDEN_DIR, 'augment_cases.npz'), **augment_cases())
     if argv and 'extras' in argv:
         np.savez_compressed(os.path.join(GOLDEN_DIR, 'extras_cases.npz'), **extras_cases())
+    if argv and 'nfft256' in argv:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, 'nfft256_cases.npz'), **nfft256_cases())
     for fn in sorted(os.listdir(GOLDEN_DIR)):
         print('{:32s} {:10d} B'.format(fn, os.path.getsize(os.path.join(GOLDEN_DIR, fn))))
     return 0

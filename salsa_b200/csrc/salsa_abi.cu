@@ -142,7 +142,9 @@ int get_tables(const double* window_host, DeviceTables* out) {
     return SALSA_OK;
 }
 
+// `out` has kNfft entries; a shorter transform (n_fft = 256) uses the first n_fft of them, the rest is zero
 void host_window(const salsa_params_t* p, double* out) {
+    for (int i = 0; i < kNfft; ++i) out[i] = 0.0;
     if (p->window) {
         memcpy(out, p->window, p->n_fft * sizeof(double));
         return;
@@ -160,8 +162,7 @@ int validate_params(const salsa_params_t* p, bool with_stft) {
     if (p->n_clips < 0) return fail(SALSA_EINVAL, "n_clips is negative");
     if (p->fs <= 0 || p->n_fft <= 0) return fail(SALSA_EINVAL, "fs and n_fft must be positive");
     if (with_stft) {
-        if (p->n_fft != 512)
-            return fail(SALSA_EINVAL, "only n_fft = 512 is implemented (reference asserts 512 or 256)");
+        if (p->n_fft != 512 && p->n_fft != 256) return fail(SALSA_EINVAL, "nfft is not 512 or 256");
         if (p->hop_len <= 0) return fail(SALSA_EINVAL, "hop_len must be positive");
         if (p->win_len <= 0 || p->win_len > p->n_fft)
             return fail(SALSA_EINVAL, "Windown length is greater than nfft!");
@@ -182,7 +183,7 @@ int validate_params(const salsa_params_t* p, bool with_stft) {
 static BandLayout band_layout(const salsa_params_t* p) {
     const int half = p->n_fft / 2;
     if (!p->is_compress_high_freq) return {half, half};
-    return {half * 3 / 4, half * 3 / 4 + 8};   // 512: 192 linear + 8 compressed = 200 (:153-162)
+    return {half * 3 / 4, half * 3 / 4 + half / 32};   // 512: 192 linear + 8 compressed = 200 (:153-162); 256: 96 + 4 = 100 (:163-170)
 }
 
 static EigArgs eig_args(const salsa_params_t* p) {
@@ -275,6 +276,14 @@ static int launch_stft(const salsa_params_t* p, const DeviceTables& tb, const fl
     int rc;
     if (ch_count != 1 && ch_count != 4) return fail(SALSA_EINVAL, "stft: 1 or 4 channels");
     const bool d = p->stft_precision == 64;
+    if (p->n_fft == 256) {                                   // the plain kernel of the second transform size
+        if (!tb.d.window) return fail(SALSA_EINVAL, "stft: n_fft = 256 takes its window from a table");
+        const size_t smem = d ? sizeof(FftSmemW<double, kStftWarps>) : sizeof(FftSmemW<float, kStftWarps>);
+        if ((rc = d ? set_smem(stft256_kernel<double>, smem) : set_smem(stft256_kernel<float>, smem))) return rc;
+        if (d) stft256_kernel<double><<<grid, kStftThreads, smem, st>>>(a, tb.d);
+        else stft256_kernel<float><<<grid, kStftThreads, smem, st>>>(a, tb.f);
+        return check_launch("stft256_kernel");
+    }
     if (x_tiles > 0 && (ch_count != 4 || !X || power0)) return fail(SALSA_EINVAL, "stft: tiled X is the clip path's layout");
     if (x_tiles > 0 && !spec)                               // clip path with a separate spectrogram window: X only
         rc = p->lower_bin < kTileBins
@@ -519,7 +528,7 @@ int salsa_stft(const salsa_params_t* p, const float* audio, float* X, float* log
     if (p->n_clips == 0) return SALSA_OK;
     if (!audio) return fail(SALSA_EINVAL, "audio is NULL");
     double win[kNfft];
-    const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
+    const bool builtin_hann = !p->window && p->win_len == p->n_fft && p->n_fft == kNfft;      // computed in the kernels, no table
     if (!builtin_hann) host_window(p, win);
     DeviceTables tb;
     if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
@@ -582,22 +591,32 @@ int salsa_extract(const salsa_params_t* p, const float* audio, float* feature, v
     const Workspace w = carve_workspace(p, workspace, pl);
     if ((p->is_tracking || pl == kPipelineSplit) && (!workspace || workspace_bytes < w.bytes))
         return fail(SALSA_ENOMEM, "workspace smaller than salsa_workspace_bytes()");
-    double win[kNfft];
-    const bool builtin_hann = !p->window && p->win_len == p->n_fft;      // computed in the kernels, no table
+    double win[kNfft], win_full[kNfft];
+    const bool default_window = !p->window && p->win_len == p->n_fft;
+    const bool builtin_hann = default_window && p->n_fft == kNfft;        // computed in the kernels, no table
     if (!builtin_hann) host_window(p, win);
     // win_len / window configure MagStftExtractor only (:324-325, :184-192); the spectrum that feeds the eigenvector step
     // is librosa's default full-length Hann whatever they are (:359-361)
     DeviceTables tb, tb_hann;
-    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb)) || (rc = get_tables(nullptr, &tb_hann))) return rc;
+    if ((rc = get_tables(builtin_hann ? nullptr : win, &tb))) return rc;
+    if (p->n_fft == kNfft) {
+        if ((rc = get_tables(nullptr, &tb_hann))) return rc;
+    } else {                                                               // n_fft = 256: the full-length Hann as a table too
+        salsa_params_t ph = *p;
+        ph.window = nullptr;
+        ph.win_len = p->n_fft;
+        host_window(&ph, win_full);
+        if ((rc = get_tables(win_full, &tb_hann))) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int n_frames = salsa_n_frames(p->n_samples, p->hop_len);
     const int n_bins = p->upper_bin - p->lower_bin;
     const uint32_t* mask = nullptr;
     if (pl == kPipelineFused && !builtin_hann)
-        return fail(SALSA_EINVAL, "SALSA_B200_PIPELINE=fused supports the full-length Hann window only");
+        return fail(SALSA_EINVAL, "SALSA_B200_PIPELINE=fused supports n_fft = 512 with the full-length Hann window only");
     if (pl == kPipelineSplit) {
         const long long clip_stride = 7LL * n_frames * band_layout(p).n_out;
-        if (builtin_hann) {
+        if (default_window) {
             if ((rc = launch_stft(p, tb, audio, w.X, 0, w.n_tiles, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
         } else {
             if ((rc = launch_stft(p, tb, audio, nullptr, 0, 0, feature, clip_stride, nullptr, p->n_chans, st))) return rc;
@@ -630,6 +649,7 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
                        void* stream) {
     int rc = validate_params(p);
     if (rc) return rc;
+    if (p->n_fft != kNfft) return fail(SALSA_EINVAL, "salsa_lite: only n_fft = 512 is implemented");
     if (mode != SALSA_LITE_NIPD && mode != SALSA_LITE_IPD) return fail(SALSA_EINVAL, "Invalid feature type");
     if (p->upper_bin > cutoff_bin || cutoff_bin > p->n_fft / 2)
         return fail(SALSA_EINVAL, "Upper bin for spatial feature is higher than cutoff bin for spectrogram!");
@@ -771,7 +791,7 @@ int salsa_logspec_gcc(const salsa_params_t* p, const float* audio, float* featur
     if (rc) return rc;
     if (!q.is_compress_high_freq) return fail(SALSA_EINVAL, "logspec_gcc: only the compressed 200-band layout is implemented");
     if (q.window) return fail(SALSA_EINVAL, "logspec_gcc: a Hann window of win_len samples is built in");
-    if (q.win_len != q.n_fft) return fail(SALSA_EINVAL, "logspec_gcc: win_len must equal n_fft (512)");
+    if (q.n_fft != kNfft || q.win_len != q.n_fft) return fail(SALSA_EINVAL, "logspec_gcc: win_len must equal n_fft (512)");
     if (q.n_clips == 0) return SALSA_OK;
     if (!audio || !feature) return fail(SALSA_EINVAL, "audio / feature is NULL");
     const GccWorkspace w = carve_gcc(&q, workspace);
@@ -830,6 +850,7 @@ int salsa_linspec_iv(const salsa_params_t* p, const float* audio, float* feature
     q.audio_format = SALSA_FORMAT_FOA;
     int rc = validate_params(&q);
     if (rc) return rc;
+    if (q.n_fft != kNfft) return fail(SALSA_EINVAL, "linspec_iv: only n_fft = 512 is implemented");
     if (!q.is_compress_high_freq)
         return fail(SALSA_EINVAL, "linspec_iv: only the compressed 200-band layout is implemented (the uncompressed one needs the Nyquist bin)");
     if (q.n_clips == 0) return SALSA_OK;

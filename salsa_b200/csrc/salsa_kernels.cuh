@@ -272,6 +272,87 @@ __global__ void __launch_bounds__(kStftThreads, STFT_MINB) stft_kernel(StftArgs 
 }
 
 // ------------------------------------------------------------------------------------------------
+// stft256_kernel: the n_fft = 256 configuration the reference also accepts (salsa_feature_extraction.py:151-152, :163-170,
+// :300-306).  No shipped config uses it, so this is the plain form of stft_kernel: one warp per (frame, channel), the 256 real
+// samples go through the 256-point COMPLEX transform of fft.cuh with zero imaginary parts (Z[k] is then the real
+// transform's bin k for k <= 128; no split step), outputs selected by the pointers of StftArgs.  The window always comes
+// from the table (entries 0..255 of FftTables::window).
+// ------------------------------------------------------------------------------------------------
+constexpr int kNfft256 = 256;
+
+// log-linear row of the n_fft = 256 layouts: p[g] = power of bin lane + 32 g (g = 0..3), p_nyq = power of bin 128.
+// Compressed (:163-170): bands 0..95 = bins 1..96, bands 96..98 = 8 bins from 97 + 8 i, band 99 = bins 121..127, all / 8.
+__device__ __forceinline__ void write_logspec_row256(const float (&p)[4], float p_nyq, float* row, BandLayout bands, int lane) {
+    const bool compress = bands.n_out > bands.n_lin;
+    if (!compress) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int band = lane + 32 * g - 1;
+            if (band >= 0) row[band] = power_db(p[g]);
+        }
+        if (lane == 0) row[kNfft256 / 2 - 1] = power_db(p_nyq);
+        return;
+    }
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+        if (g > 0 || lane > 0) row[lane + 32 * g - 1] = power_db(p[g]);
+    if (lane == 0) row[95] = power_db(p[3]);                        // bin 96
+    const float up = __shfl_down_sync(0xffffffffu, p[3], 1);         // lane l: power of bin 97 + l
+    float r = lane == 31 ? 0.0f : up;                                // the last band has 7 bins (121..127)
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+    const float v = __shfl_sync(0xffffffffu, r, 8 * (lane & 3));
+    if (lane < 4) row[bands.n_lin + lane] = power_db(0.125f * v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStftThreads) stft256_kernel(StftArgs a, FftTables<T> tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Smem = FftSmemW<T, kStftWarps>;
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    load_fft_smem(s, tb);
+    __syncthreads();
+    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
+    const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
+    const int clip = blockIdx.y;
+    const int f0 = blockIdx.x * a.frames_per_block;
+    const int f1 = min(a.n_frames, f0 + a.frames_per_block);
+    const int nb = a.upper - a.lower;
+    Cx<T>* scratch = s.scratch[warp];
+    for (int item = warp; item < (f1 - f0) * a.ch_count; item += kStftWarps) {
+        const int t = f0 + item / a.ch_count, ch = item % a.ch_count;
+        const float* x = a.audio + ((long long)clip * a.n_chans + ch) * a.n_samples;
+        const int start = t * a.hop - kNfft256 / 2;
+        Cx<T> v[8], z[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int m = lane + 32 * n1;
+            v[n1] = {(T)x[reflect_index(start + m, a.n_samples)] * s.win[m], (T)0};
+        }
+        warp_fft_core<T, 0>(v, tw, scratch, lane, z);               // z[i] = Z[lane + 32 i]
+        const long long o = ((long long)clip * a.n_frames + t);
+        float p[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int k = lane + 32 * g;
+            const float2 xf = make_float2((float)z[g].re, (float)z[g].im);     // librosa stores complex64
+            p[g] = power_f32(xf.x, xf.y);
+            if ((unsigned)(k - a.lower) < (unsigned)nb) {
+                const int b = k - a.lower;
+                if (a.X && a.x_tiles > 0) a.X[o * a.x_tiles * kTileFrameElems + (b >> 5) * kTileFrameElems + ch * kTileBins + (b & 31)] = xf;
+                else if (a.X) a.X[(o * a.n_chans + ch) * a.x_pitch + b] = xf;
+                if (a.power0 && ch == 0) a.power0[o * nb + b] = fma((double)xf.x, (double)xf.x, (double)xf.y * (double)xf.y);
+            }
+        }
+        if (a.spec) {
+            const float nyq = (float)z[4].re;                       // lane 0: Z[128], real for a real signal
+            float* row = a.spec + clip * a.spec_clip_stride + ch * a.spec_chan_stride + (long long)t * a.bands.n_out;
+            write_logspec_row256(p, nyq * nyq, row, a.bands, lane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // tracker_kernel: one thread per (clip, bin), one warp per 32-bin mask word; sequential over frames.
 // Reference: salsa_feature_extraction.py:26-36 (constants), :49-58 (signal, initial floor), :63-87.
 // ------------------------------------------------------------------------------------------------

@@ -117,11 +117,9 @@ class MagStftExtractor:
         self.win_length = self.n_fft if win_length is None else win_length
         assert self.win_length <= self.n_fft, 'Windown length is greater than nfft!'
         assert n_fft == 512 or n_fft == 256, 'nfft is not 512 or 256'
-        if n_fft != 512:
-            raise NotImplementedError('salsa_b200 implements n_fft = 512 only')
         self.is_compress_high_freq = is_compress_high_freq
         self.stft_precision = stft_precision
-        self.n_bands = 200 if is_compress_high_freq else n_fft // 2
+        self.n_bands = (200 if n_fft == 512 else 100) if is_compress_high_freq else n_fft // 2
 
     def extract(self, audio_input: np.ndarray) -> np.ndarray:
         """(4, n_samples) float32 -> (4, n_timeframes, n_bands) float32."""
@@ -129,7 +127,7 @@ class MagStftExtractor:
         audio = np.ascontiguousarray(audio_input, dtype=np.float32)
         if audio.ndim != 2 or audio.shape[0] != 4:
             raise ValueError('audio_input must be (4, n_samples), got {}'.format(audio.shape))
-        p = _params(1, audio.shape[1], n_fft=self.n_fft, hop_len=self.hop_length, win_len=self.win_length,
+        p = _params(1, audio.shape[1], n_fft=self.n_fft, hop_len=self.hop_length, win_len=self.win_length, upper_bin=self.n_fft // 2,
                     is_compress_high_freq=self.is_compress_high_freq, stft_precision=self.stft_precision,
                     window_table=_window_table(self.window, self.win_length, self.n_fft))
         lib = _native.lib()

@@ -86,6 +86,41 @@ def test_logspec_other_window(sb, golden):
     close(out, ref, 'hamming/400 window')
 
 
+# n_fft = 256 (salsa_feature_extraction.py:151-152, :163-170, :300-306): against outputs of the unmodified reference
+def test_nfft256_stft_and_logspec(sb, golden):
+    from oracle import salsa as osalsa
+    g, clips = golden('nfft256_cases'), golden('clip_cases')
+    foa = clips['audio_foa'][:, :12000]
+    ref = osalsa.multichannel_stft(foa, 256, 150)[1:128].astype(np.complex64)
+    out = sb.stft(foa, n_fft=256, hop_length=150, lower_bin=1, upper_bin=128)
+    assert out.shape == ref.shape and out.dtype == np.complex64
+    assert np.all(np.abs(out - ref) <= 1.2e-7 * np.abs(ref))
+    assert np.mean(out[:, 1:] == ref[:, 1:]) > 0.999
+    close(sb.MagStftExtractor(256, 150, 256).extract(foa), g['logspec_foa'], 'logspec 256')
+    close(sb.MagStftExtractor(256, 150, 256, is_compress_high_freq=False).extract(foa), g['logspec_foa_nocompress'], 'logspec 256 linear')
+    close(sb.MagStftExtractor(256, 150, 200).extract(foa), g['logspec_foa_win200'], 'logspec 256, window 200')
+    out32 = sb.stft(foa, n_fft=256, hop_length=150, lower_bin=1, upper_bin=128, stft_precision=32)
+    assert np.abs(out32 - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('fmt,fmax', [('foa', 9000), ('mic', 4000)])
+def test_nfft256_clip_matches_reference_golden(sb, golden, fmt, fmax):
+    g, clips = golden('nfft256_cases'), golden('clip_cases')
+    audio = clips['audio_' + fmt][:, :12000]
+    ex = sb.SalsaExtractor(audio_format=fmt, n_fft=256, hop_len=150, win_len=256, fmax_doa=fmax)
+    out = ex.extract(torch.from_numpy(audio)[None].cuda())[0].cpu().numpy()
+    assert out.shape == (7, 81, 100)
+    check_feature(out, g['salsa_' + fmt], what='n_fft 256 ' + fmt)
+    # the host-buffer entry point takes the same path
+    host = ex.extract_host(np.ascontiguousarray(audio[None]))[0]
+    assert np.array_equal(host, out)
+
+
+def test_nfft256_is_rejected_where_it_is_not_built(sb):
+    with pytest.raises(ValueError):
+        sb.SalsaLiteExtractor(n_fft=256, hop_len=150).extract(torch.zeros(1, 4, 12000, device='cuda'))
+
+
 def test_extractor_asserts_like_reference(sb):
     with pytest.raises(AssertionError):
         sb.MagStftExtractor(n_fft=1024, hop_length=300)

@@ -66,6 +66,22 @@ def test_salsa_clip_matches_golden(golden, key, fmt, fmax, trk):
     np.testing.assert_allclose(out, g[key], rtol=0, atol=1e-6)
 
 
+def test_nfft256_oracle_matches_reference_golden(golden):
+    """n_fft = 256 / hop 150 (salsa_feature_extraction.py:151-152, :163-170, :300-306): the restatement against outputs of
+    the unmodified reference (tests/golden/nfft256_cases.npz, oracle/make_golden.py nfft256)."""
+    g, clips = golden('nfft256_cases'), golden('clip_cases')
+    foa, mic = clips['audio_foa'][:, :12000], clips['audio_mic'][:, :12000]
+    np.testing.assert_array_equal(salsa.MagStftExtractor(256, 150, 256).extract(foa), g['logspec_foa'])
+    np.testing.assert_array_equal(salsa.MagStftExtractor(256, 150, 256, is_compress_high_freq=False).extract(foa), g['logspec_foa_nocompress'])
+    np.testing.assert_array_equal(salsa.MagStftExtractor(256, 150, 200).extract(foa), g['logspec_foa_win200'])
+    for fmt, audio, fmax in (('foa', foa, 9000), ('mic', mic, 4000)):
+        out = salsa.salsa_clip(audio, fmt, n_fft=256, hop_length=150, win_length=256, fmax_doa=fmax)
+        ref = g['salsa_' + fmt]
+        assert out.shape == ref.shape == (7, 81, 100)
+        assert np.array_equal(out != 0, ref != 0)
+        np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
+
+
 @pytest.mark.parametrize('ft', ['salsa_lite', 'salsa_ipd'])
 def test_salsa_lite_matches_golden(golden, ft):
     g = golden('clip_cases')
