@@ -87,23 +87,30 @@ int crnn_conv_wgrad(const void *x, const void *gy, float *dw, int32_t B, int32_t
                     int32_t ksize, void *stream);
 
 /* nn.BatchNorm2d in TRAIN mode (batch statistics; models/model_utils.py:202-203, :216, :356 in the training step), fused with
- * the residual add and the ReLU around it, on NHWC bf16 activations viewed as [n_pix][C] (C = 64, 128, 256 or 512):
- *   z = relu?(gamma (y - mean) / sqrt(var + eps) + beta (+ residual)),  mean / var = biased statistics of y over the pixels
+ * the residual add, the ReLU and the element-wise dropout around it, on NHWC bf16 activations viewed as [n_pix][C]
+ * (C = 64, 128, 256 or 512):
+ *   z = dropout?(relu?(gamma (y - mean) / sqrt(var + eps) + beta (+ residual))),  mean / var = biased statistics of y
  *   stat fp32 [C][2] receives (mean, 1 / std) for the backward pass; sums float64 [C][2] is scratch; running_mean /
- *   running_var fp32 [C] (both or neither) are updated with `momentum` (unbiased variance), like nn.BatchNorm2d. */
+ *   running_var fp32 [C] (both or neither) are updated with `momentum` (unbiased variance), like nn.BatchNorm2d.
+ *   Dropout (nn.Dropout(p) behind relu(bn1(.)), :356): drop_seed is a DEVICE scalar (NULL or drop_p = 0: none), drop_salt
+ *   tells the layers sharing it apart; kept elements are scaled by 1 / (1 - drop_p).  The keep decisions are a function of
+ *   (seed, salt, element index), so no mask is stored: the backward call recomputes them from the same three values, and a
+ *   CUDA graph of the step sees the seed the device scalar holds at replay time. */
 int crnn_bn_train_forward(const void *y, const float *gamma, const float *beta, const void *residual, void *z, float *stat,
                           double *sums, float *running_mean, float *running_var, int64_t n_pix, int32_t C, float eps,
-                          float momentum, int32_t relu, void *stream);
+                          float momentum, int32_t relu, const uint64_t *drop_seed, uint32_t drop_salt, float drop_p,
+                          void *stream);
 
 /* Its backward pass: dz = dLoss/dz (bf16), z / y / stat from the forward ->
- *   dy bf16 = gamma / std (g - mean(g) - xhat mean(g xhat)),  g = dz * mask,  xhat = (y - mean) / std
+ *   dy bf16 = gamma / std (g - mean(g) - xhat mean(g xhat)),  g = dz * mask (* keep / (1 - drop_p)),  xhat = (y - mean) / std
  *   d_residual bf16 (optional) = g;  dgamma fp32 [C] = sum g xhat;  dbeta fp32 [C] = sum g;  sums float64 [C][2] scratch.
  *   relu = 0: no ReLU in the forward (mask = 1);  1: mask = z > 0, read from z;  2: the forward had NO residual, so the mask
  *   is recomputed from y, gamma, beta and stat with the forward's own expression (bit-identical to z > 0; z may be NULL and
- *   one tensor less is read).  beta is only used by relu = 2. */
+ *   one tensor less is read).  beta is only used by relu = 2.  drop_*: the forward call's values. */
 int crnn_bn_train_backward(const void *dz, const void *z, const void *y, const float *stat, const float *gamma,
                            const float *beta, void *dy, void *d_residual, double *sums, float *dgamma, float *dbeta,
-                           int64_t n_pix, int32_t C, int32_t relu, void *stream);
+                           int64_t n_pix, int32_t C, int32_t relu, const uint64_t *drop_seed, uint32_t drop_salt,
+                           float drop_p, void *stream);
 
 /* The first convolution of the encoder (conv_block1.conv1 + bn1 + ReLU, models/model_utils.py:213-215) on an input
  * padded to 16 channels: x bf16 NHWC [B][H][W][planes*16], w bf16 [9][64][planes*16] -> out bf16 [B][H][W][planes*64]. */

@@ -89,9 +89,20 @@ def conv_wgrad(x, gy, ksize=3):
     return dw
 
 
-def bn_train_forward(y, gamma, beta, residual=None, relu=True, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
-    """Train-mode BatchNorm2d (+ residual) (+ ReLU) on NHWC bf16: y (..., C) -> (z bf16 like y, stat fp32 (C, 2) = mean | 1/std).
-    running_mean / running_var (fp32 (C,), both or neither) are updated in place like nn.BatchNorm2d does."""
+def _drop_args(drop):
+    """drop = None or (seed: CUDA int64 tensor of one element, salt: int, p: float) -> the three C arguments."""
+    if drop is None or drop[2] <= 0.0:
+        return ctypes.c_void_p(0), 0, ctypes.c_float(0.0)
+    seed, salt, p = drop
+    if not (seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 1):
+        raise ValueError('the dropout seed must be a CUDA int64 tensor of one element')
+    return _p(seed), int(salt) & 0xffffffff, ctypes.c_float(float(p))
+
+
+def bn_train_forward(y, gamma, beta, residual=None, relu=True, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, drop=None):
+    """Train-mode BatchNorm2d (+ residual) (+ ReLU) (+ dropout) on NHWC bf16: y (..., C) -> (z bf16 like y, stat fp32 (C, 2) =
+    mean | 1/std).  running_mean / running_var (fp32 (C,), both or neither) are updated in place like nn.BatchNorm2d does.
+    drop = (seed tensor on the device, salt, p): element-wise dropout behind the ReLU, recomputed (not stored) by the backward."""
     _check_act(y)
     C = y.shape[-1]
     n_pix = y.numel() // C
@@ -106,11 +117,11 @@ def bn_train_forward(y, gamma, beta, residual=None, relu=True, running_mean=None
     stat = torch.empty((C, 2), dtype=torch.float32, device=y.device)
     sums = torch.empty((C, 2), dtype=torch.float64, device=y.device)
     _call('crnn_bn_train_forward', y, _p(y), _p(gamma), _p(beta), _p(residual), _p(z), _p(stat), _p(sums), _p(running_mean), _p(running_var),
-          n_pix, C, ctypes.c_float(eps), ctypes.c_float(momentum), int(bool(relu)))
+          n_pix, C, ctypes.c_float(eps), ctypes.c_float(momentum), int(bool(relu)), *_drop_args(drop))
     return z, stat
 
 
-def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False, beta=None):
+def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False, beta=None, drop=None):
     """-> (dy bf16, d_residual bf16 or None, dgamma fp32 (C,), dbeta fp32 (C,)).  With `relu` and `beta` given and z None, the
     forward had no residual and the ReLU mask is recomputed from y (one tensor less to read)."""
     _check_act(dz)
@@ -124,7 +135,7 @@ def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False
     dbeta = torch.empty((C,), dtype=torch.float32, device=y.device)
     mode = 0 if not relu else (2 if (z is None and beta is not None) else 1)
     _call('crnn_bn_train_backward', dz, _p(dz), _p(z), _p(y), _p(stat), _p(gamma), _p(beta), _p(dy), _p(dres), _p(sums), _p(dgamma), _p(dbeta),
-          n_pix, C, mode)
+          n_pix, C, mode, *_drop_args(drop))
     return dy, dres, dgamma, dbeta
 
 

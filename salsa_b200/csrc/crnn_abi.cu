@@ -384,9 +384,21 @@ int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t
     return check_cuda(cudaGetLastError(), "conv_wgrad_kernel");
 }
 
+static int make_drop(const uint64_t* seed, uint32_t salt, float p, DropArgs* d) {
+    if (seed && !(p >= 0.0f && p < 1.0f)) return fail(SALSA_EINVAL, "dropout probability must be in [0, 1)");
+    const bool on = seed && p > 0.0f;
+    d->seed = on ? reinterpret_cast<const unsigned long long*>(seed) : nullptr;
+    d->salt = salt;
+    d->threshold = on ? (unsigned int)lrintf(p * 65536.0f) : 0u;
+    d->scale = on ? 1.0f / (1.0f - p) : 1.0f;
+    return SALSA_OK;
+}
+
 int crnn_bn_train_forward(const void* y, const float* gamma, const float* beta, const void* residual, void* z, float* stat,
                           double* sums, float* running_mean, float* running_var, int64_t n_pix, int32_t C, float eps, float momentum,
-                          int32_t relu, void* stream) {
+                          int32_t relu, const uint64_t* drop_seed, uint32_t drop_salt, float drop_p, void* stream) {
+    DropArgs drop;
+    if (int rcd = make_drop(drop_seed, drop_salt, drop_p, &drop)) return rcd;
     if (!y || !gamma || !beta || !z || !stat || !sums) return fail(SALSA_EINVAL, "bn_train_forward: null pointer");
     if (C <= 0 || C % 8 != 0 || C > 512 || 256 % (C / 8) != 0) return fail(SALSA_EINVAL, "bn_train_forward: C must be 64, 128, 256 or 512");
     if (n_pix <= 0) return fail(SALSA_EINVAL, "bn_train_forward: empty input");
@@ -401,14 +413,16 @@ int crnn_bn_train_forward(const void* y, const float* gamma, const float* beta, 
     count_launch();
     bn_apply_kernel<<<grid_for(n_pix * (C / 8), 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(y), stat, gamma, beta,
                                                                      reinterpret_cast<const __nv_bfloat16*>(residual),
-                                                                     reinterpret_cast<__nv_bfloat16*>(z), n_pix, C, relu);
+                                                                     reinterpret_cast<__nv_bfloat16*>(z), n_pix, C, relu, drop);
     count_launch();
     return check_cuda(cudaGetLastError(), "bn_train_forward");
 }
 
 int crnn_bn_train_backward(const void* dz, const void* z, const void* y, const float* stat, const float* gamma, const float* beta,
                            void* dy, void* d_residual, double* sums, float* dgamma, float* dbeta, int64_t n_pix, int32_t C,
-                           int32_t relu, void* stream) {
+                           int32_t relu, const uint64_t* drop_seed, uint32_t drop_salt, float drop_p, void* stream) {
+    DropArgs drop;
+    if (int rcd = make_drop(drop_seed, drop_salt, drop_p, &drop)) return rcd;
     if (!dz || !y || !stat || !gamma || !dy || !sums || !dgamma || !dbeta) return fail(SALSA_EINVAL, "bn_train_backward: null pointer");
     if (relu < 0 || relu > 2) return fail(SALSA_EINVAL, "bn_train_backward: relu is 0 (none), 1 (mask from z) or 2 (mask recomputed from y)");
     if (relu == 1 && !z) return fail(SALSA_EINVAL, "bn_train_backward: the ReLU mask needs the forward output");
@@ -424,14 +438,14 @@ int crnn_bn_train_backward(const void* dz, const void* z, const void* y, const f
                         *py = reinterpret_cast<const __nv_bfloat16*>(y);
     __nv_bfloat16 *pdy = reinterpret_cast<__nv_bfloat16*>(dy), *pdr = reinterpret_cast<__nv_bfloat16*>(d_residual);
     if (relu == 0) {
-        bn_bwd_reduce_kernel<0><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums);
-        bn_bwd_apply_kernel<0><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C);
+        bn_bwd_reduce_kernel<0><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums, drop);
+        bn_bwd_apply_kernel<0><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C, drop);
     } else if (relu == 1) {
-        bn_bwd_reduce_kernel<1><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums);
-        bn_bwd_apply_kernel<1><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C);
+        bn_bwd_reduce_kernel<1><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums, drop);
+        bn_bwd_apply_kernel<1><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C, drop);
     } else {
-        bn_bwd_reduce_kernel<2><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums);
-        bn_bwd_apply_kernel<2><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C);
+        bn_bwd_reduce_kernel<2><<<blocks, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, n_pix, C, sums, drop);
+        bn_bwd_apply_kernel<2><<<grid2, 256, 0, st>>>(pdz, pz, py, stat, gamma, beta, sums, pdy, pdr, n_pix, C, drop);
     }
     count_launch();
     count_launch();

@@ -581,12 +581,43 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long n_
     }
 }
 
-// z = relu?(scale y + shift (+ residual)) with scale = gamma / std, shift = beta - mean scale.  blockDim (256) is a multiple
-// of the channel groups, so a thread keeps its 8 channels for the whole grid-stride loop: coefficients live in registers.
+// Dropout fused behind the ReLU (nn.Dropout2d is NOT what the reference uses: models/model_utils.py:356 is element-wise
+// nn.Dropout(p = 0.1) on relu(bn1(conv1(x)))).  The keep decisions are a pure function of (seed, salt, element index): 16 bits
+// per element from two splitmix64 values per group of 8 channels, so the backward pass recomputes them instead of storing a
+// mask.  The seed lives in DEVICE memory (a CUDA graph of the step replays with whatever the counter holds then).
+struct DropArgs {
+    const unsigned long long* seed;   // device scalar, or null: no dropout
+    unsigned int salt;                // distinguishes the layers that share the seed
+    unsigned int threshold;           // round(p * 65536): an element is dropped when its 16 bits are below it
+    float scale;                      // 1 / (1 - p)
+};
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// keep bits of the 8 channels of 16-byte group `i` (bit k = element k survives)
+__device__ __forceinline__ unsigned int drop_keep8(unsigned long long key, long long i, unsigned int threshold) {
+    const unsigned long long h0 = splitmix64(key + 2ull * (unsigned long long)i), h1 = splitmix64(key + 2ull * (unsigned long long)i + 1ull);
+    unsigned int keep = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        keep |= (((unsigned int)(h0 >> (16 * k)) & 0xffffu) >= threshold ? 1u : 0u) << k;
+        keep |= (((unsigned int)(h1 >> (16 * k)) & 0xffffu) >= threshold ? 1u : 0u) << (4 + k);
+    }
+    return keep;
+}
+__device__ __forceinline__ unsigned long long drop_key(const DropArgs& d) {
+    return splitmix64(*d.seed ^ ((unsigned long long)d.salt << 32));
+}
+
+// z = dropout?(relu?(scale y + shift (+ residual))) with scale = gamma / std, shift = beta - mean scale.  blockDim (256) is a
+// multiple of the channel groups, so a thread keeps its 8 channels for the whole grid-stride loop: coefficients live in registers.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ z,
-                                                       long long n_pix, int C, int relu) {
+                                                       long long n_pix, int C, int relu, DropArgs drop) {
     const int groups = C >> 3;
     const long long total = n_pix * groups;
     const int c0 = (int)(threadIdx.x % groups) * 8;
@@ -596,15 +627,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
         scale[k] = gamma[c0 + k] * stat[2 * (c0 + k) + 1];
         shift[k] = fmaf(-stat[2 * (c0 + k)], scale[k], beta[c0 + k]);
     }
+    const unsigned long long key = drop.seed ? drop_key(drop) : 0ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         float v[8], r[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), v);
         if (residual) unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
+        const unsigned int keep = drop.seed ? drop_keep8(key, i, drop.threshold) : 0xffu;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float o = fmaf(v[k], scale[k], shift[k]);
             if (residual) o += r[k];
-            v[k] = relu ? fmaxf(o, 0.0f) : o;
+            o = relu ? fmaxf(o, 0.0f) : o;
+            if (drop.seed) o = ((keep >> k) & 1u) ? o * drop.scale : 0.0f;
+            v[k] = o;
         }
         reinterpret_cast<uint4*>(z)[i] = pack8(v);
     }
@@ -633,7 +668,7 @@ template <int RELU>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                             const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            long long n_pix, int C, double* __restrict__ sums) {
+                                                            long long n_pix, int C, double* __restrict__ sums, DropArgs drop) {
     // a thread keeps its channel group: mean / (1 / std) of its 8 channels live in registers
     const int c0 = (int)(threadIdx.x % (C >> 3)) * 8;
     float mean[8], inv[8];
@@ -644,22 +679,34 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     }
     BnMaskCoef mc;
     if (RELU == 2) bn_mask_coef(stat, gamma, beta, c0, mc);
-    constexpr int NT = RELU == 1 ? 3 : 2;
+    // dropout behind the ReLU: g = dz * keep / (1 - p).  With the mask read from z (RELU == 1) dropped elements have z = 0 and
+    // fall out by themselves; otherwise the keep bits are recomputed.  The last word of q carries the group index for that.
+    const unsigned long long key = drop.seed ? drop_key(drop) : 0ull;
+    const float gscale = drop.seed ? drop.scale : 1.0f;
+    const int groups = C >> 3;
+    constexpr int NT = 3;
     channel_reduce2<NT>(n_pix, C, sums,
         [&](long long p, int c8, uint4 (&q)[NT]) {
             q[0] = __ldg(reinterpret_cast<const uint4*>(dz + p * C) + c8);
             q[1] = __ldg(reinterpret_cast<const uint4*>(y + p * C) + c8);
-            if (RELU == 1) q[NT - 1] = __ldg(reinterpret_cast<const uint4*>(z + p * C) + c8);
+            if (RELU == 1) q[2] = __ldg(reinterpret_cast<const uint4*>(z + p * C) + c8);
+            else {
+                const unsigned long long gi = (unsigned long long)(p * groups + c8);
+                q[2] = make_uint4((unsigned int)gi, (unsigned int)(gi >> 32), 0u, 0u);
+            }
         },
         [&](const uint4 (&q)[NT], float (&a)[8], float (&b)[8]) {
             float g[8], zz[8], yy[8];
             unpack8(q[0], g);
             unpack8(q[1], yy);
-            if (RELU == 1) unpack8(q[NT - 1], zz);
+            if (RELU == 1) unpack8(q[2], zz);
+            unsigned int keep = 0xffu;
+            if (RELU != 1 && drop.seed) keep = drop_keep8(key, (long long)(((unsigned long long)q[2].y << 32) | q[2].x), drop.threshold);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const bool on = RELU == 0 ? true : (RELU == 1 ? zz[i] > 0.0f : bn_mask_from_y(yy[i], mc.scale[i], mc.shift[i]));
-                const float gi = on ? g[i] : 0.0f;
+                bool on = RELU == 0 ? true : (RELU == 1 ? zz[i] > 0.0f : bn_mask_from_y(yy[i], mc.scale[i], mc.shift[i]));
+                on = on && ((keep >> i) & 1u);
+                const float gi = on ? g[i] * gscale : 0.0f;
                 a[i] += gi;
                 b[i] = fmaf(gi, (yy[i] - mean[i]) * inv[i], b[i]);
             }
@@ -673,7 +720,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const double* __restrict__ sums,
                                                            __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ d_residual,
-                                                           long long n_pix, int C) {
+                                                           long long n_pix, int C, DropArgs drop) {
     const int groups = C >> 3;
     const long long total = n_pix * groups;
     const float inv_n = (float)(1.0 / (double)n_pix);
@@ -691,15 +738,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     BnMaskCoef mc;
     if (RELU == 2) bn_mask_coef(stat, gamma, beta, c0, mc);
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const unsigned long long key = drop.seed ? drop_key(drop) : 0ull;
+    const float gscale = drop.seed ? drop.scale : 1.0f;
     auto one = [&](long long i, const uint4& qg, const uint4& qy, const uint4& qz) {
         float g[8], zz[8], yy[8], o[8];
         unpack8(qg, g);
         unpack8(qy, yy);
         if (RELU == 1) unpack8(qz, zz);
+        const unsigned int keep = (RELU != 1 && drop.seed) ? drop_keep8(key, i, drop.threshold) : 0xffu;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const bool on = RELU == 0 ? true : (RELU == 1 ? zz[k] > 0.0f : bn_mask_from_y(yy[k], mc.scale[k], mc.shift[k]));
-            if (!on) g[k] = 0.0f;
+            bool on = RELU == 0 ? true : (RELU == 1 ? zz[k] > 0.0f : bn_mask_from_y(yy[k], mc.scale[k], mc.shift[k]));
+            on = on && ((keep >> k) & 1u);
+            g[k] = on ? g[k] * gscale : 0.0f;
             o[k] = fmaf(ca[k], g[k], fmaf(cy[k], yy[k], cc[k]));
         }
         reinterpret_cast<uint4*>(dy)[i] = pack8(o);

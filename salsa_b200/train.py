@@ -7,9 +7,9 @@ lr / beta1 schedule (utilities/learning_utils.py:17-52), DDP gradient all-reduce
   native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 and 1x1 convolutions' forward, input gradient
                               (the tcgen05 implicit-GEMM kernel on flipped / transposed weights) and weight gradient
                               (`crnn_conv_wgrad`), the loss with its output gradients (`crnn_seld_loss`), the Adam step,
-                              train-mode BatchNorm fused with the residual add and the ReLU, forward and backward
-                              (`crnn_bn_train_forward` / `_backward`), 2x2 average pooling forward and backward
-  torch / cuDNN (library)     the first (7-channel) convolution, dropout, the BiGRU and the heads, through autograd -- not
+                              train-mode BatchNorm fused with the residual add, the ReLU and the encoder's dropout, forward
+                              and backward (`crnn_bn_train_forward` / `_backward`), 2x2 average pooling forward and backward
+  torch / cuDNN (library)     the first (7-channel) convolution, the BiGRU and the heads with their dropouts, through autograd -- not
                               native yet, and said so wherever a number is quoted
   torch.distributed           bf16 all-reduce of the flat gradient buffer (`GradAllReduce`; NCCL on the GPU box, gloo in the
                               CPU tests): per bucket while the backward pass is still running (eager step), or one call after
@@ -90,13 +90,15 @@ class NativeBnAct(torch.autograd.Function):
     `crnn_bn_train_backward`.  Running statistics are updated in place in the forward pass."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, residual, running_mean, running_var, relu):
+    def forward(ctx, y, gamma, beta, residual, running_mean, running_var, relu, drop=None):
+        """drop = (device seed tensor, salt, p): element-wise dropout behind the ReLU (nn.Dropout after relu(bn1(.)),
+        models/model_utils.py:356), recomputed from the seed in the backward pass instead of stored."""
         yb = y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         rb = None if residual is None else residual.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         g, b = gamma.detach().contiguous(), beta.detach().contiguous()
         z, stat = ops.bn_train_forward(yb.permute(0, 2, 3, 1), g, b, None if rb is None else rb.permute(0, 2, 3, 1), relu=relu,
-                                       running_mean=running_mean, running_var=running_var)
-        ctx.relu, ctx.has_res = relu, residual is not None
+                                       running_mean=running_mean, running_var=running_var, drop=drop)
+        ctx.relu, ctx.has_res, ctx.drop = relu, residual is not None, drop
         # without a residual the ReLU mask is a function of y: the backward pass recomputes it instead of reading z
         ctx.save_for_backward(yb, z if (relu and ctx.has_res) else None, stat, g, b)
         return z.permute(0, 3, 1, 2)
@@ -106,8 +108,8 @@ class NativeBnAct(torch.autograd.Function):
         yb, z, stat, g, b = ctx.saved_tensors
         dzb = dz.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         dy, dres, dgamma, dbeta = ops.bn_train_backward(dzb.permute(0, 2, 3, 1), z, yb.permute(0, 2, 3, 1), stat, g, relu=ctx.relu, beta=b,
-                                                        want_residual_grad=ctx.has_res and ctx.needs_input_grad[3])
-        return (dy.permute(0, 3, 1, 2), dgamma, dbeta, None if dres is None else dres.permute(0, 3, 1, 2), None, None, None)
+                                                        want_residual_grad=ctx.has_res and ctx.needs_input_grad[3], drop=ctx.drop)
+        return (dy.permute(0, 3, 1, 2), dgamma, dbeta, None if dres is None else dres.permute(0, 3, 1, 2), None, None, None, None)
 
 
 class NativeAvgPool2(torch.autograd.Function):
@@ -241,6 +243,9 @@ class SeldTrainer:
         self.training = True
         self.epoch, self.batch_idx = 0, 0
         self.use_graph = use_graph and self.device.type == 'cuda'
+        # seed of the dropout fused into the BatchNorm kernels: a device counter, advanced by a launch inside the step so that a
+        # replayed CUDA graph draws new masks every time
+        self.drop_seed = torch.full((1,), 0x5A15A, dtype=torch.int64, device=self.device) if self.device.type == 'cuda' else None
         self._graphs = {}                    # batch shape -> (graph, static inputs, static loss)
         self._index_cache = {}
         self.graph_error = None              # why a capture fell back to eager launches (None: it did not)
@@ -263,16 +268,18 @@ class SeldTrainer:
             return NativeAvgPool2.apply(x)
         return F.avg_pool2d(x, 2)
 
-    def _bn(self, x, prefix, relu=False, residual=None):
-        """BatchNorm2d (+ residual) (+ ReLU): one native pass each way in train mode, torch ops otherwise."""
+    def _bn(self, x, prefix, relu=False, residual=None, drop_p=0.0, salt=0):
+        """BatchNorm2d (+ residual) (+ ReLU) (+ dropout): one native pass each way in train mode, torch ops otherwise."""
         rm, rv = self.buffers[prefix + '.running_mean'], self.buffers[prefix + '.running_var']
         w, b = self.params[prefix + '.weight'], self.params[prefix + '.bias']
         if self.native_bn and self.training and x.is_cuda and x.shape[1] in (64, 128, 256, 512):
-            return NativeBnAct.apply(x, w, b, residual, rm, rv, relu)
+            drop = (self.drop_seed, salt, drop_p) if drop_p > 0.0 else None
+            return NativeBnAct.apply(x, w, b, residual, rm, rv, relu, drop)
         out = F.batch_norm(x, rm, rv, w, b, training=self.training, momentum=0.1, eps=1e-5)
         if residual is not None:
             out = out + residual
-        return F.relu(out) if relu else out
+        out = F.relu(out) if relu else out
+        return F.dropout(out, p=drop_p, training=True) if drop_p > 0.0 else out
 
     def forward(self, x):
         """x (B, 7, T, F) float32 -> {'event_frame_logit': (B, T/16, n), 'doa_frame_output': (B, T/16, 3n)}, with autograd."""
@@ -288,8 +295,8 @@ class SeldTrainer:
                     q = 'encoder.resnet.layer{}.{}'.format(li, bi)
                     identity = x
                     pooled = self._pool(x) if (li > 1 and bi == 0) else x     # _ResnetBasicBlock.forward (:345-367)
-                    out = self._bn(self._conv3(pooled, q + '.conv1.weight'), q + '.bn1', relu=True)
-                    out = F.dropout(out, p=0.1, training=tr)
+                    # relu(bn1(conv1(.))) and the dropout behind it (:354-356) in one pass
+                    out = self._bn(self._conv3(pooled, q + '.conv1.weight'), q + '.bn1', relu=True, drop_p=0.1 if tr else 0.0, salt=2 * li + bi)
                     if li > 1 and bi == 0:                                     # downsample = AvgPool2d(2) + 1x1 conv + BN (:474-481): the same pooled tensor
                         wd = self.params[q + '.downsample.1.weight']
                         ds = NativeConv1x1.apply(pooled, wd) if self.native_conv else F.conv2d(pooled, wd)
@@ -378,6 +385,8 @@ class SeldTrainer:
         all-reduce, schedule and Adam are the caller's)."""
         self.flat_grad.zero_()
         self.reducer.reset()
+        if self.drop_seed is not None:
+            self.drop_seed.add_(1)                          # a launch: part of the captured graph, so every replay advances it
         out = self.forward(x)
         idx = self._label_index(out['event_frame_logit'].shape[1])
         logit, doa = out['event_frame_logit'][:, idx], out['doa_frame_output'][:, idx]      # interpolate_tensor (model_utils.py:57-75)

@@ -203,3 +203,40 @@ def test_native_conv1x1_all_three_directions(B, H, W, Cin, Cout):
     y = NativeConv1x1.apply(x, w)
     gx, gw = torch.autograd.grad(y, (x, w), gy)
     assert rel(y, y_ref) < 1e-2 and rel(gx, gx_ref) < 1e-2 and rel(gw, gw_ref) < 1e-4
+
+
+def test_fused_dropout_statistics_and_gradient():
+    """Dropout fused into the BatchNorm pass (nn.Dropout(0.1) behind relu(bn1(.)), models/model_utils.py:354-356): the drop
+    rate, the 1 / (1 - p) scale, a new mask per seed, and a backward pass that recomputes exactly the forward's mask."""
+    from salsa_b200.train import NativeBnAct
+    g = torch.Generator().manual_seed(7)
+    C, B, H, W, p = 64, 4, 40, 25, 0.1
+    y = (torch.randn(B, C, H, W, generator=g) * 2 + 0.5).bfloat16().float().cuda().requires_grad_(True)
+    gamma, beta = torch.ones(C).cuda().requires_grad_(True), torch.zeros(C).cuda().requires_grad_(True)
+    rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    seed = torch.full((1,), 123, dtype=torch.int64, device='cuda')
+    base = NativeBnAct.apply(y, gamma, beta, None, rm.clone(), rv.clone(), True, None).float()
+    out = NativeBnAct.apply(y, gamma, beta, None, rm.clone(), rv.clone(), True, (seed, 3, p))
+    outf = out.float()
+    live = base > 0
+    dropped = live & (outf == 0)
+    rate = dropped.sum().item() / live.sum().item()
+    assert abs(rate - p) < 0.01, rate
+    kept = live & ~dropped
+    assert rel(outf[kept], base[kept] / (1 - p)) < 1e-2
+    # the same seed and salt give the same mask, another salt or seed another one
+    again = NativeBnAct.apply(y, gamma, beta, None, rm.clone(), rv.clone(), True, (seed, 3, p)).float()
+    assert torch.equal(again, outf)
+    other = NativeBnAct.apply(y, gamma, beta, None, rm.clone(), rv.clone(), True, (seed, 4, p)).float()
+    assert not torch.equal(other == 0, outf == 0)
+    seed.add_(1)
+    nxt = NativeBnAct.apply(y, gamma, beta, None, rm.clone(), rv.clone(), True, (seed, 3, p)).float()
+    assert not torch.equal(nxt == 0, outf == 0)
+    seed.sub_(1)
+    # backward: gradient of sum(out * w) against autograd through the explicit mask
+    wgt = torch.randn(B, C, H, W, generator=g).bfloat16().float().cuda()
+    gy, ggamma, gbeta = torch.autograd.grad(out, (y, gamma, beta), wgt)
+    mask = (~dropped).float() / (1 - p)
+    ref = torch.nn.functional.relu(torch.nn.functional.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-5)) * mask
+    gy_ref, ggamma_ref, gbeta_ref = torch.autograd.grad(ref, (y, gamma, beta), wgt)
+    assert rel(gy, gy_ref) < 2e-2 and rel(ggamma, ggamma_ref) < 1e-2 and rel(gbeta, gbeta_ref) < 1e-2
