@@ -152,6 +152,20 @@ int crnn_freq_mean(const void *x, void *y, int32_t BH, int32_t W, int32_t C, int
 int crnn_gru_layer(const float *xproj, const float *w_hh, const float *b_hh, void *y, int32_t B, int32_t T, int32_t planes,
                    void *stream);
 
+/* The same recurrence for the TRAINING step (float32 throughout), keeping what back-propagation through time needs:
+ *   y    fp32 [B*T][512]       forward | backward hidden states
+ *   save fp32 [B*T][2][4][256] per direction r, z, n and hn = W_hn h + b_hn of every step */
+int crnn_gru_layer_train(const float *xproj, const float *w_hh, const float *b_hh, float *y, float *save, int32_t B,
+                         int32_t T, void *stream);
+
+/* Back-propagation through time of that layer (the backward pass of nn.GRU in models/seld_models.py:68-76): dy fp32
+ * [B*T][512] = dLoss/dy, y / save from crnn_gru_layer_train ->
+ *   dgi fp32 [B*T][1536] = dLoss/d(x W_ih^T + b_ih)  and  dgh fp32 [B*T][1536] = dLoss/d(h_prev W_hh^T + b_hh),
+ * same column layout as xproj.  The parameter and input gradients are GEMMs / column sums over them, left to the caller:
+ * dW_ih = dgi^T x, db_ih = sum dgi, dx = dgi W_ih, dW_hh = dgh^T h_prev, db_hh = sum dgh. */
+int crnn_gru_layer_backward(const float *dy, const float *y, const float *save, const float *w_hh, float *dgi, float *dgh,
+                            int32_t B, int32_t T, void *stream);
+
 /* Output stage of SeldDecoder.forward (models/decoders.py:137-147): z fp32 [rows][64] holds the fused
  * event|x|y|z second-layer outputs in columns 0..4*n_classes-1; logits = z[:, :n], doa = tanh(z[:, n:4n]). */
 int crnn_head_finish(const float *z, float *logits, float *doa, int32_t rows, int32_t n_classes, void *stream);

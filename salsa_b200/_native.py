@@ -87,6 +87,8 @@ SIGNATURES = {
     'crnn_avgpool2_backward': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'crnn_freq_mean': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'crnn_gru_layer': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    'crnn_gru_layer_train': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    'crnn_gru_layer_backward': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     'crnn_head_finish': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     'crnn_decode_events': (ctypes.c_int, [_vp, _vp, _i32, _i32, ctypes.c_float, _vp, _vp, _vp, _vp]),
     'crnn_gather_time': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -139,6 +139,32 @@ def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False
     return dy, dres, dgamma, dbeta
 
 
+def gru_layer_train(xproj, w_hh, b_hh):
+    """xproj (B, T, 1536) fp32, w_hh (2, 768, 256) fp32, b_hh (2, 768) fp32 -> (y (B, T, 512) fp32, save (B, T, 2, 4, 256) fp32)."""
+    for t in (xproj, w_hh, b_hh):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError('gru_layer_train takes contiguous CUDA float32 tensors')
+    B, T, n = xproj.shape
+    if n != 1536 or tuple(w_hh.shape) != (2, 768, 256) or tuple(b_hh.shape) != (2, 768):
+        raise ValueError('gru_layer_train: hidden size 256, both directions')
+    y = torch.empty((B, T, 512), dtype=torch.float32, device=xproj.device)
+    save = torch.empty((B, T, 2, 4, 256), dtype=torch.float32, device=xproj.device)
+    _call('crnn_gru_layer_train', xproj, _p(xproj), _p(w_hh), _p(b_hh), _p(y), _p(save), B, T)
+    return y, save
+
+
+def gru_layer_backward(dy, y, save, w_hh):
+    """dy, y (B, T, 512) fp32, save from gru_layer_train -> (dgi, dgh), both (B, T, 1536) fp32."""
+    for t in (dy, y, save, w_hh):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError('gru_layer_backward takes contiguous CUDA float32 tensors')
+    B, T, _ = y.shape
+    dgi = torch.empty((B, T, 1536), dtype=torch.float32, device=y.device)
+    dgh = torch.empty((B, T, 1536), dtype=torch.float32, device=y.device)
+    _call('crnn_gru_layer_backward', dy, _p(dy), _p(y), _p(save), _p(w_hh), _p(dgi), _p(dgh), B, T)
+    return dgi, dgh
+
+
 def conv_first(x, w, bias=None, relu=True, planes=1):
     """First convolution: x (B,H,W,planes*16) bf16, w (9,64,planes*16) bf16 -> (B,H,W,planes*64) bf16."""
     _check_act(x)

@@ -12,6 +12,7 @@
 #include "crnn_conv.cuh"
 #include "crnn_kernels.cuh"
 #include "crnn_wgrad.cuh"
+#include "crnn_gru_train.cuh"
 #include "salsa_crnn.h"
 
 namespace salsa {
@@ -295,6 +296,32 @@ int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, voi
     gru_layer_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruSmemBytes, (cudaStream_t)stream>>>(a);
     count_launch();
     return check_cuda(cudaGetLastError(), "gru_layer_kernel");
+}
+
+int crnn_gru_layer_train(const float* xproj, const float* w_hh, const float* b_hh, float* y, float* save, int32_t B, int32_t T, void* stream) {
+    if (!xproj || !w_hh || !b_hh || !y || !save) return fail(SALSA_EINVAL, "gru_layer_train: null pointer");
+    if (B <= 0 || T <= 0) return fail(SALSA_EINVAL, "gru_layer_train: bad dimensions");
+    constexpr size_t kFwdSmem = kGruSmemBytes + (size_t)kGruUnits * kGruClips * sizeof(float);        // + the broadcast staging tile
+    SALSA_CUDA(cudaFuncSetAttribute(gru_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    GruTrainArgs a;
+    a.xproj = xproj; a.w_hh = w_hh; a.b_hh = b_hh; a.y = y; a.save = save; a.B = B; a.T = T;
+    const int groups = (B + kGruClips - 1) / kGruClips;
+    gru_train_fwd_kernel<<<groups * 2 * kGruCluster, kGruThreads, kFwdSmem, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gru_train_fwd_kernel");
+}
+
+int crnn_gru_layer_backward(const float* dy, const float* y, const float* save, const float* w_hh, float* dgi, float* dgh, int32_t B,
+                            int32_t T, void* stream) {
+    if (!dy || !y || !save || !w_hh || !dgi || !dgh) return fail(SALSA_EINVAL, "gru_layer_backward: null pointer");
+    if (B <= 0 || T <= 0) return fail(SALSA_EINVAL, "gru_layer_backward: bad dimensions");
+    SALSA_CUDA(cudaFuncSetAttribute(gru_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruBwdSmemBytes));
+    GruBwdArgs a;
+    a.dy = dy; a.y = y; a.save = save; a.w_hh = w_hh; a.dgi = dgi; a.dgh = dgh; a.B = B; a.T = T;
+    const int groups = (B + kGruClips - 1) / kGruClips;
+    gru_train_bwd_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruBwdSmemBytes, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gru_train_bwd_kernel");
 }
 
 int crnn_head_finish(const float* z, float* logits, float* doa, int32_t rows, int32_t n_classes, void* stream) {

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import crnn_ops as ops
 from .optim import Adam, LearningRateScheduler
 
-__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeConv1x1', 'NativeBnAct', 'NativeAvgPool2']
+__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeConv1x1', 'NativeBnAct', 'NativeAvgPool2', 'NativeGRULayer']
 
 
 class NativeConv3x3(torch.autograd.Function):
@@ -83,6 +83,50 @@ class NativeConv1x1(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad(xb.permute(0, 2, 3, 1), gyb.permute(0, 2, 3, 1), ksize=1).reshape(w.shape).to(w.dtype)
         return dx, dw
+
+
+class NativeGRULayer(torch.autograd.Function):
+    """One bidirectional nn.GRU layer (hidden size 256, batch_first) in float32: the recurrence and back-propagation through
+    time are `crnn_gru_layer_train` / `crnn_gru_layer_backward` (cluster kernels, W_hh resident in shared memory); the input
+    projection and the parameter / input gradients are plain float32 GEMMs and column sums around them (library GEMMs).
+    Arguments after x: weight_ih, weight_hh, bias_ih, bias_hh of the forward direction, then of the reverse direction.
+    `gemm_dtype`: operand type of those GEMMs (accumulation is float32 either way): bf16 like the rest of the autocast step
+    by default, float32 for exactness tests."""
+    gemm_dtype = torch.bfloat16
+
+    @staticmethod
+    def _mm(a, b):
+        dt = NativeGRULayer.gemm_dtype
+        return a @ b if dt == torch.float32 else (a.to(dt) @ b.to(dt)).float()
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        B, T, n_in = x.shape
+        xf = x.contiguous()
+        w_ih = torch.cat([w_ih_f, w_ih_r]).contiguous()                       # (1536, In)
+        w_hh = torch.stack([w_hh_f, w_hh_r]).contiguous()                     # (2, 768, 256)
+        b_hh = torch.stack([b_hh_f, b_hh_r]).contiguous()
+        xproj = (NativeGRULayer._mm(xf.reshape(-1, n_in), w_ih.t()) + torch.cat([b_ih_f, b_ih_r])).view(B, T, 1536)
+        y, save = ops.gru_layer_train(xproj, w_hh, b_hh)
+        ctx.save_for_backward(xf, w_ih, w_hh, y, save)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type='cuda')
+    def backward(ctx, dy):
+        xf, w_ih, w_hh, y, save = ctx.saved_tensors
+        B, T, n_in = xf.shape
+        dgi, dgh = ops.gru_layer_backward(dy.float().contiguous(), y, save, w_hh)
+        gi, gh = dgi.view(-1, 1536), dgh.view(-1, 1536)
+        mm = NativeGRULayer._mm
+        dx = mm(gi, w_ih).view(B, T, n_in)
+        dw_ih, db_ih, db_hh = mm(gi.t(), xf.reshape(-1, n_in)), gi.sum(0), gh.sum(0)
+        zero = y.new_zeros(B, 1, 256)
+        hp_f = torch.cat([zero, y[:, :-1, :256]], 1).reshape(-1, 256)          # h_{t-1} of the forward direction
+        hp_r = torch.cat([y[:, 1:, 256:], zero], 1).reshape(-1, 256)           # h_{t+1} of the reverse direction
+        return (dx, dw_ih[:768], mm(gh[:, :768].t(), hp_f), db_ih[:768], db_hh[:768],
+                dw_ih[768:], mm(gh[:, 768:].t(), hp_r), db_ih[768:], db_hh[768:])
 
 
 class NativeBnAct(torch.autograd.Function):
@@ -206,7 +250,7 @@ class SeldTrainer:
     def __init__(self, state_dict, n_classes: int = 12, label_rate: int = 10, feature_rate: float = 80.0, loss_weight=(0.3, 0.7),
                  lr: float = 1e-3, device='cuda', native_conv: bool = True, group=None, scheduler: LearningRateScheduler = None,
                  bucket_bytes: int = 8 << 20, wire_dtype=torch.bfloat16, autocast: bool = True, dropout: bool = True,
-                 native_bn: bool = True, use_graph: bool = False):
+                 native_bn: bool = True, use_graph: bool = False, native_gru: bool = True):
         """native_conv / native_bn / autocast / dropout = False are for tests (a pure torch float32 reference of the same step);
         wire_dtype None sends float32 gradients.  use_graph: `step` captures forward + loss + backward as ONE CUDA graph at the
         first sighting of a batch shape and replays it afterwards (about 1000 launches per step otherwise: the step is
@@ -217,6 +261,7 @@ class SeldTrainer:
         self.ratio = 16.0 * label_rate / feature_rate                 # time_downsample_ratio * label_rate / feature_rate
         self.native_conv = native_conv and self.device.type == 'cuda'
         self.native_bn = native_bn and self.device.type == 'cuda'
+        self.native_gru = native_gru and self.device.type == 'cuda'
         self.autocast = autocast and self.device.type == 'cuda'
         self.dropout = dropout
         self.scheduler = scheduler
@@ -303,10 +348,18 @@ class SeldTrainer:
                         identity = self._bn(ds, q + '.downsample.2')
                     x = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2', relu=True, residual=identity)   # relu(bn2(.) + identity)
             x = torch.mean(x.float(), dim=3).transpose(1, 2)                  # SeldDecoder.forward (models/decoders.py:106-154)
-            gru_params = {k[len('decoder.gru.'):]: v for k, v in self.params.items() if k.startswith('decoder.gru.')}
-            self.gru.train(self.training)
-            self.gru.dropout = 0.3 if tr else 0.0                             # inter-layer dropout (models/decoders.py:44-46)
-            x, _ = torch.func.functional_call(self.gru, gru_params, (x,))
+            if self.native_gru and x.is_cuda:
+                for layer in range(2):
+                    keys = ['decoder.gru.{}_l{}{}'.format(n, layer, suf) for suf in ('', '_reverse')
+                            for n in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')]
+                    x = NativeGRULayer.apply(x, *[self.params[k] for k in keys])
+                    if layer == 0:
+                        x = F.dropout(x, 0.3, tr)                             # inter-layer dropout (models/decoders.py:44-46)
+            else:
+                gru_params = {k[len('decoder.gru.'):]: v for k, v in self.params.items() if k.startswith('decoder.gru.')}
+                self.gru.train(self.training)
+                self.gru.dropout = 0.3 if tr else 0.0
+                x, _ = torch.func.functional_call(self.gru, gru_params, (x,))
 
             def head(name, act=None):
                 h = F.relu(F.linear(F.dropout(x, 0.2, tr), self.params['decoder.{}_fc_1.weight'.format(name)], self.params['decoder.{}_fc_1.bias'.format(name)]))

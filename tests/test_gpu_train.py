@@ -240,3 +240,35 @@ def test_fused_dropout_statistics_and_gradient():
     ref = torch.nn.functional.relu(torch.nn.functional.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-5)) * mask
     gy_ref, ggamma_ref, gbeta_ref = torch.autograd.grad(ref, (y, gamma, beta), wgt)
     assert rel(gy, gy_ref) < 2e-2 and rel(ggamma, ggamma_ref) < 1e-2 and rel(gbeta, gbeta_ref) < 1e-2
+
+
+@pytest.mark.parametrize('B,T', [(5, 7), (32, 40)])
+def test_native_gru_layer_forward_and_bptt(B, T):
+    """crnn_gru_layer_train / crnn_gru_layer_backward (float32 recurrence and back-propagation through time in cluster
+    kernels) against torch.nn.GRU + autograd in float32: outputs, input gradient and all eight parameter gradients.
+    B = 5 leaves three clips of the cluster's group empty."""
+    from salsa_b200.train import NativeGRULayer
+    torch.manual_seed(B + T)
+    ref = torch.nn.GRU(input_size=512, hidden_size=256, num_layers=1, batch_first=True, bidirectional=True).cuda()
+    x = torch.randn(B, T, 512, device='cuda', requires_grad=True)
+    dy = torch.randn(B, T, 512, device='cuda')
+    names = [n + suf for suf in ('', '_reverse') for n in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')]
+    params = [getattr(ref, n) for n in names]
+    with torch.backends.cudnn.flags(enabled=False):               # torch's own float32 GRU: no TF32 / half inside
+        y_ref, _ = ref(x)
+        g_ref = torch.autograd.grad(y_ref, [x] + params, dy)
+    NativeGRULayer.gemm_dtype = torch.float32                     # the GEMMs around the recurrence in float32 too
+    try:
+        y = NativeGRULayer.apply(x, *params)
+        g = torch.autograd.grad(y, [x] + params, dy)
+    finally:
+        NativeGRULayer.gemm_dtype = torch.bfloat16
+    assert rel(y, y_ref) < 1e-5
+    for name, a, b in zip(['x'] + names, g, g_ref):
+        assert rel(a, b) < 1e-4, (name, rel(a, b))
+    # the training default: bf16 operands in the GEMMs (fp32 accumulation), like the rest of the autocast step
+    y16 = NativeGRULayer.apply(x, *params)
+    g16 = torch.autograd.grad(y16, [x] + params, dy)
+    assert rel(y16, y_ref) < 2e-2
+    for name, a, b in zip(['x'] + names, g16, g_ref):
+        assert rel(a, b) < 3e-2, (name, rel(a, b))
