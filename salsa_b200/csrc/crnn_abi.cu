@@ -277,7 +277,7 @@ int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, voi
                    void* stream) {
     if (!xproj || !w_hh || !b_hh || !y) return fail(SALSA_EINVAL, "gru_layer: null pointer");
     if (B <= 0 || T <= 0) return fail(SALSA_EINVAL, "gru_layer: bad dimensions");
-    SALSA_CUDA(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmemBytes));
+    SALSA_CUDA(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGruSmemBytes + kGruStageBytes)));
     GruArgs a;
     a.xproj = xproj;
     a.w_hh = w_hh;
@@ -293,7 +293,7 @@ int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, voi
         count_launch();
         return check_cuda(cudaGetLastError(), "gru_layer_mma_kernel");
     }
-    gru_layer_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruSmemBytes, (cudaStream_t)stream>>>(a);
+    gru_layer_kernel<<<groups * 2 * kGruCluster, kGruThreads, kGruSmemBytes + kGruStageBytes, (cudaStream_t)stream>>>(a);
     count_launch();
     return check_cuda(cudaGetLastError(), "gru_layer_kernel");
 }
@@ -301,7 +301,7 @@ int crnn_gru_layer(const float* xproj, const float* w_hh, const float* b_hh, voi
 int crnn_gru_layer_train(const float* xproj, const float* w_hh, const float* b_hh, float* y, float* save, int32_t B, int32_t T, void* stream) {
     if (!xproj || !w_hh || !b_hh || !y || !save) return fail(SALSA_EINVAL, "gru_layer_train: null pointer");
     if (B <= 0 || T <= 0) return fail(SALSA_EINVAL, "gru_layer_train: bad dimensions");
-    constexpr size_t kFwdSmem = kGruSmemBytes + (size_t)kGruUnits * kGruClips * sizeof(float);        // + the broadcast staging tile
+    constexpr size_t kFwdSmem = kGruSmemBytes + kGruStageBytes;        // + the broadcast staging tile
     SALSA_CUDA(cudaFuncSetAttribute(gru_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     GruTrainArgs a;
     a.xproj = xproj; a.w_hh = w_hh; a.b_hh = b_hh; a.y = y; a.save = save; a.B = B; a.T = T;
