@@ -10,6 +10,8 @@ What is different from the reference is only how the work is scheduled: clips ar
 batches, and the scaler statistics are accumulated on the device while the features are still there instead of reading every
 h5 file back.  File IO is pluggable: `reader(path) -> (C, N) int16 | float32` and `writer(path, {name: array})`; the defaults
 use the standard library's `wave` and `h5py` (h5 IO itself is outside this package's scope: without h5py pass a writer).
+`task` is the reference's: 'feature_scaler' (both), 'feature', or 'scaler' (the dev split's feature files are read back through
+`feature_reader(path) -> (7, T, F)`, like compute_scaler does).
 """
 import os
 import shutil
@@ -21,7 +23,7 @@ import torch
 from . import _native
 from .features import FeatureScaler, SalsaExtractor, SalsaLiteExtractor, doa_bins
 
-__all__ = ['extract_features', 'extract_features_lite', 'feature_description', 'read_wav_pcm16', 'write_h5', 'pcm16_to_float']
+__all__ = ['extract_features', 'extract_features_lite', 'feature_description', 'read_wav_pcm16', 'write_h5', 'read_h5_feature', 'pcm16_to_float']
 
 
 def _load_config(data_config):
@@ -68,6 +70,15 @@ def write_h5(path, arrays):
             hf.create_dataset(name, data=arr, dtype=np.float32)
 
 
+def read_h5_feature(path):
+    try:
+        import h5py
+    except ImportError as exc:
+        raise RuntimeError("h5py is needed for the default feature reader of task='scaler' (pass feature_reader=...)") from exc
+    with h5py.File(path, 'r') as hf:
+        return hf['feature'][:]
+
+
 def pcm16_to_float(pcm: torch.Tensor) -> torch.Tensor:
     """int16 CUDA tensor -> float32 CUDA tensor, sample / 32768 (what librosa.load returns for a 16-bit wav)."""
     import ctypes
@@ -80,7 +91,8 @@ def pcm16_to_float(pcm: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _run(cfg, feature_type, extractor, description, splits, task, batch_clips, reader, writer, device):
+def _run(cfg, feature_type, extractor, description, splits, task, batch_clips, reader, writer, device, feature_reader=None):
+    feature_reader = feature_reader or read_h5_feature
     d = cfg['data']
     audio_format = d['format']
     root = os.path.join(cfg['feature_dir'], feature_type, audio_format, description)
@@ -117,9 +129,24 @@ def _run(cfg, feature_type, extractor, description, splits, task, batch_clips, r
                 pending.append((name, audio))
             flush()
     if task == 'scaler':
-        raise NotImplementedError("task='scaler' reads the h5 features back; run task='feature_scaler' (statistics are accumulated "
-                                  'while the features are on the device)')
-    if task == 'feature_scaler':
+        # compute_scaler as the reference runs it on its own (:204-262): the feature files of the dev split are read back;
+        # the statistics are still accumulated on the device, one file batch at a time
+        train_dir = os.path.join(root, audio_format + '_dev')
+        pending = []
+
+        def flush_scaler():
+            if pending:
+                scaler.partial_fit(torch.from_numpy(np.stack(pending)).to(device))
+                pending.clear()
+
+        for name in sorted(os.listdir(train_dir)):
+            f = np.ascontiguousarray(feature_reader(os.path.join(train_dir, name)), dtype=np.float32)
+            assert f.shape[0] == 7, 'only support n_channels = 7, got {}'.format(f.shape[0])
+            if pending and (f.shape != pending[0].shape or len(pending) >= batch_clips):
+                flush_scaler()
+            pending.append(f)
+        flush_scaler()
+    if task in ('feature_scaler', 'scaler'):
         mean, std = scaler.finalize()
         writer(os.path.join(root, audio_format + '_feature_scaler.h5'), {'mean': mean, 'std': std})
     return root
@@ -127,7 +154,7 @@ def _run(cfg, feature_type, extractor, description, splits, task, batch_clips, r
 
 def extract_features(data_config='configs/tnsse2021_salsa_feature_config.yml', cond_num: float = 5, n_hopframes: int = 3,
                      is_tracking: bool = True, is_compress_high_freq: bool = True, task: str = 'feature_scaler', *,
-                     batch_clips: int = 16, reader=None, writer=None, device='cuda'):
+                     batch_clips: int = 16, reader=None, writer=None, device='cuda', feature_reader=None):
     """Drop-in for dataset/salsa_feature_extraction.py: extract_features (:265-385).  Returns the feature directory."""
     cfg = _load_config(data_config)
     d = cfg['data']
@@ -145,11 +172,12 @@ def extract_features(data_config='configs/tnsse2021_salsa_feature_config.yml', c
     desc = feature_description(cfg, 'salsa', cond_num, is_tracking, is_compress_high_freq)
     print('Feature description: {}'.format(desc))
     return _run(cfg, 'salsa', ex, desc, splits, task, batch_clips, reader or (lambda p: read_wav_pcm16(p, d['fs'])), writer or write_h5,
-                torch.device(device))
+                torch.device(device), feature_reader)
 
 
 def extract_features_lite(data_config='configs/tnsse2021_salsa_lite_feature_config.yml', feature_type: str = 'salsa_lite',
-                          task: str = 'feature_scaler', *, batch_clips: int = 16, reader=None, writer=None, device='cuda'):
+                          task: str = 'feature_scaler', *, batch_clips: int = 16, reader=None, writer=None, device='cuda',
+                          feature_reader=None):
     """Drop-in for dataset/salsa_lite_feature_extraction.py: extract_features (:18-130)."""
     assert feature_type in ['salsa_lite', 'salsa_ipd'], 'Invalid feature type {}'.format(feature_type)
     cfg = _load_config(data_config)
@@ -160,7 +188,7 @@ def extract_features_lite(data_config='configs/tnsse2021_salsa_lite_feature_conf
     desc = feature_description(cfg, feature_type)
     print('Feature description: {}'.format(desc))
     return _run(cfg, feature_type, ex, desc, ['mic_dev', 'mic_eval'], task, batch_clips,
-                reader or (lambda p: read_wav_pcm16(p, d['fs'])), writer or write_h5, torch.device(device))
+                reader or (lambda p: read_wav_pcm16(p, d['fs'])), writer or write_h5, torch.device(device), feature_reader)
 
 
 # same helper under the name the config parsing of the reference suggests

@@ -455,6 +455,17 @@ def test_script_level_seam_writes_the_reference_layout(sb, tmp_path):
     np.testing.assert_allclose(sc['mean'], mean, rtol=0, atol=2e-4)
     np.testing.assert_allclose(sc['std'], std, rtol=0, atol=2e-4)
     assert (feat_dir / 'salsa' / 'foa' / '24000fs_512nfft_300nhop_5cond_9000fmaxdoa' / 'foa_eval').is_dir()
+    # task='scaler' (:391-393): compute_scaler on its own, from the feature files of the dev split read back
+    root_dir = feat_dir / 'salsa' / 'foa' / '24000fs_512nfft_300nhop_5cond_9000fmaxdoa'
+    for path in list(written):
+        if '/foa_dev/' in path:
+            open(path, 'wb').close()                     # the files the listing finds; their content comes from `written`
+    again = {}
+    driver.extract_features(cfg, task='scaler', batch_clips=2, writer=lambda path, arrays: again.__setitem__(path, arrays),
+                            feature_reader=lambda path: written[path]['feature'])
+    assert list(again) == [str(root_dir / 'foa_feature_scaler.h5')]
+    np.testing.assert_allclose(again[str(root_dir / 'foa_feature_scaler.h5')]['mean'], sc['mean'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(again[str(root_dir / 'foa_feature_scaler.h5')]['std'], sc['std'], rtol=0, atol=1e-6)
 
 
 def test_linspec_gcc_matches_golden_and_oracle(sb, golden):
