@@ -134,7 +134,10 @@ def test_steps_reduce_the_loss_and_weights_hand_over_to_inference():
     sd = salsa_b200.crnn.random_state_dict(2)
     x, tgt = _batch(seed=5)
     # dropout off: the run is then deterministic up to the summation order of the weight gradient's atomics
-    tr = train.SeldTrainer(sd, lr=1e-3, dropout=False, scheduler=salsa_b200.optim.LearningRateScheduler(steps_per_epoch=10, max_epochs=2))
+    # the schedule peaks at 1e-3: at the reference's 1e-2 peak fifteen steps on one batch are chaotic, and the summation order of
+    # the weight gradient's atomics then decides the outcome (observed: 2 of 6 runs missed the loss bar)
+    tr = train.SeldTrainer(sd, lr=1e-3, dropout=False,
+                           scheduler=salsa_b200.optim.LearningRateScheduler(steps_per_epoch=10, max_epochs=2, lrs=(1e-4, 1e-3, 3e-4, 1e-4)))
     losses = [tr.step(x, tgt)[0].item() for _ in range(15)]
     print('losses', ['{:.4f}'.format(v) for v in losses])
     assert min(losses[-3:]) < 0.85 * losses[0] and np.isfinite(losses).all()
