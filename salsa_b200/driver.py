@@ -79,13 +79,16 @@ def read_h5_feature(path):
         return hf['feature'][:]
 
 
-def pcm16_to_float(pcm: torch.Tensor) -> torch.Tensor:
+def pcm16_to_float(pcm: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """int16 CUDA tensor -> float32 CUDA tensor, sample / 32768 (what librosa.load returns for a 16-bit wav)."""
     import ctypes
     if not (pcm.is_cuda and pcm.dtype == torch.int16):
         raise ValueError('pcm must be a CUDA int16 tensor')
     pcm = pcm.contiguous()
-    out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+    if out is None:
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == pcm.shape and out.device == pcm.device):
+        raise ValueError('out must be a contiguous CUDA float32 tensor of the shape of pcm')
     with _native.device_of(pcm) as st:
         _native.check(_native.lib().salsa_pcm16_to_float(ctypes.c_void_p(pcm.data_ptr()), ctypes.c_void_p(out.data_ptr()), pcm.numel(), st))
     return out

@@ -5,7 +5,7 @@ The reference goes through the file system: `make salsa` writes (7, 4801, 200) f
 trims to a multiple of the label resolution (dataset/database.py:196-207), and `SeldModel.forward` consumes them
 (models/seld_models.py:39-49).  Here the same three steps are three stages on device memory: per 60 s clip 23 MB of audio
 cross PCIe instead of 27 MB of features, and nothing is written in between (BASELINE.json config 5, inference side;
-SURVEY.md section 8 f2)."""
+SURVEY.md section 8 f2); with the wav files' own 16-bit samples as input, 11.5 MB."""
 import torch
 
 from .crnn import SeldModel
@@ -22,9 +22,17 @@ class SeldPipeline:
         if scaler is not None:
             model.set_scaler(*scaler)
         self._features = None
+        self._audio = None
 
     def features(self, audio: torch.Tensor) -> torch.Tensor:
-        """(B, 4, N) float32 CUDA -> (B, 7, T, F) float32 CUDA, into a buffer that is reused between calls."""
+        """(B, 4, N) float32 CUDA -- or int16, the 16-bit PCM samples of the wav files, converted on the device like
+        librosa.load does on the host (dataset/salsa_feature_extraction.py:353): half the bytes over PCIe -- ->
+        (B, 7, T, F) float32 CUDA, into a buffer that is reused between calls."""
+        if audio.dtype == torch.int16:
+            from .driver import pcm16_to_float
+            if self._audio is None or self._audio.shape != audio.shape or self._audio.device != audio.device:
+                self._audio = torch.empty(audio.shape, dtype=torch.float32, device=audio.device)
+            audio = pcm16_to_float(audio, out=self._audio)
         B, T = audio.shape[0], self.extractor.n_frames(audio.shape[2])
         shape = (B, 7, T, self.extractor.freq_dim)
         if self._features is None or tuple(self._features.shape) != shape or self._features.device != audio.device:

@@ -190,6 +190,11 @@ def test_pipeline_audio_to_outputs():
     assert tuple(pred['event_frame_logit'].shape) == (2, 32, 12)          # 16 * 10 / 80 -> ratio 2
     rows = pipe.events(audio)
     assert len(rows) == 2 and all(len(r) == 5 for clip in rows for r in clip)
+    # the wav files' own 16-bit samples as input: converted on the device, same outputs as their float32 form
+    pcm = torch.round(audio * 32768.0).clamp(-32768, 32767).to(torch.int16)
+    out16, outf = pipe(pcm), pipe(pcm.float() / 32768.0)
+    for k in outf:
+        assert torch.equal(out16[k], outf[k])
 
 
 @pytest.mark.parametrize('precision', ['bf16', 'bf16x2', 'bf16x3'])
