@@ -661,8 +661,7 @@ def bench_other_configs(args, torch, dist, rank, world, dev, peak):
 def bench_train(args, torch, dist, rank, world, dev):
     """BASELINE.json configs[4]: CRNN training on on-the-fly SALSA features, bf16, data-parallel.  Per step and rank: 32 audio
     chunks of 8 s -> SALSA FOA features (native) -> channel-swap / frequency-shift augmentation (native) -> forward + backward
-    (3x3 and 1x1 convolutions in all three directions, train-mode BatchNorm + residual + ReLU + dropout and pooling native; first
-    convolution, GRU, heads: torch / cuDNN autograd) ->
+    (3x3 and 1x1 convolutions in all three directions, train-mode BatchNorm + residual + ReLU + dropout, pooling and the BiGRU native; heads: torch autograd / cuBLAS) ->
     loss (native) -> bucketed bf16 gradient all-reduce overlapped with the backward pass (NCCL) -> Adam (native)."""
     import numpy as np
     import salsa_b200
@@ -697,8 +696,8 @@ def bench_train(args, torch, dist, rank, world, dev):
             'allreduce': ('bf16 all-reduce of the flat gradient ({:.1f} MB on the wire per step), '.format(n_params * 2 / 1e6) +
                           ('one call after the graph replay' if (tr.use_graph and tr.graph_error is None) else 'launched per bucket during the backward pass'))
                          if world > 1 else 'single rank: none',
-            'native': 'SALSA features, augmentation, 3x3 and 1x1 convolutions forward + input gradient + weight gradient (tcgen05), train-mode BatchNorm + residual + ReLU + dropout and 2x2 pooling forward / backward, loss, Adam',
-            'library': 'first (7-channel) convolution, BiGRU, heads: torch / cuDNN autograd'}
+            'native': 'SALSA features, augmentation, every convolution forward + input gradient + weight gradient (tcgen05), train-mode BatchNorm + residual + ReLU + dropout and 2x2 pooling forward / backward, BiGRU recurrence + back-propagation through time, loss, Adam',
+            'library': 'the heads (nn.Linear pairs with dropout) and the GEMMs around the GRU recurrence: torch autograd / cuBLAS; no cuDNN call in the step'}
 
 
 def main():

@@ -372,7 +372,10 @@ int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t
     if (!x || !gy || !dw) return fail(SALSA_EINVAL, "conv_wgrad: null pointer");
     if (B <= 0 || H <= 0 || W <= 0) return fail(SALSA_EINVAL, "conv_wgrad: bad dimensions");
     if (ksize != 3 && ksize != 1) return fail(SALSA_EINVAL, "conv_wgrad: ksize must be 3 or 1");
-    if (Cin % 64 != 0 || Cout % 64 != 0 || Cin <= 0 || Cout <= 0) return fail(SALSA_EINVAL, "conv_wgrad: Cin and Cout must be multiples of 64");
+    // Cin = 16: the first convolution's input (7 channels padded to 16, crnn_pack_input); the TMA box still spans 64 channels
+    // and arrives with channels 16..63 zero-filled, dw is [ksize^2][Cout][16]
+    if ((Cin % 64 != 0 && Cin != 16) || Cout % 64 != 0 || Cin <= 0 || Cout <= 0)
+        return fail(SALSA_EINVAL, "conv_wgrad: Cin must be a multiple of 64 (or 16), Cout a multiple of 64");
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return fail(SALSA_EINVAL, "conv_wgrad: unaligned pointer");
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap tx, tg;
@@ -397,12 +400,13 @@ int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t
     a.n_ktiles = B * a.tiles_h * a.tiles_w;
     a.dw = dw;
     a.taps = ksize * ksize;
+    a.cin_valid = std::min(Cin, 64);
     SALSA_CUDA(cudaMemsetAsync(dw, 0, (size_t)a.taps * Cout * Cin * sizeof(float), st));
     SALSA_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int pairs = (Cout / 64) * (Cin / 64);
+    const int pairs = (Cout / 64) * ((Cin + 63) / 64);
     // split the pixel tiles over enough CTAs to fill the GPU about twice (one CTA per SM: the three-stage ring takes the
     // whole shared memory); every split adds one pass of 9 x 64 x 64 atomic adds
     const int splits = std::max(1, std::min(a.n_ktiles, (2 * sms + pairs - 1) / pairs));

@@ -40,6 +40,8 @@ struct WgradArgs {
     int B, H, W, Cin, Cout;
     int tiles_w, tiles_h, n_ktiles;     // pixel tiles = B * tiles_h * tiles_w
     int taps;                           // 9 (3x3, pad 1) or 1 (1x1: only the centre tap = box 1, row offset 1, as one M = 64 MMA)
+    int cin_valid;                      // input channels that exist (Cin, or 16 for the padded first convolution: TMA zero-fills
+                                        // channels 16..63 of the box, and only the first 16 columns of a dW row are written)
     float* dw;                          // [taps][Cout][Cin]
 };
 
@@ -91,7 +93,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const int n_ci = a.Cin / 64;
+    const int n_ci = (a.Cin + 63) / 64;
     const int co0 = ((int)blockIdx.y / n_ci) * 64, ci0 = ((int)blockIdx.y % n_ci) * 64;
 
     if (warp == 0) {
@@ -165,7 +167,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 tc::tmem_ld_wait();
                 float* dst = a.dw + ((size_t)tap * a.Cout + row128) * a.Cin + ci0 + half * 32;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+                for (int i = 0; i < 32; i += 4)
+                    if (half * 32 + i < a.cin_valid) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
             }
         }
         // M = 64 accumulator (tap 0 = dy 0, dx 0; the only tap of a 1x1): rows 16 q .. 16 q + 15 on lanes 0-15 of this quarter
@@ -178,7 +181,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             if (lane < 16) {
                 float* dst = a.dw + (size_t)row64 * a.Cin + ci0 + half * 32;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+                for (int i = 0; i < 32; i += 4)
+                    if (half * 32 + i < a.cin_valid) red_add_v4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
             }
         }
     }

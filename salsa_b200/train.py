@@ -4,13 +4,14 @@ The reference trains through PyTorch Lightning: `training_step` (models/seld_mod
 `interpolate_tensor` to the label rate -> `compute_loss` (models/interfaces.py:273-355), Adam with the piecewise-linear
 lr / beta1 schedule (utilities/learning_utils.py:17-52), DDP gradient all-reduce (experiments/train.py:98-104).  Here:
 
-  native (libsalsa_b200.so)   SALSA features on the fly, augmentations, the 3x3 and 1x1 convolutions' forward, input gradient
+  native (libsalsa_b200.so)   SALSA features on the fly, augmentations, every convolution's forward (3x3, 1x1 and the 7-channel
+                              first one), input gradient
                               (the tcgen05 implicit-GEMM kernel on flipped / transposed weights) and weight gradient
                               (`crnn_conv_wgrad`), the loss with its output gradients (`crnn_seld_loss`), the Adam step,
                               train-mode BatchNorm fused with the residual add, the ReLU and the encoder's dropout, forward
                               and backward (`crnn_bn_train_forward` / `_backward`), 2x2 average pooling forward and backward
-  torch / cuDNN (library)     the first (7-channel) convolution, the BiGRU and the heads with their dropouts, through autograd -- not
-                              native yet, and said so wherever a number is quoted
+  torch (library)             the heads (four pairs of nn.Linear with their dropouts) and the GEMMs around the GRU recurrence,
+                              through autograd / cuBLAS -- said so wherever a number is quoted
   torch.distributed           bf16 all-reduce of the flat gradient buffer (`GradAllReduce`; NCCL on the GPU box, gloo in the
                               CPU tests): per bucket while the backward pass is still running (eager step), or one call after
                               the replay when forward + loss + backward run as ONE CUDA graph (`use_graph=True`)
@@ -25,7 +26,7 @@ import torch.nn.functional as F
 from . import crnn_ops as ops
 from .optim import Adam, LearningRateScheduler
 
-__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeConv1x1', 'NativeBnAct', 'NativeAvgPool2', 'NativeGRULayer']
+__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeConv1x1', 'NativeConvFirst', 'NativeBnAct', 'NativeAvgPool2', 'NativeGRULayer']
 
 
 class NativeConv3x3(torch.autograd.Function):
@@ -58,6 +59,30 @@ class NativeConv3x3(torch.autograd.Function):
             else:
                 dw = torch.nn.grad.conv2d_weight(xb, w.shape, gyb, padding=1).to(w.dtype)
         return dx, dw
+
+
+class NativeConvFirst(torch.autograd.Function):
+    """The first convolution (7 -> 64 channels, 3x3 / pad 1, no bias; models/model_utils.py:192-195 with in_channels = 7) on
+    the float32 NCHW feature batch: `crnn_pack_input` (NHWC bf16, channels padded to 16) -> `crnn_conv_first`; the weight
+    gradient is `crnn_conv_wgrad` on the 16-channel tensor (its TMA boxes span 64 channels and arrive zero-filled above
+    channel 15).  The input needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x16 = ops.pack_input(x.detach().float(), c_pad=16)                           # (B, T, F, 16) bf16
+        wp = torch.zeros((9, w.shape[0], 16), dtype=torch.bfloat16, device=w.device)
+        wp[:, :, :w.shape[1]] = w.detach().permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1])
+        ctx.save_for_backward(x16)
+        ctx.wshape = tuple(w.shape)
+        return ops.conv_first(x16, wp, bias=None, relu=False).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x16, = ctx.saved_tensors
+        cout, cin = ctx.wshape[:2]
+        gyb = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dw = ops.conv_wgrad(x16, gyb.permute(0, 2, 3, 1))                             # (9, 64, 16) fp32
+        return None, dw[:, :, :cin].reshape(3, 3, cout, cin).permute(2, 3, 0, 1)
 
 
 class NativeConv1x1(torch.autograd.Function):
@@ -329,10 +354,14 @@ class SeldTrainer:
     def forward(self, x):
         """x (B, 7, T, F) float32 -> {'event_frame_logit': (B, T/16, n), 'doa_frame_output': (B, T/16, 3n)}, with autograd."""
         tr = self.training and self.dropout
-        x = x.contiguous(memory_format=torch.channels_last)
         with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast):
             p = 'encoder.conv_block1'
-            x = self._bn(F.conv2d(x, self.params[p + '.conv1.weight'], padding=1), p + '.bn1', relu=True)     # 7 input channels: cuDNN
+            w0 = self.params[p + '.conv1.weight']
+            if self.native_conv and x.is_cuda and w0.shape[0] == 64 and w0.shape[1] <= 16:
+                y0 = NativeConvFirst.apply(x, w0)
+            else:
+                y0 = F.conv2d(x.contiguous(memory_format=torch.channels_last), w0, padding=1)
+            x = self._bn(y0, p + '.bn1', relu=True)
             x = self._bn(self._conv3(x, p + '.conv2.weight'), p + '.bn2', relu=True)
             x = self._pool(x)                                                 # ConvBlock.forward (models/model_utils.py:213-220)
             for li in range(1, 5):

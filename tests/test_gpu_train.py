@@ -275,3 +275,20 @@ def test_native_gru_layer_forward_and_bptt(B, T):
     assert rel(y16, y_ref) < 2e-2
     for name, a, b in zip(['x'] + names, g16, g_ref):
         assert rel(a, b) < 3e-2, (name, rel(a, b))
+
+
+def test_native_first_convolution_forward_and_weight_gradient():
+    """conv_block1.conv1 (7 -> 64) in the training step: crnn_pack_input + crnn_conv_first forward, crnn_conv_wgrad on the
+    16-channel padded input (TMA zero-fills the box above channel 15) against float32 F.conv2d + autograd on the same
+    bf16-rounded operands; ragged image (33 x 21) for the zero padding at the borders."""
+    from salsa_b200.train import NativeConvFirst
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(3, 7, 33, 21, generator=g).bfloat16().float().cuda()
+    w = (torch.randn(64, 7, 3, 3, generator=g) / 8).bfloat16().float().cuda().requires_grad_(True)
+    gy = torch.randn(3, 64, 33, 21, generator=g).bfloat16().float().cuda()
+    y_ref = F.conv2d(x, w, padding=1)
+    gw_ref, = torch.autograd.grad(y_ref, w, gy)
+    y = NativeConvFirst.apply(x, w)
+    gw, = torch.autograd.grad(y, w, gy)
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (3, 64, 33, 21)
+    assert rel(y, y_ref) < 1e-2 and rel(gw, gw_ref) < 1e-4
