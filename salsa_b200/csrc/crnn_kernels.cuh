@@ -618,14 +618,25 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
-// keep bits of the 8 channels of 16-byte group `i` (bit k = element k survives)
+// 32-bit finaliser (two multiplies): the per-element work of the dropout is four of these per group of 8 channels, cheap
+// enough that the memory-bound BatchNorm kernels stay memory-bound (two splitmix64 per group cost 15 % of their time)
+__device__ __forceinline__ unsigned int mix32(unsigned int x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    return x ^ (x >> 16);
+}
+// keep bits of the 8 channels of 16-byte group `i` (bit k = element k survives): 16 bits per element
 __device__ __forceinline__ unsigned int drop_keep8(unsigned long long key, long long i, unsigned int threshold) {
-    const unsigned long long h0 = splitmix64(key + 2ull * (unsigned long long)i), h1 = splitmix64(key + 2ull * (unsigned long long)i + 1ull);
+    const unsigned int lo = (unsigned int)key, hi = (unsigned int)(key >> 32);
+    const unsigned int base = ((unsigned int)i * 4u) ^ lo, salt = hi + (unsigned int)((unsigned long long)i >> 30) * 0x9E3779B9u;
     unsigned int keep = 0u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        keep |= (((unsigned int)(h0 >> (16 * k)) & 0xffffu) >= threshold ? 1u : 0u) << k;
-        keep |= (((unsigned int)(h1 >> (16 * k)) & 0xffffu) >= threshold ? 1u : 0u) << (4 + k);
+    for (int q = 0; q < 4; ++q) {
+        const unsigned int h = mix32((base + (unsigned int)q) ^ salt);
+        keep |= ((h & 0xffffu) >= threshold ? 1u : 0u) << (2 * q);
+        keep |= ((h >> 16) >= threshold ? 1u : 0u) << (2 * q + 1);
     }
     return keep;
 }
@@ -681,7 +692,9 @@ __device__ __forceinline__ void bn_mask_coef(const float* __restrict__ stat, con
     }
 }
 __device__ __forceinline__ bool bn_mask_from_y(float y, float scale, float shift) {
-    return __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(y, scale, shift), 0.0f))) > 0.0f;
+    // bf16(relu(o)) > 0  <=>  o rounds to a positive bf16: every positive float32 above half the smallest bf16 subnormal
+    // (2^-134, bit pattern 0x00008000; the tie rounds to even = 0) does.  As signed integers the negative floats compare below.
+    return __float_as_int(fmaf(y, scale, shift)) > 0x00008000;
 }
 
 // sums [C][2] += (sum g, sum g * xhat) with g = dz * mask, xhat = (y - mean) / std
