@@ -292,3 +292,30 @@ def test_native_first_convolution_forward_and_weight_gradient():
     gw, = torch.autograd.grad(y, w, gy)
     assert y.dtype == torch.bfloat16 and tuple(y.shape) == (3, 64, 33, 21)
     assert rel(y, y_ref) < 1e-2 and rel(gw, gw_ref) < 1e-4
+
+
+def test_training_step_gradients_at_the_benchmark_chunk_shape():
+    """The whole native step at (4, 7, 640, 200) -- the chunk shape of BASELINE.json configs[4] -- against the same step in
+    plain torch: bf16 autocast with cuDNN convolutions / BatchNorm / GRU (same rounding points) and float32.  Dropout off.
+    The all-native gradient must be as close to the float32 one as the cuDNN bf16 step is, and closer still to that step."""
+    import salsa_b200
+    from salsa_b200 import train
+    sd = salsa_b200.crnn.random_state_dict(3)
+    x, tgt = _batch(seed=17, B=4, T=640)
+
+    def make(**kw):
+        t = train.SeldTrainer(sd, dropout=False, **kw)
+        t.optimizer = None
+        return t
+
+    nat = make()
+    lib16 = make(native_conv=False, native_bn=False, native_gru=False)
+    lib32 = make(native_conv=False, native_bn=False, native_gru=False, autocast=False)
+    l_nat, l_16, l_32 = nat.step(x, tgt), lib16.step(x, tgt), lib32.step(x, tgt)
+    cos = lambda a, b: F.cosine_similarity(a.flat_grad, b.flat_grad, dim=0).item()
+    c_nat32, c_1632, c_nat16 = cos(nat, lib32), cos(lib16, lib32), cos(nat, lib16)
+    print('benchmark chunk shape: loss native {:.5f} cuDNN-bf16 {:.5f} float32 {:.5f}; gradient cosine native-float32 {:.4f}, '
+          'cuDNN-bf16-float32 {:.4f}, native-cuDNN-bf16 {:.4f}'.format(l_nat[0].item(), l_16[0].item(), l_32[0].item(), c_nat32, c_1632, c_nat16))
+    assert torch.allclose(l_nat, l_32, rtol=2e-3, atol=2e-3) and torch.allclose(l_nat, l_16, rtol=2e-3, atol=2e-3)
+    assert c_nat32 > c_1632 - 0.01 and c_nat32 > 0.95
+    assert c_nat16 > 0.97
