@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     for cmd, proc in procs:
         if proc.wait() != 0:
             raise subprocess.CalledProcessError(proc.returncode, cmd)
-    subprocess.run([nvcc, '-shared', '-o', OUT] + objs + ['-lcudart'], check=True)
+    # the link step gets the arch flags too: without them nvcc adds an (empty) default-architecture device-link stub
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', OUT] + objs + ['-lcudart'], check=True)
     return OUT
 
 

@@ -10,5 +10,5 @@ for f in crnn_abi crnn_model; do
        -c salsa_b200/csrc/$f.cu -o salsa_b200/_build/${f}_$tag.o &
 done
 wait
-nvcc -shared -o salsa_b200/_build/libsalsa_$tag.so salsa_b200/_build/salsa_abi.cu.o salsa_b200/_build/crnn_abi_$tag.o salsa_b200/_build/crnn_model_$tag.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o salsa_b200/_build/libsalsa_$tag.so salsa_b200/_build/salsa_abi.cu.o salsa_b200/_build/crnn_abi_$tag.o salsa_b200/_build/crnn_model_$tag.o -lcudart
 echo salsa_b200/_build/libsalsa_$tag.so
