@@ -112,6 +112,21 @@ int crnn_bn_train_backward(const void *dz, const void *z, const void *y, const f
                            int64_t n_pix, int32_t C, int32_t relu, const uint64_t *drop_seed, uint32_t drop_salt,
                            float drop_p, void *stream);
 
+/* BatchNorm (+ residual) + ReLU + the F.avg_pool2d(2) behind it as one pass each way, for the four places where the network
+ * pools (models/model_utils.py:220, :349, :476) and the BatchNorm output has no other consumer: y bf16 NHWC [B][H][W][C] ->
+ * pooled bf16 [B][H/2][W/2][C]; the full-resolution activation is never written.  Results are bit-identical to
+ * crnn_bn_train_forward(relu = 1) followed by crnn_avgpool2.  stat / sums / running_*: as in crnn_bn_train_forward. */
+int crnn_bn_train_forward_pool(const void *y, const float *gamma, const float *beta, const void *residual, void *pooled,
+                               float *stat, double *sums, float *running_mean, float *running_var, int32_t B, int32_t H,
+                               int32_t W, int32_t C, float eps, float momentum, void *stream);
+
+/* Its backward pass: dpool bf16 [B][H/2][W/2][C] = dLoss/dpooled -> dy bf16 [B][H][W][C], d_residual (optional; needs
+ * `residual`, the forward's residual input, from which together with y the ReLU mask is recomputed), dgamma, dbeta.
+ * Bit-identical to crnn_avgpool2_backward followed by crnn_bn_train_backward. */
+int crnn_bn_train_backward_pool(const void *dpool, const void *y, const void *residual, const float *stat,
+                                const float *gamma, const float *beta, void *dy, void *d_residual, double *sums,
+                                float *dgamma, float *dbeta, int32_t B, int32_t H, int32_t W, int32_t C, void *stream);
+
 /* The first convolution of the encoder (conv_block1.conv1 + bn1 + ReLU, models/model_utils.py:213-215) on an input
  * padded to 16 channels: x bf16 NHWC [B][H][W][planes*16], w bf16 [9][64][planes*16] -> out bf16 [B][H][W][planes*64]. */
 int crnn_conv_first(const void *x, const void *w, const float *bias, void *out, int32_t B, int32_t H, int32_t W,

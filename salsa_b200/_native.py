@@ -79,6 +79,8 @@ SIGNATURES = {
     'crnn_conv_wgrad': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_bn_train_forward': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _i32, ctypes.c_float, ctypes.c_float, _i32, _vp, ctypes.c_uint32, ctypes.c_float, _vp]),
     'crnn_bn_train_backward': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _i32, _i32, _vp, ctypes.c_uint32, ctypes.c_float, _vp]),
+    'crnn_bn_train_forward_pool': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, ctypes.c_float, ctypes.c_float, _vp]),
+    'crnn_bn_train_backward_pool': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     'crnn_conv_first': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     'crnn_set_option': (ctypes.c_int, [ctypes.c_char_p, _i32]),
     'crnn_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

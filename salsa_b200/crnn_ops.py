@@ -139,6 +139,37 @@ def bn_train_backward(dz, z, y, stat, gamma, relu=True, want_residual_grad=False
     return dy, dres, dgamma, dbeta
 
 
+def bn_train_forward_pool(y, gamma, beta, residual=None, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
+    """BatchNorm (+ residual) + ReLU + 2x2 average pooling: y (B,H,W,C) bf16 -> (pooled (B,H//2,W//2,C) bf16, stat (C,2))."""
+    _check_act(y)
+    B, H, W, C = y.shape
+    if residual is not None:
+        _check_act(residual)
+        if residual.shape != y.shape:
+            raise ValueError('residual shape mismatch')
+    pooled = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=y.device)
+    stat = torch.empty((C, 2), dtype=torch.float32, device=y.device)
+    sums = torch.empty((C, 2), dtype=torch.float64, device=y.device)
+    _call('crnn_bn_train_forward_pool', y, _p(y), _p(gamma), _p(beta), _p(residual), _p(pooled), _p(stat), _p(sums), _p(running_mean),
+          _p(running_var), B, H, W, C, ctypes.c_float(eps), ctypes.c_float(momentum))
+    return pooled, stat
+
+
+def bn_train_backward_pool(dpool, y, residual, stat, gamma, beta, want_residual_grad=False):
+    """-> (dy, d_residual or None, dgamma, dbeta) from the gradient of the pooled output."""
+    _check_act(dpool)
+    _check_act(y)
+    B, H, W, C = y.shape
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if want_residual_grad else None
+    sums = torch.empty((C, 2), dtype=torch.float64, device=y.device)
+    dgamma = torch.empty((C,), dtype=torch.float32, device=y.device)
+    dbeta = torch.empty((C,), dtype=torch.float32, device=y.device)
+    _call('crnn_bn_train_backward_pool', y, _p(dpool), _p(y), _p(residual), _p(stat), _p(gamma), _p(beta), _p(dy), _p(dres), _p(sums),
+          _p(dgamma), _p(dbeta), B, H, W, C)
+    return dy, dres, dgamma, dbeta
+
+
 def gru_layer_train(xproj, w_hh, b_hh):
     """xproj (B, T, 1536) fp32, w_hh (2, 768, 256) fp32, b_hh (2, 768) fp32 -> (y (B, T, 512) fp32, save (B, T, 2, 4, 256) fp32)."""
     for t in (xproj, w_hh, b_hh):

@@ -485,6 +485,58 @@ int crnn_bn_train_backward(const void* dz, const void* z, const void* y, const f
     return check_cuda(cudaGetLastError(), "bn_train_backward");
 }
 
+int crnn_bn_train_forward_pool(const void* y, const float* gamma, const float* beta, const void* residual, void* pooled, float* stat,
+                               double* sums, float* running_mean, float* running_var, int32_t B, int32_t H, int32_t W, int32_t C,
+                               float eps, float momentum, void* stream) {
+    if (!y || !gamma || !beta || !pooled || !stat || !sums) return fail(SALSA_EINVAL, "bn_train_forward_pool: null pointer");
+    if (C <= 0 || C % 8 != 0 || C > 512 || 256 % (C / 8) != 0) return fail(SALSA_EINVAL, "bn_train_forward_pool: C must be 64, 128, 256 or 512");
+    if (B <= 0 || H < 2 || W < 2 || (long long)B * H * W >= (1LL << 31)) return fail(SALSA_EINVAL, "bn_train_forward_pool: bad dimensions");
+    if ((running_mean == nullptr) != (running_var == nullptr)) return fail(SALSA_EINVAL, "bn_train_forward_pool: running statistics go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_pix = (long long)B * H * W;
+    SALSA_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(double), st));
+    const int lanes = 256 / (C / 8);
+    const int blocks = (int)std::min<long long>((n_pix + lanes * 32 - 1) / (lanes * 32), 148LL * 8);
+    bn_stats_kernel<<<std::max(blocks, 1), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(y), n_pix, C, sums);
+    count_launch();
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, n_pix, C, eps, momentum, stat, running_mean, running_var);
+    count_launch();
+    const PoolGeom g = {H, W, H / 2, W / 2};
+    bn_apply_pool_kernel<<<std::min(B * g.Ho, 148 * 8), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(y), stat, gamma, beta, reinterpret_cast<const __nv_bfloat16*>(residual),
+        reinterpret_cast<__nv_bfloat16*>(pooled), B, g, C);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "bn_train_forward_pool");
+}
+
+int crnn_bn_train_backward_pool(const void* dpool, const void* y, const void* residual, const float* stat, const float* gamma,
+                                const float* beta, void* dy, void* d_residual, double* sums, float* dgamma, float* dbeta, int32_t B,
+                                int32_t H, int32_t W, int32_t C, void* stream) {
+    if (!dpool || !y || !stat || !gamma || !beta || !dy || !sums || !dgamma || !dbeta) return fail(SALSA_EINVAL, "bn_train_backward_pool: null pointer");
+    if (d_residual && !residual) return fail(SALSA_EINVAL, "bn_train_backward_pool: a residual gradient needs the residual");
+    if (C <= 0 || C % 8 != 0 || C > 512 || 256 % (C / 8) != 0) return fail(SALSA_EINVAL, "bn_train_backward_pool: C must be 64, 128, 256 or 512");
+    if (B <= 0 || H < 2 || W < 2 || (long long)B * H * W >= (1LL << 31)) return fail(SALSA_EINVAL, "bn_train_backward_pool: bad dimensions");
+    cudaStream_t st = (cudaStream_t)stream;
+    SALSA_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 2 * sizeof(double), st));
+    const int blocks = std::min(B * H, 148 * 8);                     // the kernels walk image rows
+    const PoolGeom g = {H, W, H / 2, W / 2};
+    const __nv_bfloat16 *pd = reinterpret_cast<const __nv_bfloat16*>(dpool), *py = reinterpret_cast<const __nv_bfloat16*>(y),
+                        *pr = reinterpret_cast<const __nv_bfloat16*>(residual);
+    __nv_bfloat16 *pdy = reinterpret_cast<__nv_bfloat16*>(dy), *pdr = reinterpret_cast<__nv_bfloat16*>(d_residual);
+    if (residual) {
+        bn_bwd_reduce_pool_kernel<1><<<blocks, 256, 0, st>>>(pd, py, pr, stat, gamma, beta, B, C, g, sums);
+        bn_bwd_apply_pool_kernel<1><<<blocks, 256, 0, st>>>(pd, py, pr, stat, gamma, beta, sums, pdy, pdr, B, C, g);
+    } else {
+        bn_bwd_reduce_pool_kernel<0><<<blocks, 256, 0, st>>>(pd, py, pr, stat, gamma, beta, B, C, g, sums);
+        bn_bwd_apply_pool_kernel<0><<<blocks, 256, 0, st>>>(pd, py, pr, stat, gamma, beta, sums, pdy, pdr, B, C, g);
+    }
+    count_launch();
+    count_launch();
+    bn_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "bn_train_backward_pool");
+}
+
 int crnn_cutout(float* x, const int32_t* rects, const int32_t* n_rects, const double* u, float* minmax, int32_t B, int32_t C,
                 int32_t T, int32_t F, int32_t n_zero_channels, void* stream) {
     if (!x || !rects || !n_rects || !u || !minmax) return fail(SALSA_EINVAL, "cutout: null pointer");

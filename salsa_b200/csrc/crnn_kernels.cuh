@@ -520,6 +520,13 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // atomicAdd(double) per channel and block.  `load(pix, c8, q)` fetches the NT 16-byte words of pixel `pix`, channels
 // 8 c8 .. 8 c8 + 7; `acc(q, a, b)` adds their contributions.  Four pixels' loads are issued before the first is consumed
 // (the reductions are pure streaming reads: bytes in flight are what the bandwidth depends on).
+__device__ __forceinline__ void channel_reduce_tail_impl(const float (&a)[8], const float (&b)[8], bool active, int C, double* __restrict__ out,
+                                                         float* s_part);
+__device__ __forceinline__ void channel_reduce_tail(const float (&a)[8], const float (&b)[8], bool active, int C, double* __restrict__ out,
+                                                    float* s_part) {
+    channel_reduce_tail_impl(a, b, active, C, out, s_part);
+}
+
 template <int NT, typename L, typename A>
 __device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* __restrict__ out /* [C][2] */, L load, A acc) {
     __shared__ float s_part[256 * 16];
@@ -546,15 +553,22 @@ __device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* 
             acc(q, a, b);
         }
     }
-    // combine the pixel lanes of a channel group: every thread parks its 2 x 8 partial sums, then one thread per channel adds
-    // that channel's `lanes` values in float64 (one barrier; the loop-and-barrier-per-channel form cost ~8 us per launch,
-    // as much as streaming a 40 MB tensor)
+    channel_reduce_tail(a, b, pl < lanes, C, out, s_part);
+}
+
+// combine the pixel lanes of a channel group: every thread parks its 2 x 8 partial sums, then one thread per channel adds
+// that channel's `lanes` values in float64 (one barrier; the loop-and-barrier-per-channel form cost ~8 us per launch,
+// as much as streaming a 40 MB tensor)
+__device__ __forceinline__ void channel_reduce_tail_impl(const float (&a)[8], const float (&b)[8], bool active, int C, double* __restrict__ out,
+                                                         float* s_part) {
+    const int groups = C >> 3, lanes = blockDim.x / groups, pl = threadIdx.x / groups;
+    (void)pl;
     {
         float* mine = s_part + threadIdx.x * 16;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            mine[i] = pl < lanes ? a[i] : 0.0f;
-            mine[8 + i] = pl < lanes ? b[i] : 0.0f;
+            mine[i] = active ? a[i] : 0.0f;
+            mine[8 + i] = active ? b[i] : 0.0f;
         }
     }
     __syncthreads();
@@ -806,6 +820,190 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
         const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dz) + i), y0 = __ldg(reinterpret_cast<const uint4*>(y) + i);
         const uint4 z0 = RELU == 1 ? __ldg(reinterpret_cast<const uint4*>(z) + i) : make_uint4(0, 0, 0, 0);
         one(i, g0, y0, z0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (+ residual) + ReLU + the 2x2 average pooling behind it in ONE pass each way.  At the four places where the
+// network pools (after conv_block1 and at the entry of layers 2-4, models/model_utils.py:220, :349, :476) the BatchNorm
+// output is consumed by the pooling alone, so the full-resolution activation z is never written: the forward writes the
+// pooled tensor only, the backward reads the pooled gradient (dz = dpool / 4 under each window, 0 in an odd last row /
+// column) and recomputes the ReLU mask from y (+ residual).  Same arithmetic, in the same order, as bn_apply_kernel followed
+// by avgpool2_kernel / avgpool2_bwd_kernel followed by the bn_bwd kernels: bit-identical results.
+// ------------------------------------------------------------------------------------------------
+struct PoolGeom {
+    int H, W, Ho, Wo;
+};
+
+// All three kernels walk the image ROW by row (a block takes rows blockIdx.x, + gridDim.x, ...; the threads of a block share a
+// row's pixels and channel groups), so that the (batch, row, column) of a pixel costs one division per row instead of
+// three per 16 bytes: the first, per-pixel form ran the reductions at 1.9 TB/s on integer arithmetic.
+
+// a block takes POOLED rows; thread = (column, channel group) of that row, four input pixels each
+__global__ void __launch_bounds__(256) bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ pooled,
+                                                            int B, PoolGeom g, int C) {
+    const int groups = C >> 3, lg = 31 - __clz(groups);
+    const int c8 = (int)threadIdx.x & (groups - 1);
+    float scale[8], shift[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        scale[k] = gamma[c8 * 8 + k] * stat[2 * (c8 * 8 + k) + 1];
+        shift[k] = fmaf(-stat[2 * (c8 * 8 + k)], scale[k], beta[c8 * 8 + k]);
+    }
+    for (int row = blockIdx.x; row < B * g.Ho; row += gridDim.x) {
+        const int b = row / g.Ho, ho = row - b * g.Ho;
+        const __nv_bfloat16* y0 = y + ((long long)b * g.H + 2 * ho) * g.W * C;
+        const __nv_bfloat16* r0 = residual ? residual + ((long long)b * g.H + 2 * ho) * g.W * C : nullptr;
+        uint4* out = reinterpret_cast<uint4*>(pooled + (long long)row * g.Wo * C);
+        for (int e = threadIdx.x; e < g.Wo * groups; e += blockDim.x) {
+            const int wo = e >> lg;
+            uint4 qy[4], qr[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const long long off = ((long long)(d >> 1) * g.W + 2 * wo + (d & 1)) * C;
+                qy[d] = __ldg(reinterpret_cast<const uint4*>(y0 + off) + c8);
+                if (residual) qr[d] = __ldg(reinterpret_cast<const uint4*>(r0 + off) + c8);
+            }
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                float v[8], r[8];
+                unpack8(qy[d], v);
+                if (residual) unpack8(qr[d], r);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float o = fmaf(v[k], scale[k], shift[k]);
+                    if (residual) o += r[k];
+                    acc[k] += __bfloat162float(__float2bfloat16_rn(fmaxf(o, 0.0f)));      // z as bn_apply_kernel would store it
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] *= 0.25f;
+            out[e] = pack8(acc);
+        }
+    }
+}
+
+// dz word of a pixel from its window's pooled gradient word: a quarter of it, rounded as avgpool2_bwd_kernel stores it
+__device__ __forceinline__ uint4 quarter_word(const uint4& u) {
+    float v[8];
+    unpack8(u, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= 0.25f;
+    return pack8(v);
+}
+
+// RES = 0: mask from y (no residual in the forward); RES = 1: mask from y + residual
+template <int RES>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_pool_kernel(const __nv_bfloat16* __restrict__ dpool, const __nv_bfloat16* __restrict__ y,
+                                                                 const __nv_bfloat16* __restrict__ residual, const float* __restrict__ stat,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 int B, int C, PoolGeom geom, double* __restrict__ sums) {
+    __shared__ float s_part[256 * 16];
+    const int groups = C >> 3, lg = 31 - __clz(groups);
+    const int c8 = (int)threadIdx.x & (groups - 1), c0 = c8 * 8;
+    float mean[8], inv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        mean[k] = stat[2 * (c0 + k)];
+        inv[k] = stat[2 * (c0 + k) + 1];
+    }
+    BnMaskCoef mc;
+    bn_mask_coef(stat, gamma, beta, c0, mc);
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.0f;
+    const int n_e = geom.W * groups;
+    for (int row = blockIdx.x; row < B * geom.H; row += gridDim.x) {
+        const int bb = row / geom.H, h = row - bb * geom.H;
+        const uint4* yrow = reinterpret_cast<const uint4*>(y + (long long)row * geom.W * C);
+        const uint4* rrow = RES ? reinterpret_cast<const uint4*>(residual + (long long)row * geom.W * C) : nullptr;
+        const bool in_h = (h >> 1) < geom.Ho;
+        const __nv_bfloat16* drow = dpool + ((long long)bb * geom.Ho + (h >> 1)) * geom.Wo * C;
+        for (int e0 = threadIdx.x; e0 < n_e; e0 += 2 * blockDim.x) {         // two positions' loads in flight
+            uint4 qy[2], qr[2], qd[2];
+            bool on[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = e0 + u * blockDim.x;
+                on[u] = e < n_e;
+                const int w = e >> lg;
+                const bool win = on[u] && in_h && (w >> 1) < geom.Wo;
+                qy[u] = on[u] ? __ldg(yrow + e) : make_uint4(0u, 0u, 0u, 0u);
+                if (RES) qr[u] = on[u] ? __ldg(rrow + e) : make_uint4(0u, 0u, 0u, 0u);
+                qd[u] = win ? __ldg(reinterpret_cast<const uint4*>(drow + (long long)(w >> 1) * C) + c8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!on[u]) continue;
+                float g[8], yy[8], rr[8];
+                unpack8(quarter_word(qd[u]), g);
+                unpack8(qy[u], yy);
+                if (RES) unpack8(qr[u], rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float o = RES ? fmaf(yy[i], mc.scale[i], mc.shift[i]) + rr[i] : fmaf(yy[i], mc.scale[i], mc.shift[i]);
+                    const float gi = __float_as_int(o) > 0x00008000 ? g[i] : 0.0f;
+                    a[i] += gi;
+                    b[i] = fmaf(gi, (yy[i] - mean[i]) * inv[i], b[i]);
+                }
+            }
+        }
+    }
+    channel_reduce_tail(a, b, true, C, sums, s_part);
+}
+
+template <int RES>
+__global__ void __launch_bounds__(256) bn_bwd_apply_pool_kernel(const __nv_bfloat16* __restrict__ dpool, const __nv_bfloat16* __restrict__ y,
+                                                                const __nv_bfloat16* __restrict__ residual, const float* __restrict__ stat,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const double* __restrict__ sums, __nv_bfloat16* __restrict__ dy,
+                                                                __nv_bfloat16* __restrict__ d_residual, int B, int C, PoolGeom geom) {
+    const int groups = C >> 3, lg = 31 - __clz(groups);
+    const float inv_n = (float)(1.0 / ((double)B * geom.H * geom.W));
+    const int c8 = (int)threadIdx.x & (groups - 1), c0 = c8 * 8;
+    float ca[8], cy[8], cc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        const float mean = stat[2 * c], inv = stat[2 * c + 1];
+        const float dbeta = (float)sums[2 * c], dgamma = (float)sums[2 * c + 1];
+        ca[k] = gamma[c] * inv;
+        cy[k] = -ca[k] * dgamma * inv_n * inv;
+        cc[k] = -ca[k] * dbeta * inv_n - cy[k] * mean;
+    }
+    BnMaskCoef mc;
+    bn_mask_coef(stat, gamma, beta, c0, mc);
+    const int n_e = geom.W * groups;
+    for (int row = blockIdx.x; row < B * geom.H; row += gridDim.x) {
+        const int bb = row / geom.H, h = row - bb * geom.H;
+        const long long base = (long long)row * geom.W * C;
+        const uint4* yrow = reinterpret_cast<const uint4*>(y + base);
+        const uint4* rrow = RES ? reinterpret_cast<const uint4*>(residual + base) : nullptr;
+        uint4* dyrow = reinterpret_cast<uint4*>(dy + base);
+        uint4* drrow = d_residual ? reinterpret_cast<uint4*>(d_residual + base) : nullptr;
+        const bool in_h = (h >> 1) < geom.Ho;
+        const __nv_bfloat16* drow = dpool + ((long long)bb * geom.Ho + (h >> 1)) * geom.Wo * C;
+        for (int e = threadIdx.x; e < n_e; e += blockDim.x) {
+            const int w = e >> lg;
+            const bool win = in_h && (w >> 1) < geom.Wo;
+            const uint4 qd = win ? __ldg(reinterpret_cast<const uint4*>(drow + (long long)(w >> 1) * C) + c8) : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 qy = __ldg(yrow + e);
+            float g[8], yy[8], rr[8], o[8];
+            unpack8(quarter_word(qd), g);
+            unpack8(qy, yy);
+            if (RES) unpack8(__ldg(rrow + e), rr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float act = RES ? fmaf(yy[k], mc.scale[k], mc.shift[k]) + rr[k] : fmaf(yy[k], mc.scale[k], mc.shift[k]);
+                if (!(__float_as_int(act) > 0x00008000)) g[k] = 0.0f;
+                o[k] = fmaf(ca[k], g[k], fmaf(cy[k], yy[k], cc[k]));
+            }
+            dyrow[e] = pack8(o);
+            if (drrow) drrow[e] = pack8(g);
+        }
     }
 }
 

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 from . import crnn_ops as ops
 from .optim import Adam, LearningRateScheduler
 
-__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeConv1x1', 'NativeConvFirst', 'NativeBnAct', 'NativeAvgPool2', 'NativeGRULayer']
+__all__ = ['SeldTrainer', 'GradAllReduce', 'NativeConv3x3', 'NativeConv1x1', 'NativeConvFirst', 'NativeBnAct', 'NativeBnActPool', 'NativeAvgPool2', 'NativeGRULayer']
 
 
 class NativeConv3x3(torch.autograd.Function):
@@ -181,6 +181,32 @@ class NativeBnAct(torch.autograd.Function):
         return (dy.permute(0, 3, 1, 2), dgamma, dbeta, None if dres is None else dres.permute(0, 3, 1, 2), None, None, None, None)
 
 
+class NativeBnActPool(torch.autograd.Function):
+    """relu(BatchNorm2d(y) (+ residual)) followed by F.avg_pool2d(2) in one pass each way (`crnn_bn_train_forward_pool` /
+    `_backward_pool`): used where the network pools and the BatchNorm output has no other consumer, so the full-resolution
+    activation is never written and the backward reads the pooled gradient directly.  Bit-identical to NativeBnAct followed
+    by NativeAvgPool2."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, residual, running_mean, running_var):
+        yb = y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        rb = None if residual is None else residual.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        g, b = gamma.detach().contiguous(), beta.detach().contiguous()
+        pooled, stat = ops.bn_train_forward_pool(yb.permute(0, 2, 3, 1), g, b, None if rb is None else rb.permute(0, 2, 3, 1),
+                                                 running_mean=running_mean, running_var=running_var)
+        ctx.save_for_backward(yb, rb, stat, g, b)
+        return pooled.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dpool):
+        yb, rb, stat, g, b = ctx.saved_tensors
+        dpb = dpool.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dy, dres, dgamma, dbeta = ops.bn_train_backward_pool(dpb.permute(0, 2, 3, 1), yb.permute(0, 2, 3, 1),
+                                                             None if rb is None else rb.permute(0, 2, 3, 1), stat, g, b,
+                                                             want_residual_grad=rb is not None and ctx.needs_input_grad[3])
+        return dy.permute(0, 3, 1, 2), dgamma, dbeta, None if dres is None else dres.permute(0, 3, 1, 2), None, None
+
+
 class NativeAvgPool2(torch.autograd.Function):
     """F.avg_pool2d(x, 2) on channels_last bf16 tensors: `crnn_avgpool2` / `crnn_avgpool2_backward` (torch's NHWC pooling
     kernels took a third of the training step)."""
@@ -287,6 +313,7 @@ class SeldTrainer:
         self.native_conv = native_conv and self.device.type == 'cuda'
         self.native_bn = native_bn and self.device.type == 'cuda'
         self.native_gru = native_gru and self.device.type == 'cuda'
+        self.fuse_pool = True                # BatchNorm + ReLU + pooling as one pass where the network pools (False: two passes)
         self.autocast = autocast and self.device.type == 'cuda'
         self.dropout = dropout
         self.scheduler = scheduler
@@ -338,18 +365,23 @@ class SeldTrainer:
             return NativeAvgPool2.apply(x)
         return F.avg_pool2d(x, 2)
 
-    def _bn(self, x, prefix, relu=False, residual=None, drop_p=0.0, salt=0):
-        """BatchNorm2d (+ residual) (+ ReLU) (+ dropout): one native pass each way in train mode, torch ops otherwise."""
+    def _bn(self, x, prefix, relu=False, residual=None, drop_p=0.0, salt=0, pool=False):
+        """BatchNorm2d (+ residual) (+ ReLU) (+ dropout) (+ the 2x2 average pooling behind it): one native pass each way in
+        train mode, torch ops otherwise."""
         rm, rv = self.buffers[prefix + '.running_mean'], self.buffers[prefix + '.running_var']
         w, b = self.params[prefix + '.weight'], self.params[prefix + '.bias']
         if self.native_bn and self.training and x.is_cuda and x.shape[1] in (64, 128, 256, 512):
+            if pool and relu and drop_p == 0.0 and self.fuse_pool and x.shape[2] >= 2 and x.shape[3] >= 2:
+                return NativeBnActPool.apply(x, w, b, residual, rm, rv)
             drop = (self.drop_seed, salt, drop_p) if drop_p > 0.0 else None
-            return NativeBnAct.apply(x, w, b, residual, rm, rv, relu, drop)
+            out = NativeBnAct.apply(x, w, b, residual, rm, rv, relu, drop)
+            return self._pool(out) if pool else out
         out = F.batch_norm(x, rm, rv, w, b, training=self.training, momentum=0.1, eps=1e-5)
         if residual is not None:
             out = out + residual
         out = F.relu(out) if relu else out
-        return F.dropout(out, p=drop_p, training=True) if drop_p > 0.0 else out
+        out = F.dropout(out, p=drop_p, training=True) if drop_p > 0.0 else out
+        return self._pool(out) if pool else out
 
     def forward(self, x):
         """x (B, 7, T, F) float32 -> {'event_frame_logit': (B, T/16, n), 'doa_frame_output': (B, T/16, 3n)}, with autograd."""
@@ -362,20 +394,23 @@ class SeldTrainer:
             else:
                 y0 = F.conv2d(x.contiguous(memory_format=torch.channels_last), w0, padding=1)
             x = self._bn(y0, p + '.bn1', relu=True)
-            x = self._bn(self._conv3(x, p + '.conv2.weight'), p + '.bn2', relu=True)
-            x = self._pool(x)                                                 # ConvBlock.forward (models/model_utils.py:213-220)
+            # ConvBlock.forward (models/model_utils.py:213-220): bn2 + ReLU + the pooling in one pass
+            x = self._bn(self._conv3(x, p + '.conv2.weight'), p + '.bn2', relu=True, pool=True)
             for li in range(1, 5):
                 for bi in range(2):
                     q = 'encoder.resnet.layer{}.{}'.format(li, bi)
                     identity = x
-                    pooled = self._pool(x) if (li > 1 and bi == 0) else x     # _ResnetBasicBlock.forward (:345-367)
+                    # _ResnetBasicBlock.forward (:345-367) pools at the entry of layers 2-4; that pooling is the only consumer of
+                    # the previous block's output, so it already happened in that block's last BatchNorm pass (below)
+                    pooled = x
                     # relu(bn1(conv1(.))) and the dropout behind it (:354-356) in one pass
                     out = self._bn(self._conv3(pooled, q + '.conv1.weight'), q + '.bn1', relu=True, drop_p=0.1 if tr else 0.0, salt=2 * li + bi)
                     if li > 1 and bi == 0:                                     # downsample = AvgPool2d(2) + 1x1 conv + BN (:474-481): the same pooled tensor
                         wd = self.params[q + '.downsample.1.weight']
                         ds = NativeConv1x1.apply(pooled, wd) if self.native_conv else F.conv2d(pooled, wd)
                         identity = self._bn(ds, q + '.downsample.2')
-                    x = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2', relu=True, residual=identity)   # relu(bn2(.) + identity)
+                    x = self._bn(self._conv3(out, q + '.conv2.weight'), q + '.bn2', relu=True, residual=identity,   # relu(bn2(.) + identity)
+                                 pool=(bi == 1 and li < 4))
             x = torch.mean(x.float(), dim=3).transpose(1, 2)                  # SeldDecoder.forward (models/decoders.py:106-154)
             if self.native_gru and x.is_cuda:
                 for layer in range(2):

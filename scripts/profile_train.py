@@ -19,6 +19,7 @@ ex = salsa_b200.SalsaExtractor('foa')
 aug = augment.BatchAugment(augment.TfmapRandomSwapChannelFoa(n_classes=12), augment.RandomShiftUpDownNp(freq_shift_range=10))
 GRAPH = len(sys.argv) > 2 and sys.argv[2] == 'graph'
 tr = train.SeldTrainer(salsa_b200.crnn.random_state_dict(0), device=dev, use_graph=GRAPH)
+tr.fuse_pool = os.environ.get('NO_FUSE_POOL') is None
 g = torch.Generator(device=dev)
 g.manual_seed(77)
 tgt = {'event_frame_gt': (torch.rand((B, 80, 12), generator=g, device=dev) > 0.8).float(),
@@ -41,7 +42,7 @@ for _ in range(5):
     step()
 e1.record()
 torch.cuda.synchronize()
-print('ms per step (no profiler):', e0.elapsed_time(e1) / 5, 'graph' if GRAPH else 'eager', tr.graph_error)
+print('ms per step (no profiler):', e0.elapsed_time(e1) / 5, 'graph' if GRAPH else 'eager', tr.graph_error, 'fuse_pool', tr.fuse_pool)
 if GRAPH:
     sys.exit(0)
 from torch.profiler import ProfilerActivity, profile   # noqa: E402

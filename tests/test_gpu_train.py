@@ -319,3 +319,31 @@ def test_training_step_gradients_at_the_benchmark_chunk_shape():
     assert torch.allclose(l_nat, l_32, rtol=2e-3, atol=2e-3) and torch.allclose(l_nat, l_16, rtol=2e-3, atol=2e-3)
     assert c_nat32 > c_1632 - 0.01 and c_nat32 > 0.95
     assert c_nat16 > 0.97
+
+
+@pytest.mark.parametrize('C,H,W,with_res', [(64, 21, 13, False), (128, 20, 14, True), (256, 9, 12, True)])
+def test_fused_batchnorm_relu_pool_equals_the_two_passes(C, H, W, with_res):
+    """crnn_bn_train_forward_pool / _backward_pool (BatchNorm + residual + ReLU + 2x2 average pooling as one pass each way, the
+    full-resolution activation never written) against NativeBnAct followed by NativeAvgPool2: bit-identical outputs, residual
+    gradients and running statistics; parameter gradients to float32 summation order.  Odd sizes: floor mode."""
+    from salsa_b200.train import NativeBnAct, NativeAvgPool2, NativeBnActPool
+    g = torch.Generator().manual_seed(C + H)
+    B = 3
+    y = (torch.randn(B, C, H, W, generator=g) * 2 + 0.3).bfloat16().float().cuda().requires_grad_(True)
+    res = torch.randn(B, C, H, W, generator=g).bfloat16().float().cuda().requires_grad_(True) if with_res else None
+    gamma = torch.empty(C).uniform_(0.5, 1.5, generator=g).cuda().requires_grad_(True)
+    beta = torch.empty(C).uniform_(-0.3, 0.3, generator=g).cuda().requires_grad_(True)
+    dp = torch.randn(B, C, H // 2, W // 2, generator=g).bfloat16().float().cuda()
+    inputs = (y, gamma, beta) + ((res,) if with_res else ())
+    rm_a, rv_a, rm_b, rv_b = torch.zeros(C).cuda(), torch.ones(C).cuda(), torch.zeros(C).cuda(), torch.ones(C).cuda()
+    two = NativeAvgPool2.apply(NativeBnAct.apply(y, gamma, beta, res, rm_a, rv_a, True))
+    g_two = torch.autograd.grad(two, inputs, dp)
+    one = NativeBnActPool.apply(y, gamma, beta, res, rm_b, rv_b)
+    g_one = torch.autograd.grad(one, inputs, dp)
+    assert torch.equal(one, two) and torch.equal(rm_a, rm_b) and torch.equal(rv_a, rv_b)
+    # dgamma / dbeta: the same terms in another summation order; dy depends on them, so it agrees to a bf16 rounding step here
+    # and there rather than bit for bit; the residual gradient (masked dz, no sums involved) is identical
+    assert rel(g_one[1], g_two[1]) < 1e-5 and rel(g_one[2], g_two[2]) < 1e-5
+    assert rel(g_one[0], g_two[0]) < 1e-2 and (g_one[0] != g_two[0]).float().mean().item() < 1e-2
+    if with_res:
+        assert torch.equal(g_one[3], g_two[3])
