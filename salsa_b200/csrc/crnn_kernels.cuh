@@ -515,18 +515,40 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
     return make_uint4(w4[0], w4[1], w4[2], w4[3]);
 }
 
+// Block-level end of a per-channel reduction (thread = channel group threadIdx % groups, pixel lane threadIdx / groups, its
+// 2 x 8 partial sums in a / b; s_part: 256 x 16 floats of shared memory).  Combine the pixel lanes of a channel group: every thread parks its 2 x 8 partial sums, then one thread per channel adds
+// that channel's `lanes` values in float64 (one barrier; the loop-and-barrier-per-channel form cost ~8 us per launch,
+// as much as streaming a 40 MB tensor)
+__device__ __forceinline__ void channel_reduce_tail(const float (&a)[8], const float (&b)[8], bool active, int C, double* __restrict__ out,
+                                                    float* s_part) {
+    const int groups = C >> 3, lanes = blockDim.x / groups;
+    {
+        float* mine = s_part + threadIdx.x * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            mine[i] = active ? a[i] : 0.0f;
+            mine[8 + i] = active ? b[i] : 0.0f;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c >> 3, i = c & 7;
+        double sa = 0.0, sb = 0.0;
+        for (int l = 0; l < lanes; ++l) {
+            const float* p = s_part + (l * groups + g) * 16;
+            sa += (double)p[i];
+            sb += (double)p[8 + i];
+        }
+        atomicAdd(out + (size_t)c * 2, sa);
+        atomicAdd(out + (size_t)c * 2 + 1, sb);
+    }
+}
+
 // Per-channel reduction of two quantities over the pixels: every thread accumulates its channels over its pixels in fp32
 // (at most a few hundred values), threads that share a channel group are combined through shared memory in fp64, one
 // atomicAdd(double) per channel and block.  `load(pix, c8, q)` fetches the NT 16-byte words of pixel `pix`, channels
 // 8 c8 .. 8 c8 + 7; `acc(q, a, b)` adds their contributions.  Four pixels' loads are issued before the first is consumed
 // (the reductions are pure streaming reads: bytes in flight are what the bandwidth depends on).
-__device__ __forceinline__ void channel_reduce_tail_impl(const float (&a)[8], const float (&b)[8], bool active, int C, double* __restrict__ out,
-                                                         float* s_part);
-__device__ __forceinline__ void channel_reduce_tail(const float (&a)[8], const float (&b)[8], bool active, int C, double* __restrict__ out,
-                                                    float* s_part) {
-    channel_reduce_tail_impl(a, b, active, C, out, s_part);
-}
-
 template <int NT, typename L, typename A>
 __device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* __restrict__ out /* [C][2] */, L load, A acc) {
     __shared__ float s_part[256 * 16];
@@ -554,35 +576,6 @@ __device__ __forceinline__ void channel_reduce2(long long n_pix, int C, double* 
         }
     }
     channel_reduce_tail(a, b, pl < lanes, C, out, s_part);
-}
-
-// combine the pixel lanes of a channel group: every thread parks its 2 x 8 partial sums, then one thread per channel adds
-// that channel's `lanes` values in float64 (one barrier; the loop-and-barrier-per-channel form cost ~8 us per launch,
-// as much as streaming a 40 MB tensor)
-__device__ __forceinline__ void channel_reduce_tail_impl(const float (&a)[8], const float (&b)[8], bool active, int C, double* __restrict__ out,
-                                                         float* s_part) {
-    const int groups = C >> 3, lanes = blockDim.x / groups, pl = threadIdx.x / groups;
-    (void)pl;
-    {
-        float* mine = s_part + threadIdx.x * 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            mine[i] = active ? a[i] : 0.0f;
-            mine[8 + i] = active ? b[i] : 0.0f;
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c >> 3, i = c & 7;
-        double sa = 0.0, sb = 0.0;
-        for (int l = 0; l < lanes; ++l) {
-            const float* p = s_part + (l * groups + g) * 16;
-            sa += (double)p[i];
-            sb += (double)p[8 + i];
-        }
-        atomicAdd(out + (size_t)c * 2, sa);
-        atomicAdd(out + (size_t)c * 2 + 1, sb);
-    }
 }
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long n_pix, int C, double* __restrict__ sums) {
