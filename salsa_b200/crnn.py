@@ -96,7 +96,8 @@ class SeldDecoder:
 
 
 class SeldModel:
-    """Inference counterpart of models.seld_models.SeldModel."""
+    """Counterpart of models.seld_models.SeldModel: the forward / inference path on the native kernels, and -- after
+    train() -- the training step through salsa_b200.train.SeldTrainer."""
 
     def __init__(self, encoder: PannResNet22, decoder: SeldDecoder, label_rate: int = 10, feature_rate: float = None,
                  device='cuda', precision: str = 'bf16', **kwargs):
@@ -119,6 +120,9 @@ class SeldModel:
         self._native_model = None          # crnn_load_weights handle (the one-call forward)
         self._workspace = None
         self._out = None
+        self._sd = None                    # the loaded state dict (float32, CPU): what a trainer starts from
+        self._trainer = None               # salsa_b200.train.SeldTrainer, created by train()
+        self._trainer_kwargs = {'loss_weight': tuple(kwargs.get('loss_weight', (0.3, 0.7))), 'lr': float(kwargs.get('lr', 1e-3))}
 
     def __del__(self):
         self._release_native()
@@ -133,13 +137,53 @@ class SeldModel:
 
     # ---- nn.Module-like surface -----------------------------------------------------------------
     def eval(self):
+        """Back to the inference path; weights trained since train() are folded into it first."""
+        if self.training and self._trainer is not None:
+            self.load_state_dict(self._trainer.state_dict())
         self.training = False
         return self
 
-    def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError('salsa_b200.SeldModel is the forward / inference path only')
-        return self.eval()
+    def train(self, mode: bool = True, **trainer_kwargs):
+        """nn.Module.train(): the training side of the reference's LightningModule (models/seld_models.py:51-76,
+        models/interfaces.py:85-95) is `salsa_b200.train.SeldTrainer`; train() creates one from the loaded weights (keyword
+        arguments go to it: scheduler, use_graph, group, ...), `training_step` / `validation_step`-style calls go through it,
+        and eval() hands the trained weights back to the inference kernels."""
+        if not mode:
+            return self.eval()
+        if self._sd is None:
+            raise RuntimeError('load_state_dict() first')
+        if self._trainer is None or trainer_kwargs:
+            from .train import SeldTrainer
+            kw = dict(self._trainer_kwargs)
+            kw.update(trainer_kwargs)
+            self._trainer = SeldTrainer(self._sd, n_classes=self.n_classes, label_rate=self.label_rate,
+                                        feature_rate=self.feature_rate or 80.0, device=self.device, **kw)
+        self.training = True
+        return self
+
+    @property
+    def trainer(self):
+        return self._trainer
+
+    def training_step(self, train_batch, batch_idx=None):
+        """The reference's `training_step` (models/seld_models.py:68-76) INCLUDING what Lightning does around it (backward,
+        gradient all-reduce, optimiser step): train_batch = (x, y_sed, y_doa, filenames) as the data loader yields them.
+        Returns {'loss', 'sed_loss', 'doa_loss'} as 0-d CUDA tensors."""
+        if not self.training or self._trainer is None:
+            raise RuntimeError('call train() first')
+        x, y_sed, y_doa = train_batch[0], train_batch[1], train_batch[2]
+        dev = self.device
+        loss = self._trainer.step(x.to(dev, torch.float32), {'event_frame_gt': y_sed.to(dev, torch.float32),
+                                                             'doa_frame_gt': y_doa.to(dev, torch.float32)})
+        return {'loss': loss[0], 'sed_loss': loss[1], 'doa_loss': loss[2]}
+
+    def state_dict(self):
+        """Reference state-dict keys: the trainer's current weights while training, else the loaded ones."""
+        if self.training and self._trainer is not None:
+            return self._trainer.state_dict()
+        if self._sd is None:
+            raise RuntimeError('load_state_dict() first')
+        return dict(self._sd)
 
     def __call__(self, x):
         return self.forward(x)
@@ -192,6 +236,7 @@ class SeldModel:
         W['fc1'] = (ops.split_planes(w1, self.planes).to(dev), b1.contiguous().to(dev))
         W['fc2'] = (ops.split_planes(w2, self.planes).to(dev), b2.contiguous().to(dev))
         self._w = W
+        self._sd = {k: _t(v).clone() for k, v in sd.items()}
         self._load_native(sd)
         return self
 

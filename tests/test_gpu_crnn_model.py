@@ -113,8 +113,8 @@ def test_interface_errors():
     m = salsa_b200.SeldModel(salsa_b200.PannResNet22(7), salsa_b200.SeldDecoder(512, decoder_type='bigru', freq_pool='avg', decoder_size=256))
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 7, 32, 200).cuda())
-    with pytest.raises(NotImplementedError):
-        m.train()
+    with pytest.raises(RuntimeError):
+        m.train()                                   # no weights loaded yet
 
 
 def test_fused_scaler_normalisation(model):
@@ -273,3 +273,28 @@ def test_c_abi_model_entry_points_with_caller_owned_workspace():
     want = m.forward_ops(x)
     assert torch.equal(logits, want['event_frame_logit']) and torch.equal(doa, want['doa_frame_output'])
     _native.check(lib.crnn_free_model(handle))
+
+
+def test_model_train_mode_runs_the_reference_training_step():
+    """SeldModel.train() / training_step(batch) / eval(): the reference LightningModule's surface (models/seld_models.py:51-76)
+    on salsa_b200.train.SeldTrainer; the weights trained in between reach the inference kernels at eval() and state_dict()."""
+    import salsa_b200
+    model = salsa_b200.SeldModel(salsa_b200.PannResNet22(n_input_channels=7),
+                                 salsa_b200.SeldDecoder(512, n_classes=12, output_format='reg_xyz', decoder_type='bigru',
+                                                        freq_pool='avg', decoder_size=256), label_rate=10, feature_rate=80.0)
+    model.load_state_dict(salsa_b200.crnn.random_state_dict(5))
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 7, 128, 200, generator=g)
+    batch = (x, (torch.rand(2, 16, 12, generator=g) > 0.6).float(), torch.randn(2, 16, 36, generator=g).clamp(-1, 1), ['a', 'b'])
+    before = model(x.cuda())['event_frame_logit'].clone()
+    with pytest.raises(RuntimeError):
+        model.training_step(batch, 0)               # not in train mode
+    model.train(dropout=False, lr=3e-4)
+    losses = [model.training_step(batch, i)['loss'].item() for i in range(8)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    assert model.trainer.optimizer.step_count == 8
+    w_trained = model.state_dict()['encoder.conv_block1.conv2.weight']
+    model.eval()
+    after = model(x.cuda())['event_frame_logit']
+    assert not torch.equal(before, after)                                       # the inference path sees the new weights
+    assert torch.equal(model.state_dict()['encoder.conv_block1.conv2.weight'].cpu(), w_trained.cpu())
