@@ -162,8 +162,8 @@ def extras_cases():
 
 def nfft256_cases():
     """The n_fft = 256 configuration the reference accepts (salsa_feature_extraction.py:151-152, :163-170, :300-306), from
-    the unmodified reference on the first 0.5 s of the golden clips: MagStftExtractor (both band layouts, a shorter window) and
-    the per-clip SALSA body, FOA and MIC, at hop 150."""
+    the unmodified reference on the first 0.5 s of the golden clips: MagStftExtractor (both band layouts, a shorter window), the
+    per-clip SALSA body, FOA and MIC, and the SALSA-Lite / SALSA-IPD body, at hop 150."""
     ref = ref_import.features_module()
     clips = np.load(os.path.join(GOLDEN_DIR, 'clip_cases.npz'))
     foa, mic = clips['audio_foa'][:, :12000], clips['audio_mic'][:, :12000]
@@ -174,6 +174,9 @@ def nfft256_cases():
     out['logspec_foa'] = ref.MagStftExtractor(n_fft=256, hop_length=150, win_length=256).extract(foa)
     out['logspec_foa_nocompress'] = ref.MagStftExtractor(n_fft=256, hop_length=150, win_length=256, is_compress_high_freq=False).extract(foa)
     out['logspec_foa_win200'] = ref.MagStftExtractor(n_fft=256, hop_length=150, win_length=200).extract(foa)
+    lite_cfg = dict(DATA_CFG['lite'], n_fft=256, win_len=256, hop_len=150)
+    out['salsa_lite'] = ref_import.run_driver_body('salsa_lite', mic, lite_cfg, feature_type='salsa_lite')
+    out['salsa_ipd'] = ref_import.run_driver_body('salsa_lite', mic, lite_cfg, feature_type='salsa_ipd')
     return out
 
 

@@ -649,7 +649,6 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
                        void* stream) {
     int rc = validate_params(p);
     if (rc) return rc;
-    if (p->n_fft != kNfft) return fail(SALSA_EINVAL, "salsa_lite: only n_fft = 512 is implemented");
     if (mode != SALSA_LITE_NIPD && mode != SALSA_LITE_IPD) return fail(SALSA_EINVAL, "Invalid feature type");
     if (p->upper_bin > cutoff_bin || cutoff_bin > p->n_fft / 2)
         return fail(SALSA_EINVAL, "Upper bin for spatial feature is higher than cutoff bin for spectrogram!");
@@ -658,7 +657,16 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
     // the reference reads win_len from the config but never passes it on (salsa_lite_feature_extraction.py:44, :97-98):
     // every SALSA-Lite transform uses librosa's default full-length Hann, so win_len / window are ignored here too
     DeviceTables tb;
-    if ((rc = get_tables(nullptr, &tb))) return rc;
+    if (p->n_fft == kNfft) {
+        if ((rc = get_tables(nullptr, &tb))) return rc;
+    } else {                                   // n_fft = 256: the full-length Hann as a table
+        double win_full[kNfft];
+        salsa_params_t ph = *p;
+        ph.window = nullptr;
+        ph.win_len = p->n_fft;
+        host_window(&ph, win_full);
+        if ((rc = get_tables(win_full, &tb))) return rc;
+    }
     LiteArgs a;
     a.audio = audio;
     a.feature = feature;
@@ -676,6 +684,14 @@ int salsa_lite_extract(const salsa_params_t* p, int32_t cutoff_bin, int32_t mode
     ProfScope prof("lite_kernel", st);
     // bins below 32 * NJ can carry a phase difference: cropped index < upper_cropped <=> bin < upper_bin + lower_bin
     const bool narrow = p->upper_bin + p->lower_bin <= 64;
+    if (p->n_fft == 256) {
+        const bool d = p->stft_precision == 64;
+        const size_t smem = d ? sizeof(FftSmem<double>) : sizeof(FftSmem<float>);
+        if ((rc = d ? set_smem(lite256_kernel<double>, smem) : set_smem(lite256_kernel<float>, smem))) return rc;
+        if (d) lite256_kernel<double><<<grid, kThreads, smem, st>>>(a, tb.d);
+        else lite256_kernel<float><<<grid, kThreads, smem, st>>>(a, tb.f);
+        return check_launch("lite256_kernel");
+    }
     if (p->stft_precision == 64) {
         const size_t smem = sizeof(FftSmem<double>);
         if (narrow) {

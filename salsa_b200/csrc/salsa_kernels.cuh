@@ -967,6 +967,79 @@ __global__ void __launch_bounds__(kThreads, 2) lite_kernel(LiteArgs a, FftTables
     }
 }
 
+// lite256_kernel: the same features at the reference's second transform size (n_fft = 256; the SALSA-Lite script takes n_fft
+// from the config, salsa_lite_feature_extraction.py:40-66).  The plain form, like stft256_kernel: the 256 real samples of a
+// frame through the 256-point complex transform with zero imaginary parts, window (full-length Hann, :97-98) from the table.
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2) lite256_kernel(LiteArgs a, FftTables<T> tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FftSmem<T>& s = *reinterpret_cast<FftSmem<T>*>(smem_raw);
+    load_fft_smem(s, tb);
+    __syncthreads();
+    const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
+    const LaneTwiddles<T> tw = lane_twiddles(tb, lane);
+    const int clip = blockIdx.y;
+    const int f0 = blockIdx.x * a.frames_per_block;
+    const int f1 = min(a.n_frames, f0 + a.frames_per_block);
+    const int width = a.cutoff - a.lower;
+    const long long chan_stride = (long long)a.n_frames * width;
+    const float* clip_audio = a.audio + (long long)clip * 4 * a.n_samples;
+    float* clip_feat = a.feature + (long long)clip * 7 * chan_stride;
+    Cx<T>* scratch = s.scratch[warp];
+    const float inv_pi = 0.318309886183790671538f;
+    for (int t = f0 + warp; t < f1; t += kWarps) {
+        // spectrum of one channel of this frame, rounded to complex64 like librosa's: xf[g] = bin lane + 32 g
+        auto spectrum = [&](int ch, float2 (&xf)[4]) {
+            const float* x = clip_audio + (long long)ch * a.n_samples;
+            const int start = t * a.hop - kNfft256 / 2;
+            Cx<T> v[8], z[8];
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
+                const int m = lane + 32 * n1;
+                v[n1] = {(T)x[reflect_index(start + m, a.n_samples)] * s.win[m], (T)0};
+            }
+            warp_fft_core<T, 0>(v, tw, scratch, lane, z);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xf[g] = make_float2((float)z[g].re, (float)z[g].im);
+        };
+        float2 x0[4];
+        spectrum(0, x0);
+        {
+            float* srow = clip_feat + (long long)t * width - a.lower;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int k = lane + 32 * g;
+                if ((unsigned)(k - a.lower) < (unsigned)width) srow[k] = power_db(power_f32(x0[g].x, x0[g].y));
+            }
+        }
+#pragma unroll 1
+        for (int ch = 1; ch < 4; ++ch) {
+            float2 xc[4];
+            spectrum(ch, xc);
+            float* srow = clip_feat + ch * chan_stride + (long long)t * width - a.lower;
+            float* prow = clip_feat + (3 + ch) * chan_stride + (long long)t * width - a.lower;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int k = lane + 32 * g;
+                const float re = xc[g].x, im = xc[g].y;
+                if ((unsigned)(k - a.lower) < (unsigned)width) {
+                    srow[k] = power_db(power_f32(re, im));
+                    float ph = 0.0f;
+                    if (k - a.lower < a.upper_cropped) {
+                        // X_ch conj(X_0) with exact float64 products (:111), angle in float32
+                        const float2 r = x0[g];
+                        const double pr = (double)re * r.x + (double)im * r.y;
+                        const double pi = (double)im * r.x - (double)re * r.y;
+                        const float ang = atan2f((float)pi, (float)pr);
+                        ph = a.mode == SALSA_LITE_IPD ? ang * inv_pi : ang * (float)(a.inv_delta / (double)max(k, 1));
+                    }
+                    prow[k] = ph;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // iv_kernel: the intensity-vector channels of LinSpecIvExtractor.extract (dataset/feature_extraction.py:342-351), FOA:
 //     IV_c = Re(conj(X_0) X_c), c = 1..3;  normal = sqrt(IVx^2 + IVy^2 + IVz^2) + 1e-8;  feature = W (IV_c / normal)

@@ -116,9 +116,31 @@ def test_nfft256_clip_matches_reference_golden(sb, golden, fmt, fmax):
     assert np.array_equal(host, out)
 
 
+@pytest.mark.parametrize('ft', ['salsa_lite', 'salsa_ipd'])
+def test_nfft256_salsa_lite_matches_reference_golden(sb, golden, ft):
+    g, clips = golden('nfft256_cases'), golden('clip_cases')
+    audio = np.ascontiguousarray(clips['audio_mic'][:, :12000])
+    ref = g[ft]
+    ex = sb.SalsaLiteExtractor(feature_type=ft, n_fft=256, hop_len=150)
+    out = ex.extract(torch.from_numpy(audio)[None].cuda())[0].cpu().numpy()
+    assert out.shape == ref.shape == (7, 81, 95)
+    close(out[:4], ref[:4], ft + ' 256 spectrogram')
+    # a phase within rounding of +-pi may legitimately come out with the other sign
+    scale = np.pi if ft == 'salsa_lite' else 1.0
+    k = (np.arange(95) + 1)[None, None, :]
+    delta = 2 * np.pi * 24000 / (256 * 343.0)
+    raw = ref[4:] * (delta * k if ft == 'salsa_lite' else np.pi)
+    ok = np.abs(np.abs(raw) - np.pi) > 1e-3
+    assert ok.mean() > 0.99
+    close(out[4:][ok], ref[4:][ok], ft + ' 256 phase')
+    assert np.all(out[4:, :, ex.upper_bin:] == 0)
+    host = ex.extract_host(audio[None])[0]
+    assert np.array_equal(host, out)
+
+
 def test_nfft256_is_rejected_where_it_is_not_built(sb):
-    with pytest.raises(ValueError):
-        sb.SalsaLiteExtractor(n_fft=256, hop_len=150).extract(torch.zeros(1, 4, 12000, device='cuda'))
+    with pytest.raises((ValueError, NotImplementedError)):
+        sb.LinSpecIvExtractor(n_fft=256, hop_length=150).extract(np.zeros((4, 12000), np.float32))
 
 
 def test_extractor_asserts_like_reference(sb):

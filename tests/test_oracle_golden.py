@@ -80,6 +80,10 @@ def test_nfft256_oracle_matches_reference_golden(golden):
         assert out.shape == ref.shape == (7, 81, 100)
         assert np.array_equal(out != 0, ref != 0)
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
+    for ft in ('salsa_lite', 'salsa_ipd'):
+        out = salsa.salsa_lite_clip(mic, ft, n_fft=256, hop_length=150)
+        assert out.shape == g[ft].shape == (7, 81, 95)
+        np.testing.assert_allclose(out, g[ft], rtol=0, atol=1e-6)
 
 
 @pytest.mark.parametrize('ft', ['salsa_lite', 'salsa_ipd'])
