@@ -362,6 +362,25 @@ class SeldModel:
         idx = ops.interpolate_index(out['event_frame_logit'].shape[1], ratio)
         return {k: ops.gather_time(v, idx) for k, v in out.items()}
 
+    def common_step(self, batch_data):
+        """models/seld_models.py:51-66: batch (x, y_sed, y_doa, filenames) -> (target_dict, pred_dict) at the label rate."""
+        x, y_sed, y_doa = batch_data[0], batch_data[1], batch_data[2]
+        dev = self.device
+        target = {'event_frame_gt': y_sed.to(dev, torch.float32), 'doa_frame_gt': y_doa.to(dev, torch.float32)}
+        pred = self.predict(x.to(dev, torch.float32))
+        n = min(pred['event_frame_logit'].shape[1], target['event_frame_gt'].shape[1])
+        pred = {k: v[:, :n].contiguous() for k, v in pred.items()}
+        target = {k: v[:, :n].contiguous() for k, v in target.items()}
+        return target, pred
+
+    def validation_step(self, val_batch, batch_idx=None, sed_threshold: float = 0.3):
+        """models/seld_models.py:84-95 without the file system: the three losses plus, per clip, the rows the reference would
+        write to the submission csv (`events`' format)."""
+        target, pred = self.common_step(val_batch)
+        loss, sed_loss, doa_loss = self.compute_loss(target, pred, loss_weight=self._trainer_kwargs['loss_weight'])
+        return {'loss': loss, 'sed_loss': sed_loss, 'doa_loss': doa_loss,
+                'events': self.events(val_batch[0].to(self.device, torch.float32), sed_threshold=sed_threshold)}
+
     def compute_loss(self, target_dict, pred_dict, loss_weight=(0.3, 0.7)):
         """BaseModel.compute_loss (models/interfaces.py:273-286) for reg_xyz outputs at the label rate:
         target_dict['event_frame_gt' / 'doa_frame_gt'], pred_dict['event_frame_logit' / 'doa_frame_output'] (CUDA tensors)

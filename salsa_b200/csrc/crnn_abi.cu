@@ -97,7 +97,8 @@ static int conv_generic(const void* x, const void* w, const float* bias, const v
         const cuuint64_t cp = (cuuint64_t)Cin * planes;      // channels per pixel in memory
         cuuint64_t dims[4] = {cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {cp * 2, (cuuint64_t)W * cp * 2, (cuuint64_t)H * W * cp * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)kTileW, (cuuint32_t)(taps == 9 ? kTileH + 2 : kTileH), 1};
+        cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)((taps == 9 && CONV_SINGLE_HALO) ? kHalo1Cols : kTileW),
+                             (cuuint32_t)(taps == 9 ? kTileH + 2 : kTileH), 1};
         int rc = make_tmap(&ta, x, 4, dims, str, box);
         if (rc) return rc;
     }

@@ -10,10 +10,11 @@
 //
 // One CTA computes tiles of 16 x 8 = 128 output pixels (UMMA M) x N_TILE output channels (UMMA N),
 // fp32 accumulators in TMEM (two stages, so the epilogue of tile i overlaps the MMAs of tile i+1):
-//   warp 0     TMA producer.  Per 64-channel chunk of Cin it loads three column-shifted halo tiles
-//              (18 rows x 8 pixels x 64 ch, 128-byte swizzle; out-of-image pixels are zero-filled by
-//              TMA = the convolution's zero padding), from which all nine taps are addressed by a
-//              1024-byte-aligned row offset; per (chunk, tap) it loads the [N_TILE][64] weight tile.
+//   warp 0     TMA producer.  Per 64-channel chunk of Cin it loads one halo box (18 rows x 16 pixels x
+//              64 ch, 128-byte swizzle; out-of-image pixels are zero-filled by TMA = the convolution's
+//              zero padding), from which all nine taps are addressed by a start offset of
+//              (dy * 16 + dx) * 128 bytes (see CONV_SINGLE_HALO); per (chunk, tap) it loads the
+//              [N_TILE][64] weight tile.
 //   warp 1     MMA issuer: 4 x tcgen05.mma (K = 16) per (chunk, tap); tcgen05.commit releases the
 //              shared-memory stages and finally publishes the accumulator.
 //   warp 2     TMEM allocation.
@@ -33,9 +34,24 @@ constexpr int kKC = 64;                       // channels per K chunk = one 128-
 constexpr int kEpiWarps = 8;                  // two warps per TMEM lane quarter: each takes one 32-column half of a 64-channel group
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kConvThreads = 128 + kEpiThreads;
-constexpr int kAStages = 2;
+#ifndef CONV_A_STAGES
+#define CONV_A_STAGES 2
+#endif
+constexpr int kAStages = CONV_A_STAGES;
 constexpr int kHaloBytes = (kTileH + 2) * kTileW * 128;    // one column-shifted halo tile (3x3)
 constexpr int kPlainBytes = kTileH * kTileW * 128;         // A tile of a 1x1 convolution / GEMM
+// CONV_SINGLE_HALO = 2 (default): ONE halo box of 18 rows x 16 columns per 64-channel chunk; tap (dy, dx) starts
+// (dy * 16 + dx) * 128 bytes into it with its 8-row groups (one tile row of 8 pixels each) 2048 bytes apart.  For dx > 0 that
+// start address is not 1024-byte aligned -- which works because the tensor core applies the 128-byte swizzle to the ABSOLUTE
+// shared-memory address bits (like TMA did when it wrote the box), so the descriptor's base-offset field stays 0.
+// (= 1 puts the row phase dx into the base-offset field: wrong results, measured -- that was round 1's failed attempt.
+//  = 0 is the earlier arrangement, three column-shifted 18 x 8 boxes whose tap offsets are multiples of 1024 bytes: 54 KB of TMA
+//  fill per chunk instead of 36 KB; the 64-channel layers, bound by shared-memory bandwidth, run 5-9 % faster with one box.)
+#ifndef CONV_SINGLE_HALO
+#define CONV_SINGLE_HALO 2
+#endif
+constexpr int kHalo1Cols = 16;
+constexpr int kHalo1Bytes = (kTileH + 2) * kHalo1Cols * 128;
 
 struct ConvArgs {
     int B, H, W, Cin, Cout;
@@ -58,7 +74,7 @@ template <int N_TILE>
 struct ConvSmem {
     static constexpr int kBStages = N_TILE >= 256 ? 3 : 4;
     static constexpr int kBBytes = N_TILE * 128;
-    __host__ __device__ static constexpr int a_bytes(int taps) { return taps == 9 ? 3 * kHaloBytes : kPlainBytes; }
+    __host__ __device__ static constexpr int a_bytes(int taps) { return taps == 9 ? (CONV_SINGLE_HALO ? kHalo1Bytes : 3 * kHaloBytes) : kPlainBytes; }
     __host__ __device__ static constexpr int b_tiles(int taps, int resident) { return resident ? taps : kBStages; }
     static constexpr int kStgBufs = N_TILE >= 256 ? 1 : 2;          // output staging tiles (128 px x 64 ch bf16)
     static constexpr int kStgBytes = 128 * 128;
@@ -363,7 +379,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                         tc::mbar_expect_tx(a_full + sa, (uint32_t)a_bytes);
                         unsigned char* dst = a_smem + sa * a_bytes;
                         const int ch0 = ap * a.Cin + c * kKC;
-                        if (a.taps == 9) {
+                        if (a.taps == 9 && CONV_SINGLE_HALO) {
+                            tc::tma_load_4d(dst, &tm_act, a_full + sa, ch0, w0 - 1, h0 - 1, b);
+                        } else if (a.taps == 9) {
                             for (int kw = 0; kw < 3; ++kw)
                                 tc::tma_load_4d(dst + kw * kHaloBytes, &tm_act, a_full + sa, ch0, w0 - 1 + kw, h0 - 1, b);
                         } else {
@@ -394,6 +412,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             // descriptors are a constant (layout, SBO, version) plus the 16-byte-granular start address, and the
             // tap / K-step offsets are compile-time constants added to the stage's base descriptor.
             const uint64_t desc_fixed = tc::smem_desc_sw128(0, 1024);
+            // A operand of a 3x3 tap in the single halo box: the 8-row groups (tile rows) are one box row = 2048 bytes apart
+            const uint64_t desc_fixed_a = (a.taps == 9 && CONV_SINGLE_HALO) ? tc::smem_desc_sw128(0, kHalo1Cols * 128) : desc_fixed;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 tc::mbar_wait(acc_empty + as, pacc ^ 1);
                 tc::fence_after_sync();
@@ -407,7 +427,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                 for (int c = 0; c < n_chunks; ++c) {
                     for (int ap = 0; ap < a.planes; ++ap) {
                         tc::mbar_wait(a_full + sa, pa);
-                        const uint64_t a_desc = desc_fixed + (uint64_t)(tc::smem_u32(a_smem + sa * a_bytes) >> 4);
+                        const uint64_t a_desc = desc_fixed_a + (uint64_t)(tc::smem_u32(a_smem + sa * a_bytes) >> 4);
                         for (int wp = 0; wp < a.planes - ap; ++wp) {
                             const bool main_acc = ap == 0 && wp == 0;
                             const uint32_t tmem_d = main_acc ? tmem_main : tmem_corr;
@@ -431,7 +451,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
                             if (a.taps == 9) {
                                 if (a.resident_b) sb = 0;
 #pragma unroll
-                                for (int t = 0; t < 9; ++t) issue_tap(((t % 3) * kHaloBytes + (t / 3) * kTileW * 128) >> 4);
+                                for (int t = 0; t < 9; ++t)
+                                    issue_tap(CONV_SINGLE_HALO ? (((t / 3) * kHalo1Cols + (t % 3)) * 128) >> 4
+                                                               : ((t % 3) * kHaloBytes + (t / 3) * kTileW * 128) >> 4);
                             } else {
                                 issue_tap(0);
                             }

@@ -132,9 +132,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 bytes (64 bf16),
 // 8-row groups `sbo_bytes` apart.  Every start address used here is a 1024-byte-aligned tile base plus
 // k*32 bytes (the K step inside the swizzle span), so the base-offset field (address bits 7..9) is zero.
-// (Starting a descriptor at an arbitrary 128-byte row with base_offset = row phase was tried for a
-// single-halo convolution and gave wrong results; taps are therefore addressed through column-shifted
-// copies whose row offsets are multiples of 1024 bytes.)
+// A descriptor may also start at an arbitrary 128-byte row of a swizzled tile as long as the base-offset field is
+// left 0: the swizzle is a function of the absolute address bits (crnn_conv.cuh, CONV_SINGLE_HALO; putting the row
+// phase into the field, round 1's attempt, gives wrong results).
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t start, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((start >> 4) & 0x3fff);

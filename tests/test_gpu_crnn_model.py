@@ -295,6 +295,10 @@ def test_model_train_mode_runs_the_reference_training_step():
     assert model.trainer.optimizer.step_count == 8
     w_trained = model.state_dict()['encoder.conv_block1.conv2.weight']
     model.eval()
+    val = model.validation_step(batch, 0)
+    assert np.isfinite(val['loss'].item()) and len(val['events']) == 2
+    tgt, pred = model.common_step(batch)
+    assert pred['event_frame_logit'].shape == tgt['event_frame_gt'].shape == (2, 16, 12)
     after = model(x.cuda())['event_frame_logit']
     assert not torch.equal(before, after)                                       # the inference path sees the new weights
     assert torch.equal(model.state_dict()['encoder.conv_block1.conv2.weight'].cpu(), w_trained.cpu())
