@@ -390,7 +390,7 @@ int crnn_conv_wgrad(const void* x, const void* gy, float* dw, int32_t B, int32_t
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + 2), 1};      // the halo is taken on dY
+        cuuint32_t box[4] = {64, (cuuint32_t)kHalo1Cols, (cuuint32_t)(kTileH + 2), 1};      // the halo is taken on dY: one 18 x 16 box
         int rc = make_tmap(&tg, gy, 4, dims, str, box);
         if (rc) return rc;
     }

@@ -8,18 +8,19 @@
 // [16 x 8 pixels] with 128-byte swizzle lands in shared memory as 128 rows (pixels = K) of 128 bytes (64 channels = M or N),
 // which is the canonical MN-major SWIZZLE_128B layout: 8-row groups 1024 bytes apart (SBO), one MMA (K = 16) per two groups.
 //
-// The halo is taken on dY (second form above): per pixel tile one plain X box and three column-shifted 18-row boxes of dY,
-// in which tap (dy, dx) is the box shifted by 2 - dx columns, read from row 2 - dy on (a 1024-byte offset).  A 64 x 64 block
-// of one tap would be an M = 64 MMA, which runs at half the tensor rate; an M = 128 MN-major operand is TWO 64-channel
-// groups a "leading byte offset" apart, and nothing says the second group has to be other channels: with LBO = 1024 bytes it
+// The halo is taken on dY (second form above): per pixel tile one plain X box and ONE 18-row x 16-column box of dY, in
+// which tap (dy, dx) starts at box row 2 - dy, column 2 - dx (the start address is then not 1024-byte aligned: fine with the
+// base-offset field 0, see crnn_conv.cuh CONV_SINGLE_HALO) and its 8-pixel rows are one box row = 2048 bytes apart.  A 64 x 64
+// block of one tap would be an M = 64 MMA, which runs at half the tensor rate; an M = 128 MN-major operand is TWO 64-channel
+// groups a "leading byte offset" apart, and nothing says the second group has to be other channels: with LBO = one box row it
 // is the same 64 output channels one pixel row further down, i.e. the neighbouring tap.  So TWO TAPS are stacked into one
-// M = 128 MMA (rows 0-63 of the accumulator = one tap, rows 64-127 = the other): (dy 2, dy 1) of each of the three boxes,
-// then (box 0, dy 0) with (box 1, dy 0) at LBO = one box; the ninth tap stays an M = 64 MMA.  5 instead of 9 MMAs per
-// 16 pixels at the same cycles each.
+// M = 128 MMA (rows 0-63 of the accumulator = one tap, rows 64-127 = the other): (dy 2, dy 1) at each of the three columns,
+// then (column 0, dy 0) with (column 1, dy 0) at LBO = one pixel = 128 bytes; the ninth tap stays an M = 64 MMA.  5 instead
+// of 9 MMAs per 16 pixels at the same cycles each.
 //
 // One CTA owns one (64 output channels) x (64 input channels) block of all nine taps and a strided share of the pixel tiles
 // (split-K over the grid's x dimension):
-//   warp 0   TMA producer: per pixel tile the X box and the three dY halo boxes (out-of-image pixels arrive as zeros)
+//   warp 0   TMA producer: per pixel tile the X box and the dY halo box (out-of-image pixels arrive as zeros)
 //   warp 1   MMA issuer: 8 x (4 MMAs M = 128 + 1 MMA M = 64, N = 64, K = 16) per pixel tile into five accumulators that live
 //            in TMEM for the whole kernel (4 x 64 columns on all 128 lanes + 64 columns on 16 lanes of each quarter)
 //   warp 2   TMEM allocation
@@ -30,16 +31,16 @@
 namespace salsa {
 namespace crnn {
 
-constexpr int kWgStages = 3;
+constexpr int kWgStages = 4;
 constexpr int kWgXBytes = kTileH * kTileW * 128;                  // X tile: 128 pixels x 64 channels
-constexpr int kWgStageBytes = kWgXBytes + 3 * kHaloBytes;
+constexpr int kWgStageBytes = kWgXBytes + kHalo1Bytes;            // + the 18 x 16 halo box of dY
 constexpr int kWgThreads = 256;
 constexpr size_t kWgSmemBytes = 1024 + (size_t)kWgStages * kWgStageBytes + 256;
 
 struct WgradArgs {
     int B, H, W, Cin, Cout;
     int tiles_w, tiles_h, n_ktiles;     // pixel tiles = B * tiles_h * tiles_w
-    int taps;                           // 9 (3x3, pad 1) or 1 (1x1: only the centre tap = box 1, row offset 1, as one M = 64 MMA)
+    int taps;                           // 9 (3x3, pad 1) or 1 (1x1: only the centre tap = box row 1, column 1, as one M = 64 MMA)
     int cin_valid;                      // input channels that exist (Cin, or 16 for the padded first convolution: TMA zero-fills
                                         // channels 16..63 of the box, and only the first 16 columns of a dW row are written)
     float* dw;                          // [taps][Cout][Cin]
@@ -104,19 +105,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const int tw = kt % a.tiles_w, th = (kt / a.tiles_w) % a.tiles_h, b = kt / (a.tiles_w * a.tiles_h);
                 const int h0 = th * kTileH, w0 = tw * kTileW;
                 tc::mbar_wait(empty + s, ph ^ 1);
-                tc::mbar_expect_tx(full + s, (uint32_t)(a.taps == 9 ? kWgStageBytes : kWgXBytes + kHaloBytes));
+                tc::mbar_expect_tx(full + s, (uint32_t)kWgStageBytes);
                 unsigned char* dst = smem + s * kWgStageBytes;
                 tc::tma_load_4d(dst, &tm_x, full + s, ci0, w0, h0, b);
-                for (int sh = (a.taps == 9 ? 0 : 1); sh < (a.taps == 9 ? 3 : 2); ++sh)
-                    tc::tma_load_4d(dst + kWgXBytes + sh * kHaloBytes, &tm_gy, full + s, co0, w0 - 1 + sh, h0 - 1, b);
+                tc::tma_load_4d(dst + kWgXBytes, &tm_gy, full + s, co0, w0 - 1, h0 - 1, b);
                 if (++s == kWgStages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             constexpr uint32_t idesc128 = idesc_bf16_mn_n64(128), idesc64 = idesc_bf16_mn_n64(64);
-            const uint64_t desc_rows = smem_desc_mn_sw128(0, 1024, 1024);                     // second M group: one pixel row down
-            const uint64_t desc_boxes = smem_desc_mn_sw128(0, (uint32_t)kHaloBytes, 1024);    // second M group: the next box
+            constexpr uint32_t kRow = kHalo1Cols * 128;                                        // one row of the dY box (2048 bytes)
+            const uint64_t desc_x = smem_desc_mn_sw128(0, 1024, 1024);                         // X tile: dense 16 x 8 pixels
+            const uint64_t desc_rows = smem_desc_mn_sw128(0, kRow, kRow);                      // second M group: one pixel row down
+            const uint64_t desc_cols = smem_desc_mn_sw128(0, 128, kRow);                       // second M group: the next column
             int s = 0;
             uint32_t ph = 0, accumulate = 0;
             for (int kt = blockIdx.x; kt < a.n_ktiles; kt += gridDim.x) {
@@ -124,25 +126,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 tc::fence_after_sync();
                 const uint32_t base = tc::smem_u32(smem + s * kWgStageBytes);
                 const uint32_t gy = base + kWgXBytes;
-                const uint64_t b_desc = desc_rows + (uint64_t)(base >> 4);
+                const uint64_t b_desc = desc_x + (uint64_t)(base >> 4);
+                // 16 pixels per MMA = two tile rows: 2048 bytes of the X tile, two box rows of dY
                 if (a.taps == 1) {
 #pragma unroll
                     for (int k = 0; k < (kTileH * kTileW) / 16; ++k)
-                        tc::mma_bf16(tmem_base + 256u, desc_rows + (uint64_t)((gy + kHaloBytes + kTileW * 128) >> 4) + (uint64_t)(k * 128),
+                        tc::mma_bf16(tmem_base + 256u, desc_rows + (uint64_t)((gy + kRow + 128) >> 4) + (uint64_t)(k * (2 * kRow >> 4)),
                                      b_desc + (uint64_t)(k * 128), idesc64, (k == 0) ? accumulate : 1u);
                 } else
 #pragma unroll
-                for (int k = 0; k < (kTileH * kTileW) / 16; ++k) {          // 16 pixels = 16 rows of 128 bytes per MMA
+                for (int k = 0; k < (kTileH * kTileW) / 16; ++k) {
                     const uint32_t acc = (k == 0) ? accumulate : 1u;
-                    const uint64_t kb = (uint64_t)(k * 128);
+                    const uint64_t ka = (uint64_t)(k * (2 * kRow >> 4)), kb = (uint64_t)(k * 128);
 #pragma unroll
-                    for (int sh = 0; sh < 3; ++sh)      // box sh (dx = 2 - sh): rows 0-63 <- dy = 2 (row offset 0), rows 64-127 <- dy = 1
-                        tc::mma_bf16(tmem_base + (uint32_t)(sh * 64), desc_rows + (uint64_t)((gy + sh * kHaloBytes) >> 4) + kb, b_desc + kb,
-                                     idesc128, acc);
-                    // dy = 0 (row offset 2): boxes 0 and 1 stacked, box 2 alone
-                    tc::mma_bf16(tmem_base + 192u, desc_boxes + (uint64_t)((gy + 2 * kTileW * 128) >> 4) + kb, b_desc + kb, idesc128, acc);
-                    tc::mma_bf16(tmem_base + 256u, desc_rows + (uint64_t)((gy + 2 * kHaloBytes + 2 * kTileW * 128) >> 4) + kb, b_desc + kb,
-                                 idesc64, acc);
+                    for (int sh = 0; sh < 3; ++sh)      // column sh (dx = 2 - sh): rows 0-63 <- dy = 2 (box row 0), rows 64-127 <- dy = 1
+                        tc::mma_bf16(tmem_base + (uint32_t)(sh * 64), desc_rows + (uint64_t)((gy + sh * 128) >> 4) + ka, b_desc + kb, idesc128, acc);
+                    // dy = 0 (box row 2): columns 0 and 1 stacked, column 2 alone
+                    tc::mma_bf16(tmem_base + 192u, desc_cols + (uint64_t)((gy + 2 * kRow) >> 4) + ka, b_desc + kb, idesc128, acc);
+                    tc::mma_bf16(tmem_base + 256u, desc_rows + (uint64_t)((gy + 2 * kRow + 2 * 128) >> 4) + ka, b_desc + kb, idesc64, acc);
                 }
                 accumulate = 1;
                 tc::mma_commit(empty + s);
@@ -158,7 +159,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int row128 = co0 + ((32 * q + lane) & 63), upper = q >> 1;
 #pragma unroll 1
         for (int j = 0; j < (a.taps == 9 ? 4 : 0); ++j) {
-            // j < 3: box j, (dy 2 | dy 1), dx = 2 - j;   j = 3: dy 0, (box 0 -> dx 2 | box 1 -> dx 1)
+            // j < 3: column j, (dy 2 | dy 1), dx = 2 - j;   j = 3: dy 0, (column 0 -> dx 2 | column 1 -> dx 1)
             const int tap = j < 3 ? (upper ? 3 : 6) + (2 - j) : (upper ? 1 : 2);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
