@@ -72,7 +72,13 @@ struct ConvArgs {
 
 template <int N_TILE>
 struct ConvSmem {
-    static constexpr int kBStages = N_TILE >= 256 ? 3 : 4;
+#ifndef CONV_B_STAGES_256
+#define CONV_B_STAGES_256 4        // 4 x 32 KB: the single halo box freed 36 KB (3 stages before); >= 256-channel layers 5-8 % faster
+#endif
+#ifndef CONV_B_STAGES_128
+#define CONV_B_STAGES_128 6
+#endif
+    static constexpr int kBStages = N_TILE >= 256 ? CONV_B_STAGES_256 : CONV_B_STAGES_128;
     static constexpr int kBBytes = N_TILE * 128;
     __host__ __device__ static constexpr int a_bytes(int taps) { return taps == 9 ? (CONV_SINGLE_HALO ? kHalo1Bytes : 3 * kHaloBytes) : kPlainBytes; }
     __host__ __device__ static constexpr int b_tiles(int taps, int resident) { return resident ? taps : kBStages; }
