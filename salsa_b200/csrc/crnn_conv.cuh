@@ -323,7 +323,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
 #ifndef CONV_PINGPONG_ALWAYS
 #define CONV_PINGPONG_ALWAYS 0
 #endif
-    const bool pingpong = a.tma_store && S::kStgBufs == 2 && (CONV_PINGPONG_ALWAYS || a.residual != nullptr);
+    // ping-pong where the epilogue dominates: layers with a residual, and the 1x1 convolutions / GEMMs (4 MMAs per chunk;
+    // measured 0.152 -> 0.135 ms on the 64 -> 128 downsample); the 3x3 layers without residual are faster split (0.338 vs 0.367)
+    const bool pingpong = a.tma_store && S::kStgBufs == 2 && (CONV_PINGPONG_ALWAYS || a.residual != nullptr || a.taps == 1);
     if (a.Cout * (int)sizeof(float) > S::kBiasBytes) bias_s = nullptr;      // wide GEMMs read the bias from global memory
     if (a.tma_store && bias_s)
         for (int i = threadIdx.x; i < a.Cout; i += kConvThreads) bias_s[i] = a.bias ? a.bias[i] : 0.0f;
