@@ -658,7 +658,7 @@ def bench_other_configs(args, torch, dist, rank, world, dev, peak):
     return res
 
 
-def bench_train(args, torch, dist, rank, world, dev):
+def bench_train(args, torch, dist, rank, world, dev, peaks=None):
     """BASELINE.json configs[4]: CRNN training on on-the-fly SALSA features, bf16, data-parallel.  Per step and rank: 32 audio
     chunks of 8 s -> SALSA FOA features (native) -> channel-swap / frequency-shift augmentation (native) -> forward + backward
     (3x3 and 1x1 convolutions in all three directions, train-mode BatchNorm + residual + ReLU + dropout, pooling and the BiGRU native; heads: torch autograd / cuBLAS) ->
@@ -689,10 +689,15 @@ def bench_train(args, torch, dist, rank, world, dev):
     # the feature part alone, for the split
     ms_feat = time_steps(torch, dist, world, dev, lambda: ex.extract(audio), 1, 3)
     n_params = int(tr.flat.numel())
+    # forward + input gradient + weight gradient = 3 x the forward's convolution FLOPs (44.74 GFLOP per chunk)
+    tflops = 3 * 2 * 22.368e9 * B / (ms / 1e3) / 1e12
+    peak = (peaks or {}).get('bf16_tflops_sustained', 1400.0)
     return {'config': 'configs[4]: CRNN (ResNet22 + BiGRU) training step on on-the-fly SALSA FOA features, bf16 autocast, batch {} x (7, 640, 200) '
                       'per GPU, {} GPU(s) data-parallel'.format(B, world),
             'value': B * world / (ms / 1e3), 'unit': 'chunks/s (8 s each)', 'audio_min_per_s': B * world * 8 / 60.0 / (ms / 1e3),
-            'ms_per_step': ms, 'ms_features': ms_feat, 'cuda_graph': ('off' if args.no_train_graph else (tr.graph_error or 'forward + loss + backward replayed as one CUDA graph; all-reduce of the flat gradient (one NCCL call) and Adam follow it')), 'loss_first_step': first, 'loss_last_step': last, 'parameters': n_params,
+            'ms_per_step': ms, 'ms_features': ms_feat,
+            'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tflops / peak,
+                         'note': 'algorithmic convolution FLOPs of forward + dgrad + wgrad per GPU over the whole step (features, BatchNorm, GRU, Adam included in the time)'}, 'cuda_graph': ('off' if args.no_train_graph else (tr.graph_error or 'forward + loss + backward replayed as one CUDA graph; all-reduce of the flat gradient (one NCCL call) and Adam follow it')), 'loss_first_step': first, 'loss_last_step': last, 'parameters': n_params,
             'allreduce': ('bf16 all-reduce of the flat gradient ({:.1f} MB on the wire per step), '.format(n_params * 2 / 1e6) +
                           ('one call after the graph replay' if (tr.use_graph and tr.graph_error is None) else 'launched per bucket during the backward pass'))
                          if world > 1 else 'single rank: none',
@@ -889,7 +894,7 @@ def main():
     train_leg = None
     if not args.no_train and args.feature == 'salsa':
         torch.cuda.empty_cache()
-        train_leg = bench_train(args, torch, dist, rank, world, dev)
+        train_leg = bench_train(args, torch, dist, rank, world, dev, peaks)
 
     if rank != 0:
         if world > 1:
